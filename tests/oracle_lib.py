@@ -1,0 +1,182 @@
+"""ctypes bindings for the CPU checkers under oracle/ (test infrastructure only).
+
+`oracle()`  -> oracle/liboracle.so   (plain-C restatements, built by `make -C oracle oracle`)
+`ref_cuhd()` etc. -> oracle/_ref/libref_*.so (the reference's own CPU sources; prebuilt here, they
+travel to the GPU box with the snapshot).  Nothing in the product package imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+
+_cache = {}
+
+
+def build_oracle():
+    """(Re)build oracle/liboracle.so and, when /root/reference is present, oracle/_ref/."""
+    subprocess.run(["make", "-C", ORACLE_DIR, "all"], check=True, capture_output=True)
+
+
+def oracle():
+    if "oracle" in _cache:
+        return _cache["oracle"]
+    path = os.path.join(ORACLE_DIR, "liboracle.so")
+    if not os.path.exists(path):
+        build_oracle()
+    lib = C.CDLL(path)
+    lib.cuhd_oracle_decode.restype = C.c_size_t
+    lib.cuhd_oracle_decode.argtypes = [_u32p, C.c_size_t, _u8p, C.c_int, _u8p, C.c_size_t]
+    lib.cuhd_oracle_canonical.restype = None
+    lib.cuhd_oracle_canonical.argtypes = [_u8p, _u8p, C.c_size_t, _u32p, _u8p]
+    lib.cuhd_oracle_build_lut.restype = None
+    lib.cuhd_oracle_build_lut.argtypes = [_u32p, _u8p, C.c_int, _u8p]
+    lib.cuhd_oracle_compressed_units.restype = C.c_size_t
+    lib.cuhd_oracle_compressed_units.argtypes = [_u64p, _u8p]
+    lib.cuhd_oracle_encode.restype = C.c_size_t
+    lib.cuhd_oracle_encode.argtypes = [_u8p, C.c_size_t, _u32p, _u8p, _u32p, C.c_size_t,
+                                       C.POINTER(C.c_size_t)]
+    _cache["oracle"] = lib
+    return lib
+
+
+def have_ref(name):
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libref_%s.so" % name))
+
+
+def ref_cuhd():
+    if "ref_cuhd" in _cache:
+        return _cache["ref_cuhd"]
+    lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libref_cuhd.so"))
+    lib.ref_cuhd_encode.restype = C.c_int
+    lib.ref_cuhd_encode.argtypes = [_u8p, C.c_size_t, _u32p, _u8p, _u8p, _u32p, C.c_size_t,
+                                    C.POINTER(C.c_size_t)]
+    lib.ref_cuhd_encode_with_table.restype = C.c_int
+    lib.ref_cuhd_encode_with_table.argtypes = [_u8p, C.c_size_t, _u32p, _u8p, _u32p, C.c_size_t]
+    lib.ref_cuhd_max_codeword_length.restype = C.c_int
+    _cache["ref_cuhd"] = lib
+    return lib
+
+
+# ---------------------------------------------------------------------------- CUHD helpers
+def cuhd_ref_encode(data):
+    """Reference llhuff on `data` -> (code[256] u32, len[256] u8, lut[2048,2] u8, units u32)."""
+    lib = ref_cuhd()
+    n = data.size
+    code = np.zeros(256, np.uint32)
+    length = np.zeros(256, np.uint8)
+    lut = np.zeros((1 << 11) * 2, np.uint8)
+    cap = n + 16  # codes are <= 11 bits -> never more than n units
+    units = np.zeros(cap, np.uint32)
+    nu = C.c_size_t(0)
+    rc = lib.ref_cuhd_encode(np.ascontiguousarray(data), n, code, length, lut, units, cap,
+                             C.byref(nu))
+    if rc != 0:
+        raise RuntimeError("reference llhuff refused input (rc=%d)" % rc)
+    return code, length, lut.reshape(-1, 2), units[: nu.value].copy()
+
+
+def cuhd_oracle_encode(data, code, length):
+    lib = oracle()
+    hist = np.bincount(data, minlength=256).astype(np.uint64)
+    nu = lib.cuhd_oracle_compressed_units(hist, length)
+    units = np.zeros(max(nu, 1), np.uint32)
+    defined = C.c_size_t(0)
+    wrote = lib.cuhd_oracle_encode(np.ascontiguousarray(data), data.size, code, length, units,
+                                   units.size, C.byref(defined))
+    assert wrote == nu, (wrote, nu)
+    return units[:nu], defined.value
+
+
+def cuhd_oracle_decode(units, lut, n_out, max_len=11):
+    lib = oracle()
+    out = np.zeros(n_out, np.uint8)
+    got = lib.cuhd_oracle_decode(np.ascontiguousarray(units), units.size,
+                                 np.ascontiguousarray(lut).reshape(-1), max_len, out, n_out)
+    return out, got
+
+
+def cuhd_oracle_lut(code, length, max_len=11):
+    lib = oracle()
+    lut = np.zeros((1 << max_len) * 2, np.uint8)
+    lib.cuhd_oracle_build_lut(code, length, max_len, lut)
+    return lut.reshape(-1, 2)
+
+
+# ---------------------------------------------------------------------------- generators
+def zipf_bytes(n, alpha=1.1, seed=12345, nsym=256):
+    """Synthetic C2 input: symbol k with P ~ 1/(k+1)^alpha, inverse-CDF sampling."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    p = 1.0 / np.arange(1, nsym + 1, dtype=np.float64) ** alpha
+    cdf = np.cumsum(p / p.sum())
+    u = rng.random(n)
+    return np.minimum(np.searchsorted(cdf, u), nsym - 1).astype(np.uint8)
+
+
+def limited_lengths(hist, max_len=11):
+    """Test-side length-limited Huffman lengths (heap Huffman + Kraft repair), used only to make
+    decodable streams when oracle/_ref is unavailable or when a test wants a specific table."""
+    import heapq
+    syms = [s for s in range(len(hist)) if hist[s] > 0]
+    length = np.zeros(256, np.uint8)
+    if len(syms) == 1:
+        length[syms[0]] = 1
+        return length
+    heap = [(int(hist[s]), i, [s]) for i, s in enumerate(syms)]
+    heapq.heapify(heap)
+    depth = {s: 0 for s in syms}
+    tie = len(heap)
+    while len(heap) > 1:
+        a = heapq.heappop(heap)
+        b = heapq.heappop(heap)
+        for s in a[2] + b[2]:
+            depth[s] += 1
+        heapq.heappush(heap, (a[0] + b[0], tie, a[2] + b[2]))
+        tie += 1
+    lens = {s: min(d, max_len) for s, d in depth.items()}
+    kraft = sum(2 ** (max_len - l) for l in lens.values())
+    order = sorted(syms, key=lambda s: (hist[s], s))
+    while kraft > 2 ** max_len:          # lengthen the rarest symbols that still can grow
+        for s in order:
+            if lens[s] < max_len:
+                kraft -= 2 ** (max_len - lens[s] - 1)
+                lens[s] += 1
+                break
+    for s, l in lens.items():
+        length[s] = l
+    return length
+
+
+def canonical_from_lengths(length):
+    """Canonical codes in (length, symbol) order via the oracle's restatement of
+    llhuffman_encoder.cc:183-195."""
+    syms = np.array(sorted([s for s in range(256) if length[s]], key=lambda s: (length[s], s)),
+                    np.uint8)
+    lens = np.ascontiguousarray(length[syms])
+    code = np.zeros(256, np.uint32)
+    out_len = np.zeros(256, np.uint8)
+    oracle().cuhd_oracle_canonical(syms, lens, syms.size, code, out_len)
+    return code, out_len
+
+
+def cuhd_make_case(data, max_len=11, use_ref=True):
+    """-> (code, len, lut[1<<max_len, 2], units incl. one zero pad unit) for `data`."""
+    if use_ref and max_len == 11 and have_ref("cuhd") and np.unique(data).size > 1:
+        code, length, lut, _ = cuhd_ref_encode(data)
+    else:
+        hist = np.bincount(data, minlength=256)
+        length = limited_lengths(hist, max_len)
+        code, length = canonical_from_lengths(length)
+        lut = cuhd_oracle_lut(code, length, max_len)
+    units, _ = cuhd_oracle_encode(data, code, length)
+    units = np.concatenate([units, np.zeros(1, np.uint32)])
+    return code, length, lut, units
