@@ -38,6 +38,26 @@ def lib():
     L.b200lc_cuhd_decode_scratch_bytes.argtypes = [sz]
     L.b200lc_cuhd_decode.restype = i32
     L.b200lc_cuhd_decode.argtypes = [vp, sz, vp, sz, vp, i32, vp, sz, vp]
+    L.b200lc_histogram_u8.restype = i32
+    L.b200lc_histogram_u8.argtypes = [vp, sz, vp, vp]
+    L.b200lc_cuhd_build_table.restype = i32
+    L.b200lc_cuhd_build_table.argtypes = [vp, i32, vp, vp, vp]
+    L.b200lc_cuhd_compressed_units.restype = sz
+    L.b200lc_cuhd_compressed_units.argtypes = [vp, vp]
+    L.b200lc_cuhd_encode_scratch_bytes.restype = sz
+    L.b200lc_cuhd_encode_scratch_bytes.argtypes = [sz]
+    L.b200lc_cuhd_encode.restype = i32
+    L.b200lc_cuhd_encode.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, sz, vp]
+    L.b200lc_cuhd_encode_overflowed.restype = i32
+    L.b200lc_cuhd_encode_overflowed.argtypes = [vp, vp]
+    L.b200lc_cuhd_session_create.restype = i32
+    L.b200lc_cuhd_session_create.argtypes = [sz, C.POINTER(vp)]
+    L.b200lc_cuhd_session_destroy.restype = i32
+    L.b200lc_cuhd_session_destroy.argtypes = [vp]
+    L.b200lc_cuhd_session_encode.restype = i32
+    L.b200lc_cuhd_session_encode.argtypes = [vp, vp, sz, i32, vp, sz, C.POINTER(sz), vp, vp, vp]
+    L.b200lc_cuhd_session_decode.restype = i32
+    L.b200lc_cuhd_session_decode.argtypes = [vp, vp, sz, vp, i32, vp, sz]
     _lib = L
     return L
 
@@ -73,3 +93,106 @@ def cuhd_decode(units, n_out, lut, max_len=11, out=None, scratch=None, stream=No
                               max_len, scratch.data_ptr(), scratch.numel(), _stream_ptr(stream))
     check(rc, "b200lc_cuhd_decode")
     return out
+
+
+def histogram_u8(data, stream=None):
+    """256-bin histogram (cuda int64 tensor) of a cuda uint8 tensor.  Asynchronous."""
+    import torch
+    assert data.is_cuda and data.dtype == torch.uint8 and data.is_contiguous()
+    hist = torch.empty(256, dtype=torch.int64, device=data.device)
+    check(lib().b200lc_histogram_u8(data.data_ptr(), data.numel(), hist.data_ptr(),
+                                    _stream_ptr(stream)), "b200lc_histogram_u8")
+    return hist
+
+
+def cuhd_build_table(hist, max_len=11):
+    """Host: histogram (array-like of 256 counts) -> (code u32[256], len u8[256], lut u8[1<<L, 2])
+    as numpy arrays."""
+    import numpy as np
+    h = np.ascontiguousarray(np.asarray(hist, dtype=np.uint64))
+    assert h.size == 256
+    code = np.zeros(256, np.uint32)
+    length = np.zeros(256, np.uint8)
+    lut = np.zeros((1 << max_len, 2), np.uint8)
+    check(lib().b200lc_cuhd_build_table(h.ctypes.data, max_len, code.ctypes.data,
+                                        length.ctypes.data, lut.ctypes.data),
+          "b200lc_cuhd_build_table")
+    return code, length, lut
+
+
+class CuhdEncoded:
+    """Result of cuhd_encode: `units` (cuda int32, incl. one zero pad unit), `n_units`, `bits`."""
+
+    def __init__(self, units, n_units, bits):
+        self.units, self.n_units, self.bits = units, n_units, bits
+
+
+def cuhd_encode(data, code, length, units_cap=None, stream=None, scratch=None, units=None,
+                total_bits=None, sync=True):
+    """Pack a cuda uint8 tensor with the dictionary (code, length: cuda int32[256] / uint8[256]).
+
+    With sync=True (default) the bit count is read back and the unit tensor is trimmed to
+    ceil(bits/32) + 1 pad unit; with sync=False the untrimmed buffer and the device bit counter
+    are returned without synchronising.
+    """
+    import torch
+    assert data.is_cuda and data.dtype == torch.uint8 and data.is_contiguous()
+    L = lib()
+    n = data.numel()
+    if units_cap is None:
+        units_cap = (n * 13 + 31) // 32 + 2 if units is None else units.numel()
+    if units is None:
+        units = torch.empty(units_cap, dtype=torch.int32, device=data.device)
+    if total_bits is None:
+        total_bits = torch.zeros(1, dtype=torch.int64, device=data.device)
+    need = L.b200lc_cuhd_encode_scratch_bytes(n)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=data.device)
+    check(L.b200lc_cuhd_encode(data.data_ptr(), n, code.data_ptr(), length.data_ptr(),
+                               units.data_ptr(), units_cap, total_bits.data_ptr(),
+                               scratch.data_ptr(), scratch.numel(), _stream_ptr(stream)),
+          "b200lc_cuhd_encode")
+    if not sync:
+        return CuhdEncoded(units, None, total_bits)
+    check(L.b200lc_cuhd_encode_overflowed(scratch.data_ptr(), _stream_ptr(stream)),
+          "b200lc_cuhd_encode (capacity)")
+    bits = int(total_bits.item())
+    n_units = (bits + 31) // 32
+    return CuhdEncoded(units[: min(n_units + 1, units_cap)], n_units, bits)
+
+
+class CuhdSession:
+    """Host-buffer CUHD encode/decode (b200lc_cuhd_session_*).  Arguments are host tensors
+    (pinned for full PCIe speed); every call is synchronous and includes H2D + D2H."""
+
+    def __init__(self, max_symbols):
+        self._h = C.c_void_p()
+        check(lib().b200lc_cuhd_session_create(max_symbols, C.byref(self._h)),
+              "b200lc_cuhd_session_create")
+
+    def close(self):
+        if self._h:
+            lib().b200lc_cuhd_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode(self, h_in, h_units, h_code, h_len, h_lut, max_len=11):
+        """-> number of stream units written to h_units (a pad unit follows them)."""
+        n_units = C.c_size_t(0)
+        check(lib().b200lc_cuhd_session_encode(self._h, h_in.data_ptr(), h_in.numel(), max_len,
+                                               h_units.data_ptr(), h_units.numel(),
+                                               C.byref(n_units), h_code.data_ptr(),
+                                               h_len.data_ptr(), h_lut.data_ptr()),
+              "b200lc_cuhd_session_encode")
+        return n_units.value
+
+    def decode(self, h_units, n_units, h_lut, h_out, max_len=11):
+        check(lib().b200lc_cuhd_session_decode(self._h, h_units.data_ptr(), n_units,
+                                               h_lut.data_ptr(), max_len, h_out.data_ptr(),
+                                               h_out.numel()),
+              "b200lc_cuhd_session_decode")

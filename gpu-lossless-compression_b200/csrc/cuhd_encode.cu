@@ -1,0 +1,402 @@
+// GPU Huffman encoder producing CUHD-format streams + byte histogram  (SURVEY.md 8f N1).
+//
+// Replaces the sequential CPU packer llhuff::LLHuffmanEncoder::encode_memory
+// (cuhd-icpp/encoder/src/llhuffman_encoder.cc:200-238; 1.27 s per 100 MiB in the reference's
+// README) and the frequency count at :23-26.  Given the same dictionary the produced units are
+// bit-identical to the reference's wherever the reference's output is defined (all units but the
+// unused low bits of the last one); the final partial unit is
+// zero-filled and always flushed.
+//
+// One persistent kernel, one pass over the input:
+//   * tiles of kThreads*kSyms symbols are staged into shared memory by 1-D TMA bulk copies
+//     (double buffered, ticket-ordered);
+//   * each thread looks its 16 symbols up once (code|len kept in registers), a block scan gives
+//     bit offsets inside the tile, a decoupled look-back over per-tile bit counts gives the
+//     tile's global bit offset -- this is the "prefix-sum bit-pack" of the north star;
+//   * the (<32) bits that precede the tile inside its first output word come from the
+//     predecessor's published 31-bit tail, so every output word is written exactly once, with
+//     plain 128-bit stores, and the output needs no zero-initialisation and no global atomics.
+#include "common.cuh"
+#include "../../include/b200lc.h"
+
+namespace b200lc {
+namespace cuhd_enc {
+
+constexpr int kThreads = 512;
+constexpr int kSyms = 16;                      // symbols per thread
+constexpr int kTileSyms = kThreads * kSyms;    // 8192
+constexpr int kMaxLen = 13;
+constexpr int kStageWords = kTileSyms * kMaxLen / 32 + 8;
+
+// Tile descriptor: two independently published 64-bit words.
+//   agg : bit 63 valid | bits 31..51 tile bit count | bits 0..30 last 31 bits of the tile
+//   incl: bit 63 valid | bits 0..62 bit count of tiles 0..t
+struct __align__(16) EncDesc {
+    u64 agg;
+    u64 incl;
+};
+constexpr u64 kValid = 1ull << 63;
+
+struct EncParams {
+    const u8 *in;
+    u64 n;
+    const u32 *code_of_symbol;  // [256]
+    const u8 *len_of_symbol;    // [256]
+    u32 *out;
+    u64 out_cap_units;
+    u64 *total_bits;            // device scalar, written by the last tile
+    u32 *overflow;              // device flag, set if out_cap_units was too small
+    EncDesc *desc;
+    u32 *ticket;
+    u32 num_tiles;
+    u32 tma_ok_base;
+};
+
+struct EncSmem {
+    __align__(16) u8 in[2][kTileSyms];
+    __align__(16) u32 stage[kStageWords];
+    u32 tab[256];
+    u32 warp_sums[kThreads / 32];
+    u64 bar[2];
+    u64 base_bits;
+    u32 tile[2];
+    u32 total;
+    u32 prev_tail;
+    u64 tail_acc[2];   // packed codes of the last two threads (low 64 bits)
+    u32 tail_bits[2];
+};
+
+__global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p)
+{
+    __shared__ EncSmem sm;
+    const u32 tid = threadIdx.x;
+    const u32 lane = tid & 31;
+
+    if (tid < 256) sm.tab[tid] = p.code_of_symbol[tid] | ((u32)p.len_of_symbol[tid] << 16);
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto tma_ok = [&](u32 tile) -> bool {
+        return p.tma_ok_base && (u64)(tile + 1) * kTileSyms <= p.n;
+    };
+    auto issue_load = [&](u32 tile, u32 buf) {
+        if (tile < p.num_tiles && tma_ok(tile)) {
+            mbar_expect_tx(&sm.bar[buf], kTileSyms);
+            tma_load_1d(sm.in[buf], p.in + (u64)tile * kTileSyms, kTileSyms, &sm.bar[buf]);
+        }
+    };
+    if (tid == 0) {
+        const u32 t0 = atomicAdd(p.ticket, 1u);
+        sm.tile[0] = t0;
+        issue_load(t0, 0);
+    }
+    __syncthreads();
+
+    u32 cur = 0, phase0 = 0, phase1 = 0;
+    while (true) {
+        const u32 tile = sm.tile[cur];
+        if (tile >= p.num_tiles) break;
+        const u64 first = (u64)tile * kTileSyms;
+        const u32 tile_n = (u32)min((u64)kTileSyms, p.n - first);
+
+        if (tma_ok(tile)) {
+            if (cur == 0) { mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
+            else          { mbar_wait(&sm.bar[1], phase1); phase1 ^= 1; }
+        } else {
+            for (u32 i = tid; i < kTileSyms; i += kThreads)
+                sm.in[cur][i] = i < tile_n ? p.in[first + i] : (u8)0;
+            fence_proxy_async();
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const u32 nt = atomicAdd(p.ticket, 1u);
+            sm.tile[cur ^ 1] = nt;
+            issue_load(nt, cur ^ 1);
+        }
+
+        // ---------------------------------------------------------------- lookup + lengths
+        u32 e[kSyms];
+        u32 my_bits = 0;
+        {
+            const uint4 v = *reinterpret_cast<const uint4 *>(&sm.in[cur][tid * kSyms]);
+            const u32 w[4] = {v.x, v.y, v.z, v.w};
+            const u32 valid = tile_n > tid * kSyms ? min((u32)kSyms, tile_n - tid * kSyms) : 0u;
+#pragma unroll
+            for (int i = 0; i < kSyms; ++i) {
+                const u32 s = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                u32 x = sm.tab[s];
+                if ((u32)i >= valid) x = 0;  // past the end of the input: zero-length code
+                e[i] = x;
+                my_bits += x >> 16;
+            }
+            if (tid >= kThreads - 2) {  // the tile's last 31 bits live in the last two threads
+                u64 acc = 0;
+#pragma unroll
+                for (int i = 0; i < kSyms; ++i) acc = (acc << (e[i] >> 16)) | (e[i] & 0xffffu);
+                sm.tail_acc[tid - (kThreads - 2)] = acc;
+                sm.tail_bits[tid - (kThreads - 2)] = my_bits;
+            }
+        }
+        // block scan of bit counts
+        u32 incl = warp_incl_scan(my_bits);
+        if (lane == 31) sm.warp_sums[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            const u32 v = tid < kThreads / 32 ? sm.warp_sums[tid] : 0u;
+            const u32 s = warp_incl_scan(v);
+            if (tid < kThreads / 32) sm.warp_sums[tid] = s - v;
+            if (tid == kThreads / 32 - 1) sm.total = s;
+        }
+        __syncthreads();
+        const u32 pre = sm.warp_sums[tid >> 5] + incl - my_bits;
+        const u32 total = sm.total;
+
+        // ---------------------------------------------------------------- publish + look-back (warp 0)
+        if (tid < 32) {
+            // last 31 bits of the tile (only a full tile has a successor, and a full tile's last
+            // two threads hold >= 32 bits)
+            if (lane == 0) {
+                const u32 nb1 = sm.tail_bits[1];
+                u64 acc = sm.tail_acc[1];
+                if (nb1 < 31) acc |= sm.tail_acc[0] << nb1;
+                const u32 tail31 = (u32)acc & 0x7fffffffu;
+                st_release_u64(&p.desc[tile].agg, kValid | ((u64)total << 31) | tail31);
+            }
+            u64 base = 0;
+            u32 prev_tail = 0;
+            if (tile > 0) {
+                // warp-wide look-back: lane i inspects tile (k - i)
+                int k = (int)tile - 1;
+                bool done = false;
+                bool first_batch = true;
+                while (!done) {
+                    const int idx = k - (int)lane;
+                    u64 a = 0, in = 0;
+                    if (idx >= 0) {
+                        in = ld_acquire_u64(&p.desc[idx].incl);
+                        if (!(in & kValid)) a = ld_acquire_u64(&p.desc[idx].agg);
+                    }
+                    const bool has_incl = idx >= 0 && (in & kValid);
+                    const bool has_any = idx < 0 || has_incl || (a & kValid);
+                    const u32 incl_mask = __ballot_sync(0xffffffffu, has_incl);
+                    const u32 any_mask = __ballot_sync(0xffffffffu, has_any);
+                    // usable prefix of lanes: all ready up to (and including) the first inclusive
+                    const u32 first_incl = incl_mask ? (u32)__ffs(incl_mask) - 1 : 32u;
+                    const u32 need = first_incl < 32 ? ((2u << first_incl) - 1) : 0xffffffffu;
+                    if ((any_mask & need) != need) continue;  // somebody not ready yet: poll again
+                    u64 contrib = 0;
+                    if (lane < first_incl && idx >= 0) contrib = (a >> 31) & 0x1fffffu;
+                    if (lane == first_incl) contrib = in & ~kValid;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                    base += contrib;
+                    if (first_batch) {
+                        // direct predecessor's tail: from its aggregate word (always published)
+                        u64 pa = 0;
+                        if (lane == 0) {
+                            pa = a & kValid ? a : ld_acquire_u64(&p.desc[tile - 1].agg);
+                            while (!(pa & kValid)) pa = ld_acquire_u64(&p.desc[tile - 1].agg);
+                        }
+                        prev_tail = (u32)__shfl_sync(0xffffffffu, pa, 0) & 0x7fffffffu;
+                        first_batch = false;
+                    }
+                    if (first_incl < 32 || k - 32 < 0) done = true;
+                    k -= 32;
+                }
+            }
+            if (lane == 0) {
+                st_release_u64(&p.desc[tile].incl, kValid | (base + total));
+                sm.base_bits = base;
+                sm.prev_tail = prev_tail;
+            }
+        }
+        __syncthreads();
+        const u64 base = sm.base_bits;
+        const u32 r = (u32)(base & 31);            // bits of word 0 that belong to predecessors
+        const u64 w0 = base >> 5;                  // global index of staging word `salign`
+        const u32 salign = (u32)(w0 & 3);          // keep 16-byte phase of global and staging equal
+        const bool last_tile = tile == p.num_tiles - 1;
+        const u32 tile_bits = r + total;
+        // words this tile writes: all complete ones, plus the final partial one on the last tile
+        const u32 nwords = last_tile ? (tile_bits + 31) >> 5 : tile_bits >> 5;
+
+        // zero the staging words that receive atomicOr contributions
+        for (u32 i = tid; i < ((tile_bits + 31) >> 5) + 1; i += kThreads) sm.stage[salign + i] = 0;
+        __syncthreads();
+        if (tid == 0 && r) atomicOr(&sm.stage[salign], (sm.prev_tail & ((1u << r) - 1)) << (32 - r));
+
+        // ---------------------------------------------------------------- pack
+        {
+            const u32 b0 = r + pre;
+            u32 wi = salign + (b0 >> 5);
+            u32 nb = b0 & 31;          // bits already occupied in the current word
+            u64 acc = 0;
+            bool first_word = true;
+#pragma unroll
+            for (int i = 0; i < kSyms; ++i) {
+                const u32 len = e[i] >> 16;
+                acc = (acc << len) | (e[i] & 0xffffu);
+                nb += len;
+                if (nb >= 32) {
+                    const u32 word = (u32)(acc >> (nb - 32));
+                    if (first_word) { atomicOr(&sm.stage[wi], word); first_word = false; }
+                    else sm.stage[wi] = word;
+                    ++wi;
+                    nb -= 32;
+                }
+            }
+            if (nb) {
+                // partial last word: the low nb bits of acc, left-aligned.  When no word was
+                // flushed the leading (b0 & 31) bits of acc are zero padding owned by others.
+                const u32 word = (u32)(acc << (32 - nb));
+                if (my_bits) atomicOr(&sm.stage[wi], word);
+            }
+        }
+        __syncthreads();
+
+        // ---------------------------------------------------------------- copy out
+        if (w0 + nwords > p.out_cap_units) {
+            if (tid == 0) atomicExch(p.overflow, 1u);
+        } else {
+            u32 *g = p.out + w0;
+            const u32 head = min(nwords, (4u - salign) & 3u);
+            const u32 nvec = (nwords - head) >> 2;
+            const u32 tail0 = head + (nvec << 2);
+            if (tid < head) g[tid] = sm.stage[salign + tid];
+            const uint4 *sv = reinterpret_cast<const uint4 *>(&sm.stage[salign + head]);
+            uint4 *gv = reinterpret_cast<uint4 *>(g + head);
+            for (u32 i = tid; i < nvec; i += kThreads) gv[i] = sv[i];
+            if (tid < nwords - tail0) g[tail0 + tid] = sm.stage[salign + tail0 + tid];
+            if (last_tile && tid == 0) {
+                *p.total_bits = base + total;
+                if (w0 + nwords < p.out_cap_units) g[nwords] = 0;  // the reference's pad unit
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------- histogram
+constexpr int kHistThreads = 256;
+__global__ void __launch_bounds__(kHistThreads) histogram_u8_kernel(const u8 *in, u64 n,
+                                                                    unsigned long long *hist)
+{
+    __shared__ u32 sh[kHistThreads / 32][256];
+    const u32 tid = threadIdx.x, warp = tid >> 5;
+    for (u32 i = tid; i < (kHistThreads / 32) * 256; i += kHistThreads) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const u64 nvec = n >> 4;
+    const uint4 *v = reinterpret_cast<const uint4 *>(in);
+    // 16-byte aligned base assumed for the vector part (checked by the host)
+    for (u64 i = (u64)blockIdx.x * kHistThreads + tid; i < nvec; i += (u64)gridDim.x * kHistThreads) {
+        const uint4 x = v[i];
+        const u32 w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            atomicAdd(&sh[warp][w[q] & 0xff], 1u);
+            atomicAdd(&sh[warp][(w[q] >> 8) & 0xff], 1u);
+            atomicAdd(&sh[warp][(w[q] >> 16) & 0xff], 1u);
+            atomicAdd(&sh[warp][w[q] >> 24], 1u);
+        }
+    }
+    if (blockIdx.x == 0)
+        for (u64 i = (nvec << 4) + tid; i < n; i += kHistThreads) atomicAdd(&sh[warp][in[i]], 1u);
+    __syncthreads();
+    if (tid < 256) {
+        u32 s = 0;
+#pragma unroll
+        for (int w = 0; w < kHistThreads / 32; ++w) s += sh[w][tid];
+        if (s) atomicAdd(&hist[tid], (unsigned long long)s);
+    }
+}
+
+static u32 tiles_for(u64 n) { return (u32)((n + kTileSyms - 1) / kTileSyms); }
+
+}  // namespace cuhd_enc
+}  // namespace b200lc
+
+using namespace b200lc;
+
+extern "C" int b200lc_histogram_u8(const uint8_t *d_in, size_t n, uint64_t *d_hist, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_hist || (n && !d_in)) return B200LC_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_in) & 15) return B200LC_ERR_ARG;
+    B200LC_CUDA_TRY(cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint64_t), stream));
+    if (n == 0) return B200LC_OK;
+    // 32-bit per-block counters: bound the bytes one block can see below 2^32
+    const u64 min_blocks = (n >> 31) + 1;
+    const u64 want = (u64)num_sms() * 8;
+    const u64 max_useful = (n / (16 * cuhd_enc::kHistThreads)) + 1;
+    u64 grid = want < max_useful ? want : max_useful;
+    if (grid < min_blocks) grid = min_blocks;
+    cuhd_enc::histogram_u8_kernel<<<(u32)grid, cuhd_enc::kHistThreads, 0, stream>>>(
+        d_in, n, reinterpret_cast<unsigned long long *>(d_hist));
+    B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}
+
+extern "C" size_t b200lc_cuhd_encode_scratch_bytes(size_t n)
+{
+    return 256 + (size_t)cuhd_enc::tiles_for(n) * sizeof(cuhd_enc::EncDesc);
+}
+
+extern "C" int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t *d_code_of_symbol,
+                                  const uint8_t *d_len_of_symbol, uint32_t *d_units,
+                                  size_t units_cap, uint64_t *d_total_bits, void *d_scratch,
+                                  size_t scratch_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_code_of_symbol || !d_len_of_symbol || !d_units || !d_total_bits || !d_scratch)
+        return B200LC_ERR_ARG;
+    if (n && !d_in) return B200LC_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_units) & 15) return B200LC_ERR_ARG;
+    const size_t need = b200lc_cuhd_encode_scratch_bytes(n);
+    if (scratch_bytes < need) return B200LC_ERR_SCRATCH;
+    B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, need, stream));
+    if (n == 0) {
+        B200LC_CUDA_TRY(cudaMemsetAsync(d_total_bits, 0, sizeof(uint64_t), stream));
+        return B200LC_OK;
+    }
+    cuhd_enc::EncParams p;
+    p.in = d_in;
+    p.n = n;
+    p.code_of_symbol = d_code_of_symbol;
+    p.len_of_symbol = d_len_of_symbol;
+    p.out = d_units;
+    p.out_cap_units = units_cap;
+    p.total_bits = d_total_bits;
+    p.ticket = reinterpret_cast<u32 *>(d_scratch);
+    p.overflow = reinterpret_cast<u32 *>(d_scratch) + 1;
+    p.desc = reinterpret_cast<cuhd_enc::EncDesc *>(reinterpret_cast<char *>(d_scratch) + 256);
+    p.num_tiles = cuhd_enc::tiles_for(n);
+    p.tma_ok_base = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
+
+    static int occ = 0;
+    if (!occ) {
+        B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, cuhd_enc::cuhd_encode_kernel, cuhd_enc::kThreads, 0));
+        if (occ < 1) return B200LC_ERR_CUDA;
+    }
+    const u32 grid = (u32)min((u64)p.num_tiles, (u64)num_sms() * (u64)occ);
+    cuhd_enc::cuhd_encode_kernel<<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}
+
+// Overflow flag of the last b200lc_cuhd_encode call on this scratch buffer (synchronises).
+extern "C" int b200lc_cuhd_encode_overflowed(const void *d_scratch, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    u32 flag = 0;
+    B200LC_CUDA_TRY(cudaMemcpyAsync(&flag, reinterpret_cast<const u32 *>(d_scratch) + 1,
+                                    sizeof(u32), cudaMemcpyDeviceToHost, stream));
+    B200LC_CUDA_TRY(cudaStreamSynchronize(stream));
+    return flag ? B200LC_ERR_OVERFLOW : B200LC_OK;
+}

@@ -1,0 +1,129 @@
+// Host-buffer entry points for the CUHD path: what the reference's demo does around
+// CUHDGPUDecoder::decode (cuhd-icpp/src/demo.cc:122-168: allocate device buffers, H2D of table
+// and stream, decode, D2H of the symbols) and around the CPU encoder (demo.cc:90-107), as one
+// C-ABI session object that owns the device buffers, the scratch and a stream.
+//
+// Host pointers handed to these functions should be pinned (cudaHostAlloc / cudaHostRegister);
+// pageable memory works but copies are then staged by the driver.
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/b200lc.h"
+
+using namespace b200lc;
+
+struct b200lc_cuhd_session {
+    size_t max_symbols = 0;
+    size_t max_units = 0;
+    cudaStream_t stream = nullptr;
+    u8 *d_symbols = nullptr;
+    u32 *d_units = nullptr;
+    u8 *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    u8 *d_small = nullptr;   // [0,2048) hist | [2048,3072) code | [3072,3328) len | [4096,..) lut | total_bits
+    u64 *h_small = nullptr;  // pinned: hist[256] + total_bits
+};
+
+static const size_t kSmallBytes = 4096 + (size_t(2) << 13) + 64;
+
+extern "C" int b200lc_cuhd_session_create(size_t max_symbols, b200lc_cuhd_session **out)
+{
+    if (!out || max_symbols == 0) return B200LC_ERR_ARG;
+    b200lc_cuhd_session *s = new (std::nothrow) b200lc_cuhd_session();
+    if (!s) return B200LC_ERR_ARG;
+    s->max_symbols = max_symbols;
+    s->max_units = (max_symbols * 13 + 31) / 32 + 2;  // worst case for 13-bit codes + pad unit
+    size_t sa = b200lc_cuhd_decode_scratch_bytes(s->max_units);
+    size_t sb = b200lc_cuhd_encode_scratch_bytes(max_symbols);
+    s->scratch_bytes = sa > sb ? sa : sb;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_symbols, max_symbols + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_units, s->max_units * sizeof(u32));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, s->scratch_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_small, kSmallBytes);
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_small, 257 * sizeof(u64), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "b200lc: cuhd session allocation failed: %s\n", cudaGetErrorString(e));
+        b200lc_cuhd_session_destroy(s);
+        return B200LC_ERR_CUDA;
+    }
+    *out = s;
+    return B200LC_OK;
+}
+
+extern "C" int b200lc_cuhd_session_destroy(b200lc_cuhd_session *s)
+{
+    if (!s) return B200LC_OK;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_symbols);
+    cudaFree(s->d_units);
+    cudaFree(s->d_scratch);
+    cudaFree(s->d_small);
+    if (s->h_small) cudaFreeHost(s->h_small);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return B200LC_OK;
+}
+
+// host symbols -> host stream units + dictionary + LUT.  Synchronous.
+extern "C" int b200lc_cuhd_session_encode(b200lc_cuhd_session *s, const uint8_t *h_in, size_t n,
+                                          int max_len, uint32_t *h_units, size_t units_cap,
+                                          size_t *n_units, uint32_t *h_code_of_symbol,
+                                          uint8_t *h_len_of_symbol, uint8_t *h_lut)
+{
+    if (!s || !h_in || !h_units || !n_units || !h_code_of_symbol || !h_len_of_symbol)
+        return B200LC_ERR_ARG;
+    if (n == 0 || n > s->max_symbols) return B200LC_ERR_ARG;
+    if (max_len < 1 || max_len > 13) return B200LC_ERR_UNSUPPORTED;
+    u64 *d_hist = reinterpret_cast<u64 *>(s->d_small);
+    u32 *d_code = reinterpret_cast<u32 *>(s->d_small + 2048);
+    u8 *d_len = s->d_small + 3072;
+    u64 *d_bits = reinterpret_cast<u64 *>(s->d_small + 4096 + (size_t(2) << 13));
+
+    B200LC_CUDA_TRY(cudaMemcpyAsync(s->d_symbols, h_in, n, cudaMemcpyHostToDevice, s->stream));
+    int rc = b200lc_histogram_u8(s->d_symbols, n, d_hist, s->stream);
+    if (rc) return rc;
+    B200LC_CUDA_TRY(cudaMemcpyAsync(s->h_small, d_hist, 256 * sizeof(u64), cudaMemcpyDeviceToHost,
+                                    s->stream));
+    B200LC_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    rc = b200lc_cuhd_build_table(s->h_small, max_len, h_code_of_symbol, h_len_of_symbol, h_lut);
+    if (rc) return rc;
+    const size_t units = b200lc_cuhd_compressed_units(s->h_small, h_len_of_symbol);
+    *n_units = units;
+    if (units + 1 > units_cap || units + 1 > s->max_units) return B200LC_ERR_OVERFLOW;
+    B200LC_CUDA_TRY(cudaMemcpyAsync(d_code, h_code_of_symbol, 256 * sizeof(u32),
+                                    cudaMemcpyHostToDevice, s->stream));
+    B200LC_CUDA_TRY(cudaMemcpyAsync(d_len, h_len_of_symbol, 256, cudaMemcpyHostToDevice, s->stream));
+    rc = b200lc_cuhd_encode(s->d_symbols, n, d_code, d_len, s->d_units, s->max_units, d_bits,
+                            s->d_scratch, s->scratch_bytes, s->stream);
+    if (rc) return rc;
+    B200LC_CUDA_TRY(cudaMemcpyAsync(h_units, s->d_units, (units + 1) * sizeof(u32),
+                                    cudaMemcpyDeviceToHost, s->stream));
+    B200LC_CUDA_TRY(cudaMemcpyAsync(&s->h_small[256], d_bits, sizeof(u64), cudaMemcpyDeviceToHost,
+                                    s->stream));
+    B200LC_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if ((s->h_small[256] + 31) / 32 != units) return B200LC_ERR_OVERFLOW;
+    return B200LC_OK;
+}
+
+// host stream units + LUT -> host symbols.  Synchronous.  This is demo.cc:138-168 in one call.
+extern "C" int b200lc_cuhd_session_decode(b200lc_cuhd_session *s, const uint32_t *h_units,
+                                          size_t n_units, const void *h_lut, int max_len,
+                                          uint8_t *h_out, size_t n_out)
+{
+    if (!s || !h_units || !h_lut || !h_out) return B200LC_ERR_ARG;
+    if (n_units == 0 || n_units > s->max_units || n_out > s->max_symbols) return B200LC_ERR_ARG;
+    if (max_len < 1 || max_len > 13) return B200LC_ERR_UNSUPPORTED;
+    u8 *d_lut = s->d_small + 4096;
+    B200LC_CUDA_TRY(cudaMemcpyAsync(d_lut, h_lut, size_t(2) << max_len, cudaMemcpyHostToDevice,
+                                    s->stream));
+    B200LC_CUDA_TRY(cudaMemcpyAsync(s->d_units, h_units, n_units * sizeof(u32),
+                                    cudaMemcpyHostToDevice, s->stream));
+    int rc = b200lc_cuhd_decode(s->d_units, n_units, s->d_symbols, n_out, d_lut, max_len,
+                                s->d_scratch, s->scratch_bytes, s->stream);
+    if (rc) return rc;
+    B200LC_CUDA_TRY(cudaMemcpyAsync(h_out, s->d_symbols, n_out, cudaMemcpyDeviceToHost, s->stream));
+    B200LC_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return B200LC_OK;
+}

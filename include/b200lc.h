@@ -59,6 +59,59 @@ int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8_t *d_out, 
                        const void *d_table, int max_codeword_length, void *d_scratch,
                        size_t scratch_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * CUHD-format encoder side: replaces the sequential CPU stages of the
+ * reference's demo (cuhd-icpp/src/demo.cc:90-107).
+ */
+
+/* 256-bin histogram of n bytes (replaces the frequency count at llhuffman_encoder.cc:23-26).
+ * d_in must be 16-byte aligned; d_hist[256] is overwritten.  Asynchronous. */
+int b200lc_histogram_u8(const uint8_t *d_in, size_t n, uint64_t *d_hist, void *stream);
+
+/* HOST function: optimal length-limited prefix code for a 256-bin histogram, canonical codes and
+ * flat decode LUT.  Counterpart of get_symbol_lengths / get_encoder_table / get_decoder_table
+ * (llhuffman_encoder.cc:18-198,240-262), with exact integer weights and (length, symbol) tie
+ * order.  All pointers are host pointers; lut (may be NULL) receives (1 << max_len) entries of
+ * {uint8 num_bits, uint8 symbol}; len_of_symbol[s] == 0 means "symbol absent". */
+int b200lc_cuhd_build_table(const uint64_t *hist, int max_len, uint32_t *code_of_symbol,
+                            uint8_t *len_of_symbol, uint8_t *lut);
+size_t b200lc_cuhd_compressed_units(const uint64_t *hist, const uint8_t *len_of_symbol);
+
+/* MSB-first bit packer, replaces LLHuffmanEncoder::encode_memory (llhuffman_encoder.cc:200-238).
+ *   d_in[n]            symbols
+ *   d_code_of_symbol   uint32[256] right-aligned codewords, d_len_of_symbol uint8[256] lengths
+ *   d_units            output, 16-byte aligned, capacity units_cap; ceil(bits/32) units are
+ *                      written, plus one zero pad unit (cuhd_input_buffer.cc:20-27) if it fits
+ *   d_total_bits       device uint64 receiving the number of stream bits
+ *   d_scratch          >= b200lc_cuhd_encode_scratch_bytes(n), 128-byte aligned
+ * Asynchronous.  b200lc_cuhd_encode_overflowed() synchronises the stream and reports
+ * B200LC_ERR_OVERFLOW if units_cap was too small for the last call on that scratch. */
+size_t b200lc_cuhd_encode_scratch_bytes(size_t n);
+int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t *d_code_of_symbol,
+                       const uint8_t *d_len_of_symbol, uint32_t *d_units, size_t units_cap,
+                       uint64_t *d_total_bits, void *d_scratch, size_t scratch_bytes,
+                       void *stream);
+int b200lc_cuhd_encode_overflowed(const void *d_scratch, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer session for the CUHD path: the reference demo's flow around the decoder
+ * (cuhd-icpp/src/demo.cc:122-168: device buffers, H2D of table + stream, decode, D2H) and around
+ * the CPU encoder (demo.cc:90-107) as two synchronous calls.  The session owns device buffers
+ * for up to max_symbols symbols, the scratch and a stream.  Host pointers should be pinned.
+ */
+typedef struct b200lc_cuhd_session b200lc_cuhd_session;
+int b200lc_cuhd_session_create(size_t max_symbols, b200lc_cuhd_session **out);
+int b200lc_cuhd_session_destroy(b200lc_cuhd_session *s);
+/* h_in[n] -> h_units[*n_units (+1 pad unit)], dictionary (h_code_of_symbol[256],
+ * h_len_of_symbol[256]) and LUT (h_lut, (1 << max_len) * 2 bytes, may be NULL). */
+int b200lc_cuhd_session_encode(b200lc_cuhd_session *s, const uint8_t *h_in, size_t n, int max_len,
+                               uint32_t *h_units, size_t units_cap, size_t *n_units,
+                               uint32_t *h_code_of_symbol, uint8_t *h_len_of_symbol,
+                               uint8_t *h_lut);
+/* h_units[n_units] + h_lut -> h_out[n_out]. */
+int b200lc_cuhd_session_decode(b200lc_cuhd_session *s, const uint32_t *h_units, size_t n_units,
+                               const void *h_lut, int max_len, uint8_t *h_out, size_t n_out);
+
 #ifdef __cplusplus
 }
 #endif

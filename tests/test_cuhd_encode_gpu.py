@@ -1,0 +1,94 @@
+"""GPU parity: b200lc_cuhd_encode / histogram / table builder vs the reference encoder and oracle.
+
+Bit-exactness bar: with the REFERENCE's dictionary as input, every unit the reference defines
+(all full units) is identical, and the last partial unit equals the
+oracle's zero-filled flush.  Round trip through b200lc_cuhd_decode is byte-identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as O
+from pkg import b200lc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _encode_gpu(data, code, length, **kw):
+    d = torch.from_numpy(data).to(DEV)
+    c = torch.from_numpy(code.view(np.int32)).to(DEV)
+    l = torch.from_numpy(length).to(DEV)
+    enc = b200lc.cuhd_encode(d, c, l, **kw)
+    torch.cuda.synchronize()
+    return enc
+
+
+@pytest.mark.parametrize("n", [2, 3, 100, 8191, 8192, 8193, 100000, (1 << 22) + 77])
+def test_encode_matches_reference_and_oracle(n):
+    data = O.zipf_bytes(n, 1.1, seed=n)
+    if O.have_ref("cuhd"):
+        code, length, lut, ref_units = O.cuhd_ref_encode(data)
+    else:
+        code, length, lut, _ = O.cuhd_make_case(data, use_ref=False)
+        ref_units = None
+    want, defined = O.cuhd_oracle_encode(data, code, length)
+    enc = _encode_gpu(data, code, length)
+    got = enc.units.cpu().numpy().view(np.uint32)
+    assert enc.n_units == want.size
+    assert np.array_equal(got[: want.size], want)
+    assert got[want.size] == 0          # pad unit (cuhd_input_buffer.cc:20-27)
+    if ref_units is not None:
+        assert ref_units.size == want.size
+        assert np.array_equal(got[:defined], ref_units[:defined])
+
+
+@pytest.mark.parametrize("kind", ["uniform", "two", "single", "skew4", "long_codes"])
+def test_encode_roundtrip_distributions(kind):
+    rng = np.random.default_rng(5)
+    n = 3_000_001
+    if kind == "uniform":
+        data = rng.integers(0, 256, n, dtype=np.uint8)
+    elif kind == "two":
+        data = rng.integers(0, 2, n, dtype=np.uint8)
+    elif kind == "single":
+        data = np.full(n, 7, np.uint8)
+    elif kind == "skew4":
+        data = O.zipf_bytes(n, 4.0, seed=1)
+    else:
+        data = O.zipf_bytes(n, 1.1, seed=2)
+        data[100000:400000] = 255
+    d = torch.from_numpy(data).to(DEV)
+    hist = b200lc.histogram_u8(d)
+    torch.cuda.synchronize()
+    h = hist.cpu().numpy()
+    assert np.array_equal(h, np.bincount(data, minlength=256))
+    code, length, lut = b200lc.cuhd_build_table(h)
+    want, _ = O.cuhd_oracle_encode(data, code, length)
+    enc = _encode_gpu(data, code, length)
+    got = enc.units.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[: want.size], want)
+    out = b200lc.cuhd_decode(enc.units, n, torch.from_numpy(lut).to(DEV))
+    torch.cuda.synchronize()
+    assert torch.equal(out, d)
+
+
+def test_encode_capacity_overflow_is_reported():
+    data = O.zipf_bytes(200000, 1.1, seed=3)
+    code, length, lut, _ = O.cuhd_make_case(data)
+    with pytest.raises(b200lc.B200LCError):
+        _encode_gpu(data, code, length, units_cap=1000)
+
+
+def test_encode_unaligned_input_base():
+    data = O.zipf_bytes(100001, 1.1, seed=4)
+    code, length, lut, _ = O.cuhd_make_case(data)
+    want, _ = O.cuhd_oracle_encode(data, code, length)
+    buf = torch.zeros(data.size + 16, dtype=torch.uint8, device=DEV)
+    view = buf[3:3 + data.size]
+    view.copy_(torch.from_numpy(data))
+    c = torch.from_numpy(code.view(np.int32)).to(DEV)
+    l = torch.from_numpy(length).to(DEV)
+    enc = b200lc.cuhd_encode(view, c, l)
+    got = enc.units.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[: want.size], want)
