@@ -20,7 +20,7 @@
 //     buffer and leaves with 16-byte coalesced stores instead of phase 4's per-thread byte
 //     stores (:101-105).
 //
-// HBM traffic is therefore units-in + symbols-out + 128 B of descriptor per tile; the
+// HBM traffic is therefore units-in + symbols-out + 64 B of descriptor per tile; the
 // reference's 20 B of sync-point state per 16 B of input is gone.
 //
 // Decode contract (bit-exact with the reference): out[i] = symbol of
@@ -33,19 +33,25 @@ namespace b200lc {
 namespace cuhd {
 
 constexpr u32 kMaxStates = 16;       // entry states 0..L-1, L <= 13 supported
-constexpr u32 kUnknown = 0xFFu;
+constexpr int kAltMaxSub = 8;        // entry-state walks give up after this many subsequences
 constexpr u64 kInclValid = 1ull << 63;
 constexpr u64 kCountMask = (1ull << 56) - 1;
 
-struct __align__(128) TileDesc {
-    u64 incl;            // bit 63 valid | bits 56..59 end state | bits 0..55 symbols before next tile
-    u32 agg_ready;       // 1 once end[]/cnt[] are valid
-    u32 pad0;
-    u8 end[kMaxStates];  // end state per entry state, kUnknown if it did not merge in this tile
-    u32 cnt[kMaxStates]; // symbols starting in this tile per entry state
-    u32 pad1[6];
+// One 64-byte descriptor per tile, three independently readable parts:
+//   incl : bit 63 valid | bits 56..59 exit state | bits 0..55 symbols that start before the next tile
+//   agg  : bit 63 valid | bits 56..59 exit state E of every entry state that merges |
+//          bits 40..55 mask of entry states that merge | bits 0..31 symbols for entry state 0
+//   d[a] : symbols for entry state a minus symbols for entry state 0 (valid if mask bit a)
+// By construction every merging entry state leaves the tile in the same state E, so a chain of
+// tiles is traversable from aggregates alone whenever E of tile t-1 is in the mask of tile t.
+struct __align__(64) TileDesc {
+    u64 incl;
+    u64 agg;
+    short d[kMaxStates];
+    u8 pad[16];
 };
-static_assert(sizeof(TileDesc) == 128, "descriptor is one 128-byte line");
+static_assert(sizeof(TileDesc) == 64, "descriptor is 64 bytes");
+constexpr u64 kAggValid = 1ull << 63;
 
 struct DecodeParams {
     const u32 *units;
@@ -56,7 +62,8 @@ struct DecodeParams {
     u64 n_out;
     TileDesc *desc;
     u32 *ticket;
-    u32 num_tiles;
+    u32 num_subtiles;
+    u32 num_pieces;
     u32 tma_ok_base;     // 1 if units pointer is 16-byte aligned
 };
 
@@ -136,29 +143,34 @@ __device__ __forceinline__ void walk_write(const u32 (&u)[S + 1], const u32 *tab
 }
 
 // ---------------------------------------------------------------------------------- kernel
-template <int S, int T, int CAP>
+// Work decomposition: subsequence = S units (one thread), sub-tile = T subsequences (one TMA
+// transfer, T*S*4 bytes), piece = NSUB sub-tiles handled by one CTA between two look-backs.
+template <int S, int T, int NSUB, int CAP>
 struct SmemLayout {
     static constexpr int kTileUnits = T * S + 4;  // + one 16-byte lookahead
     u32 in[2][kTileUnits];
     __align__(16) u8 stage[CAP + 16];
+    u32 masks[T * S];        // sub-tile 0 only: codeword-start masks of the paths from bit 0
+    u32 pre[T + 1];          // sub-tile 0 only: exclusive prefix of resolved symbol counts
+    u16 saved[NSUB][T];      // pass A result per subsequence: entry state << 12 | symbol count
+    u32 sub_total[NSUB];     // pass A symbols per sub-tile
+    u8 sub_entry[NSUB];      // pass A entry / exit state per sub-tile
+    u8 sub_exit[NSUB];
     u32 warp_sums[T / 32];
-    u32 mask0[S];
-    u8 end[T];
+    u8 end[T];               // resolved exit state of every subsequence of the current sub-tile
+    u8 onpath[T];            // sub-tile 0 only: resolved path ends on the recorded path
     u64 bar[2];
     u64 base;
-    u32 tile[2];
+    u32 next_piece;
     u32 total;
     u32 astar;
-    u32 e0_first;
-    u32 cnt_first;
-    u32 redo;
-    int delta;
+    u32 known;
 };
 
-template <int S, int T, int CAP>
+template <int S, int T, int NSUB, int CAP>
 __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams p)
 {
-    using Smem = SmemLayout<S, T, CAP>;
+    using Smem = SmemLayout<S, T, NSUB, CAP>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     u32 *tab = reinterpret_cast<u32 *>(smem_raw + ((sizeof(Smem) + 127) & ~size_t(127)));
@@ -187,95 +199,87 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
     }
     __syncthreads();
 
-    auto tma_ok = [&](u32 tile) -> bool {
-        return p.tma_ok_base && (u64)(tile + 1) * (T * S) + 4 <= p.n_units;
+    // sub-tile index g (global) -> can it be fetched by one TMA bulk copy?
+    auto tma_ok = [&](u32 g) -> bool {
+        return p.tma_ok_base && (u64)(g + 1) * (T * S) + 4 <= p.n_units;
     };
-    auto issue_load = [&](u32 tile, u32 buf) {  // one thread
-        if (tile < p.num_tiles && tma_ok(tile)) {
+    auto issue_load = [&](u32 g, u32 buf) {  // one thread
+        if (g < p.num_subtiles && tma_ok(g)) {
             mbar_expect_tx(&sm.bar[buf], kTileBytes);
-            tma_load_1d(sm.in[buf], p.units + (u64)tile * (T * S), kTileBytes, &sm.bar[buf]);
+            tma_load_1d(sm.in[buf], p.units + (u64)g * (T * S), kTileBytes, &sm.bar[buf]);
         }
     };
 
     if (tid == 0) {
         const u32 t0 = atomicAdd(p.ticket, 1u);
-        sm.tile[0] = t0;
-        issue_load(t0, 0);
+        sm.next_piece = t0;
+        if (t0 < p.num_pieces) issue_load(t0 * NSUB, 0);
     }
     __syncthreads();
 
-    u32 cur = 0;
+    u32 step = 0;               // buffer = step & 1
     u32 phase0 = 0, phase1 = 0;
-    while (true) {
-        const u32 tile = sm.tile[cur];
-        if (tile >= p.num_tiles) break;
 
-        // ---------------------------------------------------------------- stage input
-        if (tma_ok(tile)) {
-            if (cur == 0) { mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
+    // wait for (or synchronously load) sub-tile g into buffer (step & 1)
+    auto acquire_input = [&](u32 g) {
+        const u32 buf = step & 1;
+        if (tma_ok(g)) {
+            if (buf == 0) { mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
             else          { mbar_wait(&sm.bar[1], phase1); phase1 ^= 1; }
         } else {
-            const u64 first = (u64)tile * (T * S);
+            const u64 first = (u64)g * (T * S);
             for (u32 i = tid; i < kTileUnits; i += blockDim.x) {
                 const u64 idx = first + i;
-                sm.in[cur][i] = idx < p.n_units ? p.units[idx] : 0u;
+                sm.in[buf][i] = idx < p.n_units ? p.units[idx] : 0u;
             }
             fence_proxy_async();
             __syncthreads();
         }
-        if (tid == 0) {  // ticket + TMA prefetch of the next tile into the other buffer
-            const u32 nt = atomicAdd(p.ticket, 1u);
-            sm.tile[cur ^ 1] = nt;
-            issue_load(nt, cur ^ 1);
-        }
+    };
 
-        // ---------------------------------------------------------------- round 0
+    while (true) {
+        const u32 piece = sm.next_piece;
+        if (piece >= p.num_pieces) break;
+        const u32 g0 = piece * NSUB;
+        const u32 nsub = min((u32)NSUB, p.num_subtiles - g0);
+
         u32 u[S + 1], m[S];
         u32 e0 = 0, c0 = 0;
-        if (worker) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(&sm.in[cur][tid * S]);
+        u32 my_start = 0, my_end = 0, my_cnt = 0;
+        u32 pre = 0;
+
+        auto load_units = [&](u32 buf) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(&sm.in[buf][tid * S]);
 #pragma unroll
             for (int q = 0; q < S / 4; ++q) {
                 const uint4 v = src[q];
                 u[4 * q + 0] = v.x; u[4 * q + 1] = v.y; u[4 * q + 2] = v.z; u[4 * q + 3] = v.w;
             }
-            u[S] = sm.in[cur][tid * S + S];
-            walk_record<S>(u, tab, shift, m, e0, c0);
-            sm.end[tid] = (u8)e0;
-            if (tid == 0) {
+            u[S] = sm.in[buf][tid * S + S];
+        };
+        // Round 0 + chain resolution of the current sub-tile for entry state `entry`.
+        // Leaves my_start / my_end / my_cnt per worker and sm.end[] = resolved exit states.
+        auto resolve_subtile = [&](u32 entry, bool keep_masks) {
+            if (worker) {
+                walk_record<S>(u, tab, shift, m, e0, c0);
+                sm.end[tid] = (u8)e0;
+                if (keep_masks) {
 #pragma unroll
-                for (int j = 0; j < S; ++j) sm.mask0[j] = m[j];
-                sm.e0_first = e0;
-                sm.cnt_first = c0;
+                    for (int j = 0; j < S; ++j) sm.masks[tid * S + j] = m[j];
+                }
             }
-        }
-        __syncthreads();
-
-        // ---------------------------------------------------------------- chain from state 0
-        u32 my_start = 0, my_end = e0, my_cnt = c0;
-        bool need_eval = false;
-        if (worker && tid > 0) {
-            my_start = sm.end[tid - 1];
-            need_eval = my_start != 0;
-        }
-        // entry states 1..L-1 of the tile's first subsequence (alt warp, one lane per state)
-        u32 alt_end = kUnknown, alt_cnt = 0;
-        if (!worker && lane >= 1 && lane < L) {
-            u32 au[S + 1], am[S];
-#pragma unroll
-            for (int j = 0; j <= S; ++j) au[j] = sm.in[cur][j];
-#pragma unroll
-            for (int j = 0; j < S; ++j) am[j] = sm.mask0[j];
-            walk_merge<S>(au, am, lane, sm.e0_first, tab, shift, alt_end, alt_cnt);
-        }
-        __syncthreads();
-
-        auto resolve = [&](bool eval) {
+            __syncthreads();
+            my_start = entry;
+            my_end = e0;
+            my_cnt = c0;
+            if (worker && tid > 0) my_start = sm.end[tid - 1];
+            bool eval = worker && my_start != 0;
+            __syncthreads();
             while (true) {
                 bool changed = false;
                 if (eval) {
-                    u32 ne = e0, nc = c0;
-                    if (my_start != 0) walk_merge<S>(u, m, my_start, e0, tab, shift, ne, nc);
+                    u32 ne, nc;
+                    walk_merge<S>(u, m, my_start, e0, tab, shift, ne, nc);
                     changed = ne != my_end;
                     my_end = ne;
                     my_cnt = nc;
@@ -291,10 +295,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
                 __syncthreads();
             }
         };
-        resolve(need_eval);
-
-        // ---------------------------------------------------------------- block scan of counts
-        u32 pre = 0;
+        // exclusive scan of my_cnt over the workers -> pre, sm.total
         auto block_scan = [&]() {
             u32 incl = 0;
             if (worker) {
@@ -311,171 +312,257 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             __syncthreads();
             if (worker) pre = sm.warp_sums[tid >> 5] + incl - my_cnt;
         };
-        block_scan();
-
-        // ---------------------------------------------------------------- publish + look-back
-        if (!worker) {
-            const u32 total0 = sm.total;
-            const u32 tile_end0 = sm.end[T - 1];
-            u32 f_end = kUnknown, f_cnt = 0;  // this tile as a function of entry state `lane`
-            if (lane == 0) {
-                f_end = tile_end0;
-                f_cnt = total0;
-            } else if (lane < L && alt_end == sm.e0_first) {
-                f_end = tile_end0;
-                f_cnt = total0 - sm.cnt_first + alt_cnt;
+        // prefetch the sub-tile of the NEXT step into the other buffer (one thread)
+        auto prefetch = [&](u32 pass, u32 c) {
+            if (tid != 0) return;
+            u32 g;
+            if (c + 1 < nsub) g = g0 + c + 1;
+            else if (pass == 0) g = g0;
+            else {
+                const u32 np = atomicAdd(p.ticket, 1u);
+                sm.next_piece = np;
+                if (np >= p.num_pieces) return;
+                g = np * NSUB;
             }
-            TileDesc *d = &p.desc[tile];
+            issue_load(g, (step & 1) ^ 1);
+        };
+
+        // ================================================================ pass A: states + counts
+        u32 entry = 0;
+        u32 piece_total = 0;
+        int dl = 0;            // alt warp: symbols(entry state lane) - symbols(entry state 0)
+        bool known = false;
+        for (u32 c = 0; c < nsub; ++c) {
+            acquire_input(g0 + c);
+            prefetch(0, c);
+            const u32 buf = step & 1;
+            if (worker) load_units(buf);
+            resolve_subtile(entry, c == 0);
+            block_scan();
+            if (worker) {
+                sm.saved[c][tid] = (u16)((my_start << 12) | my_cnt);
+                if (c == 0) {
+                    sm.pre[tid] = pre;
+                    sm.onpath[tid] = my_end == e0;
+                    if (tid == T - 1) sm.pre[T] = pre + my_cnt;
+                }
+                if (tid == T - 1) {
+                    sm.sub_entry[c] = (u8)entry;
+                    sm.sub_exit[c] = (u8)my_end;
+                    sm.sub_total[c] = sm.total;
+                }
+            }
+            piece_total += sm.total;
+            entry = sm.end[T - 1];
+            if (c == 0) {
+                __syncthreads();
+                // The piece as a function of its entry state `lane`: walk from bit `lane` of the
+                // first subsequence until the walk lands on the resolved path (usually within a
+                // few symbols); from there on the piece behaves as for entry state 0.
+                if (!worker) {
+                    if (lane == 0) {
+                        known = true;
+                    } else if (lane < L) {
+                        u32 at = lane, own = 0;
+                        for (u32 sq = 0; sq < (u32)min(T, kAltMaxSub); ++sq) {
+                            u32 au[S + 1], am[S];
+#pragma unroll
+                            for (int j = 0; j <= S; ++j) au[j] = sm.in[buf][sq * S + j];
+                            const bool onp = sm.onpath[sq];
+#pragma unroll
+                            for (int j = 0; j < S; ++j) am[j] = onp ? sm.masks[sq * S + j] : 0u;
+                            const u32 rend = sm.end[sq];
+                            u32 ne, nc;
+                            walk_merge<S>(au, am, at, rend, tab, shift, ne, nc);
+                            own += nc;
+                            if (ne == rend) {
+                                dl = (int)own - (int)sm.pre[sq + 1];
+                                known = dl >= -32768 && dl <= 32767;
+                                break;
+                            }
+                            at = ne;
+                        }
+                    }
+                }
+            }
+            __syncthreads();   // buffer hand-over, sm.end / sm.total reuse
+            ++step;
+        }
+
+        // ================================================================ publish + look-back
+        if (!worker) {
+            const u32 total0 = piece_total;
+            const u32 exit0 = entry;
+            const u32 known_mask = __ballot_sync(0xffffffffu, known) & 0xffffu;
+            TileDesc *d = &p.desc[piece];
             u32 astar = 0;
             u64 base = 0;
-            if (tile == 0) {
-                if (lane == 0) st_release_u64(&d->incl, kInclValid | ((u64)f_end << 56) | f_cnt);
+            if (piece == 0) {
+                if (lane == 0) st_release_u64(&d->incl, kInclValid | ((u64)exit0 << 56) | total0);
             } else {
-                if (lane < kMaxStates) {
-                    d->end[lane] = (u8)f_end;
-                    d->cnt[lane] = f_cnt;
-                }
+                if (lane < kMaxStates) d->d[lane] = (short)(known ? dl : 0);
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) st_release_u32(&d->agg_ready, 1u);
+                if (lane == 0)
+                    st_release_u64(&d->agg, kAggValid | ((u64)exit0 << 56) |
+                                                ((u64)known_mask << 40) | total0);
 
-                // comp = effect of tiles (k, tile) on the entry state of tile k+1
-                u32 comp_end = lane < kMaxStates ? lane : kUnknown;
-                u64 comp_cnt = 0;
-                u32 k = tile - 1;
+                // warp-wide look-back: lane i inspects piece k - i; windows overlap by one so
+                // that every traversed piece sees the exit state of its predecessor.
+                int k = (int)piece - 1;
+                u64 acc = 0;
+                bool first = true;
+                u32 carried = 0;   // exit state assumed for the overlap piece by the previous window
                 while (true) {
-                    const TileDesc *q = &p.desc[k];
-                    const u64 incl = ld_acquire_u64(&q->incl);
-                    if (incl & kInclValid) {
-                        const u32 x = (u32)(incl >> 56) & 0xfu;
-                        const u32 r_end = __shfl_sync(0xffffffffu, comp_end, x);
-                        const u64 r_cnt = __shfl_sync(0xffffffffu, comp_cnt, x);
-                        if (r_end != kUnknown) {
-                            astar = r_end;
-                            base = (incl & kCountMask) + r_cnt;
-                            break;
-                        }
-                        // the needed entry did not merge somewhere in (k, tile): wait for the
-                        // direct predecessor to finish its own slow path.
-                        comp_end = lane < kMaxStates ? lane : kUnknown;
-                        comp_cnt = 0;
-                        k = tile - 1;
-                        while (!(ld_acquire_u64(&p.desc[k].incl) & kInclValid)) __nanosleep(64);
+                    const int idx = k - (int)lane;
+                    u64 A = 0, I = 0;
+                    if (idx >= 0) {
+                        I = ld_acquire_u64(&p.desc[idx].incl);
+                        A = ld_acquire_u64(&p.desc[idx].agg);
+                    }
+                    const bool has_incl = (I & kInclValid) != 0;
+                    const u32 incl_mask = __ballot_sync(0xffffffffu, has_incl);
+                    const u32 pl = incl_mask ? (u32)__ffs(incl_mask) - 1 : 32u;
+                    const bool agg_ok = idx < 0 || (A & kAggValid) != 0;
+                    const u32 agg_mask = __ballot_sync(0xffffffffu, agg_ok);
+                    const u32 need = pl >= 32 ? 0xffffffffu : ((1u << pl) - 1);
+                    if ((agg_mask & need) != need) {
+                        __nanosleep(100);
                         continue;
                     }
-                    if (!ld_acquire_u32(&q->agg_ready)) {
-                        __nanosleep(32);
+                    const u32 prov = has_incl ? (u32)(I >> 56) & 0xfu : (u32)(A >> 56) & 0xfu;
+                    if (!first && __shfl_sync(0xffffffffu, prov, 0) != carried) {
+                        // the overlap piece left in another state than assumed: start over
+                        k = (int)piece - 1;
+                        acc = 0;
+                        first = true;
                         continue;
                     }
-                    u32 e = kUnknown, c = 0;
-                    if (lane < kMaxStates) {
-                        e = __ldcg(&q->end[lane]);
-                        c = __ldcg(&q->cnt[lane]);
+                    const u32 in = __shfl_down_sync(0xffffffffu, prov, 1);
+                    const u32 nl = min(pl, 31u);   // lanes [0, nl) are traversed in this window
+                    bool ok = true;
+                    u32 c = 0;
+                    if (lane < nl) {
+                        ok = ((u32)(A >> 40) >> in) & 1u;
+                        if (ok) c = (u32)((int)(u32)A + (int)__ldcg(&p.desc[idx].d[in]));
                     }
-                    const u32 src = e & 0xfu;
-                    const u32 ne = __shfl_sync(0xffffffffu, comp_end, src);
-                    const u64 nc = __shfl_sync(0xffffffffu, comp_cnt, src);
-                    if (e == kUnknown || ne == kUnknown) {
-                        comp_end = kUnknown;
-                        comp_cnt = 0;
-                    } else {
-                        comp_end = ne;
-                        comp_cnt = nc + c;
+                    if (!__all_sync(0xffffffffu, ok)) {
+                        __nanosleep(200);   // a piece on the way must publish its own inclusive state
+                        continue;
                     }
-                    --k;  // k == 0 always carries a valid inclusive prefix, so this terminates
+                    u64 sum = c;
+#pragma unroll
+                    for (int dd = 16; dd > 0; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
+                    acc += sum;
+                    if (first) {
+                        astar = __shfl_sync(0xffffffffu, prov, 0);
+                        first = false;
+                    }
+                    if (pl < 32) {
+                        base = (__shfl_sync(0xffffffffu, I, pl) & kCountMask) + acc;
+                        break;
+                    }
+                    carried = __shfl_sync(0xffffffffu, prov, 31);
+                    k -= 31;
                 }
-                // inclusive prefix of this tile, if its entry state merged
-                const u32 my_f_end = __shfl_sync(0xffffffffu, f_end, astar);
-                const u32 my_f_cnt = __shfl_sync(0xffffffffu, f_cnt, astar);
-                if (lane == 0 && my_f_end != kUnknown)
-                    st_release_u64(&d->incl, kInclValid | ((u64)my_f_end << 56) | (base + my_f_cnt));
+                // inclusive state of this piece, if its entry state merges
+                const bool my_known = (known_mask >> astar) & 1u;
+                const int my_d = __shfl_sync(0xffffffffu, dl, astar);
+                if (lane == 0 && my_known)
+                    st_release_u64(&d->incl, kInclValid | ((u64)exit0 << 56) |
+                                                 (base + (u64)((int)total0 + my_d)));
+                if (lane == 0) sm.known = my_known;
             }
             if (lane == 0) {
                 sm.astar = astar;
                 sm.base = base;
-                sm.redo = 0;
-                sm.delta = 0;
+                if (piece == 0) sm.known = 1;
             }
         }
         __syncthreads();
 
-        // ---------------------------------------------------------------- fix-up for entry state a*
-        const u32 astar = sm.astar;
-        const u64 base = sm.base;
-        if (astar != 0) {
-            if (tid == 0) {
-                u32 ne, nc;
-                walk_merge<S>(u, m, astar, e0, tab, shift, ne, nc);
-                my_start = astar;
-                if (ne == my_end) {
-                    sm.delta = (int)nc - (int)my_cnt;
-                    my_cnt = nc;
-                } else {
-                    sm.redo = 1;
-                }
-            }
-            __syncthreads();
-            if (sm.redo) {
-                // rare: the true entry state does not merge inside the first subsequence
-                resolve(tid == 0);
-                block_scan();
-                if (tid == 0)
-                    st_release_u64(&p.desc[tile].incl,
-                                   kInclValid | ((u64)sm.end[T - 1] << 56) | (base + sm.total));
+        // ================================================================ pass B: decode + write
+        u32 entry_true = sm.astar;
+        u64 base_run = sm.base;
+        const bool publish_late = !sm.known;
+        for (u32 c = 0; c < nsub; ++c) {
+            acquire_input(g0 + c);
+            prefetch(1, c);
+            const u32 buf = step & 1;
+            if (worker) load_units(buf);
+            u32 exit_state;
+            if (entry_true != sm.sub_entry[c]) {
+                // entry state differs from what pass A assumed (always for sub-tile 0 when the
+                // piece's entry state is not 0): redo states + counts for this sub-tile
+                resolve_subtile(entry_true, false);
+                exit_state = sm.end[T - 1];
             } else {
-                if (worker && tid > 0) pre += sm.delta;
-            }
-        }
-        const u32 total = sm.redo ? sm.total : (u32)((int)sm.total + sm.delta);
-
-        // ---------------------------------------------------------------- write pass
-        u64 tile_cnt = 0;
-        if (base < p.n_out) tile_cnt = min((u64)total, p.n_out - base);
-        for (u32 w0 = 0; w0 < tile_cnt; w0 += CAP) {
-            const u32 wlen = (u32)min((u64)CAP, tile_cnt - w0);
-            u8 *g = p.out + base + w0;
-            const u32 sh = (u32)(reinterpret_cast<uintptr_t>(g) & 15u);
-            if (worker) {
-                const u32 lo = w0, hi = w0 + wlen;
-                if (pre < hi && pre + my_cnt > lo) {
-                    u8 *dst = sm.stage + ((int)sh - (int)w0);
-                    if (pre >= lo && pre + my_cnt <= hi)
-                        walk_write<S, false>(u, tab, shift, my_start, dst, pre, lo, hi);
-                    else
-                        walk_write<S, true>(u, tab, shift, my_start, dst, pre, lo, hi);
+                if (worker) {
+                    const u32 sv = sm.saved[c][tid];
+                    my_start = sv >> 12;
+                    my_cnt = sv & 0xfffu;
                 }
+                exit_state = sm.sub_exit[c];
             }
-            __syncthreads();
-            const u32 head = min(wlen, (16u - sh) & 15u);
-            const u32 nvec = (wlen - head) >> 4;
-            const u32 tail0 = head + (nvec << 4);
-            if (tid < head) g[tid] = sm.stage[sh + tid];
-            const uint4 *sv = reinterpret_cast<const uint4 *>(sm.stage + sh + head);
-            uint4 *gv = reinterpret_cast<uint4 *>(g + head);
-            for (u32 i = tid; i < nvec; i += blockDim.x) gv[i] = sv[i];
-            if (tid < wlen - tail0) g[tail0 + tid] = sm.stage[sh + tail0 + tid];
-            __syncthreads();
+            block_scan();
+            const u32 total = sm.total;
+
+            u64 tile_cnt = 0;
+            if (base_run < p.n_out) tile_cnt = min((u64)total, p.n_out - base_run);
+            for (u32 w0 = 0; w0 < tile_cnt; w0 += CAP) {
+                const u32 wlen = (u32)min((u64)CAP, tile_cnt - w0);
+                u8 *g = p.out + base_run + w0;
+                const u32 sh = (u32)(reinterpret_cast<uintptr_t>(g) & 15u);
+                if (worker) {
+                    const u32 lo = w0, hi = w0 + wlen;
+                    if (pre < hi && pre + my_cnt > lo) {
+                        u8 *dst = sm.stage + ((int)sh - (int)w0);
+                        if (pre >= lo && pre + my_cnt <= hi)
+                            walk_write<S, false>(u, tab, shift, my_start, dst, pre, lo, hi);
+                        else
+                            walk_write<S, true>(u, tab, shift, my_start, dst, pre, lo, hi);
+                    }
+                }
+                __syncthreads();
+                const u32 head = min(wlen, (16u - sh) & 15u);
+                const u32 nvec = (wlen - head) >> 4;
+                const u32 tail0 = head + (nvec << 4);
+                if (tid < head) g[tid] = sm.stage[sh + tid];
+                const uint4 *sv = reinterpret_cast<const uint4 *>(sm.stage + sh + head);
+                uint4 *gv = reinterpret_cast<uint4 *>(g + head);
+                for (u32 i = tid; i < nvec; i += blockDim.x) gv[i] = sv[i];
+                if (tid < wlen - tail0) g[tail0 + tid] = sm.stage[sh + tail0 + tid];
+                __syncthreads();
+            }
+            base_run += total;
+            entry_true = exit_state;
+            __syncthreads();   // buffer hand-over, sm.total / sm.end reuse
+            ++step;
         }
-        __syncthreads();  // sm.redo/sm.delta/sm.tile reuse, input buffer hand-over
-        cur ^= 1;
+        if (publish_late && tid == 0)
+            st_release_u64(&p.desc[piece].incl,
+                           kInclValid | ((u64)entry_true << 56) | base_run);
+        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------- host
 constexpr int kS = 4;
 constexpr int kT = 256;
+constexpr int kNSub = 32;                 // piece = 32 sub-tiles = 128 KiB of stream
 constexpr int kCap = 3 * kT * kS * 4;
 
 static size_t smem_bytes(u32 L)
 {
-    return ((sizeof(SmemLayout<kS, kT, kCap>) + 127) & ~size_t(127)) + (size_t(4) << L);
+    return ((sizeof(SmemLayout<kS, kT, kNSub, kCap>) + 127) & ~size_t(127)) + (size_t(4) << L);
 }
 
-static u32 tiles_for(u64 n_units)
+static u32 subtiles_for(u64 n_units)
 {
     const u64 nsub = (n_units + kS - 1) / kS;
     return (u32)((nsub + kT - 1) / kT);
 }
+static u32 pieces_for(u64 n_units) { return (subtiles_for(n_units) + kNSub - 1) / kNSub; }
 
 }  // namespace cuhd
 }  // namespace b200lc
@@ -484,7 +571,7 @@ using namespace b200lc;
 
 extern "C" size_t b200lc_cuhd_decode_scratch_bytes(size_t n_units)
 {
-    return 128 + (size_t)cuhd::tiles_for(n_units) * sizeof(cuhd::TileDesc);
+    return 128 + (size_t)cuhd::pieces_for(n_units) * sizeof(cuhd::TileDesc);
 }
 
 extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8_t *d_out,
@@ -500,7 +587,7 @@ extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8
     if (scratch_bytes < need) return B200LC_ERR_SCRATCH;
     if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
 
-    auto kern = cuhd::cuhd_decode_kernel<cuhd::kS, cuhd::kT, cuhd::kCap>;
+    auto kern = cuhd::cuhd_decode_kernel<cuhd::kS, cuhd::kT, cuhd::kNSub, cuhd::kCap>;
     const size_t smem = cuhd::smem_bytes((u32)max_codeword_length);
     static int occ_cache[14] = {0};
     if (!occ_cache[max_codeword_length]) {
@@ -521,11 +608,12 @@ extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8
     p.n_out = n_out;
     p.ticket = reinterpret_cast<u32 *>(d_scratch);
     p.desc = reinterpret_cast<cuhd::TileDesc *>(reinterpret_cast<char *>(d_scratch) + 128);
-    p.num_tiles = cuhd::tiles_for(n_units);
+    p.num_subtiles = cuhd::subtiles_for(n_units);
+    p.num_pieces = cuhd::pieces_for(n_units);
     p.tma_ok_base = (reinterpret_cast<uintptr_t>(d_units) & 15) == 0;
 
     B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, need, stream));
-    const u32 grid = (u32)min((u64)p.num_tiles,
+    const u32 grid = (u32)min((u64)p.num_pieces,
                               (u64)num_sms() * (u64)occ_cache[max_codeword_length]);
     kern<<<grid, cuhd::kT + 32, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
