@@ -93,32 +93,37 @@ __device__ __forceinline__ void walk_record(const u32 (&u)[S + 1], const u32 *ta
 
 // Decode from entry state `a` until the walk lands on a codeword start of the recorded path
 // (then the rest of the subsequence is the recorded path: end = e0) or runs off the end.
+// No early return: a lane that has merged idles through the remaining unit loops so that the
+// warp reconverges after every unit (an early exit makes the lanes run the later loops one at
+// a time -- measured: 52% of all issued instructions at 1 active thread).
 template <int S>
 __device__ __forceinline__ void walk_merge(const u32 (&u)[S + 1], const u32 (&m)[S], u32 a, u32 e0,
                                            const u32 *tab, u32 shift, u32 &end, u32 &cnt)
 {
-    u32 at = a, k = 0;
+    u32 at = a, k = 0, rest = 0;
+    bool done = false;
 #pragma unroll
     for (int j = 0; j < S; ++j) {
-        const u32 cur = u[j], nxt = u[j + 1];
-        while (at < 32) {
-            const u32 bit = 0x80000000u >> at;
-            if (m[j] & bit) {
-                u32 rest = __popc(m[j] & (bit | (bit - 1)));
-#pragma unroll
-                for (int jj = j + 1; jj < S; ++jj) rest += __popc(m[jj]);
-                end = e0;
-                cnt = k + rest;
-                return;
+        const u32 cur = u[j], nxt = u[j + 1], mj = m[j];
+        if (done) {
+            rest += __popc(mj);
+        } else {
+            while (at < 32) {
+                const u32 bit = 0x80000000u >> at;
+                if (mj & bit) {
+                    rest = __popc(mj & (bit | (bit - 1)));
+                    done = true;
+                    break;
+                }
+                const u32 w = __funnelshift_l(nxt, cur, at);
+                at += tab[w >> shift] & 0xffu;
+                ++k;
             }
-            const u32 w = __funnelshift_l(nxt, cur, at);
-            at += tab[w >> shift] & 0xffu;
-            ++k;
+            if (!done) at -= 32;
         }
-        at -= 32;
     }
-    end = at;
-    cnt = k;
+    end = done ? e0 : at;
+    cnt = k + rest;
 }
 
 // Write pass: decode from the true entry state, symbol i of this subsequence goes to dst[i].
