@@ -26,6 +26,8 @@
 // Decode contract (bit-exact with the reference): out[i] = symbol of
 // the i-th codeword when reading the stream MSB-first from bit 0 of unit 0 through the flat LUT
 // `{u8 num_bits, u8 symbol}[1 << max_codeword_length]`; units past n_units read as zero.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/b200lc.h"
 
@@ -552,22 +554,47 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
 }
 
 // ---------------------------------------------------------------------------------- host
-constexpr int kS = 4;
-constexpr int kT = 256;
-constexpr int kNSub = 32;                 // piece = 32 sub-tiles = 128 KiB of stream
-constexpr int kCap = 3 * kT * kS * 4;
+// Kernel variants (subsequence units S, subsequences per sub-tile T, sub-tiles per piece NSUB,
+// staging bytes CAP).  Variant 0 is the default; B200LC_CUHD_VARIANT selects another one for
+// tuning runs.
+struct Variant {
+    int S, T, NSUB, CAP;
+    void (*kern)(const DecodeParams);
+    size_t smem_fixed;
+};
+#define B200LC_VARIANT(S_, T_, N_, C_) \
+    { S_, T_, N_, C_, cuhd_decode_kernel<S_, T_, N_, C_>, \
+      ((sizeof(SmemLayout<S_, T_, N_, C_>) + 127) & ~size_t(127)) }
+static const Variant kVariants[] = {
+    B200LC_VARIANT(8, 256, 32, 16384),   // 311 GB/s of output on C2 (B200, round 1)
+    B200LC_VARIANT(8, 256, 16, 16384),   // 307
+    B200LC_VARIANT(8, 128, 32, 12288),   // 271
+    B200LC_VARIANT(4, 128, 64, 6144),    // 207
+    B200LC_VARIANT(4, 256, 32, 12288),   // 279
+    B200LC_VARIANT(4, 512, 16, 24576),   // 265
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
-static size_t smem_bytes(u32 L)
+static const Variant &variant()
 {
-    return ((sizeof(SmemLayout<kS, kT, kNSub, kCap>) + 127) & ~size_t(127)) + (size_t(4) << L);
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("B200LC_CUHD_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v >= kNumVariants) v = 0;
+    }
+    return kVariants[v];
 }
 
-static u32 subtiles_for(u64 n_units)
+static u32 subtiles_for(const Variant &v, u64 n_units)
 {
-    const u64 nsub = (n_units + kS - 1) / kS;
-    return (u32)((nsub + kT - 1) / kT);
+    const u64 nsub = (n_units + v.S - 1) / v.S;
+    return (u32)((nsub + v.T - 1) / v.T);
 }
-static u32 pieces_for(u64 n_units) { return (subtiles_for(n_units) + kNSub - 1) / kNSub; }
+static u32 pieces_for(const Variant &v, u64 n_units)
+{
+    return (subtiles_for(v, n_units) + v.NSUB - 1) / v.NSUB;
+}
 
 }  // namespace cuhd
 }  // namespace b200lc
@@ -576,7 +603,13 @@ using namespace b200lc;
 
 extern "C" size_t b200lc_cuhd_decode_scratch_bytes(size_t n_units)
 {
-    return 128 + (size_t)cuhd::pieces_for(n_units) * sizeof(cuhd::TileDesc);
+    // sized for the variant with the smallest pieces so that the answer does not depend on tuning
+    size_t worst = 0;
+    for (int i = 0; i < cuhd::kNumVariants; ++i) {
+        const size_t n = cuhd::pieces_for(cuhd::kVariants[i], n_units);
+        if (n > worst) worst = n;
+    }
+    return 128 + worst * sizeof(cuhd::TileDesc);
 }
 
 extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8_t *d_out,
@@ -592,15 +625,14 @@ extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8
     if (scratch_bytes < need) return B200LC_ERR_SCRATCH;
     if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
 
-    auto kern = cuhd::cuhd_decode_kernel<cuhd::kS, cuhd::kT, cuhd::kNSub, cuhd::kCap>;
-    const size_t smem = cuhd::smem_bytes((u32)max_codeword_length);
+    const cuhd::Variant &v = cuhd::variant();
+    const size_t smem = v.smem_fixed + (size_t(4) << max_codeword_length);
     static int occ_cache[14] = {0};
     if (!occ_cache[max_codeword_length]) {
-        B200LC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B200LC_CUDA_TRY(cudaFuncSetAttribute(v.kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
         int occ = 0;
-        B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cuhd::kT + 32,
-                                                                      smem));
+        B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.kern, v.T + 32, smem));
         if (occ < 1) return B200LC_ERR_CUDA;
         occ_cache[max_codeword_length] = occ;
     }
@@ -613,14 +645,15 @@ extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8
     p.n_out = n_out;
     p.ticket = reinterpret_cast<u32 *>(d_scratch);
     p.desc = reinterpret_cast<cuhd::TileDesc *>(reinterpret_cast<char *>(d_scratch) + 128);
-    p.num_subtiles = cuhd::subtiles_for(n_units);
-    p.num_pieces = cuhd::pieces_for(n_units);
+    p.num_subtiles = cuhd::subtiles_for(v, n_units);
+    p.num_pieces = cuhd::pieces_for(v, n_units);
     p.tma_ok_base = (reinterpret_cast<uintptr_t>(d_units) & 15) == 0;
 
-    B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, need, stream));
+    B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128 + p.num_pieces * sizeof(cuhd::TileDesc),
+                                    stream));
     const u32 grid = (u32)min((u64)p.num_pieces,
                               (u64)num_sms() * (u64)occ_cache[max_codeword_length]);
-    kern<<<grid, cuhd::kT + 32, smem, stream>>>(p);
+    v.kern<<<grid, v.T + 32, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }

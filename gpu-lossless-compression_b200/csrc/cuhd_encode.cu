@@ -24,13 +24,15 @@ namespace cuhd_enc {
 
 constexpr int kThreads = 512;
 constexpr int kSyms = 16;                      // symbols per thread
-constexpr int kTileSyms = kThreads * kSyms;    // 8192
+constexpr int kTileSyms = kThreads * kSyms;    // 8192 symbols per sub-tile (one TMA transfer)
+constexpr int kNSub = 16;                      // sub-tiles per piece (128 KiB, one look-back)
+constexpr int kPieceSyms = kTileSyms * kNSub;
 constexpr int kMaxLen = 13;
 constexpr int kStageWords = kTileSyms * kMaxLen / 32 + 8;
 
-// Tile descriptor: two independently published 64-bit words.
-//   agg : bit 63 valid | bits 31..51 tile bit count | bits 0..30 last 31 bits of the tile
-//   incl: bit 63 valid | bits 0..62 bit count of tiles 0..t
+// Piece descriptor: two independently published 64-bit words.
+//   agg : bit 63 valid | bits 31..62 piece bit count | bits 0..30 last 31 bits of the piece
+//   incl: bit 63 valid | bits 0..62 bit count of pieces 0..t
 struct __align__(16) EncDesc {
     u64 agg;
     u64 incl;
@@ -44,11 +46,12 @@ struct EncParams {
     const u8 *len_of_symbol;    // [256]
     u32 *out;
     u64 out_cap_units;
-    u64 *total_bits;            // device scalar, written by the last tile
+    u64 *total_bits;            // device scalar, written by the last piece
     u32 *overflow;              // device flag, set if out_cap_units was too small
     EncDesc *desc;
     u32 *ticket;
-    u32 num_tiles;
+    u32 num_subtiles;
+    u32 num_pieces;
     u32 tma_ok_base;
 };
 
@@ -59,10 +62,11 @@ struct EncSmem {
     u32 warp_sums[kThreads / 32];
     u64 bar[2];
     u64 base_bits;
-    u32 tile[2];
+    u64 piece_bits;
+    u32 next_piece;
     u32 total;
     u32 prev_tail;
-    u64 tail_acc[2];   // packed codes of the last two threads (low 64 bits)
+    u64 tail_acc[2];   // packed codes of the piece's last two threads (low 64 bits)
     u32 tail_bits[2];
 };
 
@@ -80,97 +84,123 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
     }
     __syncthreads();
 
-    auto tma_ok = [&](u32 tile) -> bool {
-        return p.tma_ok_base && (u64)(tile + 1) * kTileSyms <= p.n;
+    auto tma_ok = [&](u32 g) -> bool {
+        return p.tma_ok_base && (u64)(g + 1) * kTileSyms <= p.n;
     };
-    auto issue_load = [&](u32 tile, u32 buf) {
-        if (tile < p.num_tiles && tma_ok(tile)) {
+    auto issue_load = [&](u32 g, u32 buf) {
+        if (g < p.num_subtiles && tma_ok(g)) {
             mbar_expect_tx(&sm.bar[buf], kTileSyms);
-            tma_load_1d(sm.in[buf], p.in + (u64)tile * kTileSyms, kTileSyms, &sm.bar[buf]);
+            tma_load_1d(sm.in[buf], p.in + (u64)g * kTileSyms, kTileSyms, &sm.bar[buf]);
         }
     };
     if (tid == 0) {
         const u32 t0 = atomicAdd(p.ticket, 1u);
-        sm.tile[0] = t0;
-        issue_load(t0, 0);
+        sm.next_piece = t0;
+        if (t0 < p.num_pieces) issue_load(t0 * kNSub, 0);
     }
     __syncthreads();
 
-    u32 cur = 0, phase0 = 0, phase1 = 0;
-    while (true) {
-        const u32 tile = sm.tile[cur];
-        if (tile >= p.num_tiles) break;
-        const u64 first = (u64)tile * kTileSyms;
-        const u32 tile_n = (u32)min((u64)kTileSyms, p.n - first);
-
-        if (tma_ok(tile)) {
-            if (cur == 0) { mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
+    u32 step = 0, phase0 = 0, phase1 = 0;
+    auto acquire_input = [&](u32 g, u32 tile_n) {
+        const u32 buf = step & 1;
+        if (tma_ok(g)) {
+            if (buf == 0) { mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
             else          { mbar_wait(&sm.bar[1], phase1); phase1 ^= 1; }
         } else {
+            const u64 first = (u64)g * kTileSyms;
             for (u32 i = tid; i < kTileSyms; i += kThreads)
-                sm.in[cur][i] = i < tile_n ? p.in[first + i] : (u8)0;
+                sm.in[buf][i] = i < tile_n ? p.in[first + i] : (u8)0;
             fence_proxy_async();
             __syncthreads();
         }
-        if (tid == 0) {
-            const u32 nt = atomicAdd(p.ticket, 1u);
-            sm.tile[cur ^ 1] = nt;
-            issue_load(nt, cur ^ 1);
-        }
+    };
 
-        // ---------------------------------------------------------------- lookup + lengths
-        u32 e[kSyms];
-        u32 my_bits = 0;
-        {
-            const uint4 v = *reinterpret_cast<const uint4 *>(&sm.in[cur][tid * kSyms]);
+    while (true) {
+        const u32 piece = sm.next_piece;
+        if (piece >= p.num_pieces) break;
+        const u32 g0 = piece * kNSub;
+        const u32 nsub = min((u32)kNSub, p.num_subtiles - g0);
+
+        auto prefetch = [&](u32 pass, u32 c) {
+            if (tid != 0) return;
+            u32 g;
+            if (c + 1 < nsub) g = g0 + c + 1;
+            else if (pass == 0) g = g0;
+            else {
+                const u32 np = atomicAdd(p.ticket, 1u);
+                sm.next_piece = np;
+                if (np >= p.num_pieces) return;
+                g = np * kNSub;
+            }
+            issue_load(g, (step & 1) ^ 1);
+        };
+        auto lookup = [&](u32 buf, u32 tile_n, u32 (&e)[kSyms]) -> u32 {
+            const uint4 v = *reinterpret_cast<const uint4 *>(&sm.in[buf][tid * kSyms]);
             const u32 w[4] = {v.x, v.y, v.z, v.w};
             const u32 valid = tile_n > tid * kSyms ? min((u32)kSyms, tile_n - tid * kSyms) : 0u;
+            u32 bits = 0;
 #pragma unroll
             for (int i = 0; i < kSyms; ++i) {
                 const u32 s = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
                 u32 x = sm.tab[s];
                 if ((u32)i >= valid) x = 0;  // past the end of the input: zero-length code
                 e[i] = x;
-                my_bits += x >> 16;
+                bits += x >> 16;
             }
-            if (tid >= kThreads - 2) {  // the tile's last 31 bits live in the last two threads
+            return bits;
+        };
+
+        // ================================================================ pass A: bit count
+        u32 my_piece_bits = 0;   // per-thread partial over all sub-tiles (<= 16*16*13 bits)
+        for (u32 c = 0; c < nsub; ++c) {
+            const u64 first = (u64)(g0 + c) * kTileSyms;
+            const u32 tile_n = (u32)min((u64)kTileSyms, p.n - first);
+            acquire_input(g0 + c, tile_n);
+            prefetch(0, c);
+            u32 e[kSyms];
+            const u32 bits = lookup(step & 1, tile_n, e);
+            my_piece_bits += bits;
+            if (c == nsub - 1 && tid >= kThreads - 2) {
+                // the piece's last 31 bits live in its last two threads (full pieces only)
                 u64 acc = 0;
 #pragma unroll
                 for (int i = 0; i < kSyms; ++i) acc = (acc << (e[i] >> 16)) | (e[i] & 0xffffu);
                 sm.tail_acc[tid - (kThreads - 2)] = acc;
-                sm.tail_bits[tid - (kThreads - 2)] = my_bits;
+                sm.tail_bits[tid - (kThreads - 2)] = bits;
             }
+            __syncthreads();   // buffer hand-over
+            ++step;
         }
-        // block scan of bit counts
-        u32 incl = warp_incl_scan(my_bits);
-        if (lane == 31) sm.warp_sums[tid >> 5] = incl;
-        __syncthreads();
-        if (tid < 32) {
-            const u32 v = tid < kThreads / 32 ? sm.warp_sums[tid] : 0u;
-            const u32 s = warp_incl_scan(v);
-            if (tid < kThreads / 32) sm.warp_sums[tid] = s - v;
-            if (tid == kThreads / 32 - 1) sm.total = s;
+        {   // block reduction of the per-thread partials
+            u32 v = my_piece_bits;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) sm.warp_sums[tid >> 5] = v;
+            __syncthreads();
+            if (tid < 32) {
+                u32 t = tid < kThreads / 32 ? sm.warp_sums[tid] : 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+                if (tid == 0) sm.piece_bits = t;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        const u32 pre = sm.warp_sums[tid >> 5] + incl - my_bits;
-        const u32 total = sm.total;
 
-        // ---------------------------------------------------------------- publish + look-back (warp 0)
+        // ================================================================ publish + look-back (warp 0)
         if (tid < 32) {
-            // last 31 bits of the tile (only a full tile has a successor, and a full tile's last
-            // two threads hold >= 32 bits)
+            const u64 piece_bits = sm.piece_bits;
             if (lane == 0) {
                 const u32 nb1 = sm.tail_bits[1];
                 u64 acc = sm.tail_acc[1];
                 if (nb1 < 31) acc |= sm.tail_acc[0] << nb1;
                 const u32 tail31 = (u32)acc & 0x7fffffffu;
-                st_release_u64(&p.desc[tile].agg, kValid | ((u64)total << 31) | tail31);
+                st_release_u64(&p.desc[piece].agg, kValid | (piece_bits << 31) | tail31);
             }
             u64 base = 0;
             u32 prev_tail = 0;
-            if (tile > 0) {
-                // warp-wide look-back: lane i inspects tile (k - i)
-                int k = (int)tile - 1;
+            if (piece > 0) {
+                // warp-wide look-back: lane i inspects piece (k - i)
+                int k = (int)piece - 1;
                 bool done = false;
                 bool first_batch = true;
                 while (!done) {
@@ -187,9 +217,12 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
                     // usable prefix of lanes: all ready up to (and including) the first inclusive
                     const u32 first_incl = incl_mask ? (u32)__ffs(incl_mask) - 1 : 32u;
                     const u32 need = first_incl < 32 ? ((2u << first_incl) - 1) : 0xffffffffu;
-                    if ((any_mask & need) != need) continue;  // somebody not ready yet: poll again
+                    if ((any_mask & need) != need) {
+                        __nanosleep(100);
+                        continue;  // somebody not ready yet: poll again
+                    }
                     u64 contrib = 0;
-                    if (lane < first_incl && idx >= 0) contrib = (a >> 31) & 0x1fffffu;
+                    if (lane < first_incl && idx >= 0) contrib = (a & ~kValid) >> 31;
                     if (lane == first_incl) contrib = in & ~kValid;
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
@@ -198,8 +231,8 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
                         // direct predecessor's tail: from its aggregate word (always published)
                         u64 pa = 0;
                         if (lane == 0) {
-                            pa = a & kValid ? a : ld_acquire_u64(&p.desc[tile - 1].agg);
-                            while (!(pa & kValid)) pa = ld_acquire_u64(&p.desc[tile - 1].agg);
+                            pa = a & kValid ? a : ld_acquire_u64(&p.desc[piece - 1].agg);
+                            while (!(pa & kValid)) pa = ld_acquire_u64(&p.desc[piece - 1].agg);
                         }
                         prev_tail = (u32)__shfl_sync(0xffffffffu, pa, 0) & 0x7fffffffu;
                         first_batch = false;
@@ -209,75 +242,103 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
                 }
             }
             if (lane == 0) {
-                st_release_u64(&p.desc[tile].incl, kValid | (base + total));
+                st_release_u64(&p.desc[piece].incl, kValid | (base + piece_bits));
                 sm.base_bits = base;
                 sm.prev_tail = prev_tail;
             }
         }
         __syncthreads();
-        const u64 base = sm.base_bits;
-        const u32 r = (u32)(base & 31);            // bits of word 0 that belong to predecessors
-        const u64 w0 = base >> 5;                  // global index of staging word `salign`
-        const u32 salign = (u32)(w0 & 3);          // keep 16-byte phase of global and staging equal
-        const bool last_tile = tile == p.num_tiles - 1;
-        const u32 tile_bits = r + total;
-        // words this tile writes: all complete ones, plus the final partial one on the last tile
-        const u32 nwords = last_tile ? (tile_bits + 31) >> 5 : tile_bits >> 5;
 
-        // zero the staging words that receive atomicOr contributions
-        for (u32 i = tid; i < ((tile_bits + 31) >> 5) + 1; i += kThreads) sm.stage[salign + i] = 0;
-        __syncthreads();
-        if (tid == 0 && r) atomicOr(&sm.stage[salign], (sm.prev_tail & ((1u << r) - 1)) << (32 - r));
-
-        // ---------------------------------------------------------------- pack
+        // ================================================================ pass B: pack + write
+        u64 base = sm.base_bits;                 // running global bit offset
+        // bits of the first output word that belong to predecessors, left-aligned
+        u32 carry = 0;
         {
-            const u32 b0 = r + pre;
-            u32 wi = salign + (b0 >> 5);
-            u32 nb = b0 & 31;          // bits already occupied in the current word
-            u64 acc = 0;
-            bool first_word = true;
+            const u32 r0 = (u32)(base & 31);
+            if (r0) carry = (sm.prev_tail & ((1u << r0) - 1)) << (32 - r0);
+        }
+        const bool last_piece = piece == p.num_pieces - 1;
+        for (u32 c = 0; c < nsub; ++c) {
+            const u64 first = (u64)(g0 + c) * kTileSyms;
+            const u32 tile_n = (u32)min((u64)kTileSyms, p.n - first);
+            acquire_input(g0 + c, tile_n);
+            prefetch(1, c);
+            u32 e[kSyms];
+            const u32 my_bits = lookup(step & 1, tile_n, e);
+
+            // block scan of bit counts
+            u32 incl = warp_incl_scan(my_bits);
+            if (lane == 31) sm.warp_sums[tid >> 5] = incl;
+            __syncthreads();
+            if (tid < 32) {
+                const u32 v = tid < kThreads / 32 ? sm.warp_sums[tid] : 0u;
+                const u32 s = warp_incl_scan(v);
+                if (tid < kThreads / 32) sm.warp_sums[tid] = s - v;
+                if (tid == kThreads / 32 - 1) sm.total = s;
+            }
+            __syncthreads();
+            const u32 pre = sm.warp_sums[tid >> 5] + incl - my_bits;
+            const u32 total = sm.total;
+
+            const u32 r = (u32)(base & 31);
+            const u64 w0 = base >> 5;                  // global index of staging word `salign`
+            const u32 salign = (u32)(w0 & 3);          // keep 16-byte phase of global and staging equal
+            const bool last_tile = last_piece && c == nsub - 1;
+            const u32 tile_bits = r + total;
+            // words written now: all complete ones, plus the final partial one at the very end
+            const u32 nwords = last_tile ? (tile_bits + 31) >> 5 : tile_bits >> 5;
+
+            // zero the staging words that receive atomicOr contributions
+            for (u32 i = tid; i < ((tile_bits + 31) >> 5) + 1; i += kThreads) sm.stage[salign + i] = 0;
+            __syncthreads();
+            if (tid == 0 && r) atomicOr(&sm.stage[salign], carry);
+
+            {
+                const u32 b0 = r + pre;
+                u32 wi = salign + (b0 >> 5);
+                u32 nb = b0 & 31;          // bits already occupied in the current word
+                u64 acc = 0;
+                bool first_word = true;
 #pragma unroll
-            for (int i = 0; i < kSyms; ++i) {
-                const u32 len = e[i] >> 16;
-                acc = (acc << len) | (e[i] & 0xffffu);
-                nb += len;
-                if (nb >= 32) {
-                    const u32 word = (u32)(acc >> (nb - 32));
-                    if (first_word) { atomicOr(&sm.stage[wi], word); first_word = false; }
-                    else sm.stage[wi] = word;
-                    ++wi;
-                    nb -= 32;
+                for (int i = 0; i < kSyms; ++i) {
+                    const u32 len = e[i] >> 16;
+                    acc = (acc << len) | (e[i] & 0xffffu);
+                    nb += len;
+                    if (nb >= 32) {
+                        const u32 word = (u32)(acc >> (nb - 32));
+                        if (first_word) { atomicOr(&sm.stage[wi], word); first_word = false; }
+                        else sm.stage[wi] = word;
+                        ++wi;
+                        nb -= 32;
+                    }
+                }
+                if (nb && my_bits) atomicOr(&sm.stage[wi], (u32)(acc << (32 - nb)));
+            }
+            __syncthreads();
+            // the partial last word travels to the next sub-tile of this piece
+            carry = sm.stage[salign + (tile_bits >> 5)];
+
+            if (w0 + nwords > p.out_cap_units) {
+                if (tid == 0) atomicExch(p.overflow, 1u);
+            } else {
+                u32 *g = p.out + w0;
+                const u32 head = min(nwords, (4u - salign) & 3u);
+                const u32 nvec = (nwords - head) >> 2;
+                const u32 tail0 = head + (nvec << 2);
+                if (tid < head) g[tid] = sm.stage[salign + tid];
+                const uint4 *sv = reinterpret_cast<const uint4 *>(&sm.stage[salign + head]);
+                uint4 *gv = reinterpret_cast<uint4 *>(g + head);
+                for (u32 i = tid; i < nvec; i += kThreads) gv[i] = sv[i];
+                if (tid < nwords - tail0) g[tail0 + tid] = sm.stage[salign + tail0 + tid];
+                if (last_tile && tid == 0) {
+                    *p.total_bits = base + total;
+                    if (w0 + nwords < p.out_cap_units) g[nwords] = 0;  // the reference's pad unit
                 }
             }
-            if (nb) {
-                // partial last word: the low nb bits of acc, left-aligned.  When no word was
-                // flushed the leading (b0 & 31) bits of acc are zero padding owned by others.
-                const u32 word = (u32)(acc << (32 - nb));
-                if (my_bits) atomicOr(&sm.stage[wi], word);
-            }
+            base += total;
+            __syncthreads();   // staging + input buffer hand-over
+            ++step;
         }
-        __syncthreads();
-
-        // ---------------------------------------------------------------- copy out
-        if (w0 + nwords > p.out_cap_units) {
-            if (tid == 0) atomicExch(p.overflow, 1u);
-        } else {
-            u32 *g = p.out + w0;
-            const u32 head = min(nwords, (4u - salign) & 3u);
-            const u32 nvec = (nwords - head) >> 2;
-            const u32 tail0 = head + (nvec << 2);
-            if (tid < head) g[tid] = sm.stage[salign + tid];
-            const uint4 *sv = reinterpret_cast<const uint4 *>(&sm.stage[salign + head]);
-            uint4 *gv = reinterpret_cast<uint4 *>(g + head);
-            for (u32 i = tid; i < nvec; i += kThreads) gv[i] = sv[i];
-            if (tid < nwords - tail0) g[tail0 + tid] = sm.stage[salign + tail0 + tid];
-            if (last_tile && tid == 0) {
-                *p.total_bits = base + total;
-                if (w0 + nwords < p.out_cap_units) g[nwords] = 0;  // the reference's pad unit
-            }
-        }
-        __syncthreads();
-        cur ^= 1;
     }
 }
 
@@ -315,7 +376,8 @@ __global__ void __launch_bounds__(kHistThreads) histogram_u8_kernel(const u8 *in
     }
 }
 
-static u32 tiles_for(u64 n) { return (u32)((n + kTileSyms - 1) / kTileSyms); }
+static u32 subtiles_for(u64 n) { return (u32)((n + kTileSyms - 1) / kTileSyms); }
+static u32 pieces_for(u64 n) { return (subtiles_for(n) + kNSub - 1) / kNSub; }
 
 }  // namespace cuhd_enc
 }  // namespace b200lc
@@ -343,7 +405,7 @@ extern "C" int b200lc_histogram_u8(const uint8_t *d_in, size_t n, uint64_t *d_hi
 
 extern "C" size_t b200lc_cuhd_encode_scratch_bytes(size_t n)
 {
-    return 256 + (size_t)cuhd_enc::tiles_for(n) * sizeof(cuhd_enc::EncDesc);
+    return 256 + (size_t)cuhd_enc::pieces_for(n) * sizeof(cuhd_enc::EncDesc);
 }
 
 extern "C" int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t *d_code_of_symbol,
@@ -375,7 +437,8 @@ extern "C" int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t 
     p.ticket = reinterpret_cast<u32 *>(d_scratch);
     p.overflow = reinterpret_cast<u32 *>(d_scratch) + 1;
     p.desc = reinterpret_cast<cuhd_enc::EncDesc *>(reinterpret_cast<char *>(d_scratch) + 256);
-    p.num_tiles = cuhd_enc::tiles_for(n);
+    p.num_subtiles = cuhd_enc::subtiles_for(n);
+    p.num_pieces = cuhd_enc::pieces_for(n);
     p.tma_ok_base = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
 
     static int occ = 0;
@@ -384,7 +447,7 @@ extern "C" int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t 
             &occ, cuhd_enc::cuhd_encode_kernel, cuhd_enc::kThreads, 0));
         if (occ < 1) return B200LC_ERR_CUDA;
     }
-    const u32 grid = (u32)min((u64)p.num_tiles, (u64)num_sms() * (u64)occ);
+    const u32 grid = (u32)min((u64)p.num_pieces, (u64)num_sms() * (u64)occ);
     cuhd_enc::cuhd_encode_kernel<<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
