@@ -58,6 +58,14 @@ def lib():
     L.b200lc_cuhd_session_encode.argtypes = [vp, vp, sz, i32, vp, sz, C.POINTER(sz), vp, vp, vp]
     L.b200lc_cuhd_session_decode.restype = i32
     L.b200lc_cuhd_session_decode.argtypes = [vp, vp, sz, vp, i32, vp, sz]
+    L.b200lc_culzss_encode_scratch_bytes.restype = sz
+    L.b200lc_culzss_encode_scratch_bytes.argtypes = [sz, sz]
+    L.b200lc_culzss_encode_batch.restype = i32
+    L.b200lc_culzss_encode_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, sz, vp]
+    L.b200lc_culzss_decode_scratch_bytes.restype = sz
+    L.b200lc_culzss_decode_scratch_bytes.argtypes = [sz, sz]
+    L.b200lc_culzss_decode_batch.restype = i32
+    L.b200lc_culzss_decode_batch.argtypes = [vp, vp, sz, sz, vp, vp, sz, vp]
     _lib = L
     return L
 
@@ -196,3 +204,48 @@ class CuhdSession:
                                                h_lut.data_ptr(), max_len, h_out.data_ptr(),
                                                h_out.numel()),
               "b200lc_cuhd_session_decode")
+
+
+# ------------------------------------------------------------------------------- CULZSS
+def culzss_out_stride(buf_length):
+    return (buf_length + buf_length // 8 + 1024 + 15) // 16 * 16
+
+
+def culzss_encode(data, buf_length=1 << 20, out=None, comp_len=None, scratch=None, stream=None):
+    """LZSS-encode a cuda uint8 tensor of nbuf * buf_length bytes.  Returns (out, comp_len):
+    out[b * stride : b * stride + comp_len[b]] is buffer b incl. trailer; comp_len[b] == 0 means
+    "store raw".  Asynchronous."""
+    import torch
+    assert data.is_cuda and data.dtype == torch.uint8 and data.is_contiguous()
+    assert data.numel() % buf_length == 0
+    L = lib()
+    nbuf = data.numel() // buf_length
+    stride = culzss_out_stride(buf_length)
+    if out is None:
+        out = torch.empty(nbuf * stride, dtype=torch.uint8, device=data.device)
+    if comp_len is None:
+        comp_len = torch.empty(nbuf, dtype=torch.int32, device=data.device)
+    need = L.b200lc_culzss_encode_scratch_bytes(nbuf, buf_length)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=data.device)
+    check(L.b200lc_culzss_encode_batch(data.data_ptr(), nbuf, buf_length, out.data_ptr(), stride,
+                                       comp_len.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                       _stream_ptr(stream)), "b200lc_culzss_encode_batch")
+    return out, comp_len
+
+
+def culzss_decode(comp, offsets, buf_length=1 << 20, out=None, scratch=None, stream=None):
+    """Decode nbuf compressed buffers: comp (cuda uint8), offsets (cuda int64[nbuf + 1])."""
+    import torch
+    assert comp.is_cuda and offsets.is_cuda and offsets.dtype == torch.int64
+    L = lib()
+    nbuf = offsets.numel() - 1
+    if out is None:
+        out = torch.empty(nbuf * buf_length, dtype=torch.uint8, device=comp.device)
+    need = L.b200lc_culzss_decode_scratch_bytes(nbuf, buf_length)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=comp.device)
+    check(L.b200lc_culzss_decode_batch(comp.data_ptr(), offsets.data_ptr(), nbuf, buf_length,
+                                       out.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                       _stream_ptr(stream)), "b200lc_culzss_decode_batch")
+    return out

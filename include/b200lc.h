@@ -112,6 +112,32 @@ int b200lc_cuhd_session_encode(b200lc_cuhd_session *s, const uint8_t *h_in, size
 int b200lc_cuhd_session_decode(b200lc_cuhd_session *s, const uint32_t *h_units, size_t n_units,
                                const void *h_lut, int max_len, uint8_t *h_out, size_t n_out);
 
+/* ------------------------------------------------------------------------------------------
+ * Hot path 2: CULZSS-compatible LZSS (cuda-lzss-cluster), device-pointer batch API.
+ * Bit-exact with the reference's EncodeKernel + aftercomp + trailer
+ * (gpu_compress.cu:104-350, :462-673) and DecodeKernel (gpu_decompress.cu:120-244):
+ * WINDOW_SIZE 128, MAX_CODED 128, 4096-byte packets, per-buffer trailer
+ * [packets][npk x u16 BE sizes][u32 BE buf_length][u16 BE pad = 0].
+ *
+ * Encode: nbuf independent buffers of buf_length bytes each (multiple of 4096; the reference
+ * uses 1 MiB, main.c:62), contiguous at d_in (16-byte aligned).  Buffer b is written to
+ * d_out + b * out_stride and its size incl. trailer to d_comp_len[b]; d_comp_len[b] == 0 means
+ * the reference would have reported "compression took more" (aftercompression_wrapper returns
+ * 0, gpu_compress.cu:494-498,661-662) and the caller stores the buffer raw (culzss.c:177-183).
+ * out_stride >= buf_length + buf_length / 8 + 1024 is always sufficient.  Asynchronous.
+ */
+size_t b200lc_culzss_encode_scratch_bytes(size_t nbuf, size_t buf_length);
+int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out,
+                               size_t out_stride, uint32_t *d_comp_len, void *d_scratch,
+                               size_t scratch_bytes, void *stream);
+/* Decode: compressed buffer b occupies d_comp[d_comp_offsets[b] .. d_comp_offsets[b+1]) and is
+ * decoded to d_out + b * buf_length (d_out 16-byte aligned).  A buffer whose stored size equals
+ * buf_length is raw and copied (decompression.c:90-108, deculzss.c:94-95).  Asynchronous. */
+size_t b200lc_culzss_decode_scratch_bytes(size_t nbuf, size_t buf_length);
+int b200lc_culzss_decode_batch(const uint8_t *d_comp, const uint64_t *d_comp_offsets, size_t nbuf,
+                               size_t buf_length, uint8_t *d_out, void *d_scratch,
+                               size_t scratch_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,16 @@ def oracle():
     lib.cuhd_oracle_encode.restype = C.c_size_t
     lib.cuhd_oracle_encode.argtypes = [_u8p, C.c_size_t, _u32p, _u8p, _u32p, C.c_size_t,
                                        C.POINTER(C.c_size_t)]
+    lib.culzss_oracle_packet_tokens.restype = None
+    lib.culzss_oracle_packet_tokens.argtypes = [_u8p, _u8p]
+    lib.culzss_oracle_buffer_tokens.restype = None
+    lib.culzss_oracle_buffer_tokens.argtypes = [_u8p, C.c_int, _u8p]
+    lib.culzss_oracle_aftercomp.restype = C.c_int
+    lib.culzss_oracle_aftercomp.argtypes = [_u8p, C.c_int, _u8p, C.POINTER(C.c_int)]
+    lib.culzss_oracle_decode_packet.restype = C.c_int
+    lib.culzss_oracle_decode_packet.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+    lib.culzss_oracle_decode_buffer.restype = C.c_int
+    lib.culzss_oracle_decode_buffer.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.POINTER(C.c_int)]
     _cache["oracle"] = lib
     return lib
 
@@ -180,3 +190,79 @@ def cuhd_make_case(data, max_len=11, use_ref=True):
     units, _ = cuhd_oracle_encode(data, code, length)
     units = np.concatenate([units, np.zeros(1, np.uint32)])
     return code, length, lut, units
+
+
+# ---------------------------------------------------------------------------- CULZSS helpers
+CULZSS_PACKET = 4096
+CULZSS_BUFFER = 1 << 20
+
+
+def ref_culzss():
+    """The reference's gpu_compress.cu + gpu_decompress.cu (oracle/_ref/libref_culzss.so).
+    aftercompression_wrapper is pure CPU code; the kernel wrappers need a GPU."""
+    if "ref_culzss" in _cache:
+        return _cache["ref_culzss"]
+    lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libref_culzss.so"))
+    vp = C.c_void_p
+    lib.aftercompression_wrapper.restype = C.c_int
+    lib.aftercompression_wrapper.argtypes = [_u8p, C.c_int, _u8p, C.POINTER(C.c_int)]
+    lib.compression_kernel_wrapper.restype = C.c_int
+    lib.compression_kernel_wrapper.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.c_int, vp, vp]
+    lib.decompression_kernel_wrapper.restype = C.c_int
+    lib.decompression_kernel_wrapper.argtypes = [_u8p, C.c_int, C.POINTER(C.c_int), C.c_int,
+                                                 C.c_int, C.c_int]
+    lib.initGPUmem.restype = vp
+    lib.initGPUmem.argtypes = [C.c_int]
+    lib.deleteGPUmem.argtypes = [vp]
+    lib.initGPU.restype = None
+    lib.onestream_finish_GPU.restype = C.c_int
+    lib.onestream_finish_GPU.argtypes = [C.c_int]
+    _cache["ref_culzss"] = lib
+    return lib
+
+
+def culzss_oracle_tokens(buf):
+    out = np.zeros(buf.size * 2, np.uint8)
+    oracle().culzss_oracle_buffer_tokens(np.ascontiguousarray(buf), buf.size, out)
+    return out
+
+
+def culzss_oracle_aftercomp(tokens, buf_length):
+    """-> (ok, compressed bytes incl. trailer)"""
+    out = np.zeros(buf_length + buf_length // 8 + 1024, np.uint8)
+    n = C.c_int(0)
+    ok = oracle().culzss_oracle_aftercomp(tokens, buf_length, out, C.byref(n))
+    return ok, out[: n.value].copy()
+
+
+def culzss_ref_aftercomp(tokens, data):
+    """Reference aftercompression_wrapper (CPU) -> (ok, compressed bytes incl. trailer)."""
+    n = data.size
+    buf = np.zeros(n + n // 8 + 1024, np.uint8)   # the reference writes in place, may overrun
+    buf[:n] = data
+    clen = C.c_int(0)
+    ok = ref_culzss().aftercompression_wrapper(buf, n, np.ascontiguousarray(tokens), C.byref(clen))
+    return ok, buf[: clen.value].copy()
+
+
+def culzss_oracle_compress(buf):
+    tokens = culzss_oracle_tokens(buf)
+    return culzss_oracle_aftercomp(tokens, buf.size)
+
+
+def culzss_oracle_decompress(comp, out_cap=CULZSS_BUFFER):
+    out = np.zeros(out_cap, np.uint8)
+    n = C.c_int(0)
+    ok = oracle().culzss_oracle_decode_buffer(np.ascontiguousarray(comp), comp.size, out, out_cap,
+                                              C.byref(n))
+    return ok, out[: n.value].copy()
+
+
+def quant_codes(n_bytes, seed=2024, dtype=np.int32):
+    """Synthetic C3 input: cuSZ-like quantisation codes 512 + round(Laplace(b=2)),
+    clipped to [0, 1023], little-endian int32 (or uint16)."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    n = n_bytes // np.dtype(dtype).itemsize
+    codes = np.clip(512 + np.rint(rng.laplace(0.0, 2.0, n)), 0, 1023).astype(dtype)
+    return codes.view(np.uint8)[:n_bytes].copy()
