@@ -1,0 +1,51 @@
+"""CPU: the C-ABI library loads and exports every symbol the public headers declare
+(no compute calls here -- there is no GPU in the build container)."""
+import ctypes
+import glob
+import os
+import re
+
+from pkg import b200lc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DECL = re.compile(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?\b([A-Za-z_]\w*)\s*\(", re.M)
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = open(h).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+        for m in DECL.finditer(text):
+            name = m.group(1)
+            if name not in ("defined", "sizeof", "if", "while", "return"):
+                names.add(name)
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = b200lc.lib()
+    names = declared_symbols()
+    assert len(names) >= 10
+    missing = []
+    for n in sorted(names):
+        try:
+            getattr(lib, n)
+        except AttributeError:
+            missing.append(n)
+    assert not missing, "declared in include/ but not exported: %s" % missing
+
+
+def test_version_string():
+    v = b200lc.lib().b200lc_version().decode()
+    assert v.startswith("b200lc ") and v.endswith("sm_100a")
+
+
+def test_errors_without_gpu_are_loud():
+    lib = b200lc.lib()
+    # null pointers are rejected before any CUDA call
+    assert lib.b200lc_cuhd_decode(None, 10, None, 10, None, 11, None, 0, None) == b200lc.ERR_ARG
+    assert lib.b200lc_cuhd_decode(None, 10, None, 10, None, 20, None, 0, None) == b200lc.ERR_UNSUPPORTED
+    assert lib.b200lc_culzss_encode_batch(None, 1, 4096, None, 0, None, None, 0, None) == b200lc.ERR_ARG
