@@ -174,3 +174,44 @@ def test_reference_kernels_agree_with_oracle_and_product():
     finally:
         ref.deleteGPUmem(in_d)
         ref.deleteGPUmem(out_d)
+
+
+def test_reference_named_wrappers_drop_in():
+    """The call protocol of culzss.c:108,170,176 / deculzss.c:98 against libb200lc.so."""
+    L = b200lc.lib()
+    vp = C.c_void_p
+    u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+    L.initGPUmem.restype = vp
+    L.initGPUmem.argtypes = [C.c_int]
+    L.deleteGPUmem.argtypes = [vp]
+    L.compression_kernel_wrapper.restype = C.c_int
+    L.compression_kernel_wrapper.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, vp, vp]
+    L.aftercompression_wrapper.restype = C.c_int
+    L.aftercompression_wrapper.argtypes = [u8p, C.c_int, u8p, C.POINTER(C.c_int)]
+    L.decompression_kernel_wrapper.restype = C.c_int
+    L.decompression_kernel_wrapper.argtypes = [u8p, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]
+    L.onestream_finish_GPU.argtypes = [C.c_int]
+    L.initGPU()
+    in_d, out_d = L.initGPUmem(MIB), L.initGPUmem(2 * MIB)
+    try:
+        for index, name in enumerate(["quant32", "text", "random", "zeros"]):
+            data = _cases()[name]
+            buf = np.zeros(2 * MIB, np.uint8)
+            buf[:MIB] = data
+            bufout = np.zeros(2 * MIB, np.uint8)
+            assert L.compression_kernel_wrapper(buf, MIB, bufout, 0, 0, 128, 0, index, in_d, out_d) == 1
+            assert L.onestream_finish_GPU(index) == 1
+            clen = C.c_int(0)
+            rc = L.aftercompression_wrapper(buf, MIB, bufout, C.byref(clen))
+            ok, want = O.culzss_oracle_compress(data)
+            assert rc == ok
+            if not ok:
+                continue
+            assert clen.value == want.size and np.array_equal(buf[: want.size], want)
+            dlen = C.c_int(0)
+            assert L.decompression_kernel_wrapper(buf, clen.value, C.byref(dlen), 0, 0, 1) == 1
+            assert dlen.value == MIB and np.array_equal(buf[:MIB], data)
+    finally:
+        L.deleteGPUmem(in_d)
+        L.deleteGPUmem(out_d)
