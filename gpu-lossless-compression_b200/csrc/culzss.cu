@@ -31,17 +31,28 @@ constexpr int kMaxPacketOut = kPacket + kPacket / 8;   // all literals: 4096 + 5
 constexpr int kOccStride = 9;                          // 8 ring words + 1 pad (bank spread)
 
 // ====================================================================================== encode
+constexpr int kLevels = 7;                             // run-length planes cover L = 1..8
 struct EncSmem {
     __align__(16) u8 pkt[kWindow + kPacket + 16];   // pkt[128 + q] = P[q]; pkt[0..127] = ' '
-    u32 occ[256 * kOccStride];                      // per byte value: ring of 256 window slots
+    union {
+        struct {
+            u32 occ[256 * kOccStride];              // per byte value: ring of 256 window slots
+            uint4 ymask[128 + kLevels + 1];         // occurrence masks of the chunk's positions (+7 of the next)
+        } a;                                        // match finding
+        struct {
+            __align__(16) u8 out[kMaxPacketOut + 16];
+            u16 FB[kPacket / 8 + 1];                // output offset of the flag byte of group g
+        } b;                                        // packing
+        struct {
+            u16 J[kPacket];                         // first token position selected after pos's 32-block
+            u8 E[kPacket / 32];                     // entry offset of the parse into each 32-block
+        } s;                                        // selection
+    } u;
     u8 tlen[kPacket];                               // token: match length, or 1 for a literal
     u8 toff[kPacket];                               // token: ring offset, or the literal byte
     u32 M[kPacket / 32];                            // bit p: token p is a match (len >= 3)
     u32 V[kPacket / 32];                            // bit p: token p is selected by the greedy parse
     u32 scan[4];
-    u16 FB[kPacket / 8 + 1];                        // output offset of the flag byte of group g
-    __align__(16) u8 out[kMaxPacketOut + 16];
-    u32 total;
 };
 
 __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict__ in, u64 npackets,
@@ -62,13 +73,13 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
             dst[tx] = src[tx];
             dst[tx + 128] = src[tx + 128];
             sm.pkt[tx] = ' ';
-            for (u32 i = tx; i < 256 * kOccStride; i += 128) sm.occ[i] = 0;
+            for (u32 i = tx; i < 256 * kOccStride; i += 128) sm.u.a.occ[i] = 0;
         }
         __syncthreads();
         // window slots 128..255 initially hold ' ' (gpu_compress.cu:208), chunk 0 enters slots 0..127
-        if (tx < 4) sm.occ[0x20 * kOccStride + 4 + tx] = 0xffffffffu;
+        if (tx < 4) sm.u.a.occ[0x20 * kOccStride + 4 + tx] = 0xffffffffu;
         __syncthreads();
-        atomicOr(&sm.occ[sm.pkt[kWindow + tx] * kOccStride + (tx >> 5)], 1u << (tx & 31));
+        atomicOr(&sm.u.a.occ[sm.pkt[kWindow + tx] * kOccStride + (tx >> 5)], 1u << (tx & 31));
         __syncthreads();
 
         for (u32 c = 0; c < kChunks; ++c) {
@@ -79,7 +90,7 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
             {
                 const u32 sb = (p + 128) & 255;       // ring slot of position p - 128
                 const u32 wo = sb >> 5, bo = sb & 31;
-                const u32 *row = &sm.occ[v * kOccStride];
+                const u32 *row = &sm.u.a.occ[v * kOccStride];
                 u32 w[5];
 #pragma unroll
                 for (int i = 0; i < 5; ++i) w[i] = row[(wo + i) & 7];
@@ -88,20 +99,54 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
             }
             // scan length (gpu_compress.cu:120,149): 127, shrinking with tx in the last chunk
             const u32 n = (c == kChunks - 1) ? max(1u, 127u - tx) : 127u;
-            __syncthreads();   // every thread has read its mask: ring slots may be recycled
+            // Publish the mask; masks of the first 7 positions of the next chunk come from
+            // direct comparisons (their window is not in the ring yet).  Row r of ymask belongs
+            // to position 128*c + r; bit t of a row: P[pos - 128 + t] == P[pos].
+            sm.u.a.ymask[tx] = make_uint4(Y[0], Y[1], Y[2], Y[3]);
+#pragma unroll
+            for (int j = 0; j < kLevels; ++j) {
+                const u32 pn = (c + 1) * 128 + j;
+                const bool eq = (c + 1 < kChunks) && tx < 127 &&
+                                sm.pkt[pn + tx] == sm.pkt[kWindow + pn];
+                const u32 bal = __ballot_sync(0xffffffffu, eq);
+                if (lane == 0) reinterpret_cast<u32 *>(&sm.u.a.ymask[128 + j])[warp] = bal;
+            }
+            __syncthreads();   // masks published; every thread has read the ring: slots may be recycled
             if (c + 1 < kChunks) {
                 // clear the ring half that chunk c+1 is about to occupy (it holds chunk c-1)
                 const u32 half = ((c + 1) & 1) * 4;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const u32 val = tx * 2 + (i >> 2);
-                    sm.occ[val * kOccStride + half + (i & 3)] = 0;
+                    sm.u.a.occ[val * kOccStride + half + (i & 3)] = 0;
                 }
             }
-            __syncthreads();
+            // Run-length planes: bit t of Y(p+k) is the comparison of byte k of the window string
+            // at scan index t with byte k of the lookahead, so the AND over k = 0..j says L > j.
+            // c0/c1/c2 hold min(L - 1, 7) bit-sliced per scan index.
+            u32 c0[4], c1[4], c2[4];
+            {
+                uint4 r[kLevels];
+#pragma unroll
+                for (int k = 0; k < kLevels; ++k) r[k] = sm.u.a.ymask[tx + 1 + k];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const u32 a1 = Y[i] & (&r[0].x)[i];
+                    const u32 a2 = a1 & (&r[1].x)[i];
+                    const u32 a3 = a2 & (&r[2].x)[i];
+                    const u32 a4 = a3 & (&r[3].x)[i];
+                    const u32 a5 = a4 & (&r[4].x)[i];
+                    const u32 a6 = a5 & (&r[5].x)[i];
+                    const u32 a7 = a6 & (&r[6].x)[i];
+                    c2[i] = a4;
+                    c1[i] = (a2 & ~a4) | a6;
+                    c0[i] = (a1 & ~a2) | (a3 & ~a4) | (a5 & ~a6) | a7;
+                }
+            }
+            __syncthreads();   // ring half cleared; ymask rows consumed
             if (c + 1 < kChunks) {
                 const u32 pn = p + 128;
-                atomicOr(&sm.occ[sm.pkt[kWindow + pn] * kOccStride + ((pn & 255) >> 5)],
+                atomicOr(&sm.u.a.occ[sm.pkt[kWindow + pn] * kOccStride + ((pn & 255) >> 5)],
                          1u << (pn & 31));
             }
 
@@ -124,8 +169,13 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
                     const u32 b = __ffs(w) - 1;
                     const u32 tt = 32 * i + b;
                     const u32 cap = n - tt;
-                    u32 L = 1;
-                    while (L < cap && srcb[tt + L] == lab[L]) ++L;
+                    const u32 cnt = ((c0[i] >> b) & 1u) | (((c1[i] >> b) & 1u) << 1) |
+                                    (((c2[i] >> b) & 1u) << 2);
+                    u32 L = 1 + cnt;
+                    if (cnt == 7) {   // 8 or more: finish by comparing bytes
+                        while (L < cap && srcb[tt + L] == lab[L]) ++L;
+                    }
+                    L = min(L, cap);
                     if (L > best_len) { best_len = L; best_t = tt; }
                     t = tt + L + 1;
                     const int nlo = (int)t - 32 * i;
@@ -138,33 +188,46 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
             sm.toff[p] = is_match ? (u8)((p + best_t) & 255) : (u8)v;
             const u32 mm = __ballot_sync(0xffffffffu, is_match);
             if (lane == 0) sm.M[p >> 5] = mm;
-            sm.V[tx] = 0xffffffffu;
             __syncthreads();   // inserts of chunk c+1 visible; tokens of chunk c written
         }
 
         // ---------------------------------------------------------------- greedy selection (aftercomp)
-        // Every position is selected except those covered by the tail of a selected match.
+        // The parse visits p -> p + step(p), step = 1 for a literal and len for a match
+        // (gpu_compress.cu:500-517).  Three short phases instead of one 4096-step chain:
+        //  S1  every thread resolves its 32 positions backwards: J[p] = first visited position
+        //      beyond the block when the parse passes through p;
+        //  S2  one thread hops block to block (<= 128 hops) and records where each block is entered;
+        //  S3  every thread replays its block from the entry offset and sets the visited bits.
+        {
+            const u32 blk_end = 32 * (tx + 1);
+            for (int i = 31; i >= 0; --i) {
+                const u32 pos = 32 * tx + i;
+                const u32 nxt = pos + sm.tlen[pos];
+                sm.u.s.J[pos] = (u16)(nxt >= blk_end ? nxt : sm.u.s.J[nxt]);
+            }
+            sm.u.s.E[tx] = 0xff;
+        }
+        __syncthreads();
         if (tx == 0) {
             u32 p = 0;
             while (p < kPacket) {
-                u32 wi = p >> 5;
-                u32 w = sm.M[wi] & (0xffffffffu << (p & 31));
-                while (w == 0 && ++wi < kPacket / 32) w = sm.M[wi];
-                if (w == 0) break;
-                const u32 m = (wi << 5) + __ffs(w) - 1;
-                const u32 end = m + sm.tlen[m];          // first position after the match
-                // clear V bits (m, end)
-                u32 a = m + 1;
-                while (a < end) {
-                    const u32 wa = a >> 5;
-                    const u32 stop = min(end, (wa + 1) << 5);
-                    const u32 nb = stop - a;
-                    const u32 mask = (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u)) << (a & 31);
-                    sm.V[wa] &= ~mask;
-                    a = stop;
-                }
-                p = end;
+                sm.u.s.E[p >> 5] = (u8)(p & 31);
+                p = sm.u.s.J[p];
             }
+        }
+        __syncthreads();
+        {
+            const u32 e = sm.u.s.E[tx];
+            u32 bits = 0;
+            if (e != 0xff) {
+                u32 pos = 32 * tx + e;
+                const u32 blk_end = 32 * (tx + 1);
+                while (pos < blk_end) {
+                    bits |= 1u << (pos & 31);
+                    pos += sm.tlen[pos];
+                }
+            }
+            sm.V[tx] = bits;
         }
         __syncthreads();
 
@@ -193,15 +256,15 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
                 const u32 pos = tx * 32 + b;
                 const u32 o = po + (k >> 3) + 1;
                 if ((k & 7) == 0) {
-                    sm.FB[k >> 3] = (u16)(o - 1);
-                    sm.out[o - 1] = 0;
+                    sm.u.b.FB[k >> 3] = (u16)(o - 1);
+                    sm.u.b.out[o - 1] = 0;
                 }
                 if ((mt >> b) & 1) {
-                    sm.out[o] = sm.tlen[pos];
-                    sm.out[o + 1] = sm.toff[pos];
+                    sm.u.b.out[o] = sm.tlen[pos];
+                    sm.u.b.out[o + 1] = sm.toff[pos];
                     po += 2;
                 } else {
-                    sm.out[o] = sm.toff[pos];
+                    sm.u.b.out[o] = sm.toff[pos];
                     po += 1;
                 }
                 ++k;
@@ -210,12 +273,12 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
         __syncthreads();
         {
             u32 k = excl & 0xffffu, bits = vt;
-            u32 *out32 = reinterpret_cast<u32 *>(sm.out);
+            u32 *out32 = reinterpret_cast<u32 *>(sm.u.b.out);
             while (bits) {
                 const u32 b = __ffs(bits) - 1;
                 bits &= bits - 1;
                 if (!((mt >> b) & 1)) {   // literal: flag bit set (gpu_compress.cu:503)
-                    const u32 fb = sm.FB[k >> 3];
+                    const u32 fb = sm.u.b.FB[k >> 3];
                     atomicOr(&out32[fb >> 2], (1u << (k & 7)) << (8 * (fb & 3)));
                 }
                 ++k;
@@ -225,39 +288,35 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
         // ---------------------------------------------------------------- write packet
         {
             uint4 *dst = reinterpret_cast<uint4 *>(tmp_out + pid * (u64)kMaxPacketOut);
-            const uint4 *src = reinterpret_cast<const uint4 *>(sm.out);
+            const uint4 *src = reinterpret_cast<const uint4 *>(sm.u.b.out);
             const u32 nvec = (out_size + 15) >> 4;
             for (u32 i = tx; i < nvec; i += 128) dst[i] = src[i];
             if (tx == 0) {
                 pkt_size[pid] = (u16)out_size;
-                last_group_size[pid] = (u8)(out_size - sm.FB[(ntok_total - 1) >> 3]);
+                last_group_size[pid] = (u8)(out_size - sm.u.b.FB[(ntok_total - 1) >> 3]);
             }
         }
         __syncthreads();
     }
 }
 
-// Concatenate the packets of each buffer, append the trailer (gpu_compress.cu:624-657), decide
-// "compression took more" exactly like aftercomp's `if (j > finish)` test (:494-498): the test
-// runs before every token, so it fires iff the output size before the final flush exceeds
-// buf_length.
-__global__ void __launch_bounds__(256) culzss_assemble_kernel(const u8 *__restrict__ tmp_out,
-                                                              const u16 *__restrict__ pkt_size,
-                                                              const u8 *__restrict__ last_group_size,
-                                                              u32 npk, u32 buf_length,
-                                                              u8 *__restrict__ out, u64 out_stride,
-                                                              u32 *__restrict__ comp_len)
+// Per buffer: packet offsets (exclusive scan of the packet sizes), the trailer
+// (gpu_compress.cu:624-657) and the "compression took more" decision, exactly like aftercomp's
+// `if (j > finish)` test (:494-498): the test runs before every token, so it fires iff the
+// output size before the final flush exceeds buf_length.
+__global__ void __launch_bounds__(256) culzss_scan_kernel(const u16 *__restrict__ pkt_size,
+                                                          const u8 *__restrict__ last_group_size,
+                                                          u32 npk, u32 buf_length,
+                                                          u8 *__restrict__ out, u64 out_stride,
+                                                          u32 *__restrict__ pkt_off,
+                                                          u32 *__restrict__ comp_len)
 {
     __shared__ u32 sums[256];
-    __shared__ u32 offs[256];
-    __shared__ u32 szs[256];
     __shared__ u32 carry_s;
     const u32 b = blockIdx.x, tx = threadIdx.x;
     const u16 *sizes = pkt_size + (u64)b * npk;
-    const u8 *src_base = tmp_out + (u64)b * npk * kMaxPacketOut;
     u8 *dst = out + (u64)b * out_stride;
 
-    // total size
     u32 local = 0;
     for (u32 i = tx; i < npk; i += 256) local += sizes[i];
     sums[tx] = local;
@@ -274,13 +333,11 @@ __global__ void __launch_bounds__(256) culzss_assemble_kernel(const u8 *__restri
         if (tx == 0) comp_len[b] = 0;   // caller stores the buffer raw (culzss.c:177-183)
         return;
     }
-    // packets, in order, 256 at a time
     if (tx == 0) carry_s = 0;
     __syncthreads();
     for (u32 base = 0; base < npk; base += 256) {
         const u32 i = base + tx;
         const u32 sz = i < npk ? sizes[i] : 0;
-        // exclusive scan of sz over the block
         sums[tx] = sz;
         __syncthreads();
         for (u32 d = 1; d < 256; d <<= 1) {
@@ -291,32 +348,12 @@ __global__ void __launch_bounds__(256) culzss_assemble_kernel(const u8 *__restri
         }
         const u32 carry = carry_s;
         __syncthreads();
-        const u32 off = carry + sums[tx] - sz;
-        if (tx == 255) carry_s = carry + sums[255];
-        offs[tx] = off;
-        szs[tx] = sz;
-        if (i < npk) {   // trailer: packet size, big endian
-            dst[total + 2 * i] = (u8)(sz >> 8);
+        if (i < npk) {
+            pkt_off[(u64)b * npk + i] = carry + sums[tx] - sz;
+            dst[total + 2 * i] = (u8)(sz >> 8);      // trailer: packet size, big endian
             dst[total + 2 * i + 1] = (u8)sz;
         }
-        __syncthreads();
-        // all threads copy packet after packet; 4-byte stores where the destination allows
-        const u32 cnt = min(256u, npk - base);
-        for (u32 j = 0; j < cnt; ++j) {
-            const u8 *s = src_base + (u64)(base + j) * kMaxPacketOut;
-            u8 *d = dst + offs[j];
-            const u32 n = szs[j];
-            const u32 head = min(n, (4u - (u32)(reinterpret_cast<uintptr_t>(d) & 3)) & 3u);
-            const u32 nw = (n - head) >> 2;
-            if (tx < head) d[tx] = s[tx];
-            for (u32 k = tx; k < nw; k += 256) {
-                const u8 *q = s + head + 4 * k;
-                *reinterpret_cast<u32 *>(d + head + 4 * k) =
-                    (u32)q[0] | ((u32)q[1] << 8) | ((u32)q[2] << 16) | ((u32)q[3] << 24);
-            }
-            const u32 tail0 = head + 4 * nw;
-            if (tx < n - tail0) d[tail0 + tx] = s[tail0 + tx];
-        }
+        if (tx == 255) carry_s = carry + sums[255];
         __syncthreads();
     }
     if (tx == 0) {
@@ -328,6 +365,38 @@ __global__ void __launch_bounds__(256) culzss_assemble_kernel(const u8 *__restri
         t[4] = 0;   // pad size (always 0 in the reference, gpu_compress.cu:646-654)
         t[5] = 0;
         comp_len[b] = clen;
+    }
+}
+
+// One warp per packet: move it from its 16-byte aligned slot to its final, byte-aligned place.
+// Destination words are 4-byte aligned; each is assembled from two aligned source words.
+__global__ void __launch_bounds__(256) culzss_gather_kernel(const u8 *__restrict__ tmp_out,
+                                                            const u16 *__restrict__ pkt_size,
+                                                            const u32 *__restrict__ pkt_off,
+                                                            const u32 *__restrict__ comp_len,
+                                                            u32 npk, u64 npackets,
+                                                            u8 *__restrict__ out, u64 out_stride)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 pid = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pid < npackets; pid += warps) {
+        const u32 b = (u32)(pid / npk);
+        if (comp_len[b] == 0) continue;
+        const u8 *s = tmp_out + pid * (u64)kMaxPacketOut;
+        u8 *d = out + (u64)b * out_stride + pkt_off[pid];
+        const u32 n = pkt_size[pid];
+        const u32 head = min(n, (4u - (u32)(reinterpret_cast<uintptr_t>(d) & 3)) & 3u);
+        if (lane < head) d[lane] = s[lane];
+        const u32 nw = (n - head) >> 2;
+        const u32 *sw = reinterpret_cast<const u32 *>(s);
+        u32 *dw = reinterpret_cast<u32 *>(d + head);
+        const u32 sh = 8 * head;            // source byte offset of destination word 0 is `head`
+        for (u32 k = lane; k < nw; k += 32) {
+            const u32 lo = sw[k], hi = sw[k + 1];   // slot is padded: k + 1 stays inside it
+            dw[k] = head ? __funnelshift_r(lo, hi, sh) : lo;
+        }
+        const u32 tail0 = head + 4 * nw;
+        if (lane < n - tail0) d[tail0 + lane] = s[tail0 + lane];
     }
 }
 
@@ -518,7 +587,8 @@ using namespace b200lc;
 extern "C" size_t b200lc_culzss_encode_scratch_bytes(size_t nbuf, size_t buf_length)
 {
     const size_t npk = nbuf * (buf_length / lzss::kPacket);
-    return npk * lzss::kMaxPacketOut + ((npk * 2 + 255) & ~size_t(255)) + ((npk + 255) & ~size_t(255)) + 256;
+    return npk * lzss::kMaxPacketOut + 16 + ((npk * 2 + 255) & ~size_t(255)) +
+           ((npk + 255) & ~size_t(255)) + ((npk * 4 + 255) & ~size_t(255)) + 256;
 }
 
 extern "C" int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length,
@@ -535,8 +605,9 @@ extern "C" int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size
     const u32 npk_buf = (u32)(buf_length / lzss::kPacket);
     const u64 npk = (u64)nbuf * npk_buf;
     u8 *tmp = reinterpret_cast<u8 *>(d_scratch);
-    u16 *sizes = reinterpret_cast<u16 *>(tmp + npk * lzss::kMaxPacketOut);
+    u16 *sizes = reinterpret_cast<u16 *>(tmp + npk * lzss::kMaxPacketOut + 16);
     u8 *lastg = reinterpret_cast<u8 *>(sizes) + ((npk * 2 + 255) & ~u64(255));
+    u32 *pkoff = reinterpret_cast<u32 *>(lastg + ((npk + 255) & ~u64(255)));
 
     static bool attr_done = false;
     if (!attr_done) {
@@ -548,9 +619,12 @@ extern "C" int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size
     const u32 grid = (u32)min(npk, (u64)num_sms() * 64);
     lzss::culzss_encode_kernel<<<grid, 128, sizeof(lzss::EncSmem), stream>>>(d_in, npk, tmp, sizes, lastg);
     B200LC_CUDA_TRY(cudaGetLastError());
-    lzss::culzss_assemble_kernel<<<(u32)nbuf, 256, 0, stream>>>(tmp, sizes, lastg, npk_buf,
-                                                               (u32)buf_length, d_out, out_stride,
-                                                               d_comp_len);
+    lzss::culzss_scan_kernel<<<(u32)nbuf, 256, 0, stream>>>(sizes, lastg, npk_buf, (u32)buf_length,
+                                                           d_out, out_stride, pkoff, d_comp_len);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    const u32 ggrid = (u32)min((npk + 7) / 8, (u64)num_sms() * 32);
+    lzss::culzss_gather_kernel<<<ggrid, 256, 0, stream>>>(tmp, sizes, pkoff, d_comp_len, npk_buf, npk,
+                                                         d_out, out_stride);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }
