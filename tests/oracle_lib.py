@@ -55,6 +55,25 @@ def oracle():
     lib.culzss_oracle_decode_packet.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
     lib.culzss_oracle_decode_buffer.restype = C.c_int
     lib.culzss_oracle_decode_buffer.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.POINTER(C.c_int)]
+    _i32a = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+    lib.cudpp_oracle_sa.restype = None
+    lib.cudpp_oracle_sa.argtypes = [_u8p, C.c_uint32, _u32p]
+    lib.cudpp_oracle_bwt.restype = None
+    lib.cudpp_oracle_bwt.argtypes = [_u8p, C.c_uint32, _u8p, C.POINTER(C.c_int)]
+    lib.cudpp_oracle_mtf.restype = None
+    lib.cudpp_oracle_mtf.argtypes = [_u8p, C.c_uint32, _u8p]
+    lib.cudpp_oracle_tree.restype = C.c_int
+    lib.cudpp_oracle_tree.argtypes = [_u32p, _i32a, _i32a, _i32a, _i32a]
+    lib.cudpp_oracle_codes.restype = None
+    lib.cudpp_oracle_codes.argtypes = [_i32a, _i32a, _i32a, _i32a, C.c_int, _u64p, _u8p]
+    lib.cudpp_oracle_huffman.restype = C.c_int
+    lib.cudpp_oracle_huffman.argtypes = [_u8p, C.c_uint32, _u32p, _u32p, C.POINTER(C.c_uint32), _u32p,
+                                         C.c_uint32]
+    lib.cudpp_oracle_compress.restype = C.c_int
+    lib.cudpp_oracle_compress.argtypes = [_u8p, C.c_uint32, C.POINTER(C.c_int), _u32p, _u32p,
+                                          C.POINTER(C.c_uint32), _u32p, C.c_uint32]
+    lib.cudpp_oracle_decompress.restype = C.c_int
+    lib.cudpp_oracle_decompress.argtypes = [_u8p, C.c_uint32, C.c_int, _u32p, _u32p, _u32p]
     _cache["oracle"] = lib
     return lib
 
@@ -266,3 +285,94 @@ def quant_codes(n_bytes, seed=2024, dtype=np.int32):
     n = n_bytes // np.dtype(dtype).itemsize
     codes = np.clip(512 + np.rint(rng.laplace(0.0, 2.0, n)), 0, 1023).astype(dtype)
     return codes.view(np.uint8)[:n_bytes].copy()
+
+
+# ---------------------------------------------------------------------------- cudppCompress helpers
+def ref_cudpp():
+    if "ref_cudpp" in _cache:
+        return _cache["ref_cudpp"]
+    lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libref_cudpp.so"))
+    i32a = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+    lib.ref_cudpp_sa.argtypes = [_u8p, _u32p, C.c_size_t]
+    lib.ref_cudpp_bwt.argtypes = [_u8p, _u8p, C.POINTER(C.c_int), C.c_uint]
+    lib.ref_cudpp_mtf.argtypes = [_u8p, _u8p, C.c_uint]
+    lib.ref_cudpp_tree.argtypes = [_u32p, i32a, i32a, i32a, i32a, C.POINTER(C.c_int)]
+    lib.ref_cudpp_decompress.argtypes = [_u8p, C.c_int, _u32p, _u32p, C.c_size_t, _u32p, C.c_size_t]
+    for f in (lib.ref_cudpp_sa, lib.ref_cudpp_bwt, lib.ref_cudpp_mtf, lib.ref_cudpp_tree,
+              lib.ref_cudpp_decompress):
+        f.restype = None
+    _cache["ref_cudpp"] = lib
+    return lib
+
+
+def cudpp_test_vector(n=1 << 20, seed=95835, lo=1, span=255, sentinel=True):
+    """The reference test input: srand(seed); bytes rand() % span + lo; for the compress test
+    the last byte is a 0 sentinel (test_compress.cpp:552-556,687-692).  glibc rand()."""
+    libc = C.CDLL("libc.so.6")
+    libc.srand(seed)
+    out = np.empty(n, np.uint8)
+    for i in range(n):
+        out[i] = libc.rand() % span + lo
+    if sentinel:
+        out[n - 1] = 0
+    return out
+
+
+def cudpp_block(n, kind="zipf", seed=0):
+    """Synthetic C4 block: bytes in 1..255 with the final byte 0."""
+    rng = np.random.Generator(np.random.MT19937(95835 + seed))
+    if kind == "zipf":
+        d = zipf_bytes(n, 1.3, seed=95835 + seed, nsym=255) + 1
+    elif kind == "markov":
+        # order-1 source: next symbol = previous + small step -> long repeated contexts
+        steps = rng.integers(-2, 3, n)
+        d = (np.cumsum(steps) % 200 + 1).astype(np.uint8)
+    elif kind == "text":
+        words = [b"alpha", b"beta", b"gamma", b"delta", b"epsilon", b"zeta", b"eta", b"theta"]
+        idx = rng.integers(0, len(words), n // 4 + 8)
+        d = np.frombuffer(b" ".join(words[i] for i in idx)[:n], np.uint8).copy()
+    else:
+        d = rng.integers(1, 256, n, dtype=np.uint8)
+    d = d.astype(np.uint8)
+    d[n - 1] = 0
+    return d
+
+
+def cudpp_oracle_bwt(data):
+    out = np.zeros(data.size, np.uint8)
+    idx = C.c_int(-1)
+    oracle().cudpp_oracle_bwt(np.ascontiguousarray(data), data.size, out, C.byref(idx))
+    return out, idx.value
+
+
+def cudpp_oracle_mtf(data):
+    out = np.zeros(data.size, np.uint8)
+    oracle().cudpp_oracle_mtf(np.ascontiguousarray(data), data.size, out)
+    return out
+
+
+def cudpp_oracle_huffman(mtf):
+    n = mtf.size
+    nb = (n + 4095) // 4096
+    hist = np.zeros(256, np.uint32)
+    offs = np.zeros(nb, np.uint32)
+    cap = nb * 1537
+    out = np.zeros(cap, np.uint32)
+    tw = C.c_uint32(0)
+    rc = oracle().cudpp_oracle_huffman(np.ascontiguousarray(mtf), n, hist, offs, C.byref(tw), out, cap)
+    return rc, hist, offs, out[: tw.value].copy()
+
+
+def cudpp_oracle_compress(data):
+    """-> (rc, bwt_index, hist[256], offsets[nblocks], words)"""
+    b, idx = cudpp_oracle_bwt(data)
+    m = cudpp_oracle_mtf(b)
+    rc, hist, offs, words = cudpp_oracle_huffman(m)
+    return rc, idx, hist, offs, words
+
+
+def cudpp_oracle_decompress(n, idx, hist, offs, words):
+    out = np.zeros(n, np.uint8)
+    rc = oracle().cudpp_oracle_decompress(out, n, idx, np.ascontiguousarray(hist),
+                                          np.ascontiguousarray(offs), np.ascontiguousarray(words))
+    return rc, out
