@@ -66,6 +66,24 @@ def lib():
     L.b200lc_culzss_decode_scratch_bytes.argtypes = [sz, sz]
     L.b200lc_culzss_decode_batch.restype = i32
     L.b200lc_culzss_decode_batch.argtypes = [vp, vp, sz, sz, vp, vp, sz, vp]
+    L.b200lc_bwt_scratch_bytes.restype = sz
+    L.b200lc_bwt_scratch_bytes.argtypes = [sz, sz]
+    L.b200lc_bwt_batch.restype = i32
+    L.b200lc_bwt_batch.argtypes = [vp, sz, sz, vp, vp, vp, sz, vp]
+    L.b200lc_suffix_array_batch.restype = i32
+    L.b200lc_suffix_array_batch.argtypes = [vp, sz, sz, vp, vp, sz, vp]
+    L.b200lc_mtf_scratch_bytes.restype = sz
+    L.b200lc_mtf_scratch_bytes.argtypes = [sz, sz]
+    L.b200lc_mtf_batch.restype = i32
+    L.b200lc_mtf_batch.argtypes = [vp, sz, sz, vp, vp, sz, vp]
+    L.b200lc_cudpp_huffman_scratch_bytes.restype = sz
+    L.b200lc_cudpp_huffman_scratch_bytes.argtypes = [sz, sz]
+    L.b200lc_cudpp_huffman_batch.restype = i32
+    L.b200lc_cudpp_huffman_batch.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, sz, vp]
+    L.b200lc_cudpp_compress_scratch_bytes.restype = sz
+    L.b200lc_cudpp_compress_scratch_bytes.argtypes = [sz, sz]
+    L.b200lc_cudpp_compress_batch.restype = i32
+    L.b200lc_cudpp_compress_batch.argtypes = [vp, sz, sz, vp, vp, vp, vp, vp, sz, vp, vp, sz, vp]
     _lib = L
     return L
 
@@ -248,4 +266,72 @@ def culzss_decode(comp, offsets, buf_length=1 << 20, out=None, scratch=None, str
     check(L.b200lc_culzss_decode_batch(comp.data_ptr(), offsets.data_ptr(), nbuf, buf_length,
                                        out.data_ptr(), scratch.data_ptr(), scratch.numel(),
                                        _stream_ptr(stream)), "b200lc_culzss_decode_batch")
+    return out
+
+
+# ------------------------------------------------------------------------------- cudppCompress path
+def _scratch(nbytes, device):
+    import torch
+    return torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+
+
+def bwt_batch(data, nblocks, n, stream=None):
+    """BWT of nblocks blocks of n bytes (cuda uint8).  Returns (bwt, index int32[nblocks])."""
+    import torch
+    L = lib()
+    out = torch.empty_like(data)
+    index = torch.empty(nblocks, dtype=torch.int32, device=data.device)
+    sc = _scratch(L.b200lc_bwt_scratch_bytes(nblocks, n), data.device)
+    check(L.b200lc_bwt_batch(data.data_ptr(), nblocks, n, out.data_ptr(), index.data_ptr(),
+                             sc.data_ptr(), sc.numel(), _stream_ptr(stream)), "b200lc_bwt_batch")
+    return out, index
+
+
+def suffix_array_batch(data, nblocks, n, stream=None):
+    import torch
+    L = lib()
+    sa = torch.empty(nblocks * n, dtype=torch.int32, device=data.device)
+    sc = _scratch(L.b200lc_bwt_scratch_bytes(nblocks, n), data.device)
+    check(L.b200lc_suffix_array_batch(data.data_ptr(), nblocks, n, sa.data_ptr(), sc.data_ptr(),
+                                      sc.numel(), _stream_ptr(stream)), "b200lc_suffix_array_batch")
+    return sa
+
+
+def mtf_batch(data, nblocks, n, stream=None):
+    import torch
+    L = lib()
+    out = torch.empty_like(data)
+    sc = _scratch(L.b200lc_mtf_scratch_bytes(nblocks, n), data.device)
+    check(L.b200lc_mtf_batch(data.data_ptr(), nblocks, n, out.data_ptr(), sc.data_ptr(), sc.numel(),
+                             _stream_ptr(stream)), "b200lc_mtf_batch")
+    return out
+
+
+class CudppCompressed:
+    def __init__(self, bwt_index, hist, offsets, total_words, words, stride, error):
+        self.bwt_index, self.hist, self.offsets = bwt_index, hist, offsets
+        self.total_words, self.words, self.stride, self.error = total_words, words, stride, error
+
+
+def cudpp_compress_batch(data, nblocks, n, stream=None, scratch=None, out=None):
+    """cudppCompress of nblocks blocks of n bytes.  Synchronises (BWT stage)."""
+    import torch
+    L = lib()
+    dev = data.device
+    nhb = (n + 4095) // 4096
+    stride = nhb * 1537
+    if out is None:
+        out = CudppCompressed(torch.empty(nblocks, dtype=torch.int32, device=dev),
+                              torch.empty(nblocks * 256, dtype=torch.int32, device=dev),
+                              torch.empty(nblocks * nhb, dtype=torch.int32, device=dev),
+                              torch.empty(nblocks, dtype=torch.int32, device=dev),
+                              torch.empty(nblocks * stride, dtype=torch.int32, device=dev), stride,
+                              torch.zeros(1, dtype=torch.int32, device=dev))
+    if scratch is None:
+        scratch = _scratch(L.b200lc_cudpp_compress_scratch_bytes(nblocks, n), dev)
+    check(L.b200lc_cudpp_compress_batch(data.data_ptr(), nblocks, n, out.bwt_index.data_ptr(),
+                                        out.hist.data_ptr(), out.offsets.data_ptr(),
+                                        out.total_words.data_ptr(), out.words.data_ptr(), stride,
+                                        out.error.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                        _stream_ptr(stream)), "b200lc_cudpp_compress_batch")
     return out

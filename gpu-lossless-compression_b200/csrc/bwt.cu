@@ -1,0 +1,231 @@
+// Burrows-Wheeler transform of many independent blocks  (hot path 1).
+//
+// Definition (bit-exact with cudppBurrowsWheelerTransform):
+// SA = suffix array of the block with an implicit terminator smaller than every byte
+// (sa_kernel.cuh:47-60: T[i] = in[i] + 1 followed by zeros); bwt[i] = in[SA[i] - 1], or
+// in[n-1] where SA[i] == 0, and index = that row (compress_kernel.cuh:55-74).
+//
+// The reference builds ONE suffix array at a time with a recursive skew/DC3 (13 small kernels,
+// 4 radix sorts and a merge per level, cudaMalloc/cudaFree around every sort,
+// sa_app.cu:61-101,125-298).  Here all blocks of a batch are sorted together by prefix
+// doubling: round r sorts the 64-bit keys (block, rank_h[i], rank_h[i+h]) of every suffix of
+// every block with one device-wide radix sort, renames the groups and doubles h, until every
+// group is a singleton.  Random-like data needs 2-3 rounds, text 4-6.
+// The radix sort itself is cub::DeviceRadixSort from the CUDA toolkit (library code; a
+// hand-written onesweep tuned for 20-bit ranks is the next step).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+#include "../../include/b200lc.h"
+
+namespace b200lc {
+namespace bwt {
+
+constexpr int kThreads = 256;
+constexpr u32 kRankBits = 21;
+
+__global__ void __launch_bounds__(kThreads) init_keys_kernel(const u8 *__restrict__ in, u64 N, u32 n,
+                                                            u64 *__restrict__ keys,
+                                                            u32 *__restrict__ iota)
+{
+    for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < N; g += (u64)gridDim.x * kThreads) {
+        const u32 blk = (u32)(g / n), i = (u32)(g - (u64)blk * n);
+        u64 k = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) k = (k << 9) | (i + c < n ? (u64)in[g + c] + 1 : 0);
+        keys[g] = ((u64)blk << 36) | k;
+        iota[g] = (u32)g;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) pair_keys_kernel(const u32 *__restrict__ rank, u64 N, u32 n,
+                                                            u32 h, u64 *__restrict__ keys)
+{
+    for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < N; g += (u64)gridDim.x * kThreads) {
+        const u32 blk = (u32)(g / n), i = (u32)(g - (u64)blk * n);
+        const u64 r1 = rank[g];
+        const u64 r2 = (i + h < n) ? rank[g + h] : 0;
+        keys[g] = ((u64)blk << (2 * kRankBits)) | (r1 << kRankBits) | r2;
+    }
+}
+
+// heads[j] = j at the first element of every group of equal keys, else 0; counts the
+// non-head elements (0 means every suffix is alone in its group).
+__global__ void __launch_bounds__(kThreads) mark_heads_kernel(const u64 *__restrict__ keys, u64 N,
+                                                             u32 *__restrict__ heads,
+                                                             unsigned long long *__restrict__ dup)
+{
+    u32 local = 0;
+    for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
+        const bool head = j == 0 || keys[j] != keys[j - 1];
+        heads[j] = head ? (u32)j : 0u;
+        local += !head;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(dup, (unsigned long long)local);
+}
+
+// rank of a suffix = 1 + position of its group's head inside the block
+__global__ void __launch_bounds__(kThreads) scatter_rank_kernel(const u32 *__restrict__ head_of,
+                                                               const u32 *__restrict__ sa, u64 N,
+                                                               u32 n, u32 *__restrict__ rank)
+{
+    for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
+        const u32 blk = (u32)(j / n);
+        rank[sa[j]] = head_of[j] - blk * n + 1;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) bwt_gather_kernel(const u8 *__restrict__ in,
+                                                             const u32 *__restrict__ sa, u64 N, u32 n,
+                                                             u8 *__restrict__ out,
+                                                             int *__restrict__ index,
+                                                             u32 *__restrict__ sa_out)
+{
+    for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
+        const u32 blk = (u32)(j / n);
+        const u64 base = (u64)blk * n;
+        const u32 pos = sa[j] - (u32)base;        // suffix start inside the block
+        if (sa_out) sa_out[j] = pos;
+        if (out) {
+            if (pos == 0) {
+                out[j] = in[base + n - 1];
+                index[blk] = (int)(j - base);
+            } else {
+                out[j] = in[base + pos - 1];
+            }
+        }
+    }
+}
+
+struct Layout {
+    size_t keys_a, keys_b, vals_a, vals_b, rank, heads, counter, cub_temp, total;
+    size_t cub_bytes;
+};
+
+static Layout layout(u64 N)
+{
+    Layout L;
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const u64 *)nullptr, (u64 *)nullptr,
+                                    (const u32 *)nullptr, (u32 *)nullptr, (long long)N, 0, 64);
+    cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, (const u32 *)nullptr, (u32 *)nullptr, cub::Max(),
+                                   (long long)N);
+    L.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t o = 0;
+    L.keys_a = o; o += up(N * 8);
+    L.keys_b = o; o += up(N * 8);
+    L.vals_a = o; o += up(N * 4);
+    L.vals_b = o; o += up(N * 4);
+    L.rank = o; o += up(N * 4);
+    L.heads = o; o += up(N * 4);
+    L.counter = o; o += 256;
+    L.cub_temp = o; o += up(L.cub_bytes);
+    L.total = o;
+    return L;
+}
+
+// Sorted suffix order of every block in scratch vals_b (global indices); returns 0 or an error.
+static int suffix_sort(const u8 *d_in, u64 nblocks, u32 n, char *scratch, const Layout &L,
+                       cudaStream_t stream, const u32 **sa_global)
+{
+    const u64 N = nblocks * n;
+    u64 *keys_a = reinterpret_cast<u64 *>(scratch + L.keys_a);
+    u64 *keys_b = reinterpret_cast<u64 *>(scratch + L.keys_b);
+    u32 *iota = reinterpret_cast<u32 *>(scratch + L.vals_a);
+    u32 *sa = reinterpret_cast<u32 *>(scratch + L.vals_b);
+    u32 *rank = reinterpret_cast<u32 *>(scratch + L.rank);
+    u32 *heads = reinterpret_cast<u32 *>(scratch + L.heads);
+    unsigned long long *dup = reinterpret_cast<unsigned long long *>(scratch + L.counter);
+    void *cub_temp = scratch + L.cub_temp;
+    size_t cub_bytes = L.cub_bytes;
+    const u32 grid = (u32)min((N + kThreads - 1) / kThreads, (u64)num_sms() * 16);
+    int blk_bits = 1;
+    while ((1ull << blk_bits) < nblocks) ++blk_bits;
+
+    init_keys_kernel<<<grid, kThreads, 0, stream>>>(d_in, N, n, keys_a, iota);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    int end_bit = 36 + blk_bits;
+    for (u32 h = 4;; h <<= 1) {
+        B200LC_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys_a, keys_b, iota, sa,
+                                                        (long long)N, 0, end_bit, stream));
+        B200LC_CUDA_TRY(cudaMemsetAsync(dup, 0, sizeof(*dup), stream));
+        mark_heads_kernel<<<grid, kThreads, 0, stream>>>(keys_b, N, heads, dup);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        unsigned long long h_dup = 0;
+        B200LC_CUDA_TRY(cudaMemcpyAsync(&h_dup, dup, sizeof(h_dup), cudaMemcpyDeviceToHost, stream));
+        B200LC_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (h_dup == 0 || h >= n) break;
+        // rename: every element learns the position of its group's head (running maximum)
+        B200LC_CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_temp, cub_bytes, heads, heads, cub::Max(),
+                                                       (long long)N, stream));
+        scatter_rank_kernel<<<grid, kThreads, 0, stream>>>(heads, sa, N, n, rank);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        pair_keys_kernel<<<grid, kThreads, 0, stream>>>(rank, N, n, h, keys_a);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        end_bit = 2 * (int)kRankBits + blk_bits;
+    }
+    *sa_global = sa;
+    return B200LC_OK;
+}
+
+}  // namespace bwt
+}  // namespace b200lc
+
+using namespace b200lc;
+
+extern "C" size_t b200lc_bwt_scratch_bytes(size_t nblocks, size_t n)
+{
+    return bwt::layout((u64)nblocks * n).total;
+}
+
+static int bwt_check(const void *d_in, size_t nblocks, size_t n, void *d_scratch, size_t scratch_bytes)
+{
+    if (!d_in || !d_scratch) return B200LC_ERR_ARG;
+    if (n == 0 || n >= (1u << bwt::kRankBits) || nblocks == 0) return B200LC_ERR_UNSUPPORTED;
+    if ((u64)nblocks * n >= (1ull << 32)) return B200LC_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(d_scratch) & 255) return B200LC_ERR_ARG;
+    if (scratch_bytes < b200lc_bwt_scratch_bytes(nblocks, n)) return B200LC_ERR_SCRATCH;
+    return B200LC_OK;
+}
+
+// Synchronises the stream (the doubling loop reads one counter per round).
+extern "C" int b200lc_bwt_batch(const uint8_t *d_in, size_t nblocks, size_t n, uint8_t *d_out,
+                                int *d_index, void *d_scratch, size_t scratch_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = bwt_check(d_in, nblocks, n, d_scratch, scratch_bytes);
+    if (rc) return rc;
+    if (!d_out || !d_index) return B200LC_ERR_ARG;
+    const bwt::Layout L = bwt::layout((u64)nblocks * n);
+    const u32 *sa = nullptr;
+    rc = bwt::suffix_sort(d_in, nblocks, (u32)n, reinterpret_cast<char *>(d_scratch), L, stream, &sa);
+    if (rc) return rc;
+    const u64 N = (u64)nblocks * n;
+    const u32 grid = (u32)min((N + bwt::kThreads - 1) / bwt::kThreads, (u64)num_sms() * 16);
+    bwt::bwt_gather_kernel<<<grid, bwt::kThreads, 0, stream>>>(d_in, sa, N, (u32)n, d_out, d_index, nullptr);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}
+
+extern "C" int b200lc_suffix_array_batch(const uint8_t *d_in, size_t nblocks, size_t n,
+                                         uint32_t *d_sa, void *d_scratch, size_t scratch_bytes,
+                                         void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = bwt_check(d_in, nblocks, n, d_scratch, scratch_bytes);
+    if (rc) return rc;
+    if (!d_sa) return B200LC_ERR_ARG;
+    const bwt::Layout L = bwt::layout((u64)nblocks * n);
+    const u32 *sa = nullptr;
+    rc = bwt::suffix_sort(d_in, nblocks, (u32)n, reinterpret_cast<char *>(d_scratch), L, stream, &sa);
+    if (rc) return rc;
+    const u64 N = (u64)nblocks * n;
+    const u32 grid = (u32)min((N + bwt::kThreads - 1) / bwt::kThreads, (u64)num_sms() * 16);
+    bwt::bwt_gather_kernel<<<grid, bwt::kThreads, 0, stream>>>(d_in, sa, N, (u32)n, nullptr, nullptr, d_sa);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}

@@ -138,6 +138,47 @@ int b200lc_culzss_decode_batch(const uint8_t *d_comp, const uint64_t *d_comp_off
                                size_t buf_length, uint8_t *d_out, void *d_scratch,
                                size_t scratch_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Hot path 1: BWT -> MTF -> Huffman as in cudppCompress (cudpp-inpar), batched over independent
+ * blocks.  The CUDPP-named single-block entry points are in include/cudpp.h.
+ * All *_batch functions take nblocks blocks of n bytes, contiguous at stride n.
+ */
+
+/* Suffix-array BWT (cudppBurrowsWheelerTransform, compress_app.cu:243-267 + sa_app.cu:125-391):
+ * d_out[b*n + i] = last column, d_index[b] = row of the original string.  n < 2^21,
+ * nblocks * n < 2^32.  Synchronises the stream (one counter read per doubling round). */
+size_t b200lc_bwt_scratch_bytes(size_t nblocks, size_t n);
+int b200lc_bwt_batch(const uint8_t *d_in, size_t nblocks, size_t n, uint8_t *d_out, int *d_index,
+                     void *d_scratch, size_t scratch_bytes, void *stream);
+/* cudppSuffixArray: d_sa[b*n + j] = start (inside block b) of its j-th smallest suffix. */
+int b200lc_suffix_array_batch(const uint8_t *d_in, size_t nblocks, size_t n, uint32_t *d_sa,
+                              void *d_scratch, size_t scratch_bytes, void *stream);
+
+/* Move-to-front with initial list 0..255 (cudppMoveToFrontTransform, compress_app.cu:133-223;
+ * gold test_compress.cpp:93-125).  Any n.  Asynchronous. */
+size_t b200lc_mtf_scratch_bytes(size_t nblocks, size_t n);
+int b200lc_mtf_batch(const uint8_t *d_in, size_t nblocks, size_t n, uint8_t *d_out, void *d_scratch,
+                     size_t scratch_bytes, void *stream);
+
+/* Huffman stage of cudppCompress (compress_app.cu:65-117) on MTF output.  Per block b:
+ * d_hist[b*256..] histogram, d_offsets[b*nhb..] word offset of each 4096-symbol block's [nWords]
+ * cell (nhb = ceil(n/4096)), d_total_words[b], stream at d_out + b*out_stride_words.
+ * *d_error (device uint32) != 0: a code is longer than 32 bits, a 4096-symbol block needs more
+ * than 1536 words (the reference's hard capacity) or out_stride_words is too small.
+ * Asynchronous. */
+size_t b200lc_cudpp_huffman_scratch_bytes(size_t nblocks, size_t n);
+int b200lc_cudpp_huffman_batch(const uint8_t *d_mtf, size_t nblocks, size_t n, uint32_t *d_hist,
+                               uint32_t *d_offsets, uint32_t *d_total_words, uint32_t *d_out,
+                               size_t out_stride_words, uint32_t *d_error, void *d_scratch,
+                               size_t scratch_bytes, void *stream);
+
+/* cudppCompress for a batch of blocks (compress_app.cu:507-526). */
+size_t b200lc_cudpp_compress_scratch_bytes(size_t nblocks, size_t n);
+int b200lc_cudpp_compress_batch(const uint8_t *d_in, size_t nblocks, size_t n, int *d_bwt_index,
+                                uint32_t *d_hist, uint32_t *d_offsets, uint32_t *d_total_words,
+                                uint32_t *d_out, size_t out_stride_words, uint32_t *d_error,
+                                void *d_scratch, size_t scratch_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,195 @@
+"""GPU parity for hot path 1 (cudppCompress = BWT -> MTF -> Huffman) against the CPU oracle
+(oracle/cudpp_oracle.c, pinned to the reference testrig golds) and, where it applies, against
+the reference's own gold code in oracle/_ref/libref_cudpp.so.  Sizes / inputs follow the
+reference tests (test_compress.cpp:375-377,439-444,515,552-556,687-692).  Bar: bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as O
+from pkg import b200lc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+MIB = 1 << 20
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ MTF
+MTF_SIZES = [39, 128, 256, 1023, 1024, 1025, 2047, 2048, 2049, 4095, 4096, 4097, 65535, 65536,
+             65537, 1048575, 1048581]
+
+
+@pytest.mark.parametrize("n", MTF_SIZES)
+def test_mtf_reference_test_sizes(n):
+    # reference test: srand(95835), bytes rand() % 255 + 1 (test_compress.cpp:439-441)
+    rng = np.random.Generator(np.random.MT19937(95835 + n))
+    data = rng.integers(1, 256, n, dtype=np.uint8)
+    got = b200lc.mtf_batch(_dev(data), 1, n).cpu().numpy()
+    assert np.array_equal(got, O.cudpp_oracle_mtf(data))
+
+
+@pytest.mark.parametrize("kind", ["zipf", "markov", "text", "zeros"])
+def test_mtf_batched_blocks(kind):
+    n, nb = 70001, 5
+    blocks = [np.zeros(n, np.uint8) if kind == "zeros" else O.cudpp_block(n, kind, seed=b) for b in range(nb)]
+    got = b200lc.mtf_batch(_dev(np.concatenate(blocks)), nb, n).cpu().numpy()
+    for b in range(nb):
+        assert np.array_equal(got[b * n:(b + 1) * n], O.cudpp_oracle_mtf(blocks[b])), b
+
+
+# ------------------------------------------------------------------------------------------ BWT
+def test_bwt_reference_test_vector():
+    # n = 1,048,576, glibc srand(95835), rand() % 255 + 1 (test_compress.cpp:552-556)
+    data = O.cudpp_test_vector(MIB, sentinel=False)
+    want, widx = O.cudpp_oracle_bwt(data)
+    got, idx = b200lc.bwt_batch(_dev(data), 1, MIB)
+    assert int(idx.cpu()[0]) == widx
+    assert np.array_equal(got.cpu().numpy(), want)
+    if O.have_ref("cudpp"):
+        rb = np.zeros(MIB, np.uint8)
+        ridx = C.c_int(-1)
+        O.ref_cudpp().ref_cudpp_bwt(data, rb, C.byref(ridx), MIB)
+        assert ridx.value == widx and np.array_equal(rb, want)
+
+
+@pytest.mark.parametrize("kind,n,nb", [("zipf", 65536, 4), ("markov", 100000, 3), ("text", 262144, 2),
+                                       ("rand", 4097, 7), ("zeros", 5000, 2), ("rand", 1, 3)])
+def test_bwt_batched_blocks(kind, n, nb):
+    blocks = [np.zeros(n, np.uint8) if kind == "zeros" else O.cudpp_block(n, kind, seed=b) for b in range(nb)]
+    got, idx = b200lc.bwt_batch(_dev(np.concatenate(blocks)), nb, n)
+    got, idx = got.cpu().numpy(), idx.cpu().numpy()
+    for b in range(nb):
+        want, widx = O.cudpp_oracle_bwt(blocks[b])
+        assert idx[b] == widx, b
+        assert np.array_equal(got[b * n:(b + 1) * n], want), b
+
+
+def test_suffix_array_matches_gold():
+    # test_sa.cpp:124-126: bytes rand() % 128 + 1
+    n = 200001
+    rng = np.random.Generator(np.random.MT19937(5))
+    data = rng.integers(1, 129, n, dtype=np.uint8)
+    sa = b200lc.suffix_array_batch(_dev(data), 1, n).cpu().numpy().astype(np.uint32)
+    want = np.zeros(n, np.uint32)
+    O.oracle().cudpp_oracle_sa(data, n, want)
+    assert np.array_equal(sa, want)
+    if O.have_ref("cudpp"):
+        ref = np.zeros(n + 3, np.uint32)
+        O.ref_cudpp().ref_cudpp_sa(data, ref, n)
+        assert np.array_equal(ref[:n], want)
+
+
+# ------------------------------------------------------------------------------------------ compress
+def _check_block(res, b, data, nhb):
+    rc, widx, whist, woffs, wwords = O.cudpp_oracle_compress(data)
+    assert rc == 0
+    stride = res.stride
+    tw = int(res.total_words.cpu()[b])
+    assert int(res.bwt_index.cpu()[b]) == widx
+    assert np.array_equal(res.hist.cpu().numpy()[b * 256:(b + 1) * 256].astype(np.uint32), whist)
+    assert np.array_equal(res.offsets.cpu().numpy()[b * nhb:(b + 1) * nhb].astype(np.uint32), woffs)
+    assert tw == wwords.size
+    words = res.words.cpu().numpy()[b * stride: b * stride + tw].view(np.uint32)
+    assert np.array_equal(words, wwords)
+    return widx, whist, woffs, wwords
+
+
+def test_compress_reference_test_vector_and_reference_decoder():
+    # test_compress.cpp:687-692: rand() % 255 + 1 with a trailing 0 sentinel, n = 1,048,576
+    data = O.cudpp_test_vector(MIB, sentinel=True)
+    res = b200lc.cudpp_compress_batch(_dev(data), 1, MIB)
+    assert int(res.error.cpu()[0]) == 0
+    idx, hist, offs, words = _check_block(res, 0, data, 256)
+    if O.have_ref("cudpp"):
+        # the reference's own decoder (computeCompressGold) must reproduce the input
+        out = np.zeros(MIB, np.uint8)
+        h257 = np.zeros(257, np.uint32)
+        h257[:256] = hist
+        O.ref_cudpp().ref_cudpp_decompress(out, idx, h257, offs.copy(), words.size, words.copy(), MIB)
+        assert np.array_equal(out, data)
+
+
+@pytest.mark.parametrize("kind", ["zipf", "markov", "text"])
+def test_compress_batch_blocks(kind):
+    n, nb = MIB, 3
+    blocks = [O.cudpp_block(n, kind, seed=10 + b) for b in range(nb)]
+    res = b200lc.cudpp_compress_batch(_dev(np.concatenate(blocks)), nb, n)
+    assert int(res.error.cpu()[0]) == 0
+    for b in range(nb):
+        idx, hist, offs, words = _check_block(res, b, blocks[b], 256)
+        rc, back = O.cudpp_oracle_decompress(n, idx, hist, offs, words)
+        assert rc == 0 and np.array_equal(back, blocks[b])
+
+
+def test_compress_small_blocks():
+    n, nb = 8192, 6
+    blocks = [O.cudpp_block(n, "zipf", seed=30 + b) for b in range(nb)]
+    res = b200lc.cudpp_compress_batch(_dev(np.concatenate(blocks)), nb, n)
+    for b in range(nb):
+        _check_block(res, b, blocks[b], 2)
+
+
+def test_cudpp_named_entry_points():
+    """cudppCreate / cudppPlan / cudppCompress / ... with the reference's call sequence
+    (test_compress.cpp:650-747) and its error codes (cudpp.cpp:776-805)."""
+    L = b200lc.lib()
+
+    class Config(C.Structure):
+        _fields_ = [("algorithm", C.c_int), ("op", C.c_int), ("datatype", C.c_int),
+                    ("options", C.c_uint), ("bucket_mapper", C.c_int)]
+    CUDPP_UCHAR, CUDPP_UINT, CUDPP_COMPRESS, CUDPP_BWT, CUDPP_MTF, CUDPP_SCAN = 1, 5, 10, 12, 13, 0
+    vp, sz = C.c_void_p, C.c_size_t
+    L.cudppCreate.argtypes = [C.POINTER(sz)]
+    L.cudppPlan.argtypes = [sz, C.POINTER(sz), Config, sz, sz, sz]
+    L.cudppCompress.argtypes = [sz, vp, vp, vp, vp, vp, vp, vp, sz]
+    L.cudppBurrowsWheelerTransform.argtypes = [sz, vp, vp, vp, sz]
+    L.cudppMoveToFrontTransform.argtypes = [sz, vp, vp, sz]
+    L.cudppDestroyPlan.argtypes = [sz]
+    L.cudppDestroy.argtypes = [sz]
+    mgr = sz(0)
+    assert L.cudppCreate(C.byref(mgr)) == 0
+    plan = sz(0)
+    assert L.cudppPlan(mgr, C.byref(plan), Config(CUDPP_SCAN, 0, CUDPP_UINT, 0, 0), MIB, 1, 0) == 2
+    assert L.cudppPlan(mgr, C.byref(plan), Config(CUDPP_COMPRESS, 0, CUDPP_UINT, 0, 0), MIB, 1, 0) == 2
+    assert L.cudppPlan(mgr, C.byref(plan), Config(CUDPP_COMPRESS, 0, CUDPP_UCHAR, 0, 0), MIB, 1, 0) == 0
+
+    data = O.cudpp_block(MIB, "zipf", seed=77)
+    d_in = _dev(data)
+    d_idx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    d_hist = torch.zeros(256, dtype=torch.int32, device=DEV)
+    d_off = torch.zeros(256, dtype=torch.int32, device=DEV)
+    d_size = torch.zeros(1, dtype=torch.int32, device=DEV)
+    d_comp = torch.zeros(256 * 1537, dtype=torch.int32, device=DEV)
+    assert L.cudppCompress(0, d_in.data_ptr(), d_idx.data_ptr(), None, d_hist.data_ptr(), d_off.data_ptr(),
+                           d_size.data_ptr(), d_comp.data_ptr(), MIB) == 1          # invalid handle
+    assert L.cudppBurrowsWheelerTransform(plan, d_in.data_ptr(), d_in.data_ptr(), d_idx.data_ptr(), MIB) == 3
+    assert L.cudppCompress(plan, d_in.data_ptr(), d_idx.data_ptr(), None, d_hist.data_ptr(),
+                           d_off.data_ptr(), d_size.data_ptr(), d_comp.data_ptr(), MIB) == 0
+    torch.cuda.synchronize()
+    rc, widx, whist, woffs, wwords = O.cudpp_oracle_compress(data)
+    assert int(d_idx.cpu()[0]) == widx and int(d_size.cpu()[0]) == wwords.size
+    assert np.array_equal(d_comp.cpu().numpy()[: wwords.size].view(np.uint32), wwords)
+    assert np.array_equal(d_off.cpu().numpy().astype(np.uint32), woffs)
+    assert L.cudppDestroyPlan(plan) == 0
+
+    # standalone BWT and MTF plans (test_compress.cpp:453,588)
+    assert L.cudppPlan(mgr, C.byref(plan), Config(CUDPP_BWT, 0, CUDPP_UCHAR, 0, 0), MIB, 1, 0) == 0
+    d_out = torch.zeros(MIB, dtype=torch.uint8, device=DEV)
+    assert L.cudppBurrowsWheelerTransform(plan, d_in.data_ptr(), d_out.data_ptr(), d_idx.data_ptr(), MIB) == 0
+    torch.cuda.synchronize()
+    wb, wi = O.cudpp_oracle_bwt(data)
+    assert int(d_idx.cpu()[0]) == wi and np.array_equal(d_out.cpu().numpy(), wb)
+    assert L.cudppDestroyPlan(plan) == 0
+    assert L.cudppPlan(mgr, C.byref(plan), Config(CUDPP_MTF, 0, CUDPP_UCHAR, 0, 0), MIB, 1, 0) == 0
+    n = 1048571      # plans are sized for max n; any smaller n is accepted (test_compress.cpp:375-377)
+    assert L.cudppMoveToFrontTransform(plan, d_in.data_ptr(), d_out.data_ptr(), n) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy()[:n], O.cudpp_oracle_mtf(data[:n]))
+    assert L.cudppDestroyPlan(plan) == 0
+    assert L.cudppDestroy(mgr) == 0
