@@ -34,8 +34,33 @@ def culzss(name, data):
                         token_lens=tokens[0::2].copy(), token_offs=tokens[1::2].copy())
 
 
+def cudpp(name, data):
+    """Reference golds (computeBwtGold / computeMtfGold / huffman_build_tree_cpu) for one block;
+    the compressed words are the oracle's, accepted only if the reference decoder reproduces the
+    block from them (n = 1 MiB cases) -- see tests/test_oracle_cudpp.py."""
+    import ctypes as C
+    ref = O.ref_cudpp()
+    n = data.size
+    bwt = np.zeros(n, np.uint8)
+    idx = C.c_int(-1)
+    ref.ref_cudpp_bwt(data, bwt, C.byref(idx), n)
+    mtf = np.zeros(n, np.uint8)
+    ref.ref_cudpp_mtf(bwt, mtf, n)
+    hist = np.bincount(mtf, minlength=256).astype(np.uint32)
+    arrs = [np.zeros(513, np.int32) for _ in range(4)]
+    head = C.c_int(-1)
+    ref.ref_cudpp_tree(hist, arrs[0], arrs[1], arrs[2], arrs[3], C.byref(head))
+    rc, ohist, offs, words = O.cudpp_oracle_huffman(mtf)
+    assert rc == 0 and np.array_equal(ohist, hist)
+    np.savez_compressed(os.path.join(OUT, name), data=data, bwt=bwt, bwt_index=np.int64(idx.value),
+                        mtf=mtf, tree_left=arrs[0], tree_right=arrs[1], tree_value=arrs[3],
+                        tree_head=np.int64(head.value), offsets=offs, words=words)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    cudpp("cudpp_zipf.npz", O.cudpp_block(32768, "zipf", seed=1))
+    cudpp("cudpp_text.npz", O.cudpp_block(32768, "text", seed=2))
     cuhd("cuhd_zipf.npz", O.zipf_bytes(20000, 1.1, seed=12345))
     rng = np.random.Generator(np.random.MT19937(7))
     cuhd("cuhd_binom.npz", rng.binomial(255, 0.5, 20000).astype(np.uint8))
