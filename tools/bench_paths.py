@@ -92,15 +92,117 @@ def bench_culzss(mib, dev, kind="quant32"):
                       "decode_hbm_frac": (n + C) / dec_ms / 1e6 / PEAK}))
 
 
+def cudpp_blocks_gpu(nblocks, n, dev, kind="zipf", seed=95835):
+    """Synthetic C4 input on the GPU: bytes 1..255 (Zipf(1.3) or order-1 Markov), last byte 0."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    N = nblocks * n
+    if kind == "zipf":
+        p = 1.0 / torch.arange(1, 256, dtype=torch.float64) ** 1.3
+        cdf = torch.cumsum(p / p.sum(), 0).to(device=dev, dtype=torch.float32)
+        out = torch.empty(N, dtype=torch.uint8, device=dev)
+        chunk = 1 << 26
+        for lo in range(0, N, chunk):
+            m = min(chunk, N - lo)
+            u = torch.rand(m, generator=g, device=dev)
+            out[lo:lo + m] = (torch.searchsorted(cdf, u).clamp_(max=254) + 1).to(torch.uint8)
+    elif kind == "markov":
+        steps = torch.randint(-2, 3, (N,), generator=g, device=dev, dtype=torch.int32)
+        out = (torch.cumsum(steps, 0) % 200 + 1).to(torch.uint8)
+    else:
+        out = torch.randint(1, 256, (N,), generator=g, device=dev, dtype=torch.uint8)
+    out.view(nblocks, n)[:, -1] = 0
+    return out
+
+
+def bench_cudpp(mib, dev, kind="zipf", batch=128):
+    n = 1 << 20
+    nblocks = mib
+    data = cudpp_blocks_gpu(nblocks, n, dev, kind)
+    L = pkg.lib()
+    nb = min(batch, nblocks)
+    nhb = n // 4096
+    stride = nhb * 1537
+    scratch = torch.empty(L.b200lc_cudpp_compress_scratch_bytes(nb, n) + 256, dtype=torch.uint8, device=dev)
+    res = None
+    stage = {}
+
+    def run_all():
+        nonlocal res
+        for lo in range(0, nblocks, nb):
+            res = pkg.cudpp_compress_batch(data[lo * n:(lo + nb) * n], nb, n, scratch=scratch, out=res)
+
+    total_ms = timeit(run_all, iters=3, warm=1)
+    # stage split on one batch
+    d0 = data[: nb * n]
+    bscr = torch.empty(L.b200lc_bwt_scratch_bytes(nb, n) + 256, dtype=torch.uint8, device=dev)
+    bout = torch.empty(nb * n, dtype=torch.uint8, device=dev)
+    bidx = torch.empty(nb, dtype=torch.int32, device=dev)
+    sp = torch.cuda.current_stream().cuda_stream
+    stage["bwt_ms"] = timeit(lambda: pkg.check(L.b200lc_bwt_batch(d0.data_ptr(), nb, n, bout.data_ptr(), bidx.data_ptr(), bscr.data_ptr(), bscr.numel(), sp), "bwt"), iters=3, warm=1)
+    mout = torch.empty(nb * n, dtype=torch.uint8, device=dev)
+    stage["mtf_ms"] = timeit(lambda: pkg.check(L.b200lc_mtf_batch(bout.data_ptr(), nb, n, mout.data_ptr(), bscr.data_ptr(), bscr.numel(), sp), "mtf"), iters=3, warm=1)
+    hist = torch.empty(nb * 256, dtype=torch.int32, device=dev)
+    offs = torch.empty(nb * nhb, dtype=torch.int32, device=dev)
+    tw = torch.empty(nb, dtype=torch.int32, device=dev)
+    words = torch.empty(nb * stride, dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    stage["huffman_ms"] = timeit(lambda: pkg.check(L.b200lc_cudpp_huffman_batch(mout.data_ptr(), nb, n, hist.data_ptr(), offs.data_ptr(), tw.data_ptr(), words.data_ptr(), stride, err.data_ptr(), bscr.data_ptr(), bscr.numel(), sp), "huff"), iters=3, warm=1)
+    comp_words = int(tw.sum().item())
+    N = nblocks * n
+    print(json.dumps({"path": "cudpp_compress", "data": kind, "mib": mib, "batch_blocks": nb,
+                      "ratio": nb * n / (4.0 * comp_words), "error": int(err.item()),
+                      "encode_ms": total_ms, "encode_gbs": N / total_ms / 1e6,
+                      "stage_ms_per_batch": stage,
+                      "stage_gbs": {k.replace("_ms", ""): nb * n / v / 1e6 for k, v in stage.items()}}))
+
+
+def bench_cuhd(mib, dev):
+    import numpy as np
+    n = mib << 20
+    sys.path.insert(0, ROOT)
+    import bench as B
+    data = B.gen_zipf_gpu(n, dev, 12345)
+    hist = pkg.histogram_u8(data).cpu().numpy()
+    code, length, lut = pkg.cuhd_build_table(hist)
+    d_code = torch.from_numpy(code.view(np.int32)).to(dev)
+    d_len = torch.from_numpy(length).to(dev)
+    d_lut = torch.from_numpy(lut).to(dev)
+    enc = pkg.cuhd_encode(data, d_code, d_len)
+    L = pkg.lib()
+    units = torch.empty((n * 11 + 31) // 32 + 2, dtype=torch.int32, device=dev)
+    bits = torch.zeros(1, dtype=torch.int64, device=dev)
+    escr = torch.empty(L.b200lc_cuhd_encode_scratch_bytes(n), dtype=torch.uint8, device=dev)
+    enc_ms = timeit(lambda: pkg.cuhd_encode(data, d_code, d_len, units=units, total_bits=bits, scratch=escr, sync=False))
+    hist_ms = timeit(lambda: pkg.histogram_u8(data))
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    dscr = torch.empty(L.b200lc_cuhd_decode_scratch_bytes(enc.units.numel()), dtype=torch.uint8, device=dev)
+    dec_ms = timeit(lambda: pkg.cuhd_decode(enc.units, n, d_lut, 11, out=out, scratch=dscr))
+    assert torch.equal(out, data)
+    C = enc.n_units * 4
+    print(json.dumps({"path": "cuhd", "data": "zipf1.1", "mib": mib, "ratio": n / C,
+                      "hist_ms": hist_ms, "encode_ms": enc_ms, "decode_ms": dec_ms,
+                      "hist_gbs": n / hist_ms / 1e6, "encode_gbs": n / enc_ms / 1e6,
+                      "decode_gbs": n / dec_ms / 1e6,
+                      "hist_hbm_frac": n / hist_ms / 1e6 / PEAK,
+                      "encode_hbm_frac": (n + C) / enc_ms / 1e6 / PEAK,
+                      "decode_hbm_frac": (n + C) / dec_ms / 1e6 / PEAK}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
     ap.add_argument("--mib", type=int, default=1024)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
+    if args.what in ("cuhd", "all"):
+        bench_cuhd(args.mib, dev)
     if args.what in ("culzss", "all"):
         for kind in ("quant32", "quant16", "text", "random"):
             bench_culzss(args.mib, dev, kind)
+    if args.what in ("cudpp", "all"):
+        for kind in ("zipf", "markov", "rand"):
+            bench_cudpp(min(args.mib, 256), dev, kind)
 
 
 if __name__ == "__main__":
