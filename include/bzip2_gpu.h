@@ -1,0 +1,48 @@
+/*
+ * bzip2_gpu.h -- the GPU block-sort entry points of cuda-bzip2 served by libb200lc.so.
+ *
+ * gpuBlockSort / gpuSetDevice keep the reference's C++ linkage and signature
+ * (cuda-bzip2-ipdpsw/bzlib_private.h:527-531; the reference Makefile compiles every .c with
+ * g++, Makefile:18, so the symbols are C++-mangled): compress.c:726,880,1099,1150 link against
+ * libb200lc.so unchanged instead of gpuBWTSort.o.
+ *
+ * Contract (gpuBWTSort.cu:202-484), all pointers HOST memory:
+ *   block[0..blockSize)            RLE1-coded block
+ *   orderFirstSort[0..f)           start positions i with i % 3 != 0 (plus i = n-1 when
+ *                                  n % 3 == 1) in cyclic-rotation order
+ *   orderFirstSortRank[0..n)       rank of position i inside orderFirstSort, 0 for the others
+ *   orderSecondSort[0..n-f)        the remaining positions (i % 3 == 0) ordered by
+ *                                  (block[i], rank[i+1]) = their rotation order
+ *   *sortingDepth                  depth of the reference's refinement schedule at which all
+ *                                  first-sort ties were resolved (only used for statistics,
+ *                                  compress.c:1036-1037)
+ *   return value                   f
+ * `order` is not written (the reference does not write it either).
+ * The rotation order comes from one suffix sort of the doubled block
+ * (b200lc_suffix_array_batch); blocks up to 1,048,575 bytes (bzip2: <= 900,000).
+ */
+#ifndef B200LC_BZIP2_GPU_H_
+#define B200LC_BZIP2_GPU_H_
+
+#ifdef __cplusplus
+int gpuBlockSort(unsigned char *block, unsigned int *order, unsigned int *orderFirstSort,
+                 unsigned int *orderSecondSort, unsigned int *orderFirstSortRank, int blockSize,
+                 int *sortingDepth);
+void gpuSetDevice(int devId);
+extern "C" {
+#endif
+
+/* Same as gpuBlockSort with C linkage. */
+int b200lc_bzip2_block_sort(unsigned char *block, unsigned int *orderFirstSort,
+                            unsigned int *orderSecondSort, unsigned int *orderFirstSortRank,
+                            int blockSize, int *sortingDepth);
+/* Whole rotation order in one array: ptr[0..n) and origPtr (row of rotation 0) -- what
+ * merge_two_sort_arrays (compress.c:609-710) computes from the three arrays above.  Host
+ * pointers.  Returns 0 or a negative B200LC_ERR_* code. */
+int b200lc_bzip2_rotation_order(const unsigned char *block, int blockSize, unsigned int *ptr,
+                                int *origPtr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LC_BZIP2_GPU_H_ */

@@ -74,6 +74,12 @@ def oracle():
                                           C.POINTER(C.c_uint32), _u32p, C.c_uint32]
     lib.cudpp_oracle_decompress.restype = C.c_int
     lib.cudpp_oracle_decompress.argtypes = [_u8p, C.c_uint32, C.c_int, _u32p, _u32p, _u32p]
+    lib.bzip2_oracle_rotation_order.restype = None
+    lib.bzip2_oracle_rotation_order.argtypes = [_u8p, C.c_uint32, _u32p]
+    lib.bzip2_oracle_block_sort.restype = C.c_int
+    lib.bzip2_oracle_block_sort.argtypes = [_u8p, C.c_uint32, _u32p, _u32p, _u32p]
+    lib.bzip2_oracle_merge.restype = C.c_int
+    lib.bzip2_oracle_merge.argtypes = [_u8p, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p]
     _cache["oracle"] = lib
     return lib
 
@@ -376,3 +382,70 @@ def cudpp_oracle_decompress(n, idx, hist, offs, words):
     rc = oracle().cudpp_oracle_decompress(out, n, idx, np.ascontiguousarray(hist),
                                           np.ascontiguousarray(offs), np.ascontiguousarray(words))
     return rc, out
+
+
+# ---------------------------------------------------------------------------- cuda-bzip2 helpers
+def ref_bzip2(flavour=""):
+    """flavour "" = reference libbz2 with its own gpuBWTSort.cu; "_b200" = the same reference
+    objects with gpuBlockSort resolved from libb200lc.so."""
+    key = "ref_bzip2" + flavour
+    if key in _cache:
+        return _cache[key]
+    lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libref_bzip2%s.so" % flavour))
+    lib.ref_bzip2_decompress.restype = C.c_int
+    lib.ref_bzip2_decompress.argtypes = [_u8p, C.POINTER(C.c_uint), _u8p, C.c_uint]
+    lib.ref_bzip2_gpuBlockSort.restype = C.c_int
+    lib.ref_bzip2_gpuBlockSort.argtypes = [_u8p, _u32p, _u32p, _u32p, C.c_int, C.POINTER(C.c_int)]
+    _cache[key] = lib
+    return lib
+
+
+def bzip2_ref_compress(data, block100k=9, num_threads=0, flavour=""):
+    """Runs the reference libbz2 in a CHILD PROCESS: its handle_compress calls exit(1) once the
+    stream has been written to strm->handle (bzlib.c:606), so the call never returns."""
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        src, dst = os.path.join(td, "in.bin"), os.path.join(td, "out.bz2")
+        np.ascontiguousarray(data).tofile(src)
+        code = (
+            "import ctypes as C, numpy as np\n"
+            "lib = C.CDLL(%r)\n"
+            "d = np.fromfile(%r, np.uint8)\n"
+            "lib.ref_bzip2_compress_to_file.argtypes = [C.c_char_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]\n"
+            "rc = lib.ref_bzip2_compress_to_file(%r, d.ctypes.data, d.size, %d, %d)\n"
+            "raise SystemExit(100 + abs(rc))\n"
+        ) % (os.path.join(ORACLE_DIR, "_ref", "libref_bzip2%s.so" % flavour), src, dst.encode(),
+             block100k, num_threads)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 1, "reference libbz2 did not reach its exit(1): rc=%d\n%s" % (
+            r.returncode, (r.stdout + r.stderr)[-800:])
+        return np.fromfile(dst, np.uint8)
+
+
+def bzip2_ref_decompress(comp, n, flavour=""):
+    lib = ref_bzip2(flavour)
+    out = np.zeros(n + 16, np.uint8)
+    olen = C.c_uint(n + 16)
+    rc = lib.ref_bzip2_decompress(out, C.byref(olen), np.ascontiguousarray(comp), comp.size)
+    assert rc == 0, rc
+    return out[: olen.value].copy()
+
+
+def bzip2_oracle_block_sort(block):
+    n = block.size
+    first = np.zeros(n, np.uint32)
+    second = np.zeros(n, np.uint32)
+    rank = np.zeros(n, np.uint32)
+    f = oracle().bzip2_oracle_block_sort(np.ascontiguousarray(block), n, first, second, rank)
+    return f, first[:f].copy(), second[: n - f].copy(), rank
+
+
+def bzip2_oracle_merge(block, f, first, second, rank):
+    n = block.size
+    order = np.zeros(n, np.uint32)
+    f1 = np.zeros(n, np.uint32); f1[:f] = first
+    s1 = np.zeros(n, np.uint32); s1[: n - f] = second
+    orig = oracle().bzip2_oracle_merge(np.ascontiguousarray(block), n, f, f1, s1, rank, order)
+    return order, orig
