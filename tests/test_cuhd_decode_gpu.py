@@ -87,3 +87,27 @@ def test_without_pad_unit_and_unaligned_base():
     _run(d, drop_pad=True)
     _run(d, misalign=1)
     _run(d, misalign=3, drop_pad=True)
+
+
+def test_reference_demo_program_unmodified_against_compat_headers(tmp_path):
+    """oracle/_ref/cuhd_demo_b200 = cuhd-icpp/src/demo.cc, unmodified, compiled against
+    include/cuhd_compat/{cuhd,llhuff}.h and linked with libb200lc.so (oracle/Makefile).  The demo
+    encodes a file, decodes it on the GPU and prints "mismatch" if the bytes differ
+    (demo.cc:176-178)."""
+    import os
+    import subprocess
+    exe = os.path.join(O.ORACLE_DIR, "_ref", "cuhd_demo_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/cuhd_demo_b200 not built")
+    data = O.zipf_bytes(3_000_001, 1.1, seed=99)
+    src, dst = tmp_path / "in.bin", tmp_path / "out.huf"
+    src.write_bytes(data.tobytes())
+    r = subprocess.run([exe, "0", str(src), str(dst)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatch" not in r.stdout and "decoding.." in r.stdout
+    # the file the demo wrote is the packed stream: decode it with the oracle
+    hist = np.bincount(data, minlength=256)
+    code, length, lut = b200lc.cuhd_build_table(hist)
+    units = np.frombuffer(dst.read_bytes(), np.uint32)
+    want, _ = O.cuhd_oracle_encode(data, code, length)
+    assert np.array_equal(units, want)
