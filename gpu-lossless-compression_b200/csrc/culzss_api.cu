@@ -1,5 +1,9 @@
 // Reference-named CULZSS entry points (include/culzss_gpu.h) on top of the batch kernels.
+#include <string.h>
+
+#include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "../../include/b200lc.h"
@@ -186,4 +190,113 @@ extern "C" int decompression_kernel_wrapper(unsigned char *buffer, int buf_lengt
     if (!ok(cudaStreamSynchronize(st), "sync")) return 0;
     *decomp_length = (int)(orig - pad);
     return 1;
+}
+
+// ============================================================================ file container
+// Format written by the reference CLI (cuda-lzss-cluster/main.c:236-245, culzss.c:220,243-264,
+// decompression.c:90-141): native-endian u32 nblocks, u32 padding, u32 cumulative_end[nblocks],
+// then the buffers; a buffer whose stored size equals the 1 MiB buffer size is raw.  The reference
+// pads a last partial buffer with stale bytes of the previous one (main.c:122-130);
+// here the padding is zero, so containers of inputs that are not a multiple of 1 MiB decode
+// correctly everywhere but are not byte-identical to the reference's.
+namespace {
+constexpr size_t kBuf = 1u << 20;   // BUFSIZE, main.c:62
+}
+
+extern "C" size_t b200lc_culzss_container_bound(size_t n)
+{
+    const size_t nb = (n + kBuf - 1) / kBuf;
+    return 8 + 4 * nb + nb * (kBuf + 2 * (kBuf / 4096) + 6 + 32);
+}
+
+extern "C" int b200lc_culzss_compress_container(const uint8_t *h_in, size_t n, uint8_t *h_out,
+                                                size_t cap, size_t *out_len)
+{
+    if (!h_in || !h_out || !out_len) return B200LC_ERR_ARG;
+    if (n < kBuf || n >= (size_t(1) << 32)) return B200LC_ERR_UNSUPPORTED;   // main.c:225-229: "too small"
+    const size_t nb = (n + kBuf - 1) / kBuf;
+    const size_t padding = nb * kBuf - n;
+    const size_t stride = (kBuf + kBuf / 8 + 1024 + 15) & ~size_t(15);
+    u8 *d_in = nullptr, *d_out = nullptr;
+    u32 *d_len = nullptr;
+    void *d_scratch = nullptr;
+    const size_t sb = b200lc_culzss_encode_scratch_bytes(nb, kBuf);
+    int rc = B200LC_OK;
+    std::vector<u32> len(nb);
+    std::vector<u8> comp;
+    cudaStream_t st = nullptr;
+    if (cudaMalloc(&d_in, nb * kBuf) != cudaSuccess || cudaMalloc(&d_out, nb * stride) != cudaSuccess ||
+        cudaMalloc(&d_len, nb * 4) != cudaSuccess || cudaMalloc(&d_scratch, sb) != cudaSuccess) {
+        rc = B200LC_ERR_CUDA;
+    }
+    if (rc == B200LC_OK) {
+        if (!ok(cudaMemcpy(d_in, h_in, n, cudaMemcpyHostToDevice), "H2D") ||
+            !ok(cudaMemset(d_in + n, 0, padding), "memset"))
+            rc = B200LC_ERR_CUDA;
+    }
+    if (rc == B200LC_OK) rc = b200lc_culzss_encode_batch(d_in, nb, kBuf, d_out, stride, d_len, d_scratch, sb, st);
+    if (rc == B200LC_OK && !ok(cudaMemcpy(len.data(), d_len, nb * 4, cudaMemcpyDeviceToHost), "D2H"))
+        rc = B200LC_ERR_CUDA;
+    if (rc == B200LC_OK) {
+        size_t total = 8 + 4 * nb;
+        for (size_t b = 0; b < nb; ++b) total += len[b] ? len[b] : kBuf;
+        if (total > cap) rc = B200LC_ERR_OVERFLOW;
+        else {
+            u32 *hdr = reinterpret_cast<u32 *>(h_out);
+            hdr[0] = (u32)nb;
+            hdr[1] = (u32)padding;
+            size_t off = 8 + 4 * nb, cum = 0;
+            for (size_t b = 0; b < nb && rc == B200LC_OK; ++b) {
+                const size_t sz = len[b] ? len[b] : kBuf;
+                if (len[b]) {
+                    if (!ok(cudaMemcpy(h_out + off, d_out + b * stride, sz, cudaMemcpyDeviceToHost), "D2H"))
+                        rc = B200LC_ERR_CUDA;
+                } else {   // "compression took more": the raw buffer (culzss.c:177-183,241-242)
+                    const size_t have = std::min(kBuf, n - b * kBuf);
+                    memcpy(h_out + off, h_in + b * kBuf, have);
+                    memset(h_out + off + have, 0, kBuf - have);
+                }
+                cum += sz;
+                hdr[2 + b] = (u32)cum;
+                off += sz;
+            }
+            *out_len = off;
+        }
+    }
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_len); cudaFree(d_scratch);
+    return rc;
+}
+
+extern "C" int b200lc_culzss_decompress_container(const uint8_t *h_in, size_t n, uint8_t *h_out,
+                                                  size_t cap, size_t *out_len)
+{
+    if (!h_in || !h_out || !out_len || n < 8) return B200LC_ERR_ARG;
+    const u32 *hdr = reinterpret_cast<const u32 *>(h_in);
+    const size_t nb = hdr[0], padding = hdr[1];
+    if (nb == 0 || n < 8 + 4 * nb || padding >= kBuf) return B200LC_ERR_ARG;
+    const size_t payload = hdr[2 + nb - 1];
+    if (8 + 4 * nb + payload > n) return B200LC_ERR_ARG;
+    const size_t out_bytes = nb * kBuf - padding;
+    if (out_bytes > cap) return B200LC_ERR_OVERFLOW;
+    std::vector<u64> offs(nb + 1);
+    offs[0] = 0;
+    for (size_t b = 0; b < nb; ++b) offs[b + 1] = hdr[2 + b];
+    u8 *d_comp = nullptr, *d_out = nullptr;
+    u64 *d_offs = nullptr;
+    void *d_scratch = nullptr;
+    const size_t sb = b200lc_culzss_decode_scratch_bytes(nb, kBuf);
+    int rc = B200LC_OK;
+    if (cudaMalloc(&d_comp, payload + 64) != cudaSuccess || cudaMalloc(&d_out, nb * kBuf) != cudaSuccess ||
+        cudaMalloc(&d_offs, (nb + 1) * 8) != cudaSuccess || cudaMalloc(&d_scratch, sb) != cudaSuccess)
+        rc = B200LC_ERR_CUDA;
+    if (rc == B200LC_OK &&
+        (!ok(cudaMemcpy(d_comp, h_in + 8 + 4 * nb, payload, cudaMemcpyHostToDevice), "H2D") ||
+         !ok(cudaMemcpy(d_offs, offs.data(), (nb + 1) * 8, cudaMemcpyHostToDevice), "H2D")))
+        rc = B200LC_ERR_CUDA;
+    if (rc == B200LC_OK) rc = b200lc_culzss_decode_batch(d_comp, d_offs, nb, kBuf, d_out, d_scratch, sb, nullptr);
+    if (rc == B200LC_OK && !ok(cudaMemcpy(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost), "D2H"))
+        rc = B200LC_ERR_CUDA;
+    if (rc == B200LC_OK) *out_len = out_bytes;
+    cudaFree(d_comp); cudaFree(d_out); cudaFree(d_offs); cudaFree(d_scratch);
+    return rc;
 }

@@ -138,6 +138,18 @@ int b200lc_culzss_decode_batch(const uint8_t *d_comp, const uint64_t *d_comp_off
                                size_t buf_length, uint8_t *d_out, void *d_scratch,
                                size_t scratch_bytes, void *stream);
 
+/* CULZSS file container, HOST buffers, synchronous: the byte layout the
+ * reference CLI writes and reads (cuda-lzss-cluster/main.c:236-245, culzss.c:220,243-264,
+ * decompression.c:90-141): u32 nblocks, u32 padding, u32 cumulative_end[nblocks], buffers of
+ * 1 MiB input each (raw when the stored size is 1 MiB).  n >= 1 MiB like the reference
+ * (main.c:225-229).  Byte-identical to the reference's file for n % 1 MiB == 0; otherwise the
+ * last buffer is zero-padded where the reference leaves stale bytes (main.c:122-130). */
+size_t b200lc_culzss_container_bound(size_t n);
+int b200lc_culzss_compress_container(const uint8_t *h_in, size_t n, uint8_t *h_out, size_t cap,
+                                     size_t *out_len);
+int b200lc_culzss_decompress_container(const uint8_t *h_in, size_t n, uint8_t *h_out, size_t cap,
+                                       size_t *out_len);
+
 /* ------------------------------------------------------------------------------------------
  * Hot path 1: BWT -> MTF -> Huffman as in cudppCompress (cudpp-inpar), batched over independent
  * blocks.  The CUDPP-named single-block entry points are in include/cudpp.h.
