@@ -72,7 +72,7 @@ struct DecodeParams {
 // ---------------------------------------------------------------------------------- walks
 // Round 0: decode the subsequence from bit 0, remember every codeword start.
 template <int S>
-__device__ __forceinline__ void walk_record(const u32 (&u)[S + 1], const u32 *tab, u32 shift,
+__device__ __forceinline__ void walk_record(const u32 (&u)[S + 1], const u8 *tab, u32 shift,
                                             u32 (&m)[S], u32 &end, u32 &cnt)
 {
     u32 at = 0, c = 0;
@@ -83,7 +83,7 @@ __device__ __forceinline__ void walk_record(const u32 (&u)[S + 1], const u32 *ta
         while (at < 32) {
             mj |= 0x80000000u >> at;
             const u32 w = __funnelshift_l(nxt, cur, at);
-            at += tab[w >> shift] & 0xffu;
+            at += tab[w >> shift];
         }
         m[j] = mj;
         c += __popc(mj);
@@ -100,7 +100,7 @@ __device__ __forceinline__ void walk_record(const u32 (&u)[S + 1], const u32 *ta
 // a time -- measured: 52% of all issued instructions at 1 active thread).
 template <int S>
 __device__ __forceinline__ void walk_merge(const u32 (&u)[S + 1], const u32 (&m)[S], u32 a, u32 e0,
-                                           const u32 *tab, u32 shift, u32 &end, u32 &cnt)
+                                           const u8 *tab, u32 shift, u32 &end, u32 &cnt)
 {
     u32 at = a, k = 0, rest = 0;
     bool done = false;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void walk_merge(const u32 (&u)[S + 1], const u32 (&m)
                     break;
                 }
                 const u32 w = __funnelshift_l(nxt, cur, at);
-                at += tab[w >> shift] & 0xffu;
+                at += tab[w >> shift];
                 ++k;
             }
             if (!done) at -= 32;
@@ -156,8 +156,10 @@ template <int S, int T, int NSUB, int CAP>
 struct SmemLayout {
     static constexpr int kTileUnits = T * S + 4;  // + one 16-byte lookahead
     u32 in[2][kTileUnits];
-    __align__(16) u8 stage[CAP + 16];
-    u32 masks[T * S];        // sub-tile 0 only: codeword-start masks of the paths from bit 0
+    union {
+        __align__(16) u8 stage[CAP + 16];   // pass B: output staging
+        u32 masks[T * S];                   // pass A, sub-tile 0: codeword-start masks of the paths from bit 0
+    };
     u32 pre[T + 1];          // sub-tile 0 only: exclusive prefix of resolved symbol counts
     u16 saved[NSUB][T];      // pass A result per subsequence: entry state << 12 | symbol count
     u32 sub_total[NSUB];     // pass A symbols per sub-tile
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     u32 *tab = reinterpret_cast<u32 *>(smem_raw + ((sizeof(Smem) + 127) & ~size_t(127)));
+    u8 *ltab = reinterpret_cast<u8 *>(tab + (size_t(1) << p.max_len));   // lengths only: 1 byte per entry
 
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31;
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
         u32 len = e & 0xffu;
         if (len == 0 || len > L) len = 1;
         tab[i] = len | (e & 0xff00u);
+        ltab[i] = (u8)len;
     }
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
         // Leaves my_start / my_end / my_cnt per worker and sm.end[] = resolved exit states.
         auto resolve_subtile = [&](u32 entry, bool keep_masks) {
             if (worker) {
-                walk_record<S>(u, tab, shift, m, e0, c0);
+                walk_record<S>(u, ltab, shift, m, e0, c0);
                 sm.end[tid] = (u8)e0;
                 if (keep_masks) {
 #pragma unroll
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
                 bool changed = false;
                 if (eval) {
                     u32 ne, nc;
-                    walk_merge<S>(u, m, my_start, e0, tab, shift, ne, nc);
+                    walk_merge<S>(u, m, my_start, e0, ltab, shift, ne, nc);
                     changed = ne != my_end;
                     my_end = ne;
                     my_cnt = nc;
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
                             for (int j = 0; j < S; ++j) am[j] = onp ? sm.masks[sq * S + j] : 0u;
                             const u32 rend = sm.end[sq];
                             u32 ne, nc;
-                            walk_merge<S>(au, am, at, rend, tab, shift, ne, nc);
+                            walk_merge<S>(au, am, at, rend, ltab, shift, ne, nc);
                             own += nc;
                             if (ne == rend) {
                                 dl = (int)own - (int)sm.pre[sq + 1];
@@ -566,8 +570,10 @@ struct Variant {
     { S_, T_, N_, C_, cuhd_decode_kernel<S_, T_, N_, C_>, \
       ((sizeof(SmemLayout<S_, T_, N_, C_>) + 127) & ~size_t(127)) }
 static const Variant kVariants[] = {
-    B200LC_VARIANT(8, 256, 32, 16384),   // 311 GB/s of output on C2 (B200, round 1)
-    B200LC_VARIANT(8, 256, 16, 16384),   // 307
+    B200LC_VARIANT(8, 256, 16, 16384),   // 388 GB/s of output on C2 (B200, round 1)
+    B200LC_VARIANT(8, 256, 32, 16384),   // 333
+    B200LC_VARIANT(8, 256, 8, 16384),    // 370
+    B200LC_VARIANT(8, 128, 16, 8192),    // 375
     B200LC_VARIANT(8, 128, 32, 12288),   // 271
     B200LC_VARIANT(4, 128, 64, 6144),    // 207
     B200LC_VARIANT(4, 256, 32, 12288),   // 279
@@ -626,7 +632,7 @@ extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8
     if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
 
     const cuhd::Variant &v = cuhd::variant();
-    const size_t smem = v.smem_fixed + (size_t(4) << max_codeword_length);
+    const size_t smem = v.smem_fixed + (size_t(5) << max_codeword_length);
     static int occ_cache[14] = {0};
     if (!occ_cache[max_codeword_length]) {
         B200LC_CUDA_TRY(cudaFuncSetAttribute(v.kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
