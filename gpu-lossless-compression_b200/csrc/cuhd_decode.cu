@@ -140,10 +140,10 @@ __device__ __forceinline__ void walk_write(const u32 (&u)[S + 1], const u32 *tab
         const u32 cur = u[j], nxt = u[j + 1];
         while (at < 32) {
             const u32 w = __funnelshift_l(nxt, cur, at);
-            const u32 e = tab[w >> shift];
-            if (!CHECK || (pos >= lo && pos < hi)) dst[pos] = (u8)(e >> 8);
+            const u32 e = tab[w >> shift];          // symbol | length << 8
+            if (!CHECK || (pos >= lo && pos < hi)) dst[pos] = (u8)e;
             ++pos;
-            at += e & 0xffu;
+            at += e >> 8;
         }
         at -= 32;
     }
@@ -193,14 +193,14 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
     constexpr u32 kTileUnits = Smem::kTileUnits;
     constexpr u32 kTileBytes = kTileUnits * 4;
 
-    // LUT -> shared memory as 32-bit entries: bits 0..7 length, 8..15 symbol.  A zero-length
+    // LUT -> shared memory as 32-bit entries: bits 0..7 symbol, 8..15 length (+ a byte table of lengths).  A zero-length
     // entry (unused prefix of an incomplete code) would stall the reference forever; it is
     // mapped to length 1 here so that garbage input still terminates.
     for (u32 i = tid; i < (1u << L); i += blockDim.x) {
         const u32 e = p.lut[i];
         u32 len = e & 0xffu;
         if (len == 0 || len > L) len = 1;
-        tab[i] = len | (e & 0xff00u);
+        tab[i] = (len << 8) | (e >> 8);
         ltab[i] = (u8)len;
     }
     if (tid == 0) {
@@ -572,7 +572,7 @@ struct Variant {
 static const Variant kVariants[] = {
     B200LC_VARIANT(8, 256, 16, 16384),   // 388 GB/s of output on C2 (B200, round 1)
     B200LC_VARIANT(8, 256, 32, 16384),   // 333
-    B200LC_VARIANT(8, 256, 8, 16384),    // 370
+    B200LC_VARIANT(8, 256, 8, 12288),    // 370 (with CAP 16384)
     B200LC_VARIANT(8, 128, 16, 8192),    // 375
     B200LC_VARIANT(8, 128, 32, 12288),   // 271
     B200LC_VARIANT(4, 128, 64, 6144),    // 207
