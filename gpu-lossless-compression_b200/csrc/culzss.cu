@@ -172,8 +172,20 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
                     const u32 cnt = ((c0[i] >> b) & 1u) | (((c1[i] >> b) & 1u) << 1) |
                                     (((c2[i] >> b) & 1u) << 2);
                     u32 L = 1 + cnt;
-                    if (cnt == 7) {   // 8 or more: finish by comparing bytes
+                    if (cnt == 7) {   // 8 or more: finish 4 bytes at a time (two unaligned words)
+                        const u32 lim = cap < 128 ? cap : 128;
+                        while (L + 4 <= lim) {
+                            const u32 pa = p + tt + L, pb = kWindow + p + L;     // byte offsets in pkt
+                            const u32 *wa = reinterpret_cast<const u32 *>(sm.pkt + (pa & ~3u));
+                            const u32 *wb = reinterpret_cast<const u32 *>(sm.pkt + (pb & ~3u));
+                            const u32 xa = __funnelshift_r(wa[0], wa[1], 8 * (pa & 3));
+                            const u32 xb = __funnelshift_r(wb[0], wb[1], 8 * (pb & 3));
+                            const u32 d = xa ^ xb;
+                            if (d) { L += (__ffs(d) - 1) >> 3; goto lcp_done; }
+                            L += 4;
+                        }
                         while (L < cap && srcb[tt + L] == lab[L]) ++L;
+                    lcp_done:;
                     }
                     L = min(L, cap);
                     if (L > best_len) { best_len = L; best_t = tt; }

@@ -91,12 +91,16 @@ __global__ void __launch_bounds__(256) mtf_lists_kernel(const u8 *__restrict__ i
 // ---------------------------------------------------------------- 2. sequential MTF per segment
 constexpr int kApplyThreads = 64;
 
+// The list of a thread is 64 little-endian words (byte 0 of word 0 = front) stored transposed,
+// W[w * 64 + t].  One pass per input byte: every word in front of the match is shifted up by one
+// byte while it is being searched (4 list entries per shared-memory access, __vcmpeq4 finds the
+// match), so the cost is rank/4 iterations instead of 2*rank byte moves.
 __global__ void __launch_bounds__(kApplyThreads) mtf_apply_kernel(const u8 *__restrict__ in, u32 n,
                                                                   u32 nseg, u64 total_segs,
                                                                   const u8 *__restrict__ lists,
                                                                   u8 *__restrict__ out)
 {
-    __shared__ u8 L[256 * kApplyThreads];   // L[j * 64 + t]: entry j of thread t's list
+    __shared__ u32 W[64 * kApplyThreads];
     const u32 t = threadIdx.x;
     const u64 seg = (u64)blockIdx.x * kApplyThreads + t;
     if (seg >= total_segs) return;
@@ -106,9 +110,10 @@ __global__ void __launch_bounds__(kApplyThreads) mtf_apply_kernel(const u8 *__re
 #pragma unroll 4
         for (int q = 0; q < 16; ++q) {
             const uint4 v = lsrc[q];
-            const u32 w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 16; ++k) L[(q * 16 + k) * kApplyThreads + t] = (u8)(w[k >> 2] >> (8 * (k & 3)));
+            W[(4 * q + 0) * kApplyThreads + t] = v.x;
+            W[(4 * q + 1) * kApplyThreads + t] = v.y;
+            W[(4 * q + 2) * kApplyThreads + t] = v.z;
+            W[(4 * q + 3) * kApplyThreads + t] = v.w;
         }
     }
     const u64 base = (u64)blk * n + (u64)s * kSeg;
@@ -116,12 +121,32 @@ __global__ void __launch_bounds__(kApplyThreads) mtf_apply_kernel(const u8 *__re
     const u8 *src = in + base;
     u8 *dst = out + base;
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    u32 front = W[t];                      // word 0 lives in a register
     auto step = [&](u32 c) -> u32 {
-        u32 j = 0;
-        while (L[j * kApplyThreads + t] != c) ++j;
-        for (u32 k = j; k > 0; --k) L[k * kApplyThreads + t] = L[(k - 1) * kApplyThreads + t];
-        L[t] = (u8)c;
-        return j;
+        const u32 cc = c * 0x01010101u;
+        u32 m = __vcmpeq4(front, cc);
+        if (m) {                           // rank 0..3: registers only
+            const u32 b = (__ffs(m) - 1) >> 3;
+            const u32 lomask = b == 3 ? 0xffffffffu : ((1u << (8 * (b + 1))) - 1u);
+            front = (front & ~lomask) | (((front << 8) | c) & lomask);
+            return b;
+        }
+        u32 carry = front >> 24;
+        front = (front << 8) | c;
+        u32 w = 1;
+        while (true) {
+            const u32 x = W[w * kApplyThreads + t];
+            m = __vcmpeq4(x, cc);
+            if (m) {
+                const u32 b = (__ffs(m) - 1) >> 3;
+                const u32 lomask = b == 3 ? 0xffffffffu : ((1u << (8 * (b + 1))) - 1u);
+                W[w * kApplyThreads + t] = (x & ~lomask) | (((x << 8) | carry) & lomask);
+                return 4 * w + b;
+            }
+            W[w * kApplyThreads + t] = (x << 8) | carry;
+            carry = x >> 24;
+            ++w;
+        }
     };
     u32 i = 0;
     if (aligned) {
