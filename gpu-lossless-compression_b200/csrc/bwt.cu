@@ -25,6 +25,13 @@ namespace bwt {
 constexpr int kThreads = 256;
 constexpr u32 kRankBits = 21;
 
+// First round: key = block number | first kFirstChars raw bytes of the suffix (zero-padded past
+// the end of the block) | number of real bytes among them.  The length field orders a short
+// suffix before every longer one that continues with zero bytes (the implicit terminator is
+// smaller than byte 0) and makes the key exact: equal keys <=> equal first kFirstChars characters
+// of the terminated string, which is what prefix doubling needs.
+constexpr u32 kFirstChars = 6;
+constexpr u32 kFirstKeyBits = 8 * kFirstChars + 3;
 __global__ void __launch_bounds__(kThreads) init_keys_kernel(const u8 *__restrict__ in, u64 N, u32 n,
                                                             u64 *__restrict__ keys,
                                                             u32 *__restrict__ iota)
@@ -33,8 +40,9 @@ __global__ void __launch_bounds__(kThreads) init_keys_kernel(const u8 *__restric
         const u32 blk = (u32)(g / n), i = (u32)(g - (u64)blk * n);
         u64 k = 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) k = (k << 9) | (i + c < n ? (u64)in[g + c] + 1 : 0);
-        keys[g] = ((u64)blk << 36) | k;
+        for (u32 c = 0; c < kFirstChars; ++c) k = (k << 8) | (i + c < n ? (u64)in[g + c] : 0);
+        const u32 real = min(kFirstChars, n - i);
+        keys[g] = ((u64)blk << kFirstKeyBits) | (k << 3) | real;
         iota[g] = (u32)g;
     }
 }
@@ -148,8 +156,8 @@ static int suffix_sort(const u8 *d_in, u64 nblocks, u32 n, char *scratch, const 
 
     init_keys_kernel<<<grid, kThreads, 0, stream>>>(d_in, N, n, keys_a, iota);
     B200LC_CUDA_TRY(cudaGetLastError());
-    int end_bit = 36 + blk_bits;
-    for (u32 h = 4;; h <<= 1) {
+    int end_bit = (int)kFirstKeyBits + blk_bits;
+    for (u32 h = kFirstChars;; h <<= 1) {
         B200LC_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys_a, keys_b, iota, sa,
                                                         (long long)N, 0, end_bit, stream));
         B200LC_CUDA_TRY(cudaMemsetAsync(dup, 0, sizeof(*dup), stream));
@@ -186,7 +194,7 @@ static int bwt_check(const void *d_in, size_t nblocks, size_t n, void *d_scratch
 {
     if (!d_in || !d_scratch) return B200LC_ERR_ARG;
     if (n == 0 || n >= (1u << bwt::kRankBits) || nblocks == 0) return B200LC_ERR_UNSUPPORTED;
-    if ((u64)nblocks * n >= (1ull << 32)) return B200LC_ERR_UNSUPPORTED;
+    if ((u64)nblocks * n >= (1ull << 32) || nblocks > 4096) return B200LC_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(d_scratch) & 255) return B200LC_ERR_ARG;
     if (scratch_bytes < b200lc_bwt_scratch_bytes(nblocks, n)) return B200LC_ERR_SCRATCH;
     return B200LC_OK;

@@ -158,7 +158,7 @@ int b200lc_culzss_decompress_container(const uint8_t *h_in, size_t n, uint8_t *h
 
 /* Suffix-array BWT (cudppBurrowsWheelerTransform, compress_app.cu:243-267 + sa_app.cu:125-391):
  * d_out[b*n + i] = last column, d_index[b] = row of the original string.  n < 2^21,
- * nblocks * n < 2^32.  Synchronises the stream (one counter read per doubling round). */
+ * nblocks <= 4096 per call, nblocks * n < 2^32.  Synchronises the stream (one counter read per doubling round). */
 size_t b200lc_bwt_scratch_bytes(size_t nblocks, size_t n);
 int b200lc_bwt_batch(const uint8_t *d_in, size_t nblocks, size_t n, uint8_t *d_out, int *d_index,
                      void *d_scratch, size_t scratch_bytes, void *stream);
