@@ -47,17 +47,6 @@ __global__ void __launch_bounds__(kThreads) init_keys_kernel(const u8 *__restric
     }
 }
 
-__global__ void __launch_bounds__(kThreads) pair_keys_kernel(const u32 *__restrict__ rank, u64 N, u32 n,
-                                                            u32 h, u64 *__restrict__ keys)
-{
-    for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < N; g += (u64)gridDim.x * kThreads) {
-        const u32 blk = (u32)(g / n), i = (u32)(g - (u64)blk * n);
-        const u64 r1 = rank[g];
-        const u64 r2 = (i + h < n) ? rank[g + h] : 0;
-        keys[g] = ((u64)blk << (2 * kRankBits)) | (r1 << kRankBits) | r2;
-    }
-}
-
 // heads[j] = j at the first element of every group of equal keys, else 0; counts the
 // non-head elements (0 means every suffix is alone in its group).
 __global__ void __launch_bounds__(kThreads) mark_heads_kernel(const u64 *__restrict__ keys, u64 N,
@@ -75,14 +64,79 @@ __global__ void __launch_bounds__(kThreads) mark_heads_kernel(const u64 *__restr
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(dup, (unsigned long long)local);
 }
 
-// rank of a suffix = 1 + position of its group's head inside the block
-__global__ void __launch_bounds__(kThreads) scatter_rank_kernel(const u32 *__restrict__ head_of,
-                                                               const u32 *__restrict__ sa, u64 N,
-                                                               u32 n, u32 *__restrict__ rank)
+// After the first (full) sort: rank of a suffix = 1 + position of its group's head inside the
+// block; a position is "unresolved" when its group has more than one member.
+__global__ void __launch_bounds__(kThreads) first_rank_kernel(const u32 *__restrict__ head_of,
+                                                             const u32 *__restrict__ sa, u64 N, u32 n,
+                                                             u32 *__restrict__ rank,
+                                                             u32 *__restrict__ uflag)
 {
     for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
         const u32 blk = (u32)(j / n);
-        rank[sa[j]] = head_of[j] - blk * n + 1;
+        const u32 hd = head_of[j];
+        rank[sa[j]] = hd - blk * n + 1;
+        const bool single = hd == (u32)j && (j + 1 == N || head_of[j + 1] == (u32)(j + 1));
+        uflag[j] = single ? 0u : 1u;
+    }
+}
+
+// Refinement round: only the members of unresolved groups are re-sorted.  Key = (position of the
+// group's head in the suffix array, rank of the suffix h characters further on).
+__global__ void __launch_bounds__(kThreads) compact_keys_kernel(const u32 *__restrict__ uflag,
+                                                               const u32 *__restrict__ cidx,
+                                                               const u32 *__restrict__ head_of,
+                                                               const u32 *__restrict__ sa,
+                                                               const u32 *__restrict__ rank, u64 N, u32 n,
+                                                               u32 h, u64 *__restrict__ ckey,
+                                                               u32 *__restrict__ cval)
+{
+    for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
+        if (!uflag[j]) continue;
+        const u32 g = sa[j];
+        const u32 blk = g / n, i = g - blk * n;
+        const u64 r2 = (i + h < n) ? rank[g + h] : 0;
+        const u32 c = cidx[j];
+        ckey[c] = ((u64)head_of[j] << kRankBits) | r2;
+        cval[c] = g;
+    }
+}
+
+// Sorted compact element c goes to suffix-array position p = head + (c - compact index of head).
+__global__ void __launch_bounds__(kThreads) place_kernel(const u64 *__restrict__ skey,
+                                                        const u32 *__restrict__ sval,
+                                                        const u32 *__restrict__ cidx, u32 M,
+                                                        u32 *__restrict__ sa, u32 *__restrict__ newhead)
+{
+    for (u32 c = blockIdx.x * kThreads + threadIdx.x; c < M; c += gridDim.x * kThreads) {
+        const u64 k = skey[c];
+        const u32 hd = (u32)(k >> kRankBits);
+        const u32 first = cidx[hd];
+        const u32 p = hd + (c - first);
+        sa[p] = sval[c];
+        newhead[c] = (c == first || k != skey[c - 1]) ? p : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) rerank_kernel(const u64 *__restrict__ skey,
+                                                         const u32 *__restrict__ sval,
+                                                         const u32 *__restrict__ cidx,
+                                                         const u32 *__restrict__ nh, u32 M, u32 n,
+                                                         u32 *__restrict__ head_of,
+                                                         u32 *__restrict__ rank, u32 *__restrict__ uflag)
+{
+    for (u32 c = blockIdx.x * kThreads + threadIdx.x; c < M; c += gridDim.x * kThreads) {
+        const u32 hd = (u32)(skey[c] >> kRankBits);
+        const u32 p = hd + (c - cidx[hd]);
+        const u32 my_head = nh[c];
+        head_of[p] = my_head;
+        rank[sval[c]] = my_head - (p / n) * n + 1;
+        bool next_is_head = true;
+        if (c + 1 < M) {
+            const u32 hd2 = (u32)(skey[c + 1] >> kRankBits);
+            const u32 p2 = hd2 + (c + 1 - cidx[hd2]);
+            next_is_head = nh[c + 1] == p2;
+        }
+        uflag[p] = (my_head == p && next_is_head) ? 0u : 1u;
     }
 }
 
@@ -109,74 +163,104 @@ __global__ void __launch_bounds__(kThreads) bwt_gather_kernel(const u8 *__restri
 }
 
 struct Layout {
-    size_t keys_a, keys_b, vals_a, vals_b, rank, heads, counter, cub_temp, total;
+    size_t keys_a, keys_b, vals_a, vals_b, sa, rank, heads, uflag, cidx, counter, cub_temp, total;
     size_t cub_bytes;
 };
 
 static Layout layout(u64 N)
 {
     Layout L;
-    size_t sort_bytes = 0, scan_bytes = 0;
+    size_t sort_bytes = 0, scan_bytes = 0, sum_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const u64 *)nullptr, (u64 *)nullptr,
                                     (const u32 *)nullptr, (u32 *)nullptr, (long long)N, 0, 64);
     cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, (const u32 *)nullptr, (u32 *)nullptr, cub::Max(),
                                    (long long)N);
-    L.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    cub::DeviceScan::ExclusiveSum(nullptr, sum_bytes, (const u32 *)nullptr, (u32 *)nullptr, (long long)N);
+    L.cub_bytes = sort_bytes;
+    if (scan_bytes > L.cub_bytes) L.cub_bytes = scan_bytes;
+    if (sum_bytes > L.cub_bytes) L.cub_bytes = sum_bytes;
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     size_t o = 0;
     L.keys_a = o; o += up(N * 8);
     L.keys_b = o; o += up(N * 8);
     L.vals_a = o; o += up(N * 4);
     L.vals_b = o; o += up(N * 4);
+    L.sa = o; o += up(N * 4);
     L.rank = o; o += up(N * 4);
     L.heads = o; o += up(N * 4);
+    L.uflag = o; o += up(N * 4);
+    L.cidx = o; o += up(N * 4);
     L.counter = o; o += 256;
     L.cub_temp = o; o += up(L.cub_bytes);
     L.total = o;
     return L;
 }
 
-// Sorted suffix order of every block in scratch vals_b (global indices); returns 0 or an error.
+// Sorted suffix order of every block (global indices) in scratch `sa`; returns 0 or an error.
 static int suffix_sort(const u8 *d_in, u64 nblocks, u32 n, char *scratch, const Layout &L,
                        cudaStream_t stream, const u32 **sa_global)
 {
     const u64 N = nblocks * n;
     u64 *keys_a = reinterpret_cast<u64 *>(scratch + L.keys_a);
     u64 *keys_b = reinterpret_cast<u64 *>(scratch + L.keys_b);
-    u32 *iota = reinterpret_cast<u32 *>(scratch + L.vals_a);
-    u32 *sa = reinterpret_cast<u32 *>(scratch + L.vals_b);
+    u32 *vals_a = reinterpret_cast<u32 *>(scratch + L.vals_a);
+    u32 *vals_b = reinterpret_cast<u32 *>(scratch + L.vals_b);
+    u32 *sa = reinterpret_cast<u32 *>(scratch + L.sa);
     u32 *rank = reinterpret_cast<u32 *>(scratch + L.rank);
     u32 *heads = reinterpret_cast<u32 *>(scratch + L.heads);
+    u32 *uflag = reinterpret_cast<u32 *>(scratch + L.uflag);
+    u32 *cidx = reinterpret_cast<u32 *>(scratch + L.cidx);
     unsigned long long *dup = reinterpret_cast<unsigned long long *>(scratch + L.counter);
     void *cub_temp = scratch + L.cub_temp;
     size_t cub_bytes = L.cub_bytes;
     const u32 grid = (u32)min((N + kThreads - 1) / kThreads, (u64)num_sms() * 16);
     int blk_bits = 1;
     while ((1ull << blk_bits) < nblocks) ++blk_bits;
-
-    init_keys_kernel<<<grid, kThreads, 0, stream>>>(d_in, N, n, keys_a, iota);
-    B200LC_CUDA_TRY(cudaGetLastError());
-    int end_bit = (int)kFirstKeyBits + blk_bits;
-    for (u32 h = kFirstChars;; h <<= 1) {
-        B200LC_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys_a, keys_b, iota, sa,
-                                                        (long long)N, 0, end_bit, stream));
-        B200LC_CUDA_TRY(cudaMemsetAsync(dup, 0, sizeof(*dup), stream));
-        mark_heads_kernel<<<grid, kThreads, 0, stream>>>(keys_b, N, heads, dup);
-        B200LC_CUDA_TRY(cudaGetLastError());
-        unsigned long long h_dup = 0;
-        B200LC_CUDA_TRY(cudaMemcpyAsync(&h_dup, dup, sizeof(h_dup), cudaMemcpyDeviceToHost, stream));
-        B200LC_CUDA_TRY(cudaStreamSynchronize(stream));
-        if (h_dup == 0 || h >= n) break;
-        // rename: every element learns the position of its group's head (running maximum)
-        B200LC_CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_temp, cub_bytes, heads, heads, cub::Max(),
-                                                       (long long)N, stream));
-        scatter_rank_kernel<<<grid, kThreads, 0, stream>>>(heads, sa, N, n, rank);
-        B200LC_CUDA_TRY(cudaGetLastError());
-        pair_keys_kernel<<<grid, kThreads, 0, stream>>>(rank, N, n, h, keys_a);
-        B200LC_CUDA_TRY(cudaGetLastError());
-        end_bit = 2 * (int)kRankBits + blk_bits;
-    }
     *sa_global = sa;
+
+    // ---- round 1: every suffix, by its first kFirstChars characters
+    init_keys_kernel<<<grid, kThreads, 0, stream>>>(d_in, N, n, keys_a, vals_a);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    B200LC_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys_a, keys_b, vals_a, sa,
+                                                    (long long)N, 0, (int)kFirstKeyBits + blk_bits, stream));
+    B200LC_CUDA_TRY(cudaMemsetAsync(dup, 0, sizeof(*dup), stream));
+    mark_heads_kernel<<<grid, kThreads, 0, stream>>>(keys_b, N, heads, dup);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    unsigned long long h_dup = 0;
+    B200LC_CUDA_TRY(cudaMemcpyAsync(&h_dup, dup, sizeof(h_dup), cudaMemcpyDeviceToHost, stream));
+    B200LC_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (h_dup == 0) return B200LC_OK;
+    // every element learns the position of its group's head (running maximum), then its rank
+    B200LC_CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_temp, cub_bytes, heads, heads, cub::Max(),
+                                                   (long long)N, stream));
+    first_rank_kernel<<<grid, kThreads, 0, stream>>>(heads, sa, N, n, rank, uflag);
+    B200LC_CUDA_TRY(cudaGetLastError());
+
+    // ---- refinement rounds: only members of unresolved groups
+    u32 *newhead = vals_a;            // reused: M entries
+    for (u32 h = kFirstChars; h < n; h <<= 1) {
+        B200LC_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, uflag, cidx, (long long)N, stream));
+        u32 last[2] = {0, 0};
+        B200LC_CUDA_TRY(cudaMemcpyAsync(&last[0], cidx + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
+        B200LC_CUDA_TRY(cudaMemcpyAsync(&last[1], uflag + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
+        B200LC_CUDA_TRY(cudaStreamSynchronize(stream));
+        const u32 M = last[0] + last[1];
+        if (M == 0) break;
+        compact_keys_kernel<<<grid, kThreads, 0, stream>>>(uflag, cidx, heads, sa, rank, N, n, h, keys_a, vals_b);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        B200LC_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys_a, keys_b, vals_b, vals_a + 0,
+                                                        (int)M, 0, 32 + (int)kRankBits, stream));
+        // vals_a now holds the sorted values; newhead needs its own storage: use keys_a's space
+        u32 *sval = vals_a;
+        newhead = reinterpret_cast<u32 *>(keys_a);
+        const u32 mgrid = (u32)min(((u64)M + kThreads - 1) / kThreads, (u64)num_sms() * 16);
+        place_kernel<<<mgrid, kThreads, 0, stream>>>(keys_b, sval, cidx, M, sa, newhead);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        B200LC_CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_temp, cub_bytes, newhead, newhead, cub::Max(),
+                                                       (int)M, stream));
+        rerank_kernel<<<mgrid, kThreads, 0, stream>>>(keys_b, sval, cidx, newhead, M, n, heads, rank, uflag);
+        B200LC_CUDA_TRY(cudaGetLastError());
+    }
     return B200LC_OK;
 }
 
