@@ -84,6 +84,15 @@ def lib():
     L.b200lc_cudpp_compress_scratch_bytes.argtypes = [sz, sz]
     L.b200lc_cudpp_compress_batch.restype = i32
     L.b200lc_cudpp_compress_batch.argtypes = [vp, sz, sz, vp, vp, vp, vp, vp, sz, vp, vp, sz, vp]
+    for name in ("inverse_mtf", "inverse_bwt", "cudpp_decompress"):
+        f = getattr(L, "b200lc_%s_scratch_bytes" % name)
+        f.restype, f.argtypes = sz, [sz, sz]
+    L.b200lc_inverse_mtf_batch.restype = i32
+    L.b200lc_inverse_mtf_batch.argtypes = [vp, sz, sz, vp, vp, sz, vp]
+    L.b200lc_inverse_bwt_batch.restype = i32
+    L.b200lc_inverse_bwt_batch.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp]
+    L.b200lc_cudpp_decompress_batch.restype = i32
+    L.b200lc_cudpp_decompress_batch.argtypes = [vp, vp, vp, vp, sz, sz, sz, vp, vp, vp, sz, vp]
     _lib = L
     return L
 
@@ -335,3 +344,45 @@ def cudpp_compress_batch(data, nblocks, n, stream=None, scratch=None, out=None):
                                         out.error.data_ptr(), scratch.data_ptr(), scratch.numel(),
                                         _stream_ptr(stream)), "b200lc_cudpp_compress_batch")
     return out
+
+
+def inverse_mtf_batch(ranks, nblocks, n, stream=None):
+    """Inverse move-to-front of nblocks blocks of n ranks (initial list 0..255)."""
+    import torch
+    L = lib()
+    out = torch.empty_like(ranks)
+    sc = _scratch(L.b200lc_inverse_mtf_scratch_bytes(nblocks, n), ranks.device)
+    check(L.b200lc_inverse_mtf_batch(ranks.data_ptr(), nblocks, n, out.data_ptr(), sc.data_ptr(),
+                                     sc.numel(), _stream_ptr(stream)), "b200lc_inverse_mtf_batch")
+    return out
+
+
+def inverse_bwt_batch(bwt, bwt_index, nblocks, n, stream=None):
+    """Inverse BWT of nblocks blocks (index convention of cudppBurrowsWheelerTransform)."""
+    import torch
+    L = lib()
+    out = torch.empty_like(bwt)
+    err = torch.zeros(1, dtype=torch.int32, device=bwt.device)
+    sc = _scratch(L.b200lc_inverse_bwt_scratch_bytes(nblocks, n), bwt.device)
+    check(L.b200lc_inverse_bwt_batch(bwt.data_ptr(), bwt_index.data_ptr(), nblocks, n, out.data_ptr(),
+                                     err.data_ptr(), sc.data_ptr(), sc.numel(), _stream_ptr(stream)),
+          "b200lc_inverse_bwt_batch")
+    return out, err
+
+
+def cudpp_decompress_batch(comp, nblocks, n, stream=None, scratch=None, out=None):
+    """Inverse of cudpp_compress_batch: CudppCompressed -> (bytes, error word)."""
+    import torch
+    L = lib()
+    dev = comp.words.device
+    if out is None:
+        out = torch.empty(nblocks * n, dtype=torch.uint8, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    if scratch is None:
+        scratch = _scratch(L.b200lc_cudpp_decompress_scratch_bytes(nblocks, n), dev)
+    check(L.b200lc_cudpp_decompress_batch(comp.bwt_index.data_ptr(), comp.hist.data_ptr(),
+                                          comp.offsets.data_ptr(), comp.words.data_ptr(), comp.stride,
+                                          nblocks, n, out.data_ptr(), err.data_ptr(), scratch.data_ptr(),
+                                          scratch.numel(), _stream_ptr(stream)),
+          "b200lc_cudpp_decompress_batch")
+    return out, err

@@ -24,6 +24,7 @@ constexpr int kEof = 256;
 constexpr int kNodes = 2 * kSyms - 1;      // 513
 constexpr int kBlockChars = 4096;          // HUFF_THREADS_PER_BLOCK * HUFF_WORK_PER_THREAD
 constexpr int kBlockWordsMax = 1536;       // HUFF_CODE_BYTES (cudpp_globals.h:65-66)
+constexpr int kTreeShorts = 3 * kNodes + 1;
 
 // ---------------------------------------------------------------- histogram (u32[256] per block)
 __global__ void __launch_bounds__(256) hist_kernel(const u8 *__restrict__ in, u32 n, u32 chunks,
@@ -76,6 +77,7 @@ __device__ __forceinline__ int find_min(const TreeSmem &t, int n, u32 lane)
 __global__ void __launch_bounds__(kTreeWarps * 32) tree_kernel(const u32 *__restrict__ hist, u32 nblocks,
                                                               u32 *__restrict__ codes,      // [nblocks][257]
                                                               u8 *__restrict__ lens,        // [nblocks][257]
+                                                              short *__restrict__ tree_out, // optional, see cudpp_tree.cuh
                                                               u32 *__restrict__ error)
 {
     __shared__ TreeSmem trees[kTreeWarps];
@@ -141,6 +143,15 @@ __global__ void __launch_bounds__(kTreeWarps * 32) tree_kernel(const u32 *__rest
         }
         ++next_free;
         __syncwarp();
+    }
+    if (tree_out) {   // explicit tree for the decoder: left[513], right[513], value[513], head
+        short *o = tree_out + (u64)blk * kTreeShorts;
+        for (int j = (int)lane; j < kNodes; j += 32) {
+            o[j] = t.left[j];
+            o[kNodes + j] = t.right[j];
+            o[2 * kNodes + j] = t.value[j];
+        }
+        if (lane == 0) o[3 * kNodes] = (short)head;
     }
     // codes: depth-first walk, left = 0, right = 1 (compress_kernel.cuh:2416-2496)
     u32 *c_out = codes + (u64)blk * kSyms;
@@ -296,6 +307,15 @@ __global__ void __launch_bounds__(128) encode_kernel(const u8 *__restrict__ in, 
     for (u32 i = tid; i < nw; i += 128) dst[i] = stage[i];
 }
 
+// Used by the decoder (cudpp_decode.cu): same tree, same tie-breaks, from the stored histogram.
+cudaError_t launch_tree(const u32 *hist, u32 nblocks, u32 *codes, u8 *lens, short *tree_out, u32 *error,
+                        cudaStream_t stream)
+{
+    tree_kernel<<<(nblocks + kTreeWarps - 1) / kTreeWarps, kTreeWarps * 32, 0, stream>>>(hist, nblocks, codes,
+                                                                                        lens, tree_out, error);
+    return cudaGetLastError();
+}
+
 }  // namespace chuff
 }  // namespace b200lc
 
@@ -336,9 +356,7 @@ extern "C" int b200lc_cudpp_huffman_batch(const uint8_t *d_mtf, size_t nblocks, 
     const u32 chunks = (u32)max((size_t)1, min((size_t)64, n / 16384));
     chuff::hist_kernel<<<(u32)(nblocks * chunks), 256, 0, stream>>>(d_mtf, (u32)n, chunks, d_hist);
     B200LC_CUDA_TRY(cudaGetLastError());
-    chuff::tree_kernel<<<(u32)((nblocks + chuff::kTreeWarps - 1) / chuff::kTreeWarps),
-                         chuff::kTreeWarps * 32, 0, stream>>>(d_hist, (u32)nblocks, codes, lens, d_error);
-    B200LC_CUDA_TRY(cudaGetLastError());
+    B200LC_CUDA_TRY(chuff::launch_tree(d_hist, (u32)nblocks, codes, lens, nullptr, d_error, stream));
     chuff::bits_kernel<<<(u32)(nblocks * nhb), 128, 0, stream>>>(d_mtf, (u32)n, nhb, lens, nwords, d_error);
     B200LC_CUDA_TRY(cudaGetLastError());
     chuff::offsets_kernel<<<(u32)nblocks, 256, 0, stream>>>(nwords, nhb, d_offsets, d_total_words, d_out,

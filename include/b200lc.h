@@ -191,6 +191,26 @@ int b200lc_cudpp_compress_batch(const uint8_t *d_in, size_t nblocks, size_t n, i
                                 uint32_t *d_out, size_t out_stride_words, uint32_t *d_error,
                                 void *d_scratch, size_t scratch_bytes, void *stream);
 
+/* ---- decoder for the cudppCompress stream -----------------------------
+ * The reference ships no GPU decoder; its CPU gold is computeCompressGold
+ * (cudpp-inpar/apps/cudpp_testrig/test_compress.cpp:192-364).  These entry points invert
+ * b200lc_cudpp_compress_batch / cudppCompress stage by stage, batched over blocks.
+ * Limits: n < 2^24, nblocks * n < 2^32.  *d_error != 0 after the stream has drained = corrupt
+ * input (4 offsets outside the stream, 5 invalid code / block too short, 6 bwt index >= n). */
+size_t b200lc_inverse_mtf_scratch_bytes(size_t nblocks, size_t n);
+int b200lc_inverse_mtf_batch(const uint8_t *d_in, size_t nblocks, size_t n, uint8_t *d_out,
+                             void *d_scratch, size_t scratch_bytes, void *stream);
+size_t b200lc_inverse_bwt_scratch_bytes(size_t nblocks, size_t n);
+int b200lc_inverse_bwt_batch(const uint8_t *d_bwt, const int *d_bwt_index, size_t nblocks, size_t n,
+                             uint8_t *d_out, uint32_t *d_error, void *d_scratch,
+                             size_t scratch_bytes, void *stream);
+size_t b200lc_cudpp_decompress_scratch_bytes(size_t nblocks, size_t n);
+int b200lc_cudpp_decompress_batch(const int *d_bwt_index, const uint32_t *d_hist,
+                                  const uint32_t *d_offsets, const uint32_t *d_comp,
+                                  size_t comp_stride_words, size_t nblocks, size_t n,
+                                  uint8_t *d_out, uint32_t *d_error, void *d_scratch,
+                                  size_t scratch_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

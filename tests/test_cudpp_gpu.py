@@ -193,3 +193,127 @@ def test_cudpp_named_entry_points():
     assert np.array_equal(d_out.cpu().numpy()[:n], O.cudpp_oracle_mtf(data[:n]))
     assert L.cudppDestroyPlan(plan) == 0
     assert L.cudppDestroy(mgr) == 0
+
+
+# ------------------------------------------------------------------------------------------ decoder (N3)
+def _np_inverse_mtf(r):
+    lst = list(range(256))
+    out = np.empty(r.size, np.uint8)
+    for i, x in enumerate(r.tolist()):
+        c = lst.pop(x)
+        out[i] = c
+        lst.insert(0, c)
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 39, 2047, 2048, 2049, 4097, 65537, 300001])
+def test_inverse_mtf_sizes(n):
+    rng = np.random.Generator(np.random.MT19937(7 + n))
+    data = rng.integers(0, 256, n, dtype=np.uint8) if n % 2 else O.cudpp_block(n, "zipf", seed=n)
+    ranks = O.cudpp_oracle_mtf(data)
+    got = b200lc.inverse_mtf_batch(_dev(ranks), 1, n).cpu().numpy()
+    assert np.array_equal(got, data)
+    if n <= 5000:
+        assert np.array_equal(_np_inverse_mtf(ranks), data)   # the oracle's MTF is what we invert
+
+
+@pytest.mark.parametrize("kind", ["zipf", "markov", "text", "rand", "zeros"])
+def test_inverse_mtf_batched(kind):
+    n, nb = 70001, 5
+    blocks = [np.zeros(n, np.uint8) if kind == "zeros" else O.cudpp_block(n, kind, seed=b) for b in range(nb)]
+    ranks = np.concatenate([O.cudpp_oracle_mtf(b) for b in blocks])
+    got = b200lc.inverse_mtf_batch(_dev(ranks), nb, n).cpu().numpy()
+    assert np.array_equal(got, np.concatenate(blocks))
+
+
+def _ibwt_case(blocks):
+    n, nb = blocks[0].size, len(blocks)
+    pairs = [O.cudpp_oracle_bwt(b) for b in blocks]
+    bwt = np.concatenate([p[0] for p in pairs])
+    idx = np.array([p[1] for p in pairs], np.int32)
+    out, err = b200lc.inverse_bwt_batch(_dev(bwt), _dev(idx), nb, n)
+    assert int(err.cpu()[0]) == 0
+    assert np.array_equal(out.cpu().numpy(), np.concatenate(blocks))
+
+
+@pytest.mark.parametrize("kind,n,nb", [("zipf", 65536, 4), ("markov", 100000, 3), ("text", 262144, 2),
+                                       ("rand", 1000, 7), ("rand", 1, 3), ("rand", 2, 2), ("zipf", 255, 1),
+                                       ("zipf", 257, 2), ("text", MIB, 2), ("zipf", (1 << 21) - 1, 1)])
+def test_inverse_bwt_blocks(kind, n, nb):
+    _ibwt_case([O.cudpp_block(n, kind, seed=40 + b) for b in range(nb)])
+
+
+@pytest.mark.parametrize("period,n", [(1, 5000), (2, 4096), (3, 3000), (7, 7 * 1024), (256, 65536), (5, 5)])
+def test_inverse_bwt_periodic_blocks(period, n):
+    """A periodic block makes the walk close its cycle before n steps (T is not one cycle); no
+    trailing sentinel here on purpose."""
+    rng = np.random.Generator(np.random.MT19937(period))
+    unit = rng.permutation(256)[:period].astype(np.uint8)
+    _ibwt_case([np.tile(unit, n // period)[:n].copy(), np.tile(unit[::-1], n // period)[:n].copy()])
+
+
+def test_inverse_bwt_rejects_bad_index():
+    n = 4096
+    blk = O.cudpp_block(n, "zipf", seed=1)
+    bwt, _ = O.cudpp_oracle_bwt(blk)
+    _, err = b200lc.inverse_bwt_batch(_dev(bwt), _dev(np.array([n], np.int32)), 1, n)
+    assert int(err.cpu()[0]) == 6
+
+
+def test_decompress_reference_test_vector():
+    data = O.cudpp_test_vector(MIB, sentinel=True)
+    res = b200lc.cudpp_compress_batch(_dev(data), 1, MIB)
+    out, err = b200lc.cudpp_decompress_batch(res, 1, MIB)
+    assert int(err.cpu()[0]) == 0
+    assert np.array_equal(out.cpu().numpy(), data)
+
+
+@pytest.mark.parametrize("kind,n,nb", [("zipf", MIB, 3), ("markov", MIB, 2), ("text", MIB, 2), ("rand", 8192, 6),
+                                       ("zipf", 100000, 3), ("zipf", 4095, 2), ("markov", 4097, 5),
+                                       ("zipf", 1, 2), ("text", 600000, 1)])
+def test_decompress_round_trip(kind, n, nb):
+    blocks = [O.cudpp_block(n, kind, seed=50 + b) for b in range(nb)]
+    data = np.concatenate(blocks)
+    res = b200lc.cudpp_compress_batch(_dev(data), nb, n)
+    assert int(res.error.cpu()[0]) == 0
+    out, err = b200lc.cudpp_decompress_batch(res, nb, n)
+    assert int(err.cpu()[0]) == 0
+    assert np.array_equal(out.cpu().numpy(), data)
+
+
+def test_decompress_oracle_stream():
+    """Streams produced by the CPU oracle (pinned to the reference golds) decode on the GPU, and
+    the GPU decoder agrees with the oracle's decoder."""
+    n, nb = 200000, 3
+    nhb = (n + 4095) // 4096
+    stride = nhb * 1537
+    blocks = [O.cudpp_block(n, k, seed=60 + i) for i, k in enumerate(["zipf", "markov", "text"])]
+    idx = np.zeros(nb, np.int32)
+    hist = np.zeros(nb * 256, np.uint32)
+    offs = np.zeros(nb * nhb, np.uint32)
+    words = np.zeros(nb * stride, np.uint32)
+    tw = np.zeros(nb, np.uint32)
+    for b, blk in enumerate(blocks):
+        rc, i, h, o, w = O.cudpp_oracle_compress(blk)
+        assert rc == 0
+        idx[b], hist[b * 256:(b + 1) * 256], offs[b * nhb:(b + 1) * nhb] = i, h, o
+        words[b * stride:b * stride + w.size] = w
+        tw[b] = w.size
+        rc, back = O.cudpp_oracle_decompress(n, i, h, o, w)
+        assert rc == 0 and np.array_equal(back, blk)
+    comp = b200lc.CudppCompressed(_dev(idx), _dev(hist.view(np.int32)), _dev(offs.view(np.int32)),
+                                  _dev(tw.view(np.int32)), _dev(words.view(np.int32)), stride,
+                                  torch.zeros(1, dtype=torch.int32, device=DEV))
+    out, err = b200lc.cudpp_decompress_batch(comp, nb, n)
+    assert int(err.cpu()[0]) == 0
+    assert np.array_equal(out.cpu().numpy(), np.concatenate(blocks))
+
+
+def test_decompress_flags_corrupt_stream():
+    n = 65536
+    data = O.cudpp_block(n, "zipf", seed=70)
+    res = b200lc.cudpp_compress_batch(_dev(data), 1, n)
+    res.words[5:40] = -1          # all-ones words: run of the longest code -> symbols no longer add up
+    res.offsets[3] = 10 ** 9      # outside the stream
+    _, err = b200lc.cudpp_decompress_batch(res, 1, n)
+    assert int(err.cpu()[0]) in (4, 5)

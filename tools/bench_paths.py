@@ -150,11 +150,29 @@ def bench_cudpp(mib, dev, kind="zipf", batch=128):
     stage["huffman_ms"] = timeit(lambda: pkg.check(L.b200lc_cudpp_huffman_batch(mout.data_ptr(), nb, n, hist.data_ptr(), offs.data_ptr(), tw.data_ptr(), words.data_ptr(), stride, err.data_ptr(), bscr.data_ptr(), bscr.numel(), sp), "huff"), iters=3, warm=1)
     comp_words = int(tw.sum().item())
     N = nblocks * n
+    # decoder (N3) on the last batch + its stages
+    del bscr
+    dscr = torch.empty(L.b200lc_cudpp_decompress_scratch_bytes(nb, n) + 256, dtype=torch.uint8, device=dev)
+    back = torch.empty(nb * n, dtype=torch.uint8, device=dev)
+    derr = None
+
+    def run_dec():
+        nonlocal derr
+        _, derr = pkg.cudpp_decompress_batch(res, nb, n, scratch=dscr, out=back)
+
+    dec_ms = timeit(run_dec, iters=3, warm=1)
+    ok = bool(torch.equal(back, data[(nblocks - nb) * n:])) and int(derr.item()) == 0
+    dstage = {}
+    dstage["imtf_ms"] = timeit(lambda: pkg.check(L.b200lc_inverse_mtf_batch(mout.data_ptr(), nb, n, words.data_ptr(), dscr.data_ptr(), dscr.numel(), sp), "imtf"), iters=3, warm=1)
+    dstage["ibwt_ms"] = timeit(lambda: pkg.check(L.b200lc_inverse_bwt_batch(bout.data_ptr(), bidx.data_ptr(), nb, n, back.data_ptr(), err.data_ptr(), dscr.data_ptr(), dscr.numel(), sp), "ibwt"), iters=3, warm=1)
+    dstage["huffman_ms"] = max(0.0, dec_ms - dstage["imtf_ms"] - dstage["ibwt_ms"])
     print(json.dumps({"path": "cudpp_compress", "data": kind, "mib": mib, "batch_blocks": nb,
                       "ratio": nb * n / (4.0 * comp_words), "error": int(err.item()),
                       "encode_ms": total_ms, "encode_gbs": N / total_ms / 1e6,
                       "stage_ms_per_batch": stage,
-                      "stage_gbs": {k.replace("_ms", ""): nb * n / v / 1e6 for k, v in stage.items()}}))
+                      "stage_gbs": {k.replace("_ms", ""): nb * n / v / 1e6 for k, v in stage.items()},
+                      "decode_ok": ok, "decode_ms_per_batch": dec_ms, "decode_gbs": nb * n / dec_ms / 1e6,
+                      "decode_stage_ms_per_batch": dstage}))
 
 
 def bench_cuhd(mib, dev):
