@@ -58,7 +58,8 @@ struct EncParams {
 struct EncSmem {
     __align__(16) u8 in[2][kTileSyms];
     __align__(16) u32 stage[kStageWords];
-    u32 tab[256];
+    u32 tab[256];      // code | len << 16
+    u8 len8[256];
     u32 warp_sums[kThreads / 32];
     u64 bar[2];
     u64 base_bits;
@@ -76,7 +77,10 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31;
 
-    if (tid < 256) sm.tab[tid] = p.code_of_symbol[tid] | ((u32)p.len_of_symbol[tid] << 16);
+    if (tid < 256) {
+        sm.tab[tid] = p.code_of_symbol[tid] | ((u32)p.len_of_symbol[tid] << 16);
+        sm.len8[tid] = p.len_of_symbol[tid];
+    }
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
@@ -134,11 +138,22 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             }
             issue_load(g, (step & 1) ^ 1);
         };
+        // code|len of the thread's 16 symbols; returns their bit count.  Full tiles (all but the
+        // very last one) take the path without end-of-input selects.
         auto lookup = [&](u32 buf, u32 tile_n, u32 (&e)[kSyms]) -> u32 {
             const uint4 v = *reinterpret_cast<const uint4 *>(&sm.in[buf][tid * kSyms]);
             const u32 w[4] = {v.x, v.y, v.z, v.w};
-            const u32 valid = tile_n > tid * kSyms ? min((u32)kSyms, tile_n - tid * kSyms) : 0u;
             u32 bits = 0;
+            if (tile_n == (u32)kTileSyms) {
+#pragma unroll
+                for (int i = 0; i < kSyms; ++i) {
+                    const u32 x = sm.tab[(w[i >> 2] >> (8 * (i & 3))) & 0xffu];
+                    e[i] = x;
+                    bits += x >> 16;
+                }
+                return bits;
+            }
+            const u32 valid = tile_n > tid * kSyms ? min((u32)kSyms, tile_n - tid * kSyms) : 0u;
 #pragma unroll
             for (int i = 0; i < kSyms; ++i) {
                 const u32 s = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
@@ -146,6 +161,22 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
                 if ((u32)i >= valid) x = 0;  // past the end of the input: zero-length code
                 e[i] = x;
                 bits += x >> 16;
+            }
+            return bits;
+        };
+        // bit count only (pass A): byte-wide length table, no scaling of the index
+        auto count_bits = [&](u32 buf, u32 tile_n) -> u32 {
+            const uint4 v = *reinterpret_cast<const uint4 *>(&sm.in[buf][tid * kSyms]);
+            const u32 w[4] = {v.x, v.y, v.z, v.w};
+            const u32 valid = tile_n > tid * kSyms ? min((u32)kSyms, tile_n - tid * kSyms) : 0u;
+            u32 bits = 0;
+            if (tile_n == (u32)kTileSyms) {
+#pragma unroll
+                for (int i = 0; i < kSyms; ++i) bits += sm.len8[(w[i >> 2] >> (8 * (i & 3))) & 0xffu];
+            } else {
+#pragma unroll
+                for (int i = 0; i < kSyms; ++i)
+                    if ((u32)i < valid) bits += sm.len8[(w[i >> 2] >> (8 * (i & 3))) & 0xffu];
             }
             return bits;
         };
@@ -157,11 +188,12 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             const u32 tile_n = (u32)min((u64)kTileSyms, p.n - first);
             acquire_input(g0 + c, tile_n);
             prefetch(0, c);
-            u32 e[kSyms];
-            const u32 bits = lookup(step & 1, tile_n, e);
+            const u32 bits = count_bits(step & 1, tile_n);
             my_piece_bits += bits;
             if (c == nsub - 1 && tid >= kThreads - 2) {
                 // the piece's last 31 bits live in its last two threads (full pieces only)
+                u32 e[kSyms];
+                lookup(step & 1, tile_n, e);
                 u64 acc = 0;
 #pragma unroll
                 for (int i = 0; i < kSyms; ++i) acc = (acc << (e[i] >> 16)) | (e[i] & 0xffffu);
@@ -288,32 +320,29 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             // words written now: all complete ones, plus the final partial one at the very end
             const u32 nwords = last_tile ? (tile_bits + 31) >> 5 : tile_bits >> 5;
 
-            // zero the staging words that receive atomicOr contributions
-            for (u32 i = tid; i < ((tile_bits + 31) >> 5) + 1; i += kThreads) sm.stage[salign + i] = 0;
-            __syncthreads();
-            if (tid == 0 && r) atomicOr(&sm.stage[salign], carry);
-
-            {
-                const u32 b0 = r + pre;
-                u32 wi = salign + (b0 >> 5);
-                u32 nb = b0 & 31;          // bits already occupied in the current word
-                u64 acc = 0;
-                bool first_word = true;
+            // Every complete word is stored (plain STS) by the one thread that holds its last bit,
+            // with zeros where other threads' bits go; after a barrier the leading bits arrive by
+            // atomicOr from the threads that hold them (one per thread: its trailing partial
+            // word).  Only the tile's last, incomplete word is never stored, so it is zeroed.
+            if (tid == 0) sm.stage[salign + (tile_bits >> 5)] = 0;
+            const u32 b0 = r + pre;
+            u32 wi = salign + (b0 >> 5);
+            u32 nb = b0 & 31;          // bits already occupied in the current word
+            u64 acc = 0;
 #pragma unroll
-                for (int i = 0; i < kSyms; ++i) {
-                    const u32 len = e[i] >> 16;
-                    acc = (acc << len) | (e[i] & 0xffffu);
-                    nb += len;
-                    if (nb >= 32) {
-                        const u32 word = (u32)(acc >> (nb - 32));
-                        if (first_word) { atomicOr(&sm.stage[wi], word); first_word = false; }
-                        else sm.stage[wi] = word;
-                        ++wi;
-                        nb -= 32;
-                    }
-                }
-                if (nb && my_bits) atomicOr(&sm.stage[wi], (u32)(acc << (32 - nb)));
+            for (int i = 0; i < kSyms; i += 2) {   // two symbols at a time (<= 26 bits)
+                const u32 lb = e[i + 1] >> 16;
+                const u32 c2 = ((e[i] & 0xffffu) << lb) | (e[i + 1] & 0xffffu);
+                const u32 l2 = (e[i] >> 16) + lb;
+                acc = (acc << l2) | c2;
+                nb += l2;
+                if (nb >= 32) sm.stage[wi] = (u32)(acc >> (nb - 32));
+                wi += nb >> 5;
+                nb &= 31;
             }
+            __syncthreads();
+            if (nb && my_bits) atomicOr(&sm.stage[wi], (u32)acc << (32 - nb));
+            if (tid == 0 && r) atomicOr(&sm.stage[salign], carry);
             __syncthreads();
             // the partial last word travels to the next sub-tile of this piece
             carry = sm.stage[salign + (tile_bits >> 5)];
