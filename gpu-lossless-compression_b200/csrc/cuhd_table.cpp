@@ -21,15 +21,6 @@
 
 #include "../../include/b200lc.h"
 
-namespace {
-
-struct Item {
-    uint64_t weight;
-    std::vector<uint8_t> count;  // how many coins of each symbol (indexed by rank) are inside
-};
-
-}  // namespace
-
 extern "C" int b200lc_cuhd_build_table(const uint64_t *hist, int max_len, uint32_t *code_of_symbol,
                                        uint8_t *len_of_symbol, uint8_t *lut)
 {
@@ -51,39 +42,42 @@ extern "C" int b200lc_cuhd_build_table(const uint64_t *hist, int max_len, uint32
         // leaves sorted by (count, symbol)
         std::stable_sort(syms.begin(), syms.end(),
                          [&](int a, int b) { return hist[a] < hist[b]; });
-        std::vector<Item> leaves(k);
-        for (size_t i = 0; i < k; ++i) {
-            leaves[i].weight = hist[syms[i]];
-            leaves[i].count.assign(k, 0);
-            leaves[i].count[i] = 1;
-        }
-        std::vector<Item> row = leaves;
+        // Package-merge without materialising the packages' contents: row l keeps, per item, its
+        // weight and whether it is a leaf.  Leaves enter every row in sorted order and packages
+        // pair up the previous row in order, so "the first t items of row l" is described by
+        // (number of leaves a_l, number of packages p_l) and pulls the first 2 p_l items of row
+        // l-1.  Symbol q (rank in sorted order) gets one more bit for every row with q < a_l.
+        // Ties: a leaf goes before a package of equal weight.
+        std::vector<uint64_t> w(k);
+        for (size_t i = 0; i < k; ++i) w[i] = hist[syms[i]];
+        std::vector<std::vector<uint64_t>> weight(max_len);
+        std::vector<std::vector<uint8_t>> is_leaf(max_len);
+        weight[0] = w;
+        is_leaf[0].assign(k, 1);
         for (int level = 1; level < max_len; ++level) {
-            std::vector<Item> packaged;
-            for (size_t j = 0; j + 1 < row.size(); j += 2) {
-                Item p;
-                p.weight = row[j].weight + row[j + 1].weight;
-                p.count = row[j].count;
-                for (size_t q = 0; q < k; ++q) p.count[q] += row[j + 1].count[q];
-                packaged.push_back(std::move(p));
-            }
-            std::vector<Item> merged;
-            merged.reserve(packaged.size() + k);
+            const std::vector<uint64_t> &prev = weight[level - 1];
+            const size_t np = prev.size() / 2;
+            std::vector<uint64_t> &cur = weight[level];
+            std::vector<uint8_t> &leaf = is_leaf[level];
+            cur.reserve(np + k);
+            leaf.reserve(np + k);
             size_t a = 0, b = 0;
-            while (a < leaves.size() || b < packaged.size()) {
-                const bool take_leaf =
-                    b >= packaged.size() ||
-                    (a < leaves.size() && leaves[a].weight <= packaged[b].weight);
-                if (take_leaf) merged.push_back(leaves[a++]);
-                else merged.push_back(std::move(packaged[b++]));
+            while (a < k || b < np) {
+                const uint64_t pw = b < np ? prev[2 * b] + prev[2 * b + 1] : 0;
+                const bool take_leaf = b >= np || (a < k && w[a] <= pw);
+                if (take_leaf) { cur.push_back(w[a++]); leaf.push_back(1); }
+                else { cur.push_back(pw); leaf.push_back(0); ++b; }
             }
-            row.swap(merged);
         }
-        const size_t take = 2 * (k - 1);
-        if (row.size() < take) return B200LC_ERR_UNSUPPORTED;
+        size_t take = 2 * (k - 1);
+        if (weight[max_len - 1].size() < take) return B200LC_ERR_UNSUPPORTED;
         std::vector<unsigned> len(k, 0);
-        for (size_t i = 0; i < take; ++i)
-            for (size_t q = 0; q < k; ++q) len[q] += row[i].count[q];
+        for (int level = max_len - 1; level >= 0 && take > 0; --level) {
+            size_t leaves_taken = 0;
+            for (size_t i = 0; i < take; ++i) leaves_taken += is_leaf[level][i];
+            for (size_t q = 0; q < leaves_taken; ++q) ++len[q];
+            take = 2 * (take - leaves_taken);
+        }
         for (size_t q = 0; q < k; ++q) len_of_symbol[syms[q]] = (uint8_t)len[q];
     }
 
