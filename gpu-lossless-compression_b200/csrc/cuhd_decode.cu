@@ -129,7 +129,12 @@ __device__ __forceinline__ void walk_merge(const u32 (&u)[S + 1], const u32 (&m)
 }
 
 // Write pass: decode from the true entry state, symbol i of this subsequence goes to dst[i].
-// With CHECK, only tile-local positions in [lo, hi) are stored (staging-window overflow path).
+// Table entries carry TWO symbols when the window holds two whole codewords: bits 0..7 first
+// symbol, 8..15 second symbol, 16..23 bits consumed, bit 31 = second symbol present.  A second
+// symbol that starts beyond this subsequence is also the next subsequence's first symbol: it is
+// stored twice with the same value at the same position (or beyond the tile, where nothing is
+// copied out).  With CHECK, only tile-local positions in [lo, hi) are stored (staging-window
+// overflow path).
 template <int S, bool CHECK>
 __device__ __forceinline__ void walk_write(const u32 (&u)[S + 1], const u32 *tab, u32 shift, u32 a,
                                            u8 *dst, u32 pos, u32 lo, u32 hi)
@@ -140,10 +145,11 @@ __device__ __forceinline__ void walk_write(const u32 (&u)[S + 1], const u32 *tab
         const u32 cur = u[j], nxt = u[j + 1];
         while (at < 32) {
             const u32 w = __funnelshift_l(nxt, cur, at);
-            const u32 e = tab[w >> shift];          // symbol | length << 8
+            const u32 e = tab[w >> shift];
             if (!CHECK || (pos >= lo && pos < hi)) dst[pos] = (u8)e;
-            ++pos;
-            at += e >> 8;
+            if ((int)e < 0 && (!CHECK || (pos + 1 >= lo && pos + 1 < hi))) dst[pos + 1] = (u8)(e >> 8);
+            pos += 1 + (e >> 31);
+            at += (e >> 16) & 0xffu;
         }
         at -= 32;
     }
@@ -193,15 +199,21 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
     constexpr u32 kTileUnits = Smem::kTileUnits;
     constexpr u32 kTileBytes = kTileUnits * 4;
 
-    // LUT -> shared memory as 32-bit entries: bits 0..7 symbol, 8..15 length (+ a byte table of lengths).  A zero-length
-    // entry (unused prefix of an incomplete code) would stall the reference forever; it is
-    // mapped to length 1 here so that garbage input still terminates.
+    // LUT -> shared memory: two-symbol entries for the write pass (see walk_write) + a byte table
+    // of first-codeword lengths for the counting passes.  A zero-length entry (unused prefix of an
+    // incomplete code) would stall the reference forever; it is mapped to length 1 here so that
+    // garbage input still terminates.
     for (u32 i = tid; i < (1u << L); i += blockDim.x) {
-        const u32 e = p.lut[i];
-        u32 len = e & 0xffu;
-        if (len == 0 || len > L) len = 1;
-        tab[i] = (len << 8) | (e >> 8);
-        ltab[i] = (u8)len;
+        const u32 e0 = p.lut[i];
+        u32 len0 = e0 & 0xffu;
+        if (len0 == 0 || len0 > L) len0 = 1;
+        const u32 e1 = p.lut[(i << len0) & ((1u << L) - 1)];
+        u32 len1 = e1 & 0xffu;
+        if (len1 == 0 || len1 > L) len1 = 1;
+        u32 entry = (e0 >> 8) | (len0 << 16);
+        if (len0 + len1 <= L) entry = (e0 >> 8) | (e1 & 0xff00u) | ((len0 + len1) << 16) | 0x80000000u;
+        tab[i] = entry;
+        ltab[i] = (u8)len0;
     }
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
