@@ -66,7 +66,7 @@ struct DecodeParams {
     u32 *ticket;
     u32 num_subtiles;
     u32 num_pieces;
-    u32 tma_ok_base;     // 1 if units pointer is 16-byte aligned
+    u32 tma_tiles;       // leading sub-tiles (+ 4 lookahead units) that one TMA bulk copy can fetch
 };
 
 // ---------------------------------------------------------------------------------- walks
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
 
     // sub-tile index g (global) -> can it be fetched by one TMA bulk copy?
     auto tma_ok = [&](u32 g) -> bool {
-        return p.tma_ok_base && (u64)(g + 1) * (T * S) + 4 <= p.n_units;
+        return g < p.tma_tiles;
     };
     auto issue_load = [&](u32 g, u32 buf) {  // one thread
         if (g < p.num_subtiles && tma_ok(g)) {
@@ -665,7 +665,9 @@ extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8
     p.desc = reinterpret_cast<cuhd::TileDesc *>(reinterpret_cast<char *>(d_scratch) + 128);
     p.num_subtiles = cuhd::subtiles_for(v, n_units);
     p.num_pieces = cuhd::pieces_for(v, n_units);
-    p.tma_ok_base = (reinterpret_cast<uintptr_t>(d_units) & 15) == 0;
+    p.tma_tiles = 0;
+    if ((reinterpret_cast<uintptr_t>(d_units) & 15) == 0 && n_units >= 4)
+        p.tma_tiles = (u32)min((u64)p.num_subtiles, (u64)(n_units - 4) / (u64)(v.T * v.S));
 
     B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128 + p.num_pieces * sizeof(cuhd::TileDesc),
                                     stream));

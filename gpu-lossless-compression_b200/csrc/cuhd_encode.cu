@@ -52,7 +52,7 @@ struct EncParams {
     u32 *ticket;
     u32 num_subtiles;
     u32 num_pieces;
-    u32 tma_ok_base;
+    u32 tma_tiles;       // leading sub-tiles that one TMA bulk copy can fetch (0: unaligned input)
 };
 
 struct EncSmem {
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
     __syncthreads();
 
     auto tma_ok = [&](u32 g) -> bool {
-        return p.tma_ok_base && (u64)(g + 1) * kTileSyms <= p.n;
+        return g < p.tma_tiles;
     };
     auto issue_load = [&](u32 g, u32 buf) {
         if (g < p.num_subtiles && tma_ok(g)) {
@@ -468,7 +468,7 @@ extern "C" int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t 
     p.desc = reinterpret_cast<cuhd_enc::EncDesc *>(reinterpret_cast<char *>(d_scratch) + 256);
     p.num_subtiles = cuhd_enc::subtiles_for(n);
     p.num_pieces = cuhd_enc::pieces_for(n);
-    p.tma_ok_base = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
+    p.tma_tiles = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 ? (u32)(n / cuhd_enc::kTileSyms) : 0u;
 
     static int occ = 0;
     if (!occ) {
