@@ -65,7 +65,8 @@ struct DecodeParams {
     TileDesc *desc;
     u32 *ticket;
     u32 num_subtiles;
-    u32 num_pieces;
+    u32 num_pieces;      // pieces [first_piece, num_pieces) are decoded by this launch
+    u32 first_piece;
     u32 tma_tiles;       // leading sub-tiles (+ 4 lookahead units) that one TMA bulk copy can fetch
 };
 
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
     };
 
     if (tid == 0) {
-        const u32 t0 = atomicAdd(p.ticket, 1u);
+        const u32 t0 = p.first_piece + atomicAdd(p.ticket, 1u);
         sm.next_piece = t0;
         if (t0 < p.num_pieces) issue_load(t0 * NSUB, 0);
     }
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             if (c + 1 < nsub) g = g0 + c + 1;
             else if (pass == 0) g = g0;
             else {
-                const u32 np = atomicAdd(p.ticket, 1u);
+                const u32 np = p.first_piece + atomicAdd(p.ticket, 1u);
                 sm.next_piece = np;
                 if (np >= p.num_pieces) return;
                 g = np * NSUB;
@@ -630,11 +631,13 @@ extern "C" size_t b200lc_cuhd_decode_scratch_bytes(size_t n_units)
     return 128 + worst * sizeof(cuhd::TileDesc);
 }
 
-extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8_t *d_out,
-                                  size_t n_out, const void *d_table, int max_codeword_length,
-                                  void *d_scratch, size_t scratch_bytes, void *stream_)
+// Decodes pieces [first_piece, end_piece) of the stream.  The descriptors of earlier pieces must
+// still be in d_scratch (first_piece == 0 clears them); units up to the end of the last piece
+// + 4 must be resident.
+static int decode_pieces(const uint32_t *d_units, size_t n_units, uint8_t *d_out, size_t n_out,
+                         const void *d_table, int max_codeword_length, void *d_scratch,
+                         size_t scratch_bytes, size_t first_piece, size_t end_piece, cudaStream_t stream)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
     if (max_codeword_length < 1 || max_codeword_length > 13) return B200LC_ERR_UNSUPPORTED;
     if (n_out == 0 || n_units == 0) return B200LC_OK;
     if (!d_units || !d_out || !d_table || !d_scratch) return B200LC_ERR_ARG;
@@ -664,16 +667,58 @@ extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8
     p.ticket = reinterpret_cast<u32 *>(d_scratch);
     p.desc = reinterpret_cast<cuhd::TileDesc *>(reinterpret_cast<char *>(d_scratch) + 128);
     p.num_subtiles = cuhd::subtiles_for(v, n_units);
-    p.num_pieces = cuhd::pieces_for(v, n_units);
+    const u32 all_pieces = cuhd::pieces_for(v, n_units);
+    if (end_piece > all_pieces) end_piece = all_pieces;
+    if (first_piece >= end_piece) return B200LC_OK;
+    p.num_pieces = (u32)end_piece;
+    p.first_piece = (u32)first_piece;
     p.tma_tiles = 0;
     if ((reinterpret_cast<uintptr_t>(d_units) & 15) == 0 && n_units >= 4)
         p.tma_tiles = (u32)min((u64)p.num_subtiles, (u64)(n_units - 4) / (u64)(v.T * v.S));
 
-    B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128 + p.num_pieces * sizeof(cuhd::TileDesc),
-                                    stream));
-    const u32 grid = (u32)min((u64)p.num_pieces,
+    if (first_piece == 0)
+        B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128 + all_pieces * sizeof(cuhd::TileDesc), stream));
+    else
+        B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128, stream));   // ticket only
+    const u32 grid = (u32)min((u64)(end_piece - first_piece),
                               (u64)num_sms() * (u64)occ_cache[max_codeword_length]);
     v.kern<<<grid, v.T + 32, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}
+
+extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8_t *d_out,
+                                  size_t n_out, const void *d_table, int max_codeword_length,
+                                  void *d_scratch, size_t scratch_bytes, void *stream_)
+{
+    return decode_pieces(d_units, n_units, d_out, n_out, d_table, max_codeword_length, d_scratch,
+                         scratch_bytes, 0, ~size_t(0), (cudaStream_t)stream_);
+}
+
+extern "C" size_t b200lc_cuhd_decode_piece_units(void)
+{
+    const cuhd::Variant &v = cuhd::variant();
+    return (size_t)v.S * v.T * v.NSUB;
+}
+
+extern "C" int b200lc_cuhd_decode_pieces(const uint32_t *d_units, size_t n_units, uint8_t *d_out,
+                                         size_t n_out, const void *d_table, int max_codeword_length,
+                                         void *d_scratch, size_t scratch_bytes, size_t first_piece,
+                                         size_t end_piece, void *stream_)
+{
+    return decode_pieces(d_units, n_units, d_out, n_out, d_table, max_codeword_length, d_scratch,
+                         scratch_bytes, first_piece, end_piece, (cudaStream_t)stream_);
+}
+
+// Asynchronous: copies the number of output symbols that are final once pieces [0, end_piece) are
+// decoded (may exceed n_out on the last piece: padding bits) into *h_symbols (pinned host memory).
+extern "C" int b200lc_cuhd_decode_progress_async(const void *d_scratch, size_t end_piece,
+                                                 uint64_t *h_symbols, void *stream_)
+{
+    if (!d_scratch || !h_symbols || end_piece == 0) return B200LC_ERR_ARG;
+    const cuhd::TileDesc *desc =
+        reinterpret_cast<const cuhd::TileDesc *>(reinterpret_cast<const char *>(d_scratch) + 128);
+    B200LC_CUDA_TRY(cudaMemcpyAsync(h_symbols, &desc[end_piece - 1].incl, sizeof(u64),
+                                    cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
     return B200LC_OK;
 }

@@ -22,8 +22,13 @@ struct b200lc_cuhd_session {
     u8 *d_scratch = nullptr;
     size_t scratch_bytes = 0;
     u8 *d_small = nullptr;   // [0,2048) hist | [2048,3072) code | [3072,3328) len | [4096,..) lut | total_bits
-    u64 *h_small = nullptr;  // pinned: hist[256] + total_bits
+    u64 *h_small = nullptr;  // pinned: hist[256] + total_bits + kMaxChunks progress words
+    cudaStream_t h2d = nullptr, d2h = nullptr;   // copy streams of the pipelined decode
+    std::vector<cudaEvent_t> events;
 };
+
+static const size_t kMaxChunks = 512;
+static const size_t kChunkBytesMin = size_t(8) << 20;
 
 static const size_t kSmallBytes = 4096 + (size_t(2) << 13) + 64;
 
@@ -42,7 +47,9 @@ extern "C" int b200lc_cuhd_session_create(size_t max_symbols, b200lc_cuhd_sessio
     if (e == cudaSuccess) e = cudaMalloc(&s->d_units, s->max_units * sizeof(u32));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, s->scratch_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_small, kSmallBytes);
-    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_small, 257 * sizeof(u64), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_small, (257 + kMaxChunks) * sizeof(u64), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         fprintf(stderr, "b200lc: cuhd session allocation failed: %s\n", cudaGetErrorString(e));
         b200lc_cuhd_session_destroy(s);
@@ -62,6 +69,9 @@ extern "C" int b200lc_cuhd_session_destroy(b200lc_cuhd_session *s)
     cudaFree(s->d_small);
     if (s->h_small) cudaFreeHost(s->h_small);
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->h2d) cudaStreamDestroy(s->h2d);
+    if (s->d2h) cudaStreamDestroy(s->d2h);
+    for (cudaEvent_t ev : s->events) cudaEventDestroy(ev);
     delete s;
     return B200LC_OK;
 }
@@ -107,7 +117,10 @@ extern "C" int b200lc_cuhd_session_encode(b200lc_cuhd_session *s, const uint8_t 
     return B200LC_OK;
 }
 
-// host stream units + LUT -> host symbols.  Synchronous.  This is demo.cc:138-168 in one call.
+// host stream units + LUT -> host symbols.  Synchronous.  This is demo.cc:138-168 in one call,
+// pipelined: the stream goes up in chunks on one copy engine, pieces are decoded as soon as their
+// units (+ 4 lookahead units) have arrived, and the symbols that are final go down on the other
+// copy engine while later chunks are still travelling up.
 extern "C" int b200lc_cuhd_session_decode(b200lc_cuhd_session *s, const uint32_t *h_units,
                                           size_t n_units, const void *h_lut, int max_len,
                                           uint8_t *h_out, size_t n_out)
@@ -118,12 +131,50 @@ extern "C" int b200lc_cuhd_session_decode(b200lc_cuhd_session *s, const uint32_t
     u8 *d_lut = s->d_small + 4096;
     B200LC_CUDA_TRY(cudaMemcpyAsync(d_lut, h_lut, size_t(2) << max_len, cudaMemcpyHostToDevice,
                                     s->stream));
-    B200LC_CUDA_TRY(cudaMemcpyAsync(s->d_units, h_units, n_units * sizeof(u32),
-                                    cudaMemcpyHostToDevice, s->stream));
-    int rc = b200lc_cuhd_decode(s->d_units, n_units, s->d_symbols, n_out, d_lut, max_len,
-                                s->d_scratch, s->scratch_bytes, s->stream);
-    if (rc) return rc;
-    B200LC_CUDA_TRY(cudaMemcpyAsync(h_out, s->d_symbols, n_out, cudaMemcpyDeviceToHost, s->stream));
+    const size_t pu = b200lc_cuhd_decode_piece_units();
+    const size_t pieces = (n_units + pu - 1) / pu;
+    size_t chunk_units = kChunkBytesMin / 4;
+    while ((n_units + chunk_units - 1) / chunk_units > kMaxChunks) chunk_units *= 2;
+    const size_t nchunks = (n_units + chunk_units - 1) / chunk_units;
+    while (s->events.size() < 2 * nchunks) {
+        cudaEvent_t ev;
+        B200LC_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        s->events.push_back(ev);
+    }
+    u64 *h_prog = s->h_small + 257;
+    std::vector<int> decoded(nchunks, 0);
+    size_t done_pieces = 0;
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t lo = k * chunk_units, hi = lo + chunk_units < n_units ? lo + chunk_units : n_units;
+        B200LC_CUDA_TRY(cudaMemcpyAsync(s->d_units + lo, h_units + lo, (hi - lo) * sizeof(u32),
+                                        cudaMemcpyHostToDevice, s->h2d));
+        B200LC_CUDA_TRY(cudaEventRecord(s->events[2 * k], s->h2d));
+        const size_t end_piece = hi == n_units ? pieces : (hi >= 4 ? (hi - 4) / pu : 0);
+        if (end_piece <= done_pieces) continue;
+        B200LC_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->events[2 * k], 0));
+        int rc = b200lc_cuhd_decode_pieces(s->d_units, n_units, s->d_symbols, n_out, d_lut, max_len,
+                                           s->d_scratch, s->scratch_bytes, done_pieces, end_piece,
+                                           s->stream);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        rc = b200lc_cuhd_decode_progress_async(s->d_scratch, end_piece, &h_prog[k], s->stream);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        B200LC_CUDA_TRY(cudaEventRecord(s->events[2 * k + 1], s->stream));
+        decoded[k] = 1;
+        done_pieces = end_piece;
+    }
+    size_t copied = 0;
+    for (size_t k = 0; k < nchunks; ++k) {
+        if (!decoded[k]) continue;
+        B200LC_CUDA_TRY(cudaEventSynchronize(s->events[2 * k + 1]));
+        size_t ready = (size_t)(h_prog[k] & ((u64(1) << 56) - 1));
+        if (ready > n_out || k + 1 == nchunks) ready = n_out;
+        if (ready > copied) {
+            B200LC_CUDA_TRY(cudaMemcpyAsync(h_out + copied, s->d_symbols + copied, ready - copied,
+                                            cudaMemcpyDeviceToHost, s->d2h));
+            copied = ready;
+        }
+    }
+    B200LC_CUDA_TRY(cudaStreamSynchronize(s->d2h));
     B200LC_CUDA_TRY(cudaStreamSynchronize(s->stream));
     return B200LC_OK;
 }

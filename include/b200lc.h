@@ -59,6 +59,21 @@ int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8_t *d_out, 
                        const void *d_table, int max_codeword_length, void *d_scratch,
                        size_t scratch_bytes, void *stream);
 
+/* Piece-wise decoding for pipelines that overlap the H2D copy of the stream with decoding and the
+ * D2H copy of the symbols (what b200lc_cuhd_session_decode does).  A piece is
+ * b200lc_cuhd_decode_piece_units() units; pieces must be decoded in increasing order with the
+ * same arguments and scratch; decoding pieces [first, end) needs the units of those pieces plus
+ * 4 to be resident (or end to be the last piece).  b200lc_cuhd_decode_progress_async copies to
+ * *h_symbols (pinned) a word whose low 56 bits = number of leading output symbols that are final
+ * once pieces [0, end_piece) are done. */
+size_t b200lc_cuhd_decode_piece_units(void);
+int b200lc_cuhd_decode_pieces(const uint32_t *d_units, size_t n_units, uint8_t *d_out, size_t n_out,
+                              const void *d_table, int max_codeword_length, void *d_scratch,
+                              size_t scratch_bytes, size_t first_piece, size_t end_piece,
+                              void *stream);
+int b200lc_cuhd_decode_progress_async(const void *d_scratch, size_t end_piece,
+                                      uint64_t *h_symbols, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * CUHD-format encoder side: replaces the sequential CPU stages of the
  * reference's demo (cuhd-icpp/src/demo.cc:90-107).

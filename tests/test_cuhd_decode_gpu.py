@@ -111,3 +111,66 @@ def test_reference_demo_program_unmodified_against_compat_headers(tmp_path):
     units = np.frombuffer(dst.read_bytes(), np.uint32)
     want, _ = O.cuhd_oracle_encode(data, code, length)
     assert np.array_equal(units, want)
+
+
+def test_piece_ranges_equal_one_shot_decode():
+    """b200lc_cuhd_decode_pieces over consecutive ranges == one b200lc_cuhd_decode call, and the
+    progress word counts exactly the symbols of the finished pieces."""
+    import ctypes as C
+    n = 3 * (1 << 20) + 12345
+    data = O.zipf_bytes(n, 1.1, seed=21)
+    code, length, lut, units = O.cuhd_make_case(data, 11, True)
+    dev = torch.device("cuda:0")
+    L = b200lc.lib()
+    L.b200lc_cuhd_decode_piece_units.restype = C.c_size_t
+    vp, sz = C.c_void_p, C.c_size_t
+    L.b200lc_cuhd_decode_pieces.argtypes = [vp, sz, vp, sz, vp, C.c_int, vp, sz, sz, sz, vp]
+    L.b200lc_cuhd_decode_progress_async.argtypes = [vp, sz, vp, vp]
+    pu = L.b200lc_cuhd_decode_piece_units()
+    pieces = (units.size + pu - 1) // pu
+    assert pieces >= 5
+    d_units = torch.from_numpy(units.view(np.int32)).to(dev)
+    d_lut = torch.from_numpy(np.ascontiguousarray(lut)).to(dev)
+    out = torch.zeros(n, dtype=torch.uint8, device=dev)
+    scr = torch.empty(L.b200lc_cuhd_decode_scratch_bytes(units.size) + 256, dtype=torch.uint8, device=dev)
+    prog = torch.zeros(4, dtype=torch.int64).pin_memory()
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cuts = [0, 1, 3, pieces - 1, pieces]
+    done = []
+    for i in range(len(cuts) - 1):
+        b200lc.check(L.b200lc_cuhd_decode_pieces(d_units.data_ptr(), units.size, out.data_ptr(), n,
+                                                 d_lut.data_ptr(), 11, scr.data_ptr(), scr.numel() - 256,
+                                                 cuts[i], cuts[i + 1], sp), "pieces")
+        b200lc.check(L.b200lc_cuhd_decode_progress_async(scr.data_ptr(), cuts[i + 1],
+                                                         prog.data_ptr() + 8 * i, sp), "progress")
+        torch.cuda.synchronize()
+        ready = min(int(prog[i]) & ((1 << 56) - 1), n)
+        done.append(ready)
+        assert np.array_equal(out[:ready].cpu().numpy(), data[:ready]), i
+    assert done == sorted(done) and done[-1] == n and 0 < done[0] < done[1] < n
+    assert np.array_equal(out.cpu().numpy(), data)
+
+
+@pytest.mark.parametrize("n,pinned", [(1000, True), (5 * (1 << 20) + 7, False), (40 * (1 << 20) + 3, True)])
+def test_session_round_trip_host_buffers(n, pinned):
+    """b200lc_cuhd_session_encode / _decode (demo.cc:90-168 as two calls); 40 MiB spans several
+    H2D chunks of the pipelined decode."""
+    data = O.zipf_bytes(n, 1.1, seed=n & 0xff)
+    mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    h_in = mk(torch.from_numpy(data.copy()))
+    cap = (n * 11 + 31) // 32 + 2
+    h_units = mk(torch.zeros(cap, dtype=torch.int32))
+    h_out = mk(torch.zeros(n, dtype=torch.uint8))
+    h_code = torch.zeros(256, dtype=torch.int32)
+    h_len = torch.zeros(256, dtype=torch.uint8)
+    h_lut = torch.zeros((1 << 11, 2), dtype=torch.uint8)
+    sess = b200lc.CuhdSession(n)
+    nu = sess.encode(h_in, h_units, h_code, h_len, h_lut, 11)
+    # the session's stream is what the oracle's packer produces with the session's table
+    want, _ = O.cuhd_oracle_encode(data, h_code.numpy().view(np.uint32), h_len.numpy())
+    assert nu == want.size
+    assert np.array_equal(h_units.numpy().view(np.uint32)[:nu], want)
+    sess.decode(h_units, nu + 1, h_lut, h_out, 11)
+    sess.decode(h_units, nu + 1, h_lut, h_out, 11)   # scratch reuse across calls
+    sess.close()
+    assert np.array_equal(h_out.numpy(), data)
