@@ -93,6 +93,16 @@ def lib():
     L.b200lc_inverse_bwt_batch.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp]
     L.b200lc_cudpp_decompress_batch.restype = i32
     L.b200lc_cudpp_decompress_batch.argtypes = [vp, vp, vp, vp, sz, sz, sz, vp, vp, vp, sz, vp]
+    L.b200lc_sort_scratch_bytes.restype = sz
+    L.b200lc_sort_scratch_bytes.argtypes = [sz, sz]
+    for name in ("b200lc_sort_pairs_u64", "b200lc_sort_pairs_u32"):
+        f = getattr(L, name)
+        f.restype, f.argtypes = i32, [vp, vp, vp, vp, sz, sz, i32, i32, vp, sz, vp, C.POINTER(i32)]
+    L.b200lc_scan_scratch_bytes.restype = sz
+    L.b200lc_scan_scratch_bytes.argtypes = [sz]
+    for name in ("b200lc_exclusive_sum_u32", "b200lc_inclusive_max_u32"):
+        f = getattr(L, name)
+        f.restype, f.argtypes = i32, [vp, vp, sz, vp, sz, vp]
     _lib = L
     return L
 
@@ -386,3 +396,40 @@ def cudpp_decompress_batch(comp, nblocks, n, stream=None, scratch=None, out=None
                                           scratch.numel(), _stream_ptr(stream)),
           "b200lc_cudpp_decompress_batch")
     return out, err
+
+
+# ------------------------------------------------------------------------------- primitives
+def sort_pairs(keys, vals, seg_len=0, begin_bit=0, end_bit=None, stream=None):
+    """Stable segmented LSD radix sort (csrc/devprims.cu).  keys: cuda int64 (u64 bit pattern) or
+    int32 (u32 bit pattern) tensor; vals: cuda int32 tensor.  Returns (sorted_keys, sorted_vals);
+    the inputs are used as one of the ping-pong buffers and are clobbered."""
+    import torch
+    assert keys.is_cuda and vals.is_cuda and keys.numel() == vals.numel()
+    L = lib()
+    wide = keys.element_size() == 8
+    if end_bit is None:
+        end_bit = 64 if wide else 32
+    n = keys.numel()
+    kb, vb = torch.empty_like(keys), torch.empty_like(vals)
+    nbytes = L.b200lc_sort_scratch_bytes(n, seg_len)
+    scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=keys.device)
+    where = C.c_int(0)
+    fn = L.b200lc_sort_pairs_u64 if wide else L.b200lc_sort_pairs_u32
+    check(fn(keys.data_ptr(), kb.data_ptr(), vals.data_ptr(), vb.data_ptr(), n, seg_len, begin_bit,
+             end_bit, scratch.data_ptr(), scratch.numel(), _stream_ptr(stream), C.byref(where)), "sort_pairs")
+    torch.cuda.current_stream().synchronize()
+    return (kb, vb) if where.value else (keys, vals)
+
+
+def scan_u32(x, kind="exclusive_sum", out=None, stream=None):
+    """kind: 'exclusive_sum' or 'inclusive_max' over a cuda int32 tensor (u32 bit pattern)."""
+    import torch
+    L = lib()
+    n = x.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    scratch = torch.empty(L.b200lc_scan_scratch_bytes(n) + 256, dtype=torch.uint8, device=x.device)
+    fn = L.b200lc_exclusive_sum_u32 if kind == "exclusive_sum" else L.b200lc_inclusive_max_u32
+    check(fn(x.data_ptr(), out.data_ptr(), n, scratch.data_ptr(), scratch.numel(), _stream_ptr(stream)), kind)
+    torch.cuda.current_stream().synchronize()
+    return out

@@ -10,13 +10,12 @@
 // sa_app.cu:61-101,125-298).  Here all blocks of a batch are sorted together by prefix
 // doubling: round r sorts the 64-bit keys (block, rank_h[i], rank_h[i+h]) of every suffix of
 // every block with one device-wide radix sort, renames the groups and doubles h, until every
-// group is a singleton.  Random-like data needs 2-3 rounds, text 4-6.
-// The radix sort itself is cub::DeviceRadixSort from the CUDA toolkit (library code; a
-// hand-written onesweep tuned for 20-bit ranks is the next step).
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
+// group is a singleton.  Random-like data needs 1-3 rounds, text 4-6.
+// The sorts and scans are the hand-written segmented one-sweep radix sort and look-back scans
+// of devprims.cu: in the first round every block is a segment of its own, so the block number
+// costs no key bits (6 passes over 48 bits of characters).
 #include "common.cuh"
+#include "devprims.cuh"
 #include "../../include/b200lc.h"
 
 namespace b200lc {
@@ -25,37 +24,45 @@ namespace bwt {
 constexpr int kThreads = 256;
 constexpr u32 kRankBits = 21;
 
-// First round: key = block number | first kFirstChars raw bytes of the suffix (zero-padded past
-// the end of the block) | number of real bytes among them.  The length field orders a short
-// suffix before every longer one that continues with zero bytes (the implicit terminator is
-// smaller than byte 0) and makes the key exact: equal keys <=> equal first kFirstChars characters
-// of the terminated string, which is what prefix doubling needs.
+// First round: key = the first kFirstChars raw bytes of the suffix, zero-padded past the end of
+// the block; every block is one sort segment.  The (at most kFirstChars - 1) suffixes that are
+// shorter than the key are ordered by the sort's stability instead of by key bits: the initial
+// order inside a block is by DESCENDING start position, so among equal keys the shorter suffix --
+// which is the smaller one, its implicit terminator being smaller than byte 0 -- comes first.
+// Such a suffix is always a group of its own (mark_heads_kernel).
 constexpr u32 kFirstChars = 6;
-constexpr u32 kFirstKeyBits = 8 * kFirstChars + 3;
+constexpr u32 kFirstKeyBits = 8 * kFirstChars;
 __global__ void __launch_bounds__(kThreads) init_keys_kernel(const u8 *__restrict__ in, u64 N, u32 n,
                                                             u64 *__restrict__ keys,
-                                                            u32 *__restrict__ iota)
+                                                            u32 *__restrict__ start)
 {
     for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < N; g += (u64)gridDim.x * kThreads) {
-        const u32 blk = (u32)(g / n), i = (u32)(g - (u64)blk * n);
+        const u32 blk = (u32)(g / n);
+        const u64 base = (u64)blk * n;
+        const u32 i = n - 1 - (u32)(g - base);
         u64 k = 0;
 #pragma unroll
-        for (u32 c = 0; c < kFirstChars; ++c) k = (k << 8) | (i + c < n ? (u64)in[g + c] : 0);
-        const u32 real = min(kFirstChars, n - i);
-        keys[g] = ((u64)blk << kFirstKeyBits) | (k << 3) | real;
-        iota[g] = (u32)g;
+        for (u32 c = 0; c < kFirstChars; ++c) k = (k << 8) | (i + c < n ? (u64)in[base + i + c] : 0);
+        keys[g] = k;
+        start[g] = (u32)(base + i);
     }
 }
 
-// heads[j] = j at the first element of every group of equal keys, else 0; counts the
-// non-head elements (0 means every suffix is alone in its group).
-__global__ void __launch_bounds__(kThreads) mark_heads_kernel(const u64 *__restrict__ keys, u64 N,
+// heads[j] = j at the first element of every group of equal first-round keys, else 0; counts
+// the non-head elements (0 means every suffix is alone in its group).  A block start and a
+// suffix shorter than the key always open a group, and so does the element after such a suffix.
+__global__ void __launch_bounds__(kThreads) mark_heads_kernel(const u64 *__restrict__ keys,
+                                                             const u32 *__restrict__ sa, u64 N, u32 n,
                                                              u32 *__restrict__ heads,
                                                              unsigned long long *__restrict__ dup)
 {
     u32 local = 0;
     for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
-        const bool head = j == 0 || keys[j] != keys[j - 1];
+        bool head = j % n == 0 || keys[j] != keys[j - 1];
+        if (!head) {
+            const u32 a = sa[j] % n, b = sa[j - 1] % n;
+            head = a + kFirstChars > n || b + kFirstChars > n;
+        }
         heads[j] = head ? (u32)j : 0u;
         local += !head;
     }
@@ -163,40 +170,35 @@ __global__ void __launch_bounds__(kThreads) bwt_gather_kernel(const u8 *__restri
 }
 
 struct Layout {
-    size_t keys_a, keys_b, vals_a, vals_b, sa, rank, heads, uflag, cidx, counter, cub_temp, total;
-    size_t cub_bytes;
+    size_t keys_a, keys_b, vals_a, vals_b, vals_c, rank, heads, uflag, cidx, counter, prim_temp, total;
+    size_t prim_bytes;
 };
 
-static Layout layout(u64 N)
+static Layout layout(u64 N, u32 n)
 {
     Layout L;
-    size_t sort_bytes = 0, scan_bytes = 0, sum_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const u64 *)nullptr, (u64 *)nullptr,
-                                    (const u32 *)nullptr, (u32 *)nullptr, (long long)N, 0, 64);
-    cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, (const u32 *)nullptr, (u32 *)nullptr, cub::Max(),
-                                   (long long)N);
-    cub::DeviceScan::ExclusiveSum(nullptr, sum_bytes, (const u32 *)nullptr, (u32 *)nullptr, (long long)N);
-    L.cub_bytes = sort_bytes;
-    if (scan_bytes > L.cub_bytes) L.cub_bytes = scan_bytes;
-    if (sum_bytes > L.cub_bytes) L.cub_bytes = sum_bytes;
+    L.prim_bytes = prims::sort_scratch_bytes(N, n);
+    const size_t whole = prims::sort_scratch_bytes(N, N), scan = prims::scan_scratch_bytes(N);
+    if (whole > L.prim_bytes) L.prim_bytes = whole;
+    if (scan > L.prim_bytes) L.prim_bytes = scan;
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     size_t o = 0;
     L.keys_a = o; o += up(N * 8);
     L.keys_b = o; o += up(N * 8);
     L.vals_a = o; o += up(N * 4);
     L.vals_b = o; o += up(N * 4);
-    L.sa = o; o += up(N * 4);
+    L.vals_c = o; o += up(N * 4);
     L.rank = o; o += up(N * 4);
     L.heads = o; o += up(N * 4);
     L.uflag = o; o += up(N * 4);
     L.cidx = o; o += up(N * 4);
     L.counter = o; o += 256;
-    L.cub_temp = o; o += up(L.cub_bytes);
+    L.prim_temp = o; o += up(L.prim_bytes);
     L.total = o;
     return L;
 }
 
-// Sorted suffix order of every block (global indices) in scratch `sa`; returns 0 or an error.
+// Sorted suffix order of every block (global indices) somewhere in scratch; returns 0 or an error.
 static int suffix_sort(const u8 *d_in, u64 nblocks, u32 n, char *scratch, const Layout &L,
                        cudaStream_t stream, const u32 **sa_global)
 {
@@ -205,60 +207,67 @@ static int suffix_sort(const u8 *d_in, u64 nblocks, u32 n, char *scratch, const 
     u64 *keys_b = reinterpret_cast<u64 *>(scratch + L.keys_b);
     u32 *vals_a = reinterpret_cast<u32 *>(scratch + L.vals_a);
     u32 *vals_b = reinterpret_cast<u32 *>(scratch + L.vals_b);
-    u32 *sa = reinterpret_cast<u32 *>(scratch + L.sa);
     u32 *rank = reinterpret_cast<u32 *>(scratch + L.rank);
     u32 *heads = reinterpret_cast<u32 *>(scratch + L.heads);
     u32 *uflag = reinterpret_cast<u32 *>(scratch + L.uflag);
     u32 *cidx = reinterpret_cast<u32 *>(scratch + L.cidx);
     unsigned long long *dup = reinterpret_cast<unsigned long long *>(scratch + L.counter);
-    void *cub_temp = scratch + L.cub_temp;
-    size_t cub_bytes = L.cub_bytes;
+    void *ptemp = scratch + L.prim_temp;
+    const size_t pbytes = L.prim_bytes;
     const u32 grid = (u32)min((N + kThreads - 1) / kThreads, (u64)num_sms() * 16);
-    int blk_bits = 1;
-    while ((1ull << blk_bits) < nblocks) ++blk_bits;
-    *sa_global = sa;
+    int pos_bits = 1;
+    while ((1ull << pos_bits) < N) ++pos_bits;
 
-    // ---- round 1: every suffix, by its first kFirstChars characters
+    // ---- round 1: every suffix, by its first kFirstChars characters, block by block
     init_keys_kernel<<<grid, kThreads, 0, stream>>>(d_in, N, n, keys_a, vals_a);
     B200LC_CUDA_TRY(cudaGetLastError());
-    B200LC_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys_a, keys_b, vals_a, sa,
-                                                    (long long)N, 0, (int)kFirstKeyBits + blk_bits, stream));
+    int in_b = 0;
+    int rc = prims::sort_pairs<u64>(keys_a, keys_b, vals_a, vals_b, N, n, 0, (int)kFirstKeyBits, ptemp,
+                                    pbytes, stream, &in_b);
+    if (rc) return rc;
+    const u64 *skeys = in_b ? keys_b : keys_a;
+    u32 *sa = in_b ? vals_b : vals_a;             // the suffix array lives here from now on
+    u32 *fvals = in_b ? vals_a : vals_b;          // free 4-byte buffer
+    *sa_global = sa;
     B200LC_CUDA_TRY(cudaMemsetAsync(dup, 0, sizeof(*dup), stream));
-    mark_heads_kernel<<<grid, kThreads, 0, stream>>>(keys_b, N, heads, dup);
+    mark_heads_kernel<<<grid, kThreads, 0, stream>>>(skeys, sa, N, n, heads, dup);
     B200LC_CUDA_TRY(cudaGetLastError());
     unsigned long long h_dup = 0;
     B200LC_CUDA_TRY(cudaMemcpyAsync(&h_dup, dup, sizeof(h_dup), cudaMemcpyDeviceToHost, stream));
     B200LC_CUDA_TRY(cudaStreamSynchronize(stream));
     if (h_dup == 0) return B200LC_OK;
     // every element learns the position of its group's head (running maximum), then its rank
-    B200LC_CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_temp, cub_bytes, heads, heads, cub::Max(),
-                                                   (long long)N, stream));
+    rc = prims::inclusive_max_u32(heads, heads, N, ptemp, pbytes, stream);
+    if (rc) return rc;
     first_rank_kernel<<<grid, kThreads, 0, stream>>>(heads, sa, N, n, rank, uflag);
     B200LC_CUDA_TRY(cudaGetLastError());
 
-    // ---- refinement rounds: only members of unresolved groups
-    u32 *newhead = vals_a;            // reused: M entries
+    // ---- refinement rounds: only members of unresolved groups.  Both key buffers and the value
+    // buffer that does not hold the suffix array are free now; vals_c is the second value buffer.
+    u32 *vals_c = reinterpret_cast<u32 *>(scratch + L.vals_c);
     for (u32 h = kFirstChars; h < n; h <<= 1) {
-        B200LC_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, uflag, cidx, (long long)N, stream));
+        rc = prims::exclusive_sum_u32(uflag, cidx, N, ptemp, pbytes, stream);
+        if (rc) return rc;
         u32 last[2] = {0, 0};
         B200LC_CUDA_TRY(cudaMemcpyAsync(&last[0], cidx + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
         B200LC_CUDA_TRY(cudaMemcpyAsync(&last[1], uflag + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
         B200LC_CUDA_TRY(cudaStreamSynchronize(stream));
         const u32 M = last[0] + last[1];
         if (M == 0) break;
-        compact_keys_kernel<<<grid, kThreads, 0, stream>>>(uflag, cidx, heads, sa, rank, N, n, h, keys_a, vals_b);
+        compact_keys_kernel<<<grid, kThreads, 0, stream>>>(uflag, cidx, heads, sa, rank, N, n, h, keys_a, fvals);
         B200LC_CUDA_TRY(cudaGetLastError());
-        B200LC_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys_a, keys_b, vals_b, vals_a + 0,
-                                                        (int)M, 0, 32 + (int)kRankBits, stream));
-        // vals_a now holds the sorted values; newhead needs its own storage: use keys_a's space
-        u32 *sval = vals_a;
-        newhead = reinterpret_cast<u32 *>(keys_a);
+        rc = prims::sort_pairs<u64>(keys_a, keys_b, fvals, vals_c, M, M, 0, (int)kRankBits + pos_bits, ptemp,
+                                    pbytes, stream, &in_b);
+        if (rc) return rc;
+        const u64 *skey = in_b ? keys_b : keys_a;
+        const u32 *sval = in_b ? vals_c : fvals;
+        u32 *newhead = reinterpret_cast<u32 *>(in_b ? keys_a : keys_b);   // the key buffer the sort left free
         const u32 mgrid = (u32)min(((u64)M + kThreads - 1) / kThreads, (u64)num_sms() * 16);
-        place_kernel<<<mgrid, kThreads, 0, stream>>>(keys_b, sval, cidx, M, sa, newhead);
+        place_kernel<<<mgrid, kThreads, 0, stream>>>(skey, sval, cidx, M, sa, newhead);
         B200LC_CUDA_TRY(cudaGetLastError());
-        B200LC_CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_temp, cub_bytes, newhead, newhead, cub::Max(),
-                                                       (int)M, stream));
-        rerank_kernel<<<mgrid, kThreads, 0, stream>>>(keys_b, sval, cidx, newhead, M, n, heads, rank, uflag);
+        rc = prims::inclusive_max_u32(newhead, newhead, M, ptemp, pbytes, stream);
+        if (rc) return rc;
+        rerank_kernel<<<mgrid, kThreads, 0, stream>>>(skey, sval, cidx, newhead, M, n, heads, rank, uflag);
         B200LC_CUDA_TRY(cudaGetLastError());
     }
     return B200LC_OK;
@@ -271,14 +280,14 @@ using namespace b200lc;
 
 extern "C" size_t b200lc_bwt_scratch_bytes(size_t nblocks, size_t n)
 {
-    return bwt::layout((u64)nblocks * n).total;
+    return bwt::layout((u64)nblocks * n, (u32)n).total;
 }
 
 static int bwt_check(const void *d_in, size_t nblocks, size_t n, void *d_scratch, size_t scratch_bytes)
 {
     if (!d_in || !d_scratch) return B200LC_ERR_ARG;
     if (n == 0 || n >= (1u << bwt::kRankBits) || nblocks == 0) return B200LC_ERR_UNSUPPORTED;
-    if ((u64)nblocks * n >= (1ull << 32) || nblocks > 4096) return B200LC_ERR_UNSUPPORTED;
+    if ((u64)nblocks * n > prims::kSortMaxElems) return B200LC_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(d_scratch) & 255) return B200LC_ERR_ARG;
     if (scratch_bytes < b200lc_bwt_scratch_bytes(nblocks, n)) return B200LC_ERR_SCRATCH;
     return B200LC_OK;
@@ -292,7 +301,7 @@ extern "C" int b200lc_bwt_batch(const uint8_t *d_in, size_t nblocks, size_t n, u
     int rc = bwt_check(d_in, nblocks, n, d_scratch, scratch_bytes);
     if (rc) return rc;
     if (!d_out || !d_index) return B200LC_ERR_ARG;
-    const bwt::Layout L = bwt::layout((u64)nblocks * n);
+    const bwt::Layout L = bwt::layout((u64)nblocks * n, (u32)n);
     const u32 *sa = nullptr;
     rc = bwt::suffix_sort(d_in, nblocks, (u32)n, reinterpret_cast<char *>(d_scratch), L, stream, &sa);
     if (rc) return rc;
@@ -311,7 +320,7 @@ extern "C" int b200lc_suffix_array_batch(const uint8_t *d_in, size_t nblocks, si
     int rc = bwt_check(d_in, nblocks, n, d_scratch, scratch_bytes);
     if (rc) return rc;
     if (!d_sa) return B200LC_ERR_ARG;
-    const bwt::Layout L = bwt::layout((u64)nblocks * n);
+    const bwt::Layout L = bwt::layout((u64)nblocks * n, (u32)n);
     const u32 *sa = nullptr;
     rc = bwt::suffix_sort(d_in, nblocks, (u32)n, reinterpret_cast<char *>(d_scratch), L, stream, &sa);
     if (rc) return rc;

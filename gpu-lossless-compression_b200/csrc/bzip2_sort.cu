@@ -7,7 +7,7 @@
 // (compress.c:609-710).  Cyclic rotation order of B equals the order of the first n suffixes of
 // BB, so here one prefix-doubling suffix sort of the doubled block gives the complete rotation
 // order; the reference's three output arrays are filtered views of it.
-#include <cub/device/device_scan.cuh>
+#include "devprims.cuh"
 
 #include "common.cuh"
 #include "../../include/b200lc.h"
@@ -90,9 +90,8 @@ static int ensure(size_t n)
     g_work.release();
     const size_t m = 2 * n;
     g_work.scratch_bytes = b200lc_bwt_scratch_bytes(1, m);
-    size_t cub_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const u32 *)nullptr, (u32 *)nullptr, (int)m);
-    if (g_work.scratch_bytes < cub_bytes) g_work.scratch_bytes = cub_bytes;
+    const size_t scan_bytes = prims::scan_scratch_bytes(m);
+    if (g_work.scratch_bytes < scan_bytes) g_work.scratch_bytes = scan_bytes;
     B200LC_CUDA_TRY(cudaMalloc(&g_work.d_dbl, m));
     B200LC_CUDA_TRY(cudaMalloc(&g_work.d_sa, m * 4));
     B200LC_CUDA_TRY(cudaMalloc(&g_work.d_ff, m * 4));
@@ -123,10 +122,10 @@ static int sort_block(const u8 *block, u32 n, bool want_depth, int *depth_out)
     if (rc) return rc;
     const u32 grid = (m + 255) / 256;
     classify_kernel<<<grid, 256>>>(w.d_sa, n, w.d_ff, w.d_fs);
-    size_t cub_bytes = w.scratch_bytes;
-    B200LC_CUDA_TRY(cub::DeviceScan::ExclusiveSum(w.d_scratch, cub_bytes, w.d_ff, w.d_pf, (int)m));
-    cub_bytes = w.scratch_bytes;
-    B200LC_CUDA_TRY(cub::DeviceScan::ExclusiveSum(w.d_scratch, cub_bytes, w.d_fs, w.d_ps, (int)m));
+    rc = prims::exclusive_sum_u32(w.d_ff, w.d_pf, m, w.d_scratch, w.scratch_bytes, nullptr);
+    if (rc) return rc;
+    rc = prims::exclusive_sum_u32(w.d_fs, w.d_ps, m, w.d_scratch, w.scratch_bytes, nullptr);
+    if (rc) return rc;
     scatter_kernel<<<grid, 256>>>(w.d_sa, n, w.d_ff, w.d_pf, w.d_ps, w.d_of, w.d_os, w.d_rank, w.d_ptr);
     B200LC_CUDA_TRY(cudaGetLastError());
     int f = 2 * (int)((n - 1) / 3) + (int)((n - 1) % 3);     // gpuBWTSort.cu:227

@@ -10,8 +10,9 @@
 //   2. inverse MTF: one thread per 2 KiB segment runs the transform on the IDENTITY list and emits
 //      "position ids" plus the segment's permutation; a chain kernel composes the permutations
 //      into the list at every segment start; a map kernel turns ids into symbols;
-//   3. inverse BWT: T = stable sort of (block, byte) -> index (cub::DeviceRadixSort, library
-//      code), packed with the first-column byte into one word per row; the n-step walk
+//   3. inverse BWT: T = stable sort of each block's bytes -> index (one 8-bit pass of the
+//      segmented one-sweep sort in devprims.cu), packed with the first-column byte into one word
+//      per row; the n-step walk
 //      idx <- T[idx] is cut at "splitter" rows (every gap-th row + the start row): every splitter
 //      walks to the next one in parallel, one thread per block ranks the <= 4097 splitters in
 //      shared memory, every splitter re-walks its piece writing output bytes (sparse ruling set
@@ -19,7 +20,7 @@
 //      by out[i] = out[i mod period].
 #include "common.cuh"
 #include "../../include/b200lc.h"
-#include <cub/device/device_radix_sort.cuh>
+#include "devprims.cuh"
 
 namespace b200lc {
 namespace chuff {
@@ -353,15 +354,8 @@ static Splitters splitters_for(u32 n)
     return sp;
 }
 
-static int key_bits(u64 nblocks)
-{
-    int b = 8;
-    while ((1ull << (b - 8)) < nblocks) ++b;
-    return b;
-}
-
 struct IbwtLayout {
-    size_t keys_a, keys_b, vals_a, vals_b, succ, plen, task, period, cub_temp, cub_bytes, total;
+    size_t keys_a, keys_b, vals_a, vals_b, succ, plen, task, period, sort_temp, sort_bytes, total;
 };
 
 static IbwtLayout ibwt_layout(u64 nblocks, u32 n)
@@ -369,9 +363,7 @@ static IbwtLayout ibwt_layout(u64 nblocks, u32 n)
     IbwtLayout L;
     const u64 N = nblocks * n;
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    cub::DoubleBuffer<u32> dk(nullptr, nullptr), dv(nullptr, nullptr);
-    L.cub_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, L.cub_bytes, dk, dv, (long long)N, 0, key_bits(nblocks));
+    L.sort_bytes = prims::sort_scratch_bytes(N, n);
     const Splitters sp = splitters_for(n);
     const size_t per = (size_t)nblocks * (sp.ns + 1) * 4;
     size_t o = 0;
@@ -383,7 +375,7 @@ static IbwtLayout ibwt_layout(u64 nblocks, u32 n)
     L.plen = o; o += up(per);
     L.task = o; o += up(per);
     L.period = o; o += up(nblocks * 4);
-    L.cub_temp = o; o += up(L.cub_bytes);
+    L.sort_temp = o; o += up(L.sort_bytes);
     L.total = o;
     return L;
 }
@@ -403,12 +395,14 @@ static int inverse_bwt(const u8 *d_bwt, const int *d_index, u64 nblocks, u32 n, 
         ibwt_keys_kernel<<<grid_n, 256, 0, stream>>>(d_bwt, N, n, keys_a, vals_a);
         B200LC_CUDA_TRY(cudaGetLastError());
     }
-    cub::DoubleBuffer<u32> dk(keys_a, keys_b), dv(vals_a, vals_b);
-    size_t cub_bytes = L.cub_bytes;
-    B200LC_CUDA_TRY(cub::DeviceRadixSort::SortPairs(scratch + L.cub_temp, cub_bytes, dk, dv, (long long)N, 0,
-                                                    key_bits(nblocks), stream));
-    u32 *packed = dk.Alternate();
-    ibwt_pack_kernel<<<grid_n, 256, 0, stream>>>(dk.Current(), dv.Current(), N, packed);
+    // every block is a sort segment, so the block number in bits 8.. of the key is not sorted on:
+    // one 8-bit pass = a stable counting sort of each block's bytes
+    int in_b = 0;
+    const int rc = prims::sort_pairs<u32>(keys_a, keys_b, vals_a, vals_b, N, n, 0, 8, scratch + L.sort_temp,
+                                          L.sort_bytes, stream, &in_b);
+    if (rc) return rc;
+    u32 *packed = in_b ? keys_a : keys_b;
+    ibwt_pack_kernel<<<grid_n, 256, 0, stream>>>(in_b ? keys_b : keys_a, in_b ? vals_b : vals_a, N, packed);
     B200LC_CUDA_TRY(cudaGetLastError());
     const Splitters sp = splitters_for(n);
     const u64 tasks = nblocks * (sp.ns + 1);
@@ -426,7 +420,7 @@ static int inverse_bwt(const u8 *d_bwt, const int *d_index, u64 nblocks, u32 n, 
 
 static bool shape_ok(size_t nblocks, size_t n)
 {
-    return n < (1ull << 24) && nblocks <= (1ull << 23) && (u64)nblocks * n < (1ull << 32);
+    return n < (1ull << 24) && nblocks <= (1ull << 23) && (u64)nblocks * n <= prims::kSortMaxElems;
 }
 
 }  // namespace cdec

@@ -173,7 +173,7 @@ int b200lc_culzss_decompress_container(const uint8_t *h_in, size_t n, uint8_t *h
 
 /* Suffix-array BWT (cudppBurrowsWheelerTransform, compress_app.cu:243-267 + sa_app.cu:125-391):
  * d_out[b*n + i] = last column, d_index[b] = row of the original string.  n < 2^21,
- * nblocks <= 4096 per call, nblocks * n < 2^32.  Synchronises the stream (one counter read per doubling round). */
+ * nblocks * n < 2^30 per call.  Synchronises the stream (one counter read per doubling round). */
 size_t b200lc_bwt_scratch_bytes(size_t nblocks, size_t n);
 int b200lc_bwt_batch(const uint8_t *d_in, size_t nblocks, size_t n, uint8_t *d_out, int *d_index,
                      void *d_scratch, size_t scratch_bytes, void *stream);
@@ -210,7 +210,7 @@ int b200lc_cudpp_compress_batch(const uint8_t *d_in, size_t nblocks, size_t n, i
  * The reference ships no GPU decoder; its CPU gold is computeCompressGold
  * (cudpp-inpar/apps/cudpp_testrig/test_compress.cpp:192-364).  These entry points invert
  * b200lc_cudpp_compress_batch / cudppCompress stage by stage, batched over blocks.
- * Limits: n < 2^24, nblocks * n < 2^32.  *d_error != 0 after the stream has drained = corrupt
+ * Limits: n < 2^24, nblocks * n < 2^30.  *d_error != 0 after the stream has drained = corrupt
  * input (4 offsets outside the stream, 5 invalid code / block too short, 6 bwt index >= n). */
 size_t b200lc_inverse_mtf_scratch_bytes(size_t nblocks, size_t n);
 int b200lc_inverse_mtf_batch(const uint8_t *d_in, size_t nblocks, size_t n, uint8_t *d_out,
@@ -225,6 +225,31 @@ int b200lc_cudpp_decompress_batch(const int *d_bwt_index, const uint32_t *d_hist
                                   size_t comp_stride_words, size_t nblocks, size_t n,
                                   uint8_t *d_out, uint32_t *d_error, void *d_scratch,
                                   size_t scratch_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-wide primitives under the BWT paths (csrc/devprims.cu): hand-written replacements for
+ * the library sorts/scans the reference leans on (CUB sorts + moderngpu merge in
+ * cudpp-inpar/src/cudpp/app/sa_app.cu:125-298, Thrust sorts in
+ * cuda-bzip2-ipdpsw/gpuBWTSort.cu:290-418, thrust::exclusive_scan in
+ * cuhd-icpp/src/cuhd_gpu_decoder.cu:498-509).  Exported so that they can be tested on their own.
+ *
+ * Stable LSD radix sort of (key, uint32 value) pairs on key bits [begin_bit, end_bit), every
+ * segment of seg_len consecutive elements sorted independently (seg_len == 0 or >= n: one
+ * segment).  The pairs start in (d_keys_a, d_vals_a) and ping-pong with (d_keys_b, d_vals_b);
+ * *result_in_b (host int) tells where they ended up.  n < 2^30.  Asynchronous. */
+size_t b200lc_sort_scratch_bytes(size_t n, size_t seg_len);
+int b200lc_sort_pairs_u64(uint64_t *d_keys_a, uint64_t *d_keys_b, uint32_t *d_vals_a,
+                          uint32_t *d_vals_b, size_t n, size_t seg_len, int begin_bit, int end_bit,
+                          void *d_scratch, size_t scratch_bytes, void *stream, int *result_in_b);
+int b200lc_sort_pairs_u32(uint32_t *d_keys_a, uint32_t *d_keys_b, uint32_t *d_vals_a,
+                          uint32_t *d_vals_b, size_t n, size_t seg_len, int begin_bit, int end_bit,
+                          void *d_scratch, size_t scratch_bytes, void *stream, int *result_in_b);
+/* Single-pass scans over n uint32 (d_in == d_out allowed): exclusive sum, inclusive running max. */
+size_t b200lc_scan_scratch_bytes(size_t n);
+int b200lc_exclusive_sum_u32(const uint32_t *d_in, uint32_t *d_out, size_t n, void *d_scratch,
+                             size_t scratch_bytes, void *stream);
+int b200lc_inclusive_max_u32(const uint32_t *d_in, uint32_t *d_out, size_t n, void *d_scratch,
+                             size_t scratch_bytes, void *stream);
 
 #ifdef __cplusplus
 }

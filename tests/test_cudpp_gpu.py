@@ -70,6 +70,23 @@ def test_bwt_batched_blocks(kind, n, nb):
         assert np.array_equal(got[b * n:(b + 1) * n], want), b
 
 
+@pytest.mark.parametrize("n", [2, 5, 6, 7, 13, 100, 4099])
+@pytest.mark.parametrize("alphabet", [1, 2, 3])
+def test_bwt_short_suffixes_and_zero_bytes(n, alphabet):
+    # bytes from {0..alphabet-1}: many suffixes tie on their first six bytes with zero padding,
+    # which is where the first-round key relies on sort stability instead of a length field
+    nb = 9
+    rng = np.random.default_rng(n * 10 + alphabet)
+    blocks = [rng.integers(0, alphabet, n, dtype=np.uint8) for _ in range(nb)]
+    blocks[0][:] = 0
+    got, idx = b200lc.bwt_batch(_dev(np.concatenate(blocks)), nb, n)
+    got, idx = got.cpu().numpy(), idx.cpu().numpy()
+    for b in range(nb):
+        want, widx = O.cudpp_oracle_bwt(blocks[b])
+        assert idx[b] == widx, b
+        assert np.array_equal(got[b * n:(b + 1) * n], want), b
+
+
 def test_suffix_array_matches_gold():
     # test_sa.cpp:124-126: bytes rand() % 128 + 1
     n = 200001
