@@ -24,6 +24,17 @@ namespace bwt {
 constexpr int kThreads = 256;
 constexpr u32 kRankBits = 21;
 
+// Every element-wise kernel below gives CTA b the contiguous elements [b * kChunk, (b + 1) * kChunk):
+// CTAs are scheduled in order, so at any moment the whole GPU works inside a window of a few
+// blocks and the random accesses of the suffix-array kernels (rank[sa[j]], rank[g + h],
+// in[pos - 1]) stay in L2.  (A grid-stride loop lets the CTAs drift apart: measured 32 B read +
+// 32 B written in DRAM per scattered 4-byte rank.)
+constexpr u32 kChunk = 16 * kThreads;
+#define B200LC_FOR_CHUNK(var, count)                                                            \
+    for (u32 var = blockIdx.x * kChunk + threadIdx.x, var##_end = min((u32)(count), (blockIdx.x + 1) * kChunk); \
+         var < var##_end; var += kThreads)
+static inline u32 chunk_grid(u64 count) { return (u32)((count + kChunk - 1) / kChunk); }
+
 // First round: key = the first kFirstChars raw bytes of the suffix, zero-padded past the end of
 // the block; every block is one sort segment.  The (at most kFirstChars - 1) suffixes that are
 // shorter than the key are ordered by the sort's stability instead of by key bits: the initial
@@ -36,10 +47,10 @@ __global__ void __launch_bounds__(kThreads) init_keys_kernel(const u8 *__restric
                                                             u64 *__restrict__ keys,
                                                             u32 *__restrict__ start)
 {
-    for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < N; g += (u64)gridDim.x * kThreads) {
-        const u32 blk = (u32)(g / n);
-        const u64 base = (u64)blk * n;
-        const u32 i = n - 1 - (u32)(g - base);
+    B200LC_FOR_CHUNK(g, N) {
+        const u32 blk = g / n;
+        const u32 base = blk * n;
+        const u32 i = n - 1 - (g - base);
         u64 k = 0;
 #pragma unroll
         for (u32 c = 0; c < kFirstChars; ++c) k = (k << 8) | (i + c < n ? (u64)in[base + i + c] : 0);
@@ -57,7 +68,7 @@ __global__ void __launch_bounds__(kThreads) mark_heads_kernel(const u64 *__restr
                                                              unsigned long long *__restrict__ dup)
 {
     u32 local = 0;
-    for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
+    B200LC_FOR_CHUNK(j, N) {
         bool head = j % n == 0 || keys[j] != keys[j - 1];
         if (!head) {
             const u32 a = sa[j] % n, b = sa[j - 1] % n;
@@ -78,8 +89,8 @@ __global__ void __launch_bounds__(kThreads) first_rank_kernel(const u32 *__restr
                                                              u32 *__restrict__ rank,
                                                              u32 *__restrict__ uflag)
 {
-    for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
-        const u32 blk = (u32)(j / n);
+    B200LC_FOR_CHUNK(j, N) {
+        const u32 blk = j / n;
         const u32 hd = head_of[j];
         rank[sa[j]] = hd - blk * n + 1;
         const bool single = hd == (u32)j && (j + 1 == N || head_of[j + 1] == (u32)(j + 1));
@@ -97,7 +108,7 @@ __global__ void __launch_bounds__(kThreads) compact_keys_kernel(const u32 *__res
                                                                u32 h, u64 *__restrict__ ckey,
                                                                u32 *__restrict__ cval)
 {
-    for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
+    B200LC_FOR_CHUNK(j, N) {
         if (!uflag[j]) continue;
         const u32 g = sa[j];
         const u32 blk = g / n, i = g - blk * n;
@@ -114,7 +125,7 @@ __global__ void __launch_bounds__(kThreads) place_kernel(const u64 *__restrict__
                                                         const u32 *__restrict__ cidx, u32 M,
                                                         u32 *__restrict__ sa, u32 *__restrict__ newhead)
 {
-    for (u32 c = blockIdx.x * kThreads + threadIdx.x; c < M; c += gridDim.x * kThreads) {
+    B200LC_FOR_CHUNK(c, M) {
         const u64 k = skey[c];
         const u32 hd = (u32)(k >> kRankBits);
         const u32 first = cidx[hd];
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) rerank_kernel(const u64 *__restrict_
                                                          u32 *__restrict__ head_of,
                                                          u32 *__restrict__ rank, u32 *__restrict__ uflag)
 {
-    for (u32 c = blockIdx.x * kThreads + threadIdx.x; c < M; c += gridDim.x * kThreads) {
+    B200LC_FOR_CHUNK(c, M) {
         const u32 hd = (u32)(skey[c] >> kRankBits);
         const u32 p = hd + (c - cidx[hd]);
         const u32 my_head = nh[c];
@@ -153,10 +164,10 @@ __global__ void __launch_bounds__(kThreads) bwt_gather_kernel(const u8 *__restri
                                                              int *__restrict__ index,
                                                              u32 *__restrict__ sa_out)
 {
-    for (u64 j = (u64)blockIdx.x * kThreads + threadIdx.x; j < N; j += (u64)gridDim.x * kThreads) {
-        const u32 blk = (u32)(j / n);
-        const u64 base = (u64)blk * n;
-        const u32 pos = sa[j] - (u32)base;        // suffix start inside the block
+    B200LC_FOR_CHUNK(j, N) {
+        const u32 blk = j / n;
+        const u32 base = blk * n;
+        const u32 pos = sa[j] - base;             // suffix start inside the block
         if (sa_out) sa_out[j] = pos;
         if (out) {
             if (pos == 0) {
@@ -214,7 +225,7 @@ static int suffix_sort(const u8 *d_in, u64 nblocks, u32 n, char *scratch, const 
     unsigned long long *dup = reinterpret_cast<unsigned long long *>(scratch + L.counter);
     void *ptemp = scratch + L.prim_temp;
     const size_t pbytes = L.prim_bytes;
-    const u32 grid = (u32)min((N + kThreads - 1) / kThreads, (u64)num_sms() * 16);
+    const u32 grid = chunk_grid(N);
     int pos_bits = 1;
     while ((1ull << pos_bits) < N) ++pos_bits;
 
@@ -262,7 +273,7 @@ static int suffix_sort(const u8 *d_in, u64 nblocks, u32 n, char *scratch, const 
         const u64 *skey = in_b ? keys_b : keys_a;
         const u32 *sval = in_b ? vals_c : fvals;
         u32 *newhead = reinterpret_cast<u32 *>(in_b ? keys_a : keys_b);   // the key buffer the sort left free
-        const u32 mgrid = (u32)min(((u64)M + kThreads - 1) / kThreads, (u64)num_sms() * 16);
+        const u32 mgrid = chunk_grid(M);
         place_kernel<<<mgrid, kThreads, 0, stream>>>(skey, sval, cidx, M, sa, newhead);
         B200LC_CUDA_TRY(cudaGetLastError());
         rc = prims::inclusive_max_u32(newhead, newhead, M, ptemp, pbytes, stream);
@@ -306,7 +317,7 @@ extern "C" int b200lc_bwt_batch(const uint8_t *d_in, size_t nblocks, size_t n, u
     rc = bwt::suffix_sort(d_in, nblocks, (u32)n, reinterpret_cast<char *>(d_scratch), L, stream, &sa);
     if (rc) return rc;
     const u64 N = (u64)nblocks * n;
-    const u32 grid = (u32)min((N + bwt::kThreads - 1) / bwt::kThreads, (u64)num_sms() * 16);
+    const u32 grid = bwt::chunk_grid(N);
     bwt::bwt_gather_kernel<<<grid, bwt::kThreads, 0, stream>>>(d_in, sa, N, (u32)n, d_out, d_index, nullptr);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
@@ -325,7 +336,7 @@ extern "C" int b200lc_suffix_array_batch(const uint8_t *d_in, size_t nblocks, si
     rc = bwt::suffix_sort(d_in, nblocks, (u32)n, reinterpret_cast<char *>(d_scratch), L, stream, &sa);
     if (rc) return rc;
     const u64 N = (u64)nblocks * n;
-    const u32 grid = (u32)min((N + bwt::kThreads - 1) / bwt::kThreads, (u64)num_sms() * 16);
+    const u32 grid = bwt::chunk_grid(N);
     bwt::bwt_gather_kernel<<<grid, bwt::kThreads, 0, stream>>>(d_in, sa, N, (u32)n, nullptr, nullptr, d_sa);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;

@@ -130,7 +130,7 @@ template <typename K>
 struct SortSmem {
     alignas(128) K keys[kSortTile];
     alignas(128) u32 vals[kSortTile];
-    u32 warp_cnt[kSortWarps][256];
+    u16 warp_cnt[kSortWarps][256];   // per-warp digit counts (<= 512), later offsets inside the tile (< 4096)
     u32 digit_start[256];
     u32 gbase[256];
     u32 ws[kSortWarps];
@@ -139,7 +139,7 @@ struct SortSmem {
 };
 
 template <typename K>
-__global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(const SortArgs<K> a)
+__global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(const SortArgs<K> a)
 {
     extern __shared__ __align__(128) unsigned char sort_smem_raw[];
     SortSmem<K> &sm = *reinterpret_cast<SortSmem<K> *>(sort_smem_raw);
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(const SortA
         mbar_init(&sm.bar, 1);
         mbar_fence_init();
     }
-    for (u32 i = lane; i < 256; i += 32) sm.warp_cnt[warp][i] = 0;
+    for (u32 i = lane; i < 128; i += 32) reinterpret_cast<u32 *>(sm.warp_cnt[warp])[i] = 0;
     __syncthreads();
 
     const u32 tile = sm.tile;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(const SortA
     const u32 my0 = warp * (32 * kSortItems) + lane;
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) key[i] = sm.keys[my0 + i * 32];
-    u32 *wc = sm.warp_cnt[warp];
+    u16 *wc = sm.warp_cnt[warp];
     const u32 lt = (1u << lane) - 1;
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(const SortA
         u32 old = 0;
         if (lane == leader) {
             old = wc[dg];
-            wc[dg] = old + (u32)__popc(peers);
+            wc[dg] = (u16)(old + (u32)__popc(peers));
         }
         old = __shfl_sync(0xffffffffu, old, leader);
         pos[i] = old + (u32)__popc(peers & lt);
@@ -201,35 +201,22 @@ __global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(const SortA
     }
     __syncthreads();   // every key is in registers, warp counters are final
 
-    // ---- thread d owns digit d: warp offsets, tile count, look-back
+    // ---- thread d owns digit d: warp offsets, tile count; the count is published right away so
+    // that later tiles can start summing while this one reorders its data
     const u32 d = tid;
     u32 count = 0;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
         const u32 t = sm.warp_cnt[w][d];
-        sm.warp_cnt[w][d] = count;
+        sm.warp_cnt[w][d] = (u16)count;
         count += t;
     }
     u32 *st = a.status + (size_t)tile * 256;
     const bool seg_first = tseg == 0;
     st_relaxed_u32(&st[d], (seg_first ? kFlagIncl : kFlagAgg) | count);
+    const u32 gstart = a.base[((size_t)seg * a.passes + a.pass) * 256 + d];
     const u32 start = block_excl_sum_256(count, sm.ws);
     sm.digit_start[d] = start;
-    u32 excl = 0;
-    if (!seg_first) {
-        const u32 *prev = st + d - 256;
-        while (true) {
-            u32 s;
-            do {
-                s = ld_relaxed_u32(prev);
-            } while ((s >> 30) == 0);
-            excl += s & kValueMask;
-            if (s & kFlagIncl) break;
-            prev -= 256;
-        }
-        st_relaxed_u32(&st[d], kFlagIncl | (excl + count));
-    }
-    sm.gbase[d] = a.base[((size_t)seg * a.passes + a.pass) * 256 + d] + excl - start;
     __syncthreads();
 
     // ---- reorder inside shared memory
@@ -246,6 +233,23 @@ __global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(const SortA
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) sm.vals[pos[i]] = val[i];
+
+    // ---- look-back over the earlier tiles of the segment (their counts have had time to land)
+    u32 excl = 0;
+    if (!seg_first) {
+        const u32 *prev = st + d - 256;
+        while (true) {
+            u32 s;
+            do {
+                s = ld_relaxed_u32(prev);
+            } while ((s >> 30) == 0);
+            excl += s & kValueMask;
+            if (s & kFlagIncl) break;
+            prev -= 256;
+        }
+        st_relaxed_u32(&st[d], kFlagIncl | (excl + count));
+    }
+    sm.gbase[d] = gstart + excl - start;
     __syncthreads();
 
     // ---- digit runs leave with consecutive addresses
