@@ -283,7 +283,11 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
         };
         // Round 0 + chain resolution of the current sub-tile for entry state `entry`.
         // Leaves my_start / my_end / my_cnt per worker and sm.end[] = resolved exit states.
-        auto resolve_subtile = [&](u32 entry, bool keep_masks) {
+        // Only the first `real` subsequences hold stream units; the rest of the last sub-tile is
+        // zero padding whose symbols lie beyond n_out.  Their entry states are not resolved: a
+        // run of zeros never re-synchronises when the all-zero codeword is longer than one bit,
+        // and the chain would crawl through it one subsequence per round.
+        auto resolve_subtile = [&](u32 entry, bool keep_masks, u32 real) {
             if (worker) {
                 walk_record<S>(u, ltab, shift, m, e0, c0);
                 sm.end[tid] = (u8)e0;
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             my_end = e0;
             my_cnt = c0;
             if (worker && tid > 0) my_start = sm.end[tid - 1];
-            bool eval = worker && my_start != 0;
+            bool eval = worker && my_start != 0 && tid < real;
             __syncthreads();
             while (true) {
                 bool changed = false;
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
                 eval = false;
                 if (worker && tid > 0) {
                     const u32 ns = sm.end[tid - 1];
-                    eval = ns != my_start;
+                    eval = ns != my_start && tid < real;
                     my_start = ns;
                 }
                 __syncthreads();
@@ -351,6 +355,13 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             issue_load(g, (step & 1) ^ 1);
         };
 
+        // number of subsequences of sub-tile g that start inside the stream
+        const u64 total_subseq = (p.n_units + S - 1) / S;
+        auto real_subseq = [&](u32 g) -> u32 {
+            const u64 s0 = (u64)g * T;
+            return s0 >= total_subseq ? 0u : (u32)min((u64)T, total_subseq - s0);
+        };
+
         // ================================================================ pass A: states + counts
         u32 entry = 0;
         u32 piece_total = 0;
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             prefetch(0, c);
             const u32 buf = step & 1;
             if (worker) load_units(buf);
-            resolve_subtile(entry, c == 0);
+            resolve_subtile(entry, c == 0, real_subseq(g0 + c));
             block_scan();
             if (worker) {
                 sm.saved[c][tid] = (u16)((my_start << 12) | my_cnt);
@@ -518,7 +529,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             if (entry_true != sm.sub_entry[c]) {
                 // entry state differs from what pass A assumed (always for sub-tile 0 when the
                 // piece's entry state is not 0): redo states + counts for this sub-tile
-                resolve_subtile(entry_true, false);
+                resolve_subtile(entry_true, false, real_subseq(g0 + c));
                 exit_state = sm.end[T - 1];
             } else {
                 if (worker) {
@@ -583,14 +594,14 @@ struct Variant {
     { S_, T_, N_, C_, cuhd_decode_kernel<S_, T_, N_, C_>, \
       ((sizeof(SmemLayout<S_, T_, N_, C_>) + 127) & ~size_t(127)) }
 static const Variant kVariants[] = {
-    B200LC_VARIANT(8, 256, 16, 16384),   // 388 GB/s of output on C2 (B200, round 1)
-    B200LC_VARIANT(8, 256, 32, 16384),   // 333
-    B200LC_VARIANT(8, 256, 8, 12288),    // 370 (with CAP 16384)
+    B200LC_VARIANT(8, 256, 16, 16384),   // default for long streams: 407 GB/s of output on C2 (B200, round 1)
+    B200LC_VARIANT(8, 256, 8, 16384),    // shorter pieces for shorter streams (see pick_variant)
+    B200LC_VARIANT(8, 256, 4, 16384),
+    B200LC_VARIANT(8, 256, 2, 16384),
+    B200LC_VARIANT(8, 256, 1, 16384),
+    B200LC_VARIANT(8, 256, 32, 16384),   // tuning points: 333
     B200LC_VARIANT(8, 128, 16, 8192),    // 375
-    B200LC_VARIANT(8, 128, 32, 12288),   // 271
-    B200LC_VARIANT(4, 128, 64, 6144),    // 207
     B200LC_VARIANT(4, 256, 32, 12288),   // 279
-    B200LC_VARIANT(4, 512, 16, 24576),   // 265
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -603,6 +614,22 @@ static const Variant &variant()
         if (v < 0 || v >= kNumVariants) v = 0;
     }
     return kVariants[v];
+}
+
+// One-shot decodes pick the piece length by stream size: a piece is decoded by one CTA, two
+// passes over NSUB sub-tiles back to back (~5 us each), so a stream with fewer pieces than the
+// GPU has CTA slots is latency-bound by its piece length.  Halve it until the pieces fill the
+// machine (variants 0..4 differ only in NSUB).  B200LC_CUHD_VARIANT pins one variant.
+static const Variant &pick_variant(u64 n_units)
+{
+    if (getenv("B200LC_CUHD_VARIANT")) return variant();
+    const u64 want = (u64)num_sms() * 4;
+    for (int i = 0; i < 4; ++i) {
+        const Variant &v = kVariants[i];
+        const u64 sub = ((n_units + v.S - 1) / v.S + v.T - 1) / v.T;
+        if ((sub + v.NSUB - 1) / v.NSUB >= want) return v;
+    }
+    return kVariants[4];
 }
 
 static u32 subtiles_for(const Variant &v, u64 n_units)
@@ -634,9 +661,10 @@ extern "C" size_t b200lc_cuhd_decode_scratch_bytes(size_t n_units)
 // Decodes pieces [first_piece, end_piece) of the stream.  The descriptors of earlier pieces must
 // still be in d_scratch (first_piece == 0 clears them); units up to the end of the last piece
 // + 4 must be resident.
-static int decode_pieces(const uint32_t *d_units, size_t n_units, uint8_t *d_out, size_t n_out,
-                         const void *d_table, int max_codeword_length, void *d_scratch,
-                         size_t scratch_bytes, size_t first_piece, size_t end_piece, cudaStream_t stream)
+static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t n_units,
+                         uint8_t *d_out, size_t n_out, const void *d_table, int max_codeword_length,
+                         void *d_scratch, size_t scratch_bytes, size_t first_piece, size_t end_piece,
+                         cudaStream_t stream)
 {
     if (max_codeword_length < 1 || max_codeword_length > 13) return B200LC_ERR_UNSUPPORTED;
     if (n_out == 0 || n_units == 0) return B200LC_OK;
@@ -646,9 +674,9 @@ static int decode_pieces(const uint32_t *d_units, size_t n_units, uint8_t *d_out
     if (scratch_bytes < need) return B200LC_ERR_SCRATCH;
     if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
 
-    const cuhd::Variant &v = cuhd::variant();
     const size_t smem = v.smem_fixed + (size_t(5) << max_codeword_length);
-    static int occ_cache[14] = {0};
+    static int occ_table[cuhd::kNumVariants][14] = {{0}};
+    int *occ_cache = occ_table[&v - cuhd::kVariants];
     if (!occ_cache[max_codeword_length]) {
         B200LC_CUDA_TRY(cudaFuncSetAttribute(v.kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
@@ -691,8 +719,8 @@ extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8
                                   size_t n_out, const void *d_table, int max_codeword_length,
                                   void *d_scratch, size_t scratch_bytes, void *stream_)
 {
-    return decode_pieces(d_units, n_units, d_out, n_out, d_table, max_codeword_length, d_scratch,
-                         scratch_bytes, 0, ~size_t(0), (cudaStream_t)stream_);
+    return decode_pieces(cuhd::pick_variant(n_units), d_units, n_units, d_out, n_out, d_table,
+                         max_codeword_length, d_scratch, scratch_bytes, 0, ~size_t(0), (cudaStream_t)stream_);
 }
 
 extern "C" size_t b200lc_cuhd_decode_piece_units(void)
@@ -706,8 +734,8 @@ extern "C" int b200lc_cuhd_decode_pieces(const uint32_t *d_units, size_t n_units
                                          void *d_scratch, size_t scratch_bytes, size_t first_piece,
                                          size_t end_piece, void *stream_)
 {
-    return decode_pieces(d_units, n_units, d_out, n_out, d_table, max_codeword_length, d_scratch,
-                         scratch_bytes, first_piece, end_piece, (cudaStream_t)stream_);
+    return decode_pieces(cuhd::variant(), d_units, n_units, d_out, n_out, d_table, max_codeword_length,
+                         d_scratch, scratch_bytes, first_piece, end_piece, (cudaStream_t)stream_);
 }
 
 // Asynchronous: copies the number of output symbols that are final once pieces [0, end_piece) are

@@ -1,0 +1,207 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: block-size x entropy sweep, encode + decode GB/s and ratio for the
+three paths on one GPU (device-resident, CUDA events, best of 3).  One JSON line per point.
+
+  python tools/sweep.py [--mib 256] [--paths cuhd,culzss,cudpp] [--md out.md]
+
+Input: order-0 bytes with Zipf exponent solved for the target entropy H (H = 8: uniform).
+Block size means: CULZSS buffer length (the reference fixes 1 MiB, main.c:62 -- other sizes are
+extensions of the same format), cudppCompress block length (the reference validates 1 MiB only;
+n < 2 MiB here), CUHD: length of one independent stream (own table), decoded one after another.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+pkg = importlib.import_module("gpu-lossless-compression_b200")
+from bench_paths import PEAK, timeit  # noqa: E402
+
+KIB, MIB = 1 << 10, 1 << 20
+
+
+def zipf_probs_for_entropy(H, nsym=256):
+    """Zipf(s) over nsym symbols with Shannon entropy H bits (bisection on s)."""
+    def ent(s):
+        p = 1.0 / np.arange(1, nsym + 1, dtype=np.float64) ** s
+        p /= p.sum()
+        return float(-(p * np.log2(p)).sum()), p
+    if H >= np.log2(nsym) - 1e-9:
+        return ent(0.0)[1]
+    lo, hi = 0.0, 20.0
+    for _ in range(80):
+        mid = 0.5 * (lo + hi)
+        if ent(mid)[0] > H:
+            lo = mid
+        else:
+            hi = mid
+    return ent(0.5 * (lo + hi))[1]
+
+
+def gen(n, H, dev, seed, lo_sym=0):
+    """n bytes with order-0 entropy H; symbols lo_sym .. (lo_sym = 1 keeps byte 0 out)."""
+    nsym = 256 - lo_sym
+    p = zipf_probs_for_entropy(min(H, np.log2(nsym)), nsym)
+    cdf = torch.from_numpy(np.cumsum(p)).to(device=dev, dtype=torch.float32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    for lo in range(0, n, 1 << 26):
+        m = min(1 << 26, n - lo)
+        u = torch.rand(m, generator=g, device=dev)
+        out[lo:lo + m] = (torch.searchsorted(cdf, u).clamp_(max=nsym - 1) + lo_sym).to(torch.uint8)
+    return out
+
+
+def point_cuhd(data, block, dev):
+    n = data.numel()
+    nstreams = n // block
+    L = pkg.lib()
+    encs, luts = [], []
+    units = torch.empty((block * 11 + 31) // 32 + 2, dtype=torch.int32, device=dev)
+    bits = torch.zeros(1, dtype=torch.int64, device=dev)
+    escr = torch.empty(L.b200lc_cuhd_encode_scratch_bytes(block), dtype=torch.uint8, device=dev)
+    out = torch.empty(block, dtype=torch.uint8, device=dev)
+    # encode every stream once (tables on the host), then time encode / decode over all streams
+    tabs = []
+    for s in range(nstreams):
+        part = data[s * block:(s + 1) * block]
+        hist = pkg.histogram_u8(part).cpu().numpy()
+        code, length, lut = pkg.cuhd_build_table(hist)
+        tabs.append((torch.from_numpy(code.view(np.int32)).to(dev), torch.from_numpy(length).to(dev),
+                     torch.from_numpy(lut).to(dev)))
+        encs.append(pkg.cuhd_encode(part, tabs[-1][0], tabs[-1][1]))
+    comp = sum(e.n_units * 4 for e in encs)
+
+    def enc_all():
+        for s in range(nstreams):
+            pkg.histogram_u8(data[s * block:(s + 1) * block])
+            pkg.cuhd_encode(data[s * block:(s + 1) * block], tabs[s][0], tabs[s][1], units=units,
+                            total_bits=bits, scratch=escr, sync=False)
+
+    dscr = torch.empty(L.b200lc_cuhd_decode_scratch_bytes(units.numel()), dtype=torch.uint8, device=dev)
+
+    def dec_all():
+        for s in range(nstreams):
+            pkg.cuhd_decode(encs[s].units, block, tabs[s][2], 11, out=out, scratch=dscr)
+
+    enc_ms = timeit(enc_all, iters=3, warm=1)
+    dec_ms = timeit(dec_all, iters=3, warm=1)
+    ok = bool(torch.equal(out, data[(nstreams - 1) * block:]))
+    return enc_ms, dec_ms, comp, ok
+
+
+def point_culzss(data, block, dev):
+    n = data.numel()
+    nbuf = n // block
+    L = pkg.lib()
+    stride = pkg.culzss_out_stride(block)
+    out = torch.empty(nbuf * stride, dtype=torch.uint8, device=dev)
+    clen = torch.empty(nbuf, dtype=torch.int32, device=dev)
+    scr = torch.empty(L.b200lc_culzss_encode_scratch_bytes(nbuf, block), dtype=torch.uint8, device=dev)
+    enc_ms = timeit(lambda: pkg.culzss_encode(data, block, out, clen, scr), iters=3, warm=1)
+    cl = clen.cpu().numpy().astype(np.int64)
+    sizes = np.where(cl == 0, block, cl)
+    offs = np.zeros(nbuf + 1, np.int64)
+    offs[1:] = np.cumsum(sizes)
+    comp = torch.empty(int(offs[-1]), dtype=torch.uint8, device=dev)
+    rows = out.view(nbuf, stride)
+    d_sz = torch.from_numpy(sizes).to(dev)
+    raw = torch.from_numpy(cl == 0).to(dev)
+    col = torch.arange(stride, device=dev)
+    step = max(1, (64 * MIB) // stride)
+    for lo in range(0, nbuf, step):
+        hi = min(nbuf, lo + step)
+        src = rows[lo:hi].clone()
+        if bool(raw[lo:hi].any()):
+            src[:, :block][raw[lo:hi]] = data.view(nbuf, block)[lo:hi][raw[lo:hi]]
+        comp[int(offs[lo]):int(offs[hi])] = src[col[None, :] < d_sz[lo:hi, None]]
+    d_offs = torch.from_numpy(offs).to(dev)
+    dec = torch.empty(n, dtype=torch.uint8, device=dev)
+    dscr = torch.empty(L.b200lc_culzss_decode_scratch_bytes(nbuf, block), dtype=torch.uint8, device=dev)
+    dec_ms = timeit(lambda: pkg.culzss_decode(comp, d_offs, block, dec, dscr), iters=3, warm=1)
+    return enc_ms, dec_ms, int(offs[-1]), bool(torch.equal(dec, data))
+
+
+def point_cudpp(data, block, dev):
+    n = data.numel()
+    nblocks = n // block
+    data = data.clone()
+    data.view(nblocks, block)[:, -1] = 0       # the reference's validated domain: 1..255 + final 0
+    L = pkg.lib()
+    scr = torch.empty(max(L.b200lc_cudpp_compress_scratch_bytes(nblocks, block),
+                          L.b200lc_cudpp_decompress_scratch_bytes(nblocks, block)) + 256,
+                      dtype=torch.uint8, device=dev)
+    res = [None]
+
+    def enc():
+        res[0] = pkg.cudpp_compress_batch(data, nblocks, block, scratch=scr, out=res[0])
+
+    enc_ms = timeit(enc, iters=3, warm=1)
+    if int(res[0].error.item()) != 0:
+        return enc_ms, None, None, False
+    comp = int(res[0].total_words.sum().item()) * 4
+    back = torch.empty(n, dtype=torch.uint8, device=dev)
+    err = [None]
+
+    def dec():
+        _, err[0] = pkg.cudpp_decompress_batch(res[0], nblocks, block, scratch=scr, out=back)
+
+    dec_ms = timeit(dec, iters=3, warm=1)
+    return enc_ms, dec_ms, comp, bool(torch.equal(back, data)) and int(err[0].item()) == 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mib", type=int, default=256)
+    ap.add_argument("--paths", default="cuhd,culzss,cudpp")
+    ap.add_argument("--blocks", default="65536,262144,1048576,4194304")
+    ap.add_argument("--entropies", default="1,2,3,4,5,6,7,8")
+    ap.add_argument("--md", default=None)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    rows = []
+    for path in args.paths.split(","):
+        fn = {"cuhd": point_cuhd, "culzss": point_culzss, "cudpp": point_cudpp}[path]
+        total = (args.mib if path != "cudpp" else min(args.mib, 128)) * MIB
+        for H in [float(x) for x in args.entropies.split(",")]:
+            data = gen(total, H, dev, seed=1000 + int(H * 10), lo_sym=1 if path == "cudpp" else 0)
+            for block in [int(x) for x in args.blocks.split(",")]:
+                rec = {"path": path, "H": H, "block": block, "mib": total // MIB}
+                if path == "cudpp" and block >= (1 << 21):
+                    rec["skipped"] = "block length >= 2 MiB is outside the 21-bit rank range"
+                else:
+                    enc_ms, dec_ms, comp, ok = fn(data, block, dev)
+                    rec.update({"encode_gbs": total / enc_ms / 1e6,
+                                "decode_gbs": total / dec_ms / 1e6 if dec_ms else None,
+                                "ratio": total / comp if comp else None, "round_trip": ok,
+                                "encode_hbm_frac": (total + comp) / enc_ms / 1e6 / PEAK if comp else None,
+                                "decode_hbm_frac": (total + comp) / dec_ms / 1e6 / PEAK if comp and dec_ms else None})
+                rows.append(rec)
+                print(json.dumps(rec), flush=True)
+            del data
+            torch.cuda.empty_cache()
+    if args.md:
+        with open(args.md, "w") as f:
+            f.write("| path | H (bits/byte) | block | encode GB/s | decode GB/s | ratio | %HBM enc / dec | round trip |\n")
+            f.write("|---|---|---|---|---|---|---|---|\n")
+            for r in rows:
+                if "skipped" in r:
+                    f.write("| %s | %g | %d KiB | - | - | - | - | skipped: %s |\n" % (r["path"], r["H"], r["block"] // KIB, r["skipped"]))
+                    continue
+                fmt = lambda v, s="%.1f": "-" if v is None else s % v  # noqa: E731
+                f.write("| %s | %g | %d KiB | %s | %s | %s | %s / %s | %s |\n" % (
+                    r["path"], r["H"], r["block"] // KIB, fmt(r["encode_gbs"]), fmt(r["decode_gbs"]),
+                    fmt(r["ratio"], "%.3f"), fmt(r["encode_hbm_frac"] and 100 * r["encode_hbm_frac"], "%.2f"),
+                    fmt(r["decode_hbm_frac"] and 100 * r["decode_hbm_frac"], "%.2f"), "ok" if r["round_trip"] else "FAIL"))
+
+
+if __name__ == "__main__":
+    main()
