@@ -103,6 +103,9 @@ def lib():
     for name in ("b200lc_exclusive_sum_u32", "b200lc_inclusive_max_u32"):
         f = getattr(L, name)
         f.restype, f.argtypes = i32, [vp, vp, sz, vp, sz, vp]
+    L.bsc_bwt_encode.restype = i32
+    L.bsc_bwt_encode.argtypes = [vp, i32, vp, vp, i32]
+    L.b200lc_bsc_release.restype = None
     _lib = L
     return L
 
@@ -433,3 +436,17 @@ def scan_u32(x, kind="exclusive_sum", out=None, stream=None):
     check(fn(x.data_ptr(), out.data_ptr(), n, scratch.data_ptr(), scratch.numel(), _stream_ptr(stream)), kind)
     torch.cuda.current_stream().synchronize()
     return out
+
+
+# ------------------------------------------------------------------------------- libbsc BWT stage
+def bsc_bwt_encode(data):
+    """libbsc's bsc_bwt_encode on the GPU (include/libbsc_gpu.h).  data: numpy uint8 (host).
+    Returns (U, primary_index, indexes) like the reference call does through its out-parameters."""
+    import numpy as np
+    t = np.ascontiguousarray(data, dtype=np.uint8).copy()
+    num = np.zeros(1, np.uint8)
+    idx = np.zeros(256, np.int32)
+    p = lib().bsc_bwt_encode(t.ctypes.data, t.size, num.ctypes.data, idx.ctypes.data, 0)
+    if p < 0:
+        raise B200LCError("bsc_bwt_encode failed with LIBBSC code %d" % p)
+    return t, p, idx[: int(num[0])].copy()

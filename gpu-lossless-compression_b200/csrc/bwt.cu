@@ -22,7 +22,6 @@ namespace b200lc {
 namespace bwt {
 
 constexpr int kThreads = 256;
-constexpr u32 kRankBits = 21;
 
 // Every element-wise kernel below gives CTA b the contiguous elements [b * kChunk, (b + 1) * kChunk):
 // CTAs are scheduled in order, so at any moment the whole GPU works inside a window of a few
@@ -105,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) compact_keys_kernel(const u32 *__res
                                                                const u32 *__restrict__ head_of,
                                                                const u32 *__restrict__ sa,
                                                                const u32 *__restrict__ rank, u64 N, u32 n,
-                                                               u32 h, u64 *__restrict__ ckey,
+                                                               u32 h, u32 rank_bits, u64 *__restrict__ ckey,
                                                                u32 *__restrict__ cval)
 {
     B200LC_FOR_CHUNK(j, N) {
@@ -114,7 +113,7 @@ __global__ void __launch_bounds__(kThreads) compact_keys_kernel(const u32 *__res
         const u32 blk = g / n, i = g - blk * n;
         const u64 r2 = (i + h < n) ? rank[g + h] : 0;
         const u32 c = cidx[j];
-        ckey[c] = ((u64)head_of[j] << kRankBits) | r2;
+        ckey[c] = ((u64)head_of[j] << rank_bits) | r2;
         cval[c] = g;
     }
 }
@@ -122,12 +121,12 @@ __global__ void __launch_bounds__(kThreads) compact_keys_kernel(const u32 *__res
 // Sorted compact element c goes to suffix-array position p = head + (c - compact index of head).
 __global__ void __launch_bounds__(kThreads) place_kernel(const u64 *__restrict__ skey,
                                                         const u32 *__restrict__ sval,
-                                                        const u32 *__restrict__ cidx, u32 M,
+                                                        const u32 *__restrict__ cidx, u32 M, u32 rank_bits,
                                                         u32 *__restrict__ sa, u32 *__restrict__ newhead)
 {
     B200LC_FOR_CHUNK(c, M) {
         const u64 k = skey[c];
-        const u32 hd = (u32)(k >> kRankBits);
+        const u32 hd = (u32)(k >> rank_bits);
         const u32 first = cidx[hd];
         const u32 p = hd + (c - first);
         sa[p] = sval[c];
@@ -139,18 +138,18 @@ __global__ void __launch_bounds__(kThreads) rerank_kernel(const u64 *__restrict_
                                                          const u32 *__restrict__ sval,
                                                          const u32 *__restrict__ cidx,
                                                          const u32 *__restrict__ nh, u32 M, u32 n,
-                                                         u32 *__restrict__ head_of,
+                                                         u32 rank_bits, u32 *__restrict__ head_of,
                                                          u32 *__restrict__ rank, u32 *__restrict__ uflag)
 {
     B200LC_FOR_CHUNK(c, M) {
-        const u32 hd = (u32)(skey[c] >> kRankBits);
+        const u32 hd = (u32)(skey[c] >> rank_bits);
         const u32 p = hd + (c - cidx[hd]);
         const u32 my_head = nh[c];
         head_of[p] = my_head;
         rank[sval[c]] = my_head - (p / n) * n + 1;
         bool next_is_head = true;
         if (c + 1 < M) {
-            const u32 hd2 = (u32)(skey[c + 1] >> kRankBits);
+            const u32 hd2 = (u32)(skey[c + 1] >> rank_bits);
             const u32 p2 = hd2 + (c + 1 - cidx[hd2]);
             next_is_head = nh[c + 1] == p2;
         }
@@ -228,6 +227,8 @@ static int suffix_sort(const u8 *d_in, u64 nblocks, u32 n, char *scratch, const 
     const u32 grid = chunk_grid(N);
     int pos_bits = 1;
     while ((1ull << pos_bits) < N) ++pos_bits;
+    u32 rank_bits = 1;                       // ranks run from 0 (past the end) to n
+    while ((1ull << rank_bits) <= n) ++rank_bits;
 
     // ---- round 1: every suffix, by its first kFirstChars characters, block by block
     init_keys_kernel<<<grid, kThreads, 0, stream>>>(d_in, N, n, keys_a, vals_a);
@@ -265,20 +266,20 @@ static int suffix_sort(const u8 *d_in, u64 nblocks, u32 n, char *scratch, const 
         B200LC_CUDA_TRY(cudaStreamSynchronize(stream));
         const u32 M = last[0] + last[1];
         if (M == 0) break;
-        compact_keys_kernel<<<grid, kThreads, 0, stream>>>(uflag, cidx, heads, sa, rank, N, n, h, keys_a, fvals);
+        compact_keys_kernel<<<grid, kThreads, 0, stream>>>(uflag, cidx, heads, sa, rank, N, n, h, rank_bits, keys_a, fvals);
         B200LC_CUDA_TRY(cudaGetLastError());
-        rc = prims::sort_pairs<u64>(keys_a, keys_b, fvals, vals_c, M, M, 0, (int)kRankBits + pos_bits, ptemp,
+        rc = prims::sort_pairs<u64>(keys_a, keys_b, fvals, vals_c, M, M, 0, (int)rank_bits + pos_bits, ptemp,
                                     pbytes, stream, &in_b);
         if (rc) return rc;
         const u64 *skey = in_b ? keys_b : keys_a;
         const u32 *sval = in_b ? vals_c : fvals;
         u32 *newhead = reinterpret_cast<u32 *>(in_b ? keys_a : keys_b);   // the key buffer the sort left free
         const u32 mgrid = chunk_grid(M);
-        place_kernel<<<mgrid, kThreads, 0, stream>>>(skey, sval, cidx, M, sa, newhead);
+        place_kernel<<<mgrid, kThreads, 0, stream>>>(skey, sval, cidx, M, rank_bits, sa, newhead);
         B200LC_CUDA_TRY(cudaGetLastError());
         rc = prims::inclusive_max_u32(newhead, newhead, M, ptemp, pbytes, stream);
         if (rc) return rc;
-        rerank_kernel<<<mgrid, kThreads, 0, stream>>>(skey, sval, cidx, newhead, M, n, heads, rank, uflag);
+        rerank_kernel<<<mgrid, kThreads, 0, stream>>>(skey, sval, cidx, newhead, M, n, rank_bits, heads, rank, uflag);
         B200LC_CUDA_TRY(cudaGetLastError());
     }
     return B200LC_OK;
@@ -297,7 +298,7 @@ extern "C" size_t b200lc_bwt_scratch_bytes(size_t nblocks, size_t n)
 static int bwt_check(const void *d_in, size_t nblocks, size_t n, void *d_scratch, size_t scratch_bytes)
 {
     if (!d_in || !d_scratch) return B200LC_ERR_ARG;
-    if (n == 0 || n >= (1u << bwt::kRankBits) || nblocks == 0) return B200LC_ERR_UNSUPPORTED;
+    if (n == 0 || nblocks == 0) return B200LC_ERR_UNSUPPORTED;
     if ((u64)nblocks * n > prims::kSortMaxElems) return B200LC_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(d_scratch) & 255) return B200LC_ERR_ARG;
     if (scratch_bytes < b200lc_bwt_scratch_bytes(nblocks, n)) return B200LC_ERR_SCRATCH;

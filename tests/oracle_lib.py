@@ -80,6 +80,8 @@ def oracle():
     lib.bzip2_oracle_block_sort.argtypes = [_u8p, C.c_uint32, _u32p, _u32p, _u32p]
     lib.bzip2_oracle_merge.restype = C.c_int
     lib.bzip2_oracle_merge.argtypes = [_u8p, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p]
+    lib.bsc_oracle_bwt_encode.restype = C.c_int
+    lib.bsc_oracle_bwt_encode.argtypes = [_u8p, C.c_int, _u8p, _u8p, _i32p]
     _cache["oracle"] = lib
     return lib
 
@@ -449,3 +451,38 @@ def bzip2_oracle_merge(block, f, first, second, rank):
     s1 = np.zeros(n, np.uint32); s1[: n - f] = second
     orig = oracle().bzip2_oracle_merge(np.ascontiguousarray(block), n, f, f1, s1, rank, order)
     return order, orig
+
+
+# ---------------------------------------------------------------------------- libbsc helpers
+def ref_bsc():
+    """The reference's libbsc (CPU build, oracle/_ref/libref_bsc.so)."""
+    if "ref_bsc" in _cache:
+        return _cache["ref_bsc"]
+    lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libref_bsc.so"))
+    lib.bsc_bwt_encode.restype = C.c_int
+    lib.bsc_bwt_encode.argtypes = [_u8p, C.c_int, _u8p, _i32p, C.c_int]
+    lib.bsc_bwt_decode.restype = C.c_int
+    lib.bsc_bwt_decode.argtypes = [_u8p, C.c_int, C.c_int, C.c_ubyte, _i32p, C.c_int]
+    lib.bsc_init.restype = C.c_int
+    lib.bsc_init.argtypes = [C.c_int]
+    lib.bsc_init(0)
+    _cache["ref_bsc"] = lib
+    return lib
+
+
+def bsc_ref_bwt_encode(data):
+    """Reference bsc_bwt_encode (divbwt) -> (U, primary index, indexes[num_indexes])."""
+    t = np.ascontiguousarray(data).copy()
+    num = np.zeros(1, np.uint8)
+    idx = np.zeros(256, np.int32)
+    p = ref_bsc().bsc_bwt_encode(t, t.size, num, idx, 0)
+    return t, p, idx[: int(num[0])].copy()
+
+
+def bsc_oracle_bwt_encode(data):
+    t = np.ascontiguousarray(data)
+    u = np.zeros(max(1, t.size), np.uint8)
+    num = np.zeros(1, np.uint8)
+    idx = np.zeros(256, np.int32)
+    p = oracle().bsc_oracle_bwt_encode(t, t.size, u, num, idx)
+    return u[: t.size], p, idx[: int(num[0])].copy()

@@ -1,0 +1,41 @@
+"""CPU: the oracle's restatement of libbsc's BWT stage (oracle/bsc_oracle.c) against the
+reference's own bsc_bwt_encode = divbwt (oracle/_ref/libref_bsc.so, built from
+cuda-bsc/libbsc without CUDA), and the reference's bsc_bwt_decode as the inverse."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.skipif(not O.have_ref("bsc"), reason="oracle/_ref/libref_bsc.so not built")
+
+
+def _cases():
+    rng = np.random.default_rng(5)
+    text = np.frombuffer((b"the quick brown fox jumps over the lazy dog. " * 3000), np.uint8)
+    return {
+        "n2": np.array([7, 7], np.uint8),
+        "n3": np.array([2, 1, 2], np.uint8),
+        "n9_binary": rng.integers(0, 2, 9, dtype=np.uint8),
+        "zeros_1000": np.zeros(1000, np.uint8),
+        "periodic": np.tile(np.array([5, 0, 9], np.uint8), 4000),
+        "random_70001": rng.integers(0, 256, 70001, dtype=np.uint8),
+        "zipf_200k": O.zipf_bytes(200000, 1.3, seed=3),
+        "text_135k": text.copy(),
+        "quant_1m": O.quant_codes(1 << 20),
+    }
+
+
+@pytest.mark.parametrize("name", list(_cases().keys()))
+def test_oracle_equals_reference_divbwt(name):
+    data = _cases()[name]
+    ru, rp, ri = O.bsc_ref_bwt_encode(data)
+    ou, op, oi = O.bsc_oracle_bwt_encode(data)
+    assert op == rp
+    assert np.array_equal(ou, ru)
+    assert np.array_equal(oi, ri)
+    # and the reference's inverse reproduces the input from it
+    back = ou.copy()
+    idx = np.zeros(256, np.int32)
+    idx[: oi.size] = oi
+    assert O.ref_bsc().bsc_bwt_decode(back, back.size, op, oi.size, idx, 0) == 0
+    assert np.array_equal(back, data)
