@@ -296,31 +296,42 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
                     for (int j = 0; j < S; ++j) sm.masks[tid * S + j] = m[j];
                 }
             }
-            __syncthreads();
-            my_start = entry;
+            __syncthreads();   // tentative exit states (paths from bit 0) visible
+            my_start = 0;
             my_end = e0;
             my_cnt = c0;
-            if (worker && tid > 0) my_start = sm.end[tid - 1];
-            bool eval = worker && my_start != 0 && tid < real;
-            __syncthreads();
+            // Fixed point of "entry state = exit state of the predecessor".  Inside a warp the
+            // chain is followed with shuffles (no CTA barrier); between warps through sm.end[]:
+            // a warp starts from the published exit state of its left neighbour's last lane, and
+            // a CTA round is repeated only if some warp's last lane changed what it published --
+            // rare, because nearly every subsequence ends on the recorded path whatever its entry.
+            u32 evaluated = 0;   // entry state for which my_end / my_cnt currently hold
             while (true) {
-                bool changed = false;
-                if (eval) {
-                    u32 ne, nc;
-                    walk_merge<S>(u, m, my_start, e0, ltab, shift, ne, nc);
-                    changed = ne != my_end;
-                    my_end = ne;
-                    my_cnt = nc;
-                    if (changed) sm.end[tid] = (u8)ne;
+                bool pub_changed = false;
+                if (worker) {
+                    const u32 warp_in = tid == 0 ? entry : (lane == 0 ? (u32)sm.end[tid - 1] : 0u);
+                    while (true) {
+                        u32 sv = __shfl_up_sync(0xffffffffu, my_end, 1);
+                        if (lane == 0) sv = warp_in;
+                        my_start = sv;
+                        const bool eval = sv != evaluated && tid < real;
+                        bool changed = false;
+                        if (eval) {
+                            u32 ne, nc;
+                            walk_merge<S>(u, m, sv, e0, ltab, shift, ne, nc);
+                            changed = ne != my_end;
+                            my_end = ne;
+                            my_cnt = nc;
+                            evaluated = sv;
+                        }
+                        if (!__any_sync(0xffffffffu, changed)) break;
+                    }
+                    if (my_end != (u32)sm.end[tid]) {
+                        sm.end[tid] = (u8)my_end;
+                        pub_changed = lane == 31;
+                    }
                 }
-                if (!__syncthreads_or(changed)) break;
-                eval = false;
-                if (worker && tid > 0) {
-                    const u32 ns = sm.end[tid - 1];
-                    eval = ns != my_start && tid < real;
-                    my_start = ns;
-                }
-                __syncthreads();
+                if (!__syncthreads_or(pub_changed)) break;
             }
         };
         // exclusive scan of my_cnt over the workers -> pre, sm.total

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-path device-resident timings (CUDA events, best of N) for BASELINE.md section 4.
-Usage: python tools/bench_paths.py [culzss|all] [--mib M]   (one JSON line per measurement)"""
+Usage: python tools/bench_paths.py [cuhd|culzss|cudpp|bsc|all] [--mib M]   (one JSON line per measurement)"""
 import argparse
 import importlib
 import json
@@ -207,6 +207,37 @@ def bench_cuhd(mib, dev):
                       "decode_hbm_frac": (n + C) / dec_ms / 1e6 / PEAK}))
 
 
+def bench_bsc(mib):
+    """libbsc BWT stage (row N4), HOST buffers: GPU bsc_bwt_encode (H2D + suffix sort + D2H inside)
+    next to the reference's divbwt on the host cores (oracle/_ref/libref_bsc.so)."""
+    import time
+    import oracle_lib as O
+    from test_ref_bsc_cpu import synthetic_largefile
+    n = mib << 20
+    for kind, data in (("text", np.frombuffer(synthetic_largefile(n, seed=11), np.uint8)),
+                       ("quant32", O.quant_codes(n))):
+        pkg.bsc_bwt_encode(data[: 1 << 20])          # warm-up: context, work area
+        pkg.bsc_bwt_encode(data)
+        t0 = time.perf_counter()
+        gu, gp, gi = pkg.bsc_bwt_encode(data)
+        gpu_s = time.perf_counter() - t0
+        rec = {"path": "bsc_bwt_encode", "data": kind, "mib": mib, "gpu_ms": gpu_s * 1e3,
+               "gpu_gbs_host_buffers": n / gpu_s / 1e9}
+        if O.have_ref("bsc"):
+            for feat, label in ((0, "cpu_1thread"), (2, "cpu_openmp")):
+                t = data.copy()
+                num = np.zeros(1, np.uint8)
+                idx = np.zeros(256, np.int32)
+                t0 = time.perf_counter()
+                rp = O.ref_bsc().bsc_bwt_encode(t, n, num, idx, feat)
+                s_ = time.perf_counter() - t0
+                rec[label + "_ms"] = s_ * 1e3
+                rec[label + "_gbs"] = n / s_ / 1e9
+                rec["identical"] = bool(rp == gp and np.array_equal(t, gu))
+            rec["host_cores"] = os.cpu_count()
+        print(json.dumps(rec))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -221,6 +252,8 @@ def main():
     if args.what in ("cudpp", "all"):
         for kind in ("zipf", "markov", "rand"):
             bench_cudpp(min(args.mib, 256), dev, kind)
+    if args.what in ("bsc", "all"):
+        bench_bsc(25)
 
 
 if __name__ == "__main__":
