@@ -109,6 +109,13 @@ def cudpp_blocks_gpu(nblocks, n, dev, kind="zipf", seed=95835):
     elif kind == "markov":
         steps = torch.randint(-2, 3, (N,), generator=g, device=dev, dtype=torch.int32)
         out = (torch.cumsum(steps, 0) % 200 + 1).to(torch.uint8)
+    elif kind == "text":
+        # word-structured text (long repeated substrings: many prefix-doubling rounds); 8 distinct
+        # blocks from the CPU generator of tests/test_ref_bsc_cpu.py, repeated
+        from test_ref_bsc_cpu import synthetic_largefile
+        distinct = [torch.frombuffer(bytearray(synthetic_largefile(n, seed=seed + b)), dtype=torch.uint8)
+                    for b in range(min(8, nblocks))]
+        out = torch.cat([distinct[b % len(distinct)] for b in range(nblocks)]).to(dev)
     else:
         out = torch.randint(1, 256, (N,), generator=g, device=dev, dtype=torch.uint8)
     out.view(nblocks, n)[:, -1] = 0
