@@ -174,6 +174,7 @@ struct SmemLayout {
     u8 sub_exit[NSUB];
     u32 warp_sums[T / 32];
     u8 end[T];               // resolved exit state of every subsequence of the current sub-tile
+    u8 wexit[2][T / 32];     // exit state of each warp's last lane, double-buffered by resolution round
     u8 onpath[T];            // sub-tile 0 only: resolved path ends on the recorded path
     u64 bar[2];
     u64 base;
@@ -296,20 +297,23 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
                     for (int j = 0; j < S; ++j) sm.masks[tid * S + j] = m[j];
                 }
             }
+            if (worker && lane == 31) sm.wexit[1][tid >> 5] = (u8)e0;
             __syncthreads();   // tentative exit states (paths from bit 0) visible
             my_start = 0;
             my_end = e0;
             my_cnt = c0;
             // Fixed point of "entry state = exit state of the predecessor".  Inside a warp the
-            // chain is followed with shuffles (no CTA barrier); between warps through sm.end[]:
-            // a warp starts from the published exit state of its left neighbour's last lane, and
-            // a CTA round is repeated only if some warp's last lane changed what it published --
-            // rare, because nearly every subsequence ends on the recorded path whatever its entry.
+            // chain is followed with shuffles (no CTA barrier); between warps through wexit[]:
+            // in round r a warp starts from what its left neighbour's last lane published in
+            // round r-1 and publishes its own exit state for round r+1.  Another CTA round runs
+            // only if some warp published a different state than before -- rare, because nearly
+            // every subsequence ends on the recorded path whatever its entry.
             u32 evaluated = 0;   // entry state for which my_end / my_cnt currently hold
-            while (true) {
+            for (u32 round = 0;; ++round) {
                 bool pub_changed = false;
                 if (worker) {
-                    const u32 warp_in = tid == 0 ? entry : (lane == 0 ? (u32)sm.end[tid - 1] : 0u);
+                    const u32 rd = (round + 1) & 1, wr = round & 1, wid = tid >> 5;
+                    const u32 warp_in = tid == 0 ? entry : (lane == 0 ? (u32)sm.wexit[rd][wid - 1] : 0u);
                     while (true) {
                         u32 sv = __shfl_up_sync(0xffffffffu, my_end, 1);
                         if (lane == 0) sv = warp_in;
@@ -326,9 +330,10 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
                         }
                         if (!__any_sync(0xffffffffu, changed)) break;
                     }
-                    if (my_end != (u32)sm.end[tid]) {
-                        sm.end[tid] = (u8)my_end;
-                        pub_changed = lane == 31;
+                    sm.end[tid] = (u8)my_end;
+                    if (lane == 31) {
+                        pub_changed = my_end != (u32)sm.wexit[rd][wid];
+                        sm.wexit[wr][wid] = (u8)my_end;
                     }
                 }
                 if (!__syncthreads_or(pub_changed)) break;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-path device-resident timings (CUDA events, best of N) for BASELINE.md section 4.
-Usage: python tools/bench_paths.py [cuhd|culzss|cudpp|bsc|all] [--mib M]   (one JSON line per measurement)"""
+Usage: python tools/bench_paths.py [cuhd|culzss|cudpp|bsc|cpu|all] [--mib M]   (one JSON line per measurement)"""
 import argparse
 import importlib
 import json
@@ -214,6 +214,78 @@ def bench_cuhd(mib, dev):
                       "decode_hbm_frac": (n + C) / dec_ms / 1e6 / PEAK}))
 
 
+def _pool_time(fn, items, threads):
+    """Wall time of fn over items on `threads` host threads (ctypes calls release the GIL)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    t0 = time.perf_counter()
+    if threads == 1:
+        out = [fn(x) for x in items]
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            out = list(ex.map(fn, items))
+    return time.perf_counter() - t0, out
+
+
+def bench_cpu(what):
+    """CPU paths timed beside the GPU numbers on the box's own host cores, on a bounded sample of the
+    same synthetic inputs: 1 thread and one block/buffer per core.  CULZSS: the oracle port
+    (oracle/culzss_oracle.c) of EncodeKernel + aftercomp / DecodeKernel -- the reference has no CPU
+    encoder.  cudppCompress: the reference's own CPU golds (computeBwtGold = DC3 sa_gold,
+    computeMtfGold, decoder computeCompressGold; oracle/_ref/libref_cudpp.so) with the oracle port
+    of the Huffman stage (the reference has no CPU Huffman encoder for this stream)."""
+    import ctypes as C
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    buf = 1 << 20
+    if what in ("culzss", "all"):
+        for kind, gen in (("quant32", lambda b: O.quant_codes(buf, seed=2024 + b)),
+                          ("text", lambda b: np.frombuffer((b"the quick brown fox jumps over the lazy dog. " * 23302)[:buf], np.uint8).copy())):
+            bufs = [gen(b) for b in range(cores)]
+            enc1, r1 = _pool_time(lambda x: O.culzss_oracle_compress(x), bufs[:2], 1)
+            encn, rn = _pool_time(lambda x: O.culzss_oracle_compress(x), bufs, cores)
+            comps = [c for ok, c in rn if ok]
+            dec1, _ = _pool_time(lambda c: O.culzss_oracle_decompress(c, buf), comps[:2], 1)
+            decn, back = _pool_time(lambda c: O.culzss_oracle_decompress(c, buf), comps, cores)
+            print(json.dumps({"path": "culzss_cpu", "kind": "port", "data": kind, "cores": cores,
+                              "sample": "%d buffers of 1 MiB (2 for the 1-thread figure)" % len(bufs),
+                              "encode_gbs_1thread": 2 * buf / enc1 / 1e9, "encode_gbs_all_cores": len(bufs) * buf / encn / 1e9,
+                              "decode_gbs_1thread": min(2, len(comps)) * buf / dec1 / 1e9 if comps else None,
+                              "decode_gbs_all_cores": len(comps) * buf / decn / 1e9 if comps else None,
+                              "round_trip": all(bool(np.array_equal(b[1], x)) for b, x in zip(back, bufs))}))
+    if what in ("cudpp", "all") and O.have_ref("cudpp"):
+        R = O.ref_cudpp()
+        for kind in ("zipf", "markov"):
+            blocks = [O.cudpp_block(buf, kind, seed=b) for b in range(cores)]
+
+            def encode(data):
+                bw = np.zeros(buf, np.uint8)
+                idx = C.c_int(-1)
+                R.ref_cudpp_bwt(data, bw, C.byref(idx), buf)
+                mt = np.zeros(buf, np.uint8)
+                R.ref_cudpp_mtf(bw, mt, buf)
+                rc, hist, offs, words = O.cudpp_oracle_huffman(mt)
+                return idx.value, hist, offs, words
+
+            def decode(enc):
+                idx, hist, offs, words = enc
+                out = np.zeros(buf, np.uint8)
+                h257 = np.zeros(257, np.uint32)
+                h257[:256] = hist
+                R.ref_cudpp_decompress(out, idx, h257, offs.copy(), words.size, words.copy(), buf)
+                return out
+
+            enc1, _ = _pool_time(encode, blocks[:1], 1)
+            encn, encs = _pool_time(encode, blocks, cores)
+            dec1, _ = _pool_time(decode, encs[:1], 1)
+            decn, back = _pool_time(decode, encs, cores)
+            print(json.dumps({"path": "cudpp_cpu", "kind": "reference golds + oracle Huffman port", "data": kind,
+                              "cores": cores, "sample": "%d blocks of 1 MiB (1 for the 1-thread figure)" % len(blocks),
+                              "encode_gbs_1thread": buf / enc1 / 1e9, "encode_gbs_all_cores": len(blocks) * buf / encn / 1e9,
+                              "decode_gbs_1thread": buf / dec1 / 1e9, "decode_gbs_all_cores": len(blocks) * buf / decn / 1e9,
+                              "round_trip": all(bool(np.array_equal(b, x)) for b, x in zip(back, blocks))}))
+
+
 def bench_bsc(mib):
     """libbsc BWT stage (row N4), HOST buffers: GPU bsc_bwt_encode (H2D + suffix sort + D2H inside)
     next to the reference's divbwt on the host cores (oracle/_ref/libref_bsc.so)."""
@@ -250,6 +322,9 @@ def main():
     ap.add_argument("what", nargs="?", default="all")
     ap.add_argument("--mib", type=int, default=1024)
     args = ap.parse_args()
+    if args.what == "cpu":
+        bench_cpu("all")
+        return
     dev = torch.device("cuda:0")
     if args.what in ("cuhd", "all"):
         bench_cuhd(args.mib, dev)
@@ -261,6 +336,8 @@ def main():
             bench_cudpp(min(args.mib, 256), dev, kind)
     if args.what in ("bsc", "all"):
         bench_bsc(25)
+    if args.what in ("cpu", "all"):
+        bench_cpu("all")
 
 
 if __name__ == "__main__":

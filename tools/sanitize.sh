@@ -15,4 +15,6 @@ for tool in racecheck memcheck; do
     run $tool culzss tests/test_culzss_gpu.py -k "small_and_multi or hostile or unaligned_offsets"
     run $tool cudpp tests/test_cudpp_gpu.py -k "compress_small_blocks or (inverse_mtf_sizes and (2049 or 4097)) or periodic or (round_trip and (4095 or 4097 or 8192))"
     run $tool bzip2 tests/test_bzip2_gpu.py -k "rotation_order or (block_sort_arrays and 30001)"
+    run $tool prims tests/test_prims_gpu.py -k "(sort_pairs_matches and (4095 or 4097 or 50000 or 300000)) or (scans and (4097 or 31-))"
+    run $tool bsc tests/test_bsc_gpu.py -k "matches_oracle and (n9 or periodic or random_70001)"
 done
