@@ -103,6 +103,8 @@ def lib():
     for name in ("b200lc_exclusive_sum_u32", "b200lc_inclusive_max_u32"):
         f = getattr(L, name)
         f.restype, f.argtypes = i32, [vp, vp, sz, vp, sz, vp]
+    L.b200lc_bzip2_mtf_rle.restype = i32
+    L.b200lc_bzip2_mtf_rle.argtypes = [vp, vp, i32, vp, vp, C.POINTER(i32), vp, C.POINTER(i32)]
     L.bsc_bwt_encode.restype = i32
     L.bsc_bwt_encode.argtypes = [vp, i32, vp, vp, i32]
     L.b200lc_bsc_release.restype = None
@@ -450,3 +452,22 @@ def bsc_bwt_encode(data):
     if p < 0:
         raise B200LCError("bsc_bwt_encode failed with LIBBSC code %d" % p)
     return t, p, idx[: int(num[0])].copy()
+
+
+# ------------------------------------------------------------------------------- bzip2 MTF + RLE stage
+def bzip2_mtf_rle(block, ptr):
+    """bzip2's generateMTFValues on the GPU (include/bzip2_gpu.h).  block: numpy uint8, ptr: numpy
+    uint32 sorted rotation order (host).  Returns (mtfv[nMTF], freq[nInUse + 2], nInUse)."""
+    import numpy as np
+    block = np.ascontiguousarray(block, dtype=np.uint8)
+    ptr = np.ascontiguousarray(ptr, dtype=np.uint32)
+    n = block.size
+    in_use = np.zeros(256, np.uint8)
+    in_use[np.unique(block)] = 1
+    mtfv = np.zeros(n + 1, np.uint16)
+    freq = np.zeros(258, np.int32)
+    n_mtf, used = C.c_int(0), C.c_int(0)
+    check(lib().b200lc_bzip2_mtf_rle(block.ctypes.data, ptr.ctypes.data, n, in_use.ctypes.data,
+                                     mtfv.ctypes.data, C.byref(n_mtf), freq.ctypes.data, C.byref(used)),
+          "b200lc_bzip2_mtf_rle")
+    return mtfv[: n_mtf.value].copy(), freq[: used.value + 2].copy(), used.value

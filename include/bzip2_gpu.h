@@ -42,6 +42,20 @@ int b200lc_bzip2_block_sort(unsigned char *block, unsigned int *orderFirstSort,
 int b200lc_bzip2_rotation_order(const unsigned char *block, int blockSize, unsigned int *ptr,
                                 int *origPtr);
 
+/* bzip2's MTF + zero-run stage: what generateMTFValues computes
+ * (compress.c:122-246).  HOST pointers, synchronous, thread-safe (serialised):
+ *   block[nblock], ptr[nblock]   the block and its sorted rotation order (s->block, s->ptr)
+ *   in_use[256]                  s->inUse (Bool = unsigned char)
+ *   mtfv[nblock + 1]             out: RUNA/RUNB digits, rank + 1 symbols, EOB (s->mtfv; may alias
+ *                                ptr like in the reference: ptr is consumed before mtfv is written)
+ *   *n_mtf                       out: s->nMTF
+ *   mtf_freq[nInUse + 2]         out: s->mtfFreq[0 .. EOB]
+ *   *n_in_use                    out (may be NULL): s->nInUse as makeMaps_e computes it
+ * Returns 0 or a negative B200LC_ERR_* code. */
+int b200lc_bzip2_mtf_rle(const unsigned char *block, const unsigned int *ptr, int nblock,
+                         const unsigned char *in_use, unsigned short *mtfv, int *n_mtf,
+                         int *mtf_freq, int *n_in_use);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,3 +94,50 @@ int bzip2_oracle_merge(const uint8_t *block, int n, int f, const uint32_t *first
     while (b < sl) { order[k] = second[b++]; if (order[k] == 0) origPtr = k; ++k; }
     return origPtr;
 }
+
+/* MTF + zero-run coding of a sorted block: restatement of generateMTFValues
+ * (cuda-bzip2-ipdpsw/compress.c:122-246; makeMaps_e :109-118).  The last column of the sorted
+ * rotations, mapped to the block's dense alphabet, goes through a move-to-front list; runs of
+ * rank 0 are written as their length in bijective base 2 (digits RUNA = 0 / RUNB = 1, least
+ * significant first), every other rank r as r + 1, and EOB = nInUse + 1 closes the block.
+ * Returns nMTF; freq[0 .. EOB] are the symbol counts; *n_in_use the alphabet size. */
+int bzip2_oracle_mtf_rle(const uint8_t *block, const uint32_t *ptr, int n, const uint8_t *in_use,
+                         uint16_t *mtfv, int *freq, int *n_in_use)
+{
+    uint8_t seq[256], list[256];
+    int used = 0;
+    for (int i = 0; i < 256; ++i) if (in_use[i]) seq[i] = (uint8_t)used++;
+    *n_in_use = used;
+    const int eob = used + 1;
+    for (int i = 0; i <= eob; ++i) freq[i] = 0;
+    for (int i = 0; i < used; ++i) list[i] = (uint8_t)i;
+    int wr = 0;
+    long run = 0;
+    for (int i = 0; i <= n; ++i) {
+        int r = 0;
+        if (i < n) {
+            const uint32_t p = ptr[i];
+            const uint8_t c = seq[block[p ? p - 1 : (uint32_t)n - 1]];
+            while (list[r] != c) ++r;
+            if (r == 0) { ++run; continue; }
+            for (int k = r; k > 0; --k) list[k] = list[k - 1];
+            list[0] = c;
+        }
+        /* a non-zero rank or the end of the block flushes the pending run */
+        if (run > 0) {
+            long z = run - 1;
+            for (;;) {
+                const int sym = (int)(z & 1);
+                mtfv[wr++] = (uint16_t)sym;
+                freq[sym]++;
+                if (z < 2) break;
+                z = (z - 2) / 2;
+            }
+            run = 0;
+        }
+        if (i < n) { mtfv[wr++] = (uint16_t)(r + 1); freq[r + 1]++; }
+    }
+    mtfv[wr++] = (uint16_t)eob;
+    freq[eob]++;
+    return wr;
+}

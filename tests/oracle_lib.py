@@ -80,6 +80,9 @@ def oracle():
     lib.bzip2_oracle_block_sort.argtypes = [_u8p, C.c_uint32, _u32p, _u32p, _u32p]
     lib.bzip2_oracle_merge.restype = C.c_int
     lib.bzip2_oracle_merge.argtypes = [_u8p, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p]
+    _u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+    lib.bzip2_oracle_mtf_rle.restype = C.c_int
+    lib.bzip2_oracle_mtf_rle.argtypes = [_u8p, _u32p, C.c_int, _u8p, _u16p, _i32p, C.POINTER(C.c_int)]
     lib.bsc_oracle_bwt_encode.restype = C.c_int
     lib.bsc_oracle_bwt_encode.argtypes = [_u8p, C.c_int, _u8p, _u8p, _i32p]
     _cache["oracle"] = lib
@@ -433,6 +436,41 @@ def bzip2_ref_decompress(comp, n, flavour=""):
     rc = lib.ref_bzip2_decompress(out, C.byref(olen), np.ascontiguousarray(comp), comp.size)
     assert rc == 0, rc
     return out[: olen.value].copy()
+
+
+def bzip2_in_use(block):
+    u = np.zeros(256, np.uint8)
+    u[np.unique(block)] = 1
+    return u
+
+
+def bzip2_oracle_mtf_rle(block, ptr):
+    """-> (mtfv[nMTF], freq[nInUse + 2], nInUse): oracle restatement of generateMTFValues."""
+    n = block.size
+    mtfv = np.zeros(n + 1, np.uint16)
+    freq = np.zeros(258, np.int32)
+    used = C.c_int(0)
+    k = oracle().bzip2_oracle_mtf_rle(np.ascontiguousarray(block), np.ascontiguousarray(ptr, dtype=np.uint32), n,
+                                      bzip2_in_use(block), mtfv, freq, C.byref(used))
+    return mtfv[:k].copy(), freq[: used.value + 2].copy(), used.value
+
+
+def bzip2_ref_mtf_rle(block, ptr):
+    """The reference's own (static) generateMTFValues through oracle/_ref/libref_bzip2_mtf.so."""
+    if "ref_bzip2_mtf" not in _cache:
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libref_bzip2_mtf.so"))
+        lib.ref_bzip2_generate_mtf.restype = C.c_int
+        lib.ref_bzip2_generate_mtf.argtypes = [_u8p, _u32p, C.c_int, _u8p, np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS"),
+                                               _i32p, C.POINTER(C.c_int)]
+        _cache["ref_bzip2_mtf"] = lib
+    n = block.size
+    mtfv = np.zeros(n + 1, np.uint16)
+    freq = np.zeros(258, np.int32)
+    used = C.c_int(0)
+    k = _cache["ref_bzip2_mtf"].ref_bzip2_generate_mtf(np.ascontiguousarray(block),
+                                                       np.ascontiguousarray(ptr, dtype=np.uint32).copy(), n,
+                                                       bzip2_in_use(block), mtfv, freq, C.byref(used))
+    return mtfv[:k].copy(), freq[: used.value + 2].copy(), used.value
 
 
 def bzip2_oracle_block_sort(block):

@@ -106,3 +106,56 @@ def test_reference_libbz2_links_against_libb200lc_and_output_is_identical():
     # (BZ_INITIALISE_CRC at the top of blocksort_wrapper, compress.c:716) and emits zero CRCs, which
     # any bzip2 decoder -- its own included -- rejects.  The block contents are covered by the
     # array-level parity tests above.
+
+
+# ------------------------------------------------------------------------------ MTF + RLE stage (row N2)
+from test_oracle_bzip2 import _mtf_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(_mtf_cases().keys()))
+def test_mtf_rle_matches_oracle_and_reference(name):
+    block = _mtf_cases()[name]
+    n = block.size
+    ptr = np.zeros(n, np.uint32)
+    O.oracle().bzip2_oracle_rotation_order(block, n, ptr)
+    gm, gf, gu = b200lc.bzip2_mtf_rle(block, ptr)
+    om, of, ou = O.bzip2_oracle_mtf_rle(block, ptr)
+    assert gu == ou and gm.size == om.size
+    assert np.array_equal(gm, om) and np.array_equal(gf, of)
+    if O.have_ref("bzip2_mtf"):
+        rm, rf, ru = O.bzip2_ref_mtf_rle(block, ptr)
+        assert np.array_equal(gm, rm) and np.array_equal(gf, rf) and gu == ru
+
+
+def test_mtf_rle_full_900k_block_on_gpu_rotation_order():
+    # a full -9 block: rotation order from the GPU sorter, MTF + RLE on the GPU, against the oracle
+    n = 900000 - 19
+    block = np.concatenate([texty(n // 2, 5), norun_bytes(n - n // 2, 6, alphabet=40)])
+    ptr = np.zeros(n, np.uint32)
+    orig = C.c_int(-1)
+    L = b200lc.lib()
+    L.b200lc_bzip2_rotation_order.restype = C.c_int
+    L.b200lc_bzip2_rotation_order.argtypes = [np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_int,
+                                              np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), C.POINTER(C.c_int)]
+    block = np.ascontiguousarray(block)
+    assert L.b200lc_bzip2_rotation_order(block, n, ptr, C.byref(orig)) == 0
+    gm, gf, gu = b200lc.bzip2_mtf_rle(block, ptr)
+    om, of, ou = O.bzip2_oracle_mtf_rle(block, ptr)
+    assert gu == ou and np.array_equal(gm, om) and np.array_equal(gf, of)
+
+
+@pytest.mark.skipif(not (O.have_ref("bzip2") and O.have_ref("bzip2_b200mtf")), reason="oracle/_ref bzip2 libs not built")
+def test_reference_libbz2_with_gpu_sort_and_gpu_mtf_rle_is_byte_identical():
+    # the reference library with BOTH its block sort and its generateMTFValues replaced by
+    # libb200lc.so (oracle/_ref/libref_bzip2_b200mtf.so) writes the same .bz2 stream
+    data = np.concatenate([norun_bytes(250000, 1, alphabet=16), texty(199905, 2)])
+    bs = 100000 - 19
+    for lo in range(0, data.size, bs):
+        blk = np.ascontiguousarray(data[lo:lo + bs])
+        f, a, b, r = O.bzip2_oracle_block_sort(blk)
+        _, orig = O.bzip2_oracle_merge(blk, f, a, b, r)
+        if orig < 0:
+            pytest.skip("input would trip the reference's origPtr bug")
+    ref = O.bzip2_ref_compress(data, 1, 0, "")
+    mine = O.bzip2_ref_compress(data, 1, 0, "_b200mtf")
+    assert ref.size == mine.size and np.array_equal(ref, mine)

@@ -28,3 +28,31 @@ def test_merge_of_block_sort_arrays_is_rotation_order(n, kind):
     order, orig = O.bzip2_oracle_merge(block, f, first, second, rank)
     assert np.array_equal(order, ptr)
     assert orig == -1 or ptr[orig] == 0
+
+
+def _mtf_cases():
+    rng = np.random.default_rng(9)
+    text = np.frombuffer((b"it was the best of times, it was the worst of times, " * 2000), np.uint8)
+    return {
+        "single_symbol": np.full(5000, 65, np.uint8),                  # one long zero run
+        "two_symbols": rng.integers(7, 9, 3000, dtype=np.uint8),
+        "binary_runs": np.repeat(rng.integers(0, 2, 400, dtype=np.uint8), rng.integers(1, 40, 400)),
+        "text_100k": text[:100000].copy(),
+        "random_50k": rng.integers(0, 256, 50000, dtype=np.uint8),
+        "zipf_120k": O.zipf_bytes(120000, 1.5, seed=4),
+        "n1": np.array([200], np.uint8),
+    }
+
+
+@pytest.mark.skipif(not O.have_ref("bzip2_mtf"), reason="oracle/_ref/libref_bzip2_mtf.so not built")
+@pytest.mark.parametrize("name", list(_mtf_cases().keys()))
+def test_mtf_rle_oracle_equals_reference_generateMTFValues(name):
+    block = _mtf_cases()[name]
+    n = block.size
+    ptr = np.zeros(n, np.uint32)
+    O.oracle().bzip2_oracle_rotation_order(block, n, ptr)
+    om, of, ou = O.bzip2_oracle_mtf_rle(block, ptr)
+    rm, rf, ru = O.bzip2_ref_mtf_rle(block, ptr)
+    assert ou == ru and om.size == rm.size
+    assert np.array_equal(om, rm) and np.array_equal(of, rf)
+    assert om[-1] == ou + 1 and int(of.sum()) == om.size       # EOB last; every symbol counted once
