@@ -105,6 +105,8 @@ def lib():
         f.restype, f.argtypes = i32, [vp, vp, sz, vp, sz, vp]
     L.b200lc_bzip2_mtf_rle.restype = i32
     L.b200lc_bzip2_mtf_rle.argtypes = [vp, vp, i32, vp, vp, C.POINTER(i32), vp, C.POINTER(i32)]
+    L.b200lc_bzip2_send_mtf_values.restype = i32
+    L.b200lc_bzip2_send_mtf_values.argtypes = [vp, i32, vp, vp, i32, vp, sz, C.POINTER(C.c_ulonglong), vp, vp]
     L.bsc_bwt_encode.restype = i32
     L.bsc_bwt_encode.argtypes = [vp, i32, vp, vp, i32]
     L.b200lc_bsc_release.restype = None
@@ -471,3 +473,23 @@ def bzip2_mtf_rle(block, ptr):
                                      mtfv.ctypes.data, C.byref(n_mtf), freq.ctypes.data, C.byref(used)),
           "b200lc_bzip2_mtf_rle")
     return mtfv[: n_mtf.value].copy(), freq[: used.value + 2].copy(), used.value
+
+
+def bzip2_send_mtf_values(mtfv, freq, in_use, n_in_use):
+    """bzip2's sendMTFValues on the GPU (include/bzip2_gpu.h), host numpy arrays.
+    Returns (bits bytes, nbits, len[6][258], selector[ceil(nMTF / 50)])."""
+    import numpy as np
+    mtfv = np.ascontiguousarray(mtfv, dtype=np.uint16)
+    n = mtfv.size
+    f = np.zeros(258, np.int32)
+    f[: len(freq)] = freq
+    iu = np.ascontiguousarray(in_use, dtype=np.uint8)
+    cap = n * 17 // 8 + n // 50 + 8192
+    bits = np.zeros(cap, np.uint8)
+    nbits = C.c_ulonglong(0)
+    lens = np.zeros((6, 258), np.uint8)
+    sel = np.zeros((n + 49) // 50, np.uint8)
+    check(lib().b200lc_bzip2_send_mtf_values(mtfv.ctypes.data, n, f.ctypes.data, iu.ctypes.data, n_in_use,
+                                             bits.ctypes.data, cap, C.byref(nbits), lens.ctypes.data,
+                                             sel.ctypes.data), "b200lc_bzip2_send_mtf_values")
+    return bits[: (nbits.value + 7) // 8].copy(), nbits.value, lens, sel

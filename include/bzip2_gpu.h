@@ -56,6 +56,21 @@ int b200lc_bzip2_mtf_rle(const unsigned char *block, const unsigned int *ptr, in
                          const unsigned char *in_use, unsigned short *mtfv, int *n_mtf,
                          int *mtf_freq, int *n_in_use);
 
+/* bzip2's Huffman stage: the bit string sendMTFValues hands to bsW
+ * (compress.c:252-606; huffman.c:63-153): symbol map, 5-bit table count and 17-bit selector count
+ * (this fork's field widths, compress.c:524-527), unary move-to-front coded selectors, delta coded
+ * code lengths, the symbols.  HOST pointers, synchronous, thread-safe (serialised):
+ *   mtfv[n_mtf], mtf_freq[n_in_use + 2], in_use[256], n_in_use    outputs of the MTF + RLE stage
+ *   bits[bits_cap]     out: the bit string, MSB first; *n_bits its length in bits
+ *   len_out            out (may be NULL): s->len, unsigned char [6][258]
+ *   selector_out       out (may be NULL): s->selector[ceil(n_mtf / 50)]
+ * Returns 0 or a negative B200LC_ERR_* code (B200LC_ERR_OVERFLOW: bits_cap too small;
+ * n_mtf * 17 / 8 + n_mtf / 50 + 8192 bytes always suffice). */
+int b200lc_bzip2_send_mtf_values(const unsigned short *mtfv, int n_mtf, const int *mtf_freq,
+                                 const unsigned char *in_use, int n_in_use, unsigned char *bits,
+                                 size_t bits_cap, unsigned long long *n_bits, unsigned char *len_out,
+                                 unsigned char *selector_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,3 +141,178 @@ int bzip2_oracle_mtf_rle(const uint8_t *block, const uint32_t *ptr, int n, const
     freq[eob]++;
     return wr;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Huffman stage of a bzip2 block: restatement of sendMTFValues
+ * (cuda-bzip2-ipdpsw/compress.c:252-606) with BZ2_hbMakeCodeLengths / BZ2_hbAssignCodes
+ * (huffman.c:63-153), written as separate steps:
+ *   tables      2..6 by nMTF (:274-279); initial tables = consecutive symbol ranges of roughly
+ *               equal total frequency, cost 0 inside / 15 outside (:282-319)
+ *   4 rounds    every 50-symbol group picks the FIRST cheapest table, the table's frequencies
+ *               are re-counted from its groups and its code lengths rebuilt (limit 17) (:324-444)
+ *   lengths     a min-heap on weight = freq << 8 | depth merges the two lightest nodes (ties by
+ *               heap order); if a length exceeds the limit all weights are halved (+1) and the
+ *               build repeats (huffman.c:63-153)
+ *   stream      used-symbol map (16 + 16 per non-empty row), 5 bits nGroups and 17 bits
+ *               nSelectors (this fork widened both fields, :524-527), selectors move-to-front
+ *               coded in unary, code lengths delta coded, then the symbols (:458-603)
+ * Bits are written MSB first into `bits` (zeroed by the caller); *nbits = their number. */
+typedef struct { uint8_t *buf; uint64_t n; } bz_bits_t;
+
+static void bz_put(bz_bits_t *w, int nb, uint32_t v)
+{
+    for (int k = nb - 1; k >= 0; --k, ++w->n)
+        if ((v >> k) & 1u) w->buf[w->n >> 3] |= (uint8_t)(0x80u >> (w->n & 7));
+}
+
+static void bz_sift_up(int *heap, const int *weight, int z)
+{
+    const int node = heap[z];
+    while (weight[node] < weight[heap[z >> 1]]) { heap[z] = heap[z >> 1]; z >>= 1; }
+    heap[z] = node;
+}
+
+static void bz_sift_down(int *heap, const int *weight, int count, int z)
+{
+    const int node = heap[z];
+    for (;;) {
+        int child = z << 1;
+        if (child > count) break;
+        if (child < count && weight[heap[child + 1]] < weight[heap[child]]) ++child;
+        if (weight[node] < weight[heap[child]]) break;
+        heap[z] = heap[child];
+        z = child;
+    }
+    heap[z] = node;
+}
+
+void bzip2_oracle_code_lengths(uint8_t *len, const int *freq, int alpha, int limit)
+{
+    int heap[260], weight[516], parent[516];
+    for (int i = 0; i < alpha; ++i) weight[i + 1] = (freq[i] == 0 ? 1 : freq[i]) << 8;
+    for (;;) {
+        int nodes = alpha, count = 0;
+        heap[0] = 0; weight[0] = 0; parent[0] = -2;
+        for (int i = 1; i <= alpha; ++i) { parent[i] = -1; heap[++count] = i; bz_sift_up(heap, weight, count); }
+        while (count > 1) {
+            const int a = heap[1]; heap[1] = heap[count--]; bz_sift_down(heap, weight, count, 1);
+            const int b = heap[1]; heap[1] = heap[count--]; bz_sift_down(heap, weight, count, 1);
+            ++nodes;
+            parent[a] = parent[b] = nodes;
+            const int da = weight[a] & 0xff, db = weight[b] & 0xff;
+            weight[nodes] = (int)(((uint32_t)weight[a] & 0xffffff00u) + ((uint32_t)weight[b] & 0xffffff00u)) |
+                            (1 + (da > db ? da : db));
+            parent[nodes] = -1;
+            heap[++count] = nodes;
+            bz_sift_up(heap, weight, count);
+        }
+        int too_long = 0;
+        for (int i = 1; i <= alpha; ++i) {
+            int depth = 0;
+            for (int k = i; parent[k] >= 0; k = parent[k]) ++depth;
+            len[i - 1] = (uint8_t)depth;
+            if (depth > limit) too_long = 1;
+        }
+        if (!too_long) return;
+        for (int i = 1; i <= alpha; ++i) weight[i] = (1 + (weight[i] >> 8) / 2) << 8;
+    }
+}
+
+int bzip2_oracle_send_mtf(const uint16_t *mtfv, int nMTF, const int *mtfFreq, const uint8_t *in_use,
+                          int n_in_use, uint8_t *bits, uint64_t *nbits, uint8_t *len_out /*[6][258]*/,
+                          uint8_t *selector_out, int *n_groups_out, int *n_selectors_out)
+{
+    enum { G = 50, MAXA = 258 };
+    const int alpha = n_in_use + 2;
+    static uint8_t len[6][MAXA];
+    static int code[6][MAXA], rfreq[6][MAXA];
+    if (nMTF <= 0 || alpha > MAXA) return -1;
+    const int groups = nMTF < 200 ? 2 : nMTF < 600 ? 3 : nMTF < 1200 ? 4 : nMTF < 2400 ? 5 : 6;
+    const int nsel = (nMTF + G - 1) / G;
+    uint8_t *selector = (uint8_t *)malloc((size_t)nsel);
+    for (int t = 0; t < 6; ++t) for (int v = 0; v < alpha; ++v) len[t][v] = 15;
+
+    /* initial tables */
+    {
+        int part = groups, remaining = nMTF, first = 0;
+        while (part > 0) {
+            const int target = remaining / part;
+            int last = first - 1, acc = 0;
+            while (acc < target && last < alpha - 1) acc += mtfFreq[++last];
+            if (last > first && part != groups && part != 1 && ((groups - part) % 2 == 1)) acc -= mtfFreq[last--];
+            for (int v = 0; v < alpha; ++v) len[part - 1][v] = (v >= first && v <= last) ? 0 : 15;
+            --part;
+            first = last + 1;
+            remaining -= acc;
+        }
+    }
+    /* refinement rounds */
+    for (int round = 0; round < 4; ++round) {
+        for (int t = 0; t < groups; ++t) for (int v = 0; v < alpha; ++v) rfreq[t][v] = 0;
+        for (int g = 0; g < nsel; ++g) {
+            const int lo = g * G, hi = lo + G < nMTF ? lo + G : nMTF;
+            int best = -1;
+            uint32_t best_cost = 999999999u;
+            for (int t = 0; t < groups; ++t) {
+                uint16_t c = 0;                               /* UInt16 cost[] (:259) */
+                for (int i = lo; i < hi; ++i) c = (uint16_t)(c + len[t][mtfv[i]]);
+                if (c < best_cost) { best_cost = c; best = t; }
+            }
+            selector[g] = (uint8_t)best;
+            for (int i = lo; i < hi; ++i) rfreq[best][mtfv[i]]++;
+        }
+        for (int t = 0; t < groups; ++t) bzip2_oracle_code_lengths(len[t], rfreq[t], alpha, 17);
+    }
+    /* canonical codes per table (huffman.c:134-153) */
+    for (int t = 0; t < groups; ++t) {
+        int lo = 32, hi = 0, next = 0;
+        for (int i = 0; i < alpha; ++i) { if (len[t][i] > hi) hi = len[t][i]; if (len[t][i] < lo) lo = len[t][i]; }
+        for (int n = lo; n <= hi; ++n) {
+            for (int i = 0; i < alpha; ++i) if (len[t][i] == n) code[t][i] = next++;
+            next <<= 1;
+        }
+    }
+    bz_bits_t w = { bits, 0 };
+    /* symbol map */
+    int row_used[16];
+    for (int r = 0; r < 16; ++r) { row_used[r] = 0; for (int c = 0; c < 16; ++c) if (in_use[r * 16 + c]) row_used[r] = 1; }
+    for (int r = 0; r < 16; ++r) bz_put(&w, 1, (uint32_t)row_used[r]);
+    for (int r = 0; r < 16; ++r) if (row_used[r]) for (int c = 0; c < 16; ++c) bz_put(&w, 1, in_use[r * 16 + c] ? 1u : 0u);
+    bz_put(&w, 5, (uint32_t)groups);
+    bz_put(&w, 17, (uint32_t)nsel);
+    /* selectors: move-to-front rank in unary */
+    {
+        uint8_t order[6];
+        for (int t = 0; t < groups; ++t) order[t] = (uint8_t)t;
+        for (int g = 0; g < nsel; ++g) {
+            int r = 0;
+            while (order[r] != selector[g]) ++r;
+            for (int k = r; k > 0; --k) order[k] = order[k - 1];
+            order[0] = selector[g];
+            for (int k = 0; k < r; ++k) bz_put(&w, 1, 1);
+            bz_put(&w, 1, 0);
+        }
+    }
+    /* code lengths, delta coded */
+    for (int t = 0; t < groups; ++t) {
+        int cur = len[t][0];
+        bz_put(&w, 5, (uint32_t)cur);
+        for (int i = 0; i < alpha; ++i) {
+            while (cur < len[t][i]) { bz_put(&w, 2, 2); ++cur; }
+            while (cur > len[t][i]) { bz_put(&w, 2, 3); --cur; }
+            bz_put(&w, 1, 0);
+        }
+    }
+    /* symbols */
+    for (int i = 0; i < nMTF; ++i) {
+        const int t = selector[i / G];
+        bz_put(&w, len[t][mtfv[i]], (uint32_t)code[t][mtfv[i]]);
+    }
+    *nbits = w.n;
+    if (len_out) memcpy(len_out, len, sizeof(len));
+    if (selector_out) memcpy(selector_out, selector, (size_t)nsel);
+    if (n_groups_out) *n_groups_out = groups;
+    if (n_selectors_out) *n_selectors_out = nsel;
+    free(selector);
+    return 0;
+}

@@ -83,6 +83,11 @@ def oracle():
     _u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
     lib.bzip2_oracle_mtf_rle.restype = C.c_int
     lib.bzip2_oracle_mtf_rle.argtypes = [_u8p, _u32p, C.c_int, _u8p, _u16p, _i32p, C.POINTER(C.c_int)]
+    lib.bzip2_oracle_send_mtf.restype = C.c_int
+    lib.bzip2_oracle_send_mtf.argtypes = [_u16p, C.c_int, _i32p, _u8p, C.c_int, _u8p, C.POINTER(C.c_uint64), _u8p,
+                                          _u8p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.bzip2_oracle_code_lengths.restype = None
+    lib.bzip2_oracle_code_lengths.argtypes = [_u8p, _i32p, C.c_int, C.c_int]
     lib.bsc_oracle_bwt_encode.restype = C.c_int
     lib.bsc_oracle_bwt_encode.argtypes = [_u8p, C.c_int, _u8p, _u8p, _i32p]
     _cache["oracle"] = lib
@@ -471,6 +476,42 @@ def bzip2_ref_mtf_rle(block, ptr):
                                                        np.ascontiguousarray(ptr, dtype=np.uint32).copy(), n,
                                                        bzip2_in_use(block), mtfv, freq, C.byref(used))
     return mtfv[:k].copy(), freq[: used.value + 2].copy(), used.value
+
+
+def bzip2_oracle_send_mtf(mtfv, freq, in_use, n_in_use):
+    """Oracle restatement of sendMTFValues -> (bits bytes, nbits, len[6][258], selector[nsel], nGroups)."""
+    n = mtfv.size
+    bits = np.zeros(n * 3 + 4096, np.uint8)
+    nbits = C.c_uint64(0)
+    lens = np.zeros((6, 258), np.uint8)
+    sel = np.zeros((n + 49) // 50 + 1, np.uint8)
+    ng, ns = C.c_int(0), C.c_int(0)
+    f = np.zeros(258, np.int32)
+    f[: freq.size] = freq
+    rc = oracle().bzip2_oracle_send_mtf(np.ascontiguousarray(mtfv), n, f, np.ascontiguousarray(in_use), n_in_use,
+                                        bits, C.byref(nbits), lens, sel, C.byref(ng), C.byref(ns))
+    assert rc == 0
+    return bits[: (nbits.value + 7) // 8].copy(), nbits.value, lens, sel[: ns.value].copy(), ng.value
+
+
+def bzip2_ref_send_mtf(mtfv, freq, in_use, n_in_use):
+    """The reference's own (static) sendMTFValues through oracle/_ref/libref_bzip2_mtf.so."""
+    bzip2_ref_mtf_rle(np.array([1], np.uint8), np.array([0], np.uint32))      # loads the library
+    lib = _cache["ref_bzip2_mtf"]
+    _u16 = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+    lib.ref_bzip2_send_mtf.restype = C.c_int
+    lib.ref_bzip2_send_mtf.argtypes = [_u16, C.c_int, _i32p, _u8p, C.c_int, _u8p, C.POINTER(C.c_uint64), _u8p, _u8p]
+    n = mtfv.size
+    bits = np.zeros(n * 3 + 4096, np.uint8)
+    nbits = C.c_uint64(0)
+    lens = np.zeros((6, 258), np.uint8)
+    sel = np.zeros((n + 49) // 50 + 1, np.uint8)
+    f = np.zeros(258, np.int32)
+    f[: freq.size] = freq
+    rc = lib.ref_bzip2_send_mtf(np.ascontiguousarray(mtfv).copy(), n, f, np.ascontiguousarray(in_use), n_in_use, bits,
+                                C.byref(nbits), lens, sel)
+    assert rc == 0
+    return bits[: (nbits.value + 7) // 8].copy(), nbits.value, lens, sel[: (n + 49) // 50].copy()
 
 
 def bzip2_oracle_block_sort(block):

@@ -159,3 +159,57 @@ def test_reference_libbz2_with_gpu_sort_and_gpu_mtf_rle_is_byte_identical():
     ref = O.bzip2_ref_compress(data, 1, 0, "")
     mine = O.bzip2_ref_compress(data, 1, 0, "_b200mtf")
     assert ref.size == mine.size and np.array_equal(ref, mine)
+
+
+# ------------------------------------------------------------------------------ Huffman stage (row N2)
+@pytest.mark.parametrize("name", list(_mtf_cases().keys()))
+def test_send_mtf_values_matches_oracle_and_reference(name):
+    block = _mtf_cases()[name]
+    n = block.size
+    ptr = np.zeros(n, np.uint32)
+    O.oracle().bzip2_oracle_rotation_order(block, n, ptr)
+    mtfv, freq, used = O.bzip2_oracle_mtf_rle(block, ptr)
+    in_use = O.bzip2_in_use(block)
+    gb, gn, gl, gsel = b200lc.bzip2_send_mtf_values(mtfv, freq, in_use, used)
+    ob, on, ol, osel, og = O.bzip2_oracle_send_mtf(mtfv, freq, in_use, used)
+    assert gn == on and np.array_equal(gsel, osel)
+    assert np.array_equal(gl[:og, : used + 2], ol[:og, : used + 2])
+    assert np.array_equal(gb, ob)
+    if O.have_ref("bzip2_mtf"):
+        rb, rn, rl, rsel = O.bzip2_ref_send_mtf(mtfv, freq, in_use, used)
+        assert gn == rn and np.array_equal(gb, rb)
+
+
+def test_back_end_of_a_full_900k_block_on_the_gpu():
+    # sort -> MTF + RLE -> Huffman stage of one -9 block, every stage on the GPU, against the oracle
+    n = 900000 - 19
+    block = np.ascontiguousarray(np.concatenate([texty(n // 2, 5), norun_bytes(n - n // 2, 6, alphabet=40)]))
+    L = b200lc.lib()
+    L.b200lc_bzip2_rotation_order.restype = C.c_int
+    L.b200lc_bzip2_rotation_order.argtypes = [np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_int,
+                                              np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), C.POINTER(C.c_int)]
+    ptr = np.zeros(n, np.uint32)
+    orig = C.c_int(-1)
+    assert L.b200lc_bzip2_rotation_order(block, n, ptr, C.byref(orig)) == 0
+    mtfv, freq, used = b200lc.bzip2_mtf_rle(block, ptr)
+    in_use = O.bzip2_in_use(block)
+    gb, gn, gl, gsel = b200lc.bzip2_send_mtf_values(mtfv, freq, in_use, used)
+    ob, on, ol, osel, og = O.bzip2_oracle_send_mtf(mtfv, freq, in_use, used)
+    assert og == 6 and gn == on and np.array_equal(gsel, osel) and np.array_equal(gb, ob)
+    assert gn < 8 * n // 2
+
+
+@pytest.mark.skipif(not (O.have_ref("bzip2") and O.have_ref("bzip2_b200full")), reason="oracle/_ref bzip2 libs not built")
+def test_reference_libbz2_with_whole_gpu_back_end_is_byte_identical():
+    # sort, generateMTFValues and sendMTFValues all from libb200lc.so (oracle/_ref/libref_bzip2_b200full.so)
+    data = np.concatenate([norun_bytes(250000, 1, alphabet=16), texty(199905, 2)])
+    bs = 100000 - 19
+    for lo in range(0, data.size, bs):
+        blk = np.ascontiguousarray(data[lo:lo + bs])
+        f, a, b, r = O.bzip2_oracle_block_sort(blk)
+        _, orig = O.bzip2_oracle_merge(blk, f, a, b, r)
+        if orig < 0:
+            pytest.skip("input would trip the reference's origPtr bug")
+    ref = O.bzip2_ref_compress(data, 1, 0, "")
+    mine = O.bzip2_ref_compress(data, 1, 0, "_b200full")
+    assert ref.size == mine.size and np.array_equal(ref, mine)

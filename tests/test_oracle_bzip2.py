@@ -56,3 +56,52 @@ def test_mtf_rle_oracle_equals_reference_generateMTFValues(name):
     assert ou == ru and om.size == rm.size
     assert np.array_equal(om, rm) and np.array_equal(of, rf)
     assert om[-1] == ou + 1 and int(of.sum()) == om.size       # EOB last; every symbol counted once
+
+
+@pytest.mark.skipif(not O.have_ref("bzip2_mtf"), reason="oracle/_ref/libref_bzip2_mtf.so not built")
+@pytest.mark.parametrize("name", list(_mtf_cases().keys()))
+def test_send_mtf_oracle_equals_reference_sendMTFValues(name):
+    block = _mtf_cases()[name]
+    n = block.size
+    ptr = np.zeros(n, np.uint32)
+    O.oracle().bzip2_oracle_rotation_order(block, n, ptr)
+    mtfv, freq, used = O.bzip2_oracle_mtf_rle(block, ptr)
+    in_use = O.bzip2_in_use(block)
+    ob, on, ol, osel, og = O.bzip2_oracle_send_mtf(mtfv, freq, in_use, used)
+    rb, rn, rl, rsel = O.bzip2_ref_send_mtf(mtfv, freq, in_use, used)
+    assert on == rn
+    assert np.array_equal(osel, rsel)
+    assert np.array_equal(ol[:og, : used + 2], rl[:og, : used + 2])
+    assert np.array_equal(ob, rb)
+
+
+@pytest.mark.skipif(not O.have_ref("bzip2"), reason="oracle/_ref/libref_bzip2.so not built")
+def test_code_lengths_oracle_equals_reference_hbMakeCodeLengths():
+    import ctypes as C
+    import os
+    lib = C.CDLL(os.path.join(O.ORACLE_DIR, "_ref", "libref_bzip2.so"))
+    ref = getattr(lib, "_Z21BZ2_hbMakeCodeLengthsPhPiii")        # compiled as C++ (Makefile:18)
+    ref.restype = None
+    rng = np.random.default_rng(3)
+    for trial in range(60):
+        alpha = int(rng.integers(3, 259))
+        kind = trial % 4
+        if kind == 0:
+            freq = rng.integers(0, 50, alpha)
+        elif kind == 1:
+            freq = (rng.pareto(0.7, alpha) * 10).astype(np.int64) % 2000000      # heavy tail: limit 17 gets hit
+        elif kind == 2:
+            freq = np.zeros(alpha, np.int64)
+            freq[rng.integers(0, alpha, 3)] = rng.integers(1, 1000, 3)
+        else:
+            fib = [1, 1]
+            while len(fib) < alpha:
+                fib.append(min(fib[-1] + fib[-2], 4000000 // alpha))     # (freq << 8) must stay inside int32
+            freq = np.array(fib[:alpha])
+        freq = np.ascontiguousarray(freq, dtype=np.int32)
+        a = np.zeros(alpha, np.uint8)
+        b = np.zeros(alpha, np.uint8)
+        O.oracle().bzip2_oracle_code_lengths(a, freq, alpha, 17)
+        ref(b.ctypes.data_as(C.c_void_p), freq.ctypes.data_as(C.c_void_p), alpha, 17)
+        assert np.array_equal(a, b), (trial, alpha)
+        assert a.max() <= 17 and a.min() >= 1

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-path device-resident timings (CUDA events, best of N) for BASELINE.md section 4.
-Usage: python tools/bench_paths.py [cuhd|culzss|cudpp|bsc|cpu|all] [--mib M]   (one JSON line per measurement)"""
+Usage: python tools/bench_paths.py [cuhd|culzss|cudpp|bsc|bzip2|cpu|all] [--mib M]   (one JSON line per measurement)"""
 import argparse
 import importlib
 import json
@@ -286,6 +286,52 @@ def bench_cpu(what):
                               "round_trip": all(bool(np.array_equal(b, x)) for b, x in zip(back, blocks))}))
 
 
+def bench_bzip2():
+    """cuda-bzip2 back end of one -9 block (900 kB), HOST pointers like the reference's gpuBlockSort:
+    GPU sort (b200lc_bzip2_rotation_order), MTF + RUNA/RUNB (b200lc_bzip2_mtf_rle), Huffman stage
+    (b200lc_bzip2_send_mtf_values) next to the reference's own generateMTFValues + sendMTFValues
+    on one host core (oracle/_ref/libref_bzip2_mtf.so: the "serial huffman.c stage" baseline)."""
+    import ctypes as C
+    import time
+    import oracle_lib as O
+    from test_ref_bsc_cpu import synthetic_largefile
+    n = 900000 - 19
+    L = pkg.lib()
+    L.b200lc_bzip2_rotation_order.restype = C.c_int
+    L.b200lc_bzip2_rotation_order.argtypes = [np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_int,
+                                              np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), C.POINTER(C.c_int)]
+    for kind, block in (("text", np.frombuffer(synthetic_largefile(n, seed=3), np.uint8).copy()),
+                        ("quant32", O.quant_codes(n + 3)[:n].copy())):
+        ptr = np.zeros(n, np.uint32)
+        orig = C.c_int(-1)
+        in_use = O.bzip2_in_use(block)
+
+        def best(fn, reps=3):
+            out, t = None, 1e30
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                out = fn()
+                t = min(t, time.perf_counter() - t0)
+            return t, out
+
+        L.b200lc_bzip2_rotation_order(block, n, ptr, C.byref(orig))      # warm-up (context, work areas)
+        t_sort, _ = best(lambda: L.b200lc_bzip2_rotation_order(block, n, ptr, C.byref(orig)))
+        pkg.bzip2_mtf_rle(block, ptr)
+        t_mtf, (mtfv, freq, used) = best(lambda: pkg.bzip2_mtf_rle(block, ptr))
+        pkg.bzip2_send_mtf_values(mtfv, freq, in_use, used)
+        t_huf, (gb, gn, _, _) = best(lambda: pkg.bzip2_send_mtf_values(mtfv, freq, in_use, used))
+        rec = {"path": "bzip2_block_back_end", "data": kind, "block_bytes": n, "ratio": 8.0 * n / gn,
+               "gpu_sort_ms": t_sort * 1e3, "gpu_mtf_rle_ms": t_mtf * 1e3, "gpu_huffman_ms": t_huf * 1e3,
+               "gpu_gbs_host_buffers": n / (t_sort + t_mtf + t_huf) / 1e9}
+        if O.have_ref("bzip2_mtf"):
+            c_mtf, (rm, rf, ru) = best(lambda: O.bzip2_ref_mtf_rle(block, ptr), 2)
+            c_huf, (rb, rn, _, _) = best(lambda: O.bzip2_ref_send_mtf(rm, rf, in_use, ru), 2)
+            rec.update({"cpu_generateMTFValues_ms": c_mtf * 1e3, "cpu_sendMTFValues_ms": c_huf * 1e3, "cpu_cores": 1,
+                        "cpu_gbs_mtf_huffman": n / (c_mtf + c_huf) / 1e9,
+                        "identical": bool(rn == gn and np.array_equal(rb, gb) and np.array_equal(rm, mtfv))})
+        print(json.dumps(rec))
+
+
 def bench_bsc(mib):
     """libbsc BWT stage (row N4), HOST buffers: GPU bsc_bwt_encode (H2D + suffix sort + D2H inside)
     next to the reference's divbwt on the host cores (oracle/_ref/libref_bsc.so)."""
@@ -336,6 +382,8 @@ def main():
             bench_cudpp(min(args.mib, 256), dev, kind)
     if args.what in ("bsc", "all"):
         bench_bsc(25)
+    if args.what in ("bzip2", "all"):
+        bench_bzip2()
     if args.what in ("cpu", "all"):
         bench_cpu("all")
 
