@@ -38,6 +38,10 @@ def lib():
     L.b200lc_cuhd_decode_scratch_bytes.argtypes = [sz]
     L.b200lc_cuhd_decode.restype = i32
     L.b200lc_cuhd_decode.argtypes = [vp, sz, vp, sz, vp, i32, vp, sz, vp]
+    L.b200lc_cuhd_decode_batch_scratch_bytes.restype = sz
+    L.b200lc_cuhd_decode_batch_scratch_bytes.argtypes = [vp, sz]
+    L.b200lc_cuhd_decode_batch.restype = i32
+    L.b200lc_cuhd_decode_batch.argtypes = [vp, vp, vp, sz, vp, i32, vp, sz, vp]
     L.b200lc_histogram_u8.restype = i32
     L.b200lc_histogram_u8.argtypes = [vp, sz, vp, vp]
     L.b200lc_cuhd_build_table.restype = i32
@@ -144,6 +148,24 @@ def cuhd_decode(units, n_out, lut, max_len=11, out=None, scratch=None, stream=No
     rc = L.b200lc_cuhd_decode(units.data_ptr(), n_units, out.data_ptr(), n_out, lut.data_ptr(),
                               max_len, scratch.data_ptr(), scratch.numel(), _stream_ptr(stream))
     check(rc, "b200lc_cuhd_decode")
+    return out
+
+
+def cuhd_decode_batch(units, out, streams, lut, max_len=11, scratch=None, stream=None):
+    """Decode many independent streams sharing one table with one launch.  units: cuda int32 tensor
+    holding all streams, out: cuda uint8 tensor, streams: numpy uint64 array [n, 4] of
+    (unit_offset, n_units, out_offset, n_out).  Asynchronous."""
+    import numpy as np
+    import torch
+    st = np.ascontiguousarray(streams, dtype=np.uint64)
+    assert st.ndim == 2 and st.shape[1] == 4
+    L = lib()
+    need = L.b200lc_cuhd_decode_batch_scratch_bytes(st.ctypes.data, st.shape[0])
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=units.device)
+    check(L.b200lc_cuhd_decode_batch(units.data_ptr(), out.data_ptr(), st.ctypes.data, st.shape[0],
+                                     lut.data_ptr(), max_len, scratch.data_ptr(), scratch.numel(),
+                                     _stream_ptr(stream)), "b200lc_cuhd_decode_batch")
     return out
 
 

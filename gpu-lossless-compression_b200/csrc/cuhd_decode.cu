@@ -28,6 +28,8 @@
 // `{u8 num_bits, u8 symbol}[1 << max_codeword_length]`; units past n_units read as zero.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "../../include/b200lc.h"
 
@@ -55,19 +57,31 @@ struct __align__(64) TileDesc {
 static_assert(sizeof(TileDesc) == 64, "descriptor is 64 bytes");
 constexpr u64 kAggValid = 1ull << 63;
 
-struct DecodeParams {
+// One independent bit stream (codes start at bit 0 of its first unit, entry state 0) and the
+// range of pieces that decodes it.  A single-stream call carries its view inside the kernel
+// parameters; a batch call (b200lc_cuhd_decode_batch) keeps one view per stream in global memory
+// plus the stream number of every piece.
+struct StreamView {
     const u32 *units;
     u64 n_units;
-    const u16 *lut;      // {u8 num_bits, u8 symbol} little-endian pairs
-    u32 max_len;         // L
     u8 *out;
     u64 n_out;
+    u32 first_piece;     // global number of the stream's first piece
+    u32 num_subtiles;
+    u32 tma_tiles;       // leading sub-tiles (+ 4 lookahead units) that one TMA bulk copy can fetch
+    u32 pad;
+};
+
+struct DecodeParams {
+    StreamView one;      // the stream of a single-stream call
+    const StreamView *streams;    // batch: views in global memory (nullptr: single stream)
+    const u32 *piece_stream;      // batch: stream number of every piece
+    const u16 *lut;      // {u8 num_bits, u8 symbol} little-endian pairs
+    u32 max_len;         // L
     TileDesc *desc;
     u32 *ticket;
-    u32 num_subtiles;
     u32 num_pieces;      // pieces [first_piece, num_pieces) are decoded by this launch
     u32 first_piece;
-    u32 tma_tiles;       // leading sub-tiles (+ 4 lookahead units) that one TMA bulk copy can fetch
 };
 
 // ---------------------------------------------------------------------------------- walks
@@ -178,13 +192,18 @@ struct SmemLayout {
     u8 onpath[T];            // sub-tile 0 only: resolved path ends on the recorded path
     u64 bar[2];
     u64 base;
+    StreamView view[2];      // stream of the current piece / of the piece being prefetched (by piece parity)
     u32 next_piece;
     u32 total;
     u32 astar;
     u32 known;
 };
 
-template <int S, int T, int NSUB, int CAP>
+// BATCH = false: one stream, its view comes from the kernel parameters (warp-uniform values the
+// compiler keeps in uniform registers -- reading the same numbers from shared memory instead cost
+// 8 % on C2); BATCH = true: the view of each piece's stream is fetched from global memory into
+// shared memory by the thread that claims the piece.
+template <int S, int T, int NSUB, int CAP, bool BATCH>
 __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams p)
 {
     using Smem = SmemLayout<S, T, NSUB, CAP>;
@@ -224,38 +243,50 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
     }
     __syncthreads();
 
-    // sub-tile index g (global) -> can it be fetched by one TMA bulk copy?
-    auto tma_ok = [&](u32 g) -> bool {
-        return g < p.tma_tiles;
+    // the stream a piece belongs to
+    auto view_of = [&](u32 piece) -> StreamView {
+        return p.streams[p.piece_stream[piece]];
     };
-    auto issue_load = [&](u32 g, u32 buf) {  // one thread
-        if (g < p.num_subtiles && tma_ok(g)) {
+    // sub-tile index g (inside its stream) -> can it be fetched by one TMA bulk copy?
+    auto tma_ok = [&](const StreamView &v, u32 g) -> bool {
+        return g < v.tma_tiles;
+    };
+    auto issue_load = [&](const StreamView &v, u32 g, u32 buf) {  // one thread
+        if (g < v.num_subtiles && tma_ok(v, g)) {
             mbar_expect_tx(&sm.bar[buf], kTileBytes);
-            tma_load_1d(sm.in[buf], p.units + (u64)g * (T * S), kTileBytes, &sm.bar[buf]);
+            tma_load_1d(sm.in[buf], v.units + (u64)g * (T * S), kTileBytes, &sm.bar[buf]);
         }
     };
 
     if (tid == 0) {
         const u32 t0 = p.first_piece + atomicAdd(p.ticket, 1u);
         sm.next_piece = t0;
-        if (t0 < p.num_pieces) issue_load(t0 * NSUB, 0);
+        if (t0 < p.num_pieces) {
+            if (BATCH) {
+                sm.view[0] = view_of(t0);
+                issue_load(sm.view[0], (t0 - sm.view[0].first_piece) * NSUB, 0);
+            } else {
+                issue_load(p.one, t0 * NSUB, 0);
+            }
+        }
     }
     __syncthreads();
+    u32 turn = 0;               // pieces this CTA has started: its view is sm.view[turn & 1]
 
     u32 step = 0;               // buffer = step & 1
     u32 phase0 = 0, phase1 = 0;
 
     // wait for (or synchronously load) sub-tile g into buffer (step & 1)
-    auto acquire_input = [&](u32 g) {
+    auto acquire_input = [&](const StreamView &v, u32 g) {
         const u32 buf = step & 1;
-        if (tma_ok(g)) {
+        if (tma_ok(v, g)) {
             if (buf == 0) { mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
             else          { mbar_wait(&sm.bar[1], phase1); phase1 ^= 1; }
         } else {
             const u64 first = (u64)g * (T * S);
             for (u32 i = tid; i < kTileUnits; i += blockDim.x) {
                 const u64 idx = first + i;
-                sm.in[buf][i] = idx < p.n_units ? p.units[idx] : 0u;
+                sm.in[buf][i] = idx < v.n_units ? v.units[idx] : 0u;
             }
             fence_proxy_async();
             __syncthreads();
@@ -265,8 +296,10 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
     while (true) {
         const u32 piece = sm.next_piece;
         if (piece >= p.num_pieces) break;
-        const u32 g0 = piece * NSUB;
-        const u32 nsub = min((u32)NSUB, p.num_subtiles - g0);
+        const StreamView &V = BATCH ? sm.view[turn & 1] : p.one;
+        const u32 lp = piece - V.first_piece;          // piece number inside its stream
+        const u32 g0 = lp * NSUB;
+        const u32 nsub = min((u32)NSUB, V.num_subtiles - g0);
 
         u32 u[S + 1], m[S];
         u32 e0 = 0, c0 = 0;
@@ -359,20 +392,24 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
         // prefetch the sub-tile of the NEXT step into the other buffer (one thread)
         auto prefetch = [&](u32 pass, u32 c) {
             if (tid != 0) return;
-            u32 g;
-            if (c + 1 < nsub) g = g0 + c + 1;
-            else if (pass == 0) g = g0;
+            if (c + 1 < nsub) issue_load(V, g0 + c + 1, (step & 1) ^ 1);
+            else if (pass == 0) issue_load(V, g0, (step & 1) ^ 1);
             else {
                 const u32 np = p.first_piece + atomicAdd(p.ticket, 1u);
                 sm.next_piece = np;
                 if (np >= p.num_pieces) return;
-                g = np * NSUB;
+                if (BATCH) {
+                    StreamView &vn = sm.view[(turn + 1) & 1];
+                    vn = view_of(np);
+                    issue_load(vn, (np - vn.first_piece) * NSUB, (step & 1) ^ 1);
+                } else {
+                    issue_load(p.one, np * NSUB, (step & 1) ^ 1);
+                }
             }
-            issue_load(g, (step & 1) ^ 1);
         };
 
         // number of subsequences of sub-tile g that start inside the stream
-        const u64 total_subseq = (p.n_units + S - 1) / S;
+        const u64 total_subseq = (V.n_units + S - 1) / S;
         auto real_subseq = [&](u32 g) -> u32 {
             const u64 s0 = (u64)g * T;
             return s0 >= total_subseq ? 0u : (u32)min((u64)T, total_subseq - s0);
@@ -384,7 +421,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
         int dl = 0;            // alt warp: symbols(entry state lane) - symbols(entry state 0)
         bool known = false;
         for (u32 c = 0; c < nsub; ++c) {
-            acquire_input(g0 + c);
+            acquire_input(V, g0 + c);
             prefetch(0, c);
             const u32 buf = step & 1;
             if (worker) load_units(buf);
@@ -448,7 +485,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             TileDesc *d = &p.desc[piece];
             u32 astar = 0;
             u64 base = 0;
-            if (piece == 0) {
+            if (lp == 0) {
                 if (lane == 0) st_release_u64(&d->incl, kInclValid | ((u64)exit0 << 56) | total0);
             } else {
                 if (lane < kMaxStates) d->d[lane] = (short)(known ? dl : 0);
@@ -467,14 +504,14 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
                 while (true) {
                     const int idx = k - (int)lane;
                     u64 A = 0, I = 0;
-                    if (idx >= 0) {
+                    if (idx >= (int)V.first_piece) {
                         I = ld_acquire_u64(&p.desc[idx].incl);
                         A = ld_acquire_u64(&p.desc[idx].agg);
                     }
                     const bool has_incl = (I & kInclValid) != 0;
                     const u32 incl_mask = __ballot_sync(0xffffffffu, has_incl);
                     const u32 pl = incl_mask ? (u32)__ffs(incl_mask) - 1 : 32u;
-                    const bool agg_ok = idx < 0 || (A & kAggValid) != 0;
+                    const bool agg_ok = idx < (int)V.first_piece || (A & kAggValid) != 0;
                     const u32 agg_mask = __ballot_sync(0xffffffffu, agg_ok);
                     const u32 need = pl >= 32 ? 0xffffffffu : ((1u << pl) - 1);
                     if ((agg_mask & need) != need) {
@@ -527,7 +564,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             if (lane == 0) {
                 sm.astar = astar;
                 sm.base = base;
-                if (piece == 0) sm.known = 1;
+                if (lp == 0) sm.known = 1;
             }
         }
         __syncthreads();
@@ -537,7 +574,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
         u64 base_run = sm.base;
         const bool publish_late = !sm.known;
         for (u32 c = 0; c < nsub; ++c) {
-            acquire_input(g0 + c);
+            acquire_input(V, g0 + c);
             prefetch(1, c);
             const u32 buf = step & 1;
             if (worker) load_units(buf);
@@ -559,10 +596,10 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             const u32 total = sm.total;
 
             u64 tile_cnt = 0;
-            if (base_run < p.n_out) tile_cnt = min((u64)total, p.n_out - base_run);
+            if (base_run < V.n_out) tile_cnt = min((u64)total, V.n_out - base_run);
             for (u32 w0 = 0; w0 < tile_cnt; w0 += CAP) {
                 const u32 wlen = (u32)min((u64)CAP, tile_cnt - w0);
-                u8 *g = p.out + base_run + w0;
+                u8 *g = V.out + base_run + w0;
                 const u32 sh = (u32)(reinterpret_cast<uintptr_t>(g) & 15u);
                 if (worker) {
                     const u32 lo = w0, hi = w0 + wlen;
@@ -594,6 +631,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
             st_release_u64(&p.desc[piece].incl,
                            kInclValid | ((u64)entry_true << 56) | base_run);
         __syncthreads();
+        ++turn;
     }
 }
 
@@ -604,10 +642,11 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
 struct Variant {
     int S, T, NSUB, CAP;
     void (*kern)(const DecodeParams);
+    void (*kern_batch)(const DecodeParams);
     size_t smem_fixed;
 };
 #define B200LC_VARIANT(S_, T_, N_, C_) \
-    { S_, T_, N_, C_, cuhd_decode_kernel<S_, T_, N_, C_>, \
+    { S_, T_, N_, C_, cuhd_decode_kernel<S_, T_, N_, C_, false>, cuhd_decode_kernel<S_, T_, N_, C_, true>, \
       ((sizeof(SmemLayout<S_, T_, N_, C_>) + 127) & ~size_t(127)) }
 static const Variant kVariants[] = {
     B200LC_VARIANT(8, 256, 16, 16384),   // default for long streams: 407 GB/s of output on C2 (B200, round 1)
@@ -658,6 +697,36 @@ static u32 pieces_for(const Variant &v, u64 n_units)
     return (subtiles_for(v, n_units) + v.NSUB - 1) / v.NSUB;
 }
 
+static StreamView make_view(const Variant &v, const u32 *units, u64 n_units, u8 *out, u64 n_out, u32 first_piece)
+{
+    StreamView s;
+    s.units = units;
+    s.n_units = n_units;
+    s.out = out;
+    s.n_out = n_out;
+    s.first_piece = first_piece;
+    s.num_subtiles = subtiles_for(v, n_units);
+    s.tma_tiles = 0;
+    if ((reinterpret_cast<uintptr_t>(units) & 15) == 0 && n_units >= 4)
+        s.tma_tiles = (u32)min((u64)s.num_subtiles, (u64)(n_units - 4) / (u64)(v.T * v.S));
+    s.pad = 0;
+    return s;
+}
+
+// batch: stream number of every piece (views are sorted by first_piece)
+__global__ void piece_stream_kernel(const StreamView *__restrict__ views, u32 n_views, u32 n_pieces,
+                                    u32 *__restrict__ piece_stream)
+{
+    const u32 piece = blockIdx.x * blockDim.x + threadIdx.x;
+    if (piece >= n_pieces) return;
+    u32 lo = 0, hi = n_views;             // last view with first_piece <= piece
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (views[mid].first_piece <= piece) lo = mid; else hi = mid;
+    }
+    piece_stream[piece] = lo;
+}
+
 }  // namespace cuhd
 }  // namespace b200lc
 
@@ -702,23 +771,18 @@ static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t
         occ_cache[max_codeword_length] = occ;
     }
     cuhd::DecodeParams p;
-    p.units = d_units;
-    p.n_units = n_units;
+    p.one = cuhd::make_view(v, d_units, n_units, d_out, n_out, 0);
+    p.streams = nullptr;
+    p.piece_stream = nullptr;
     p.lut = reinterpret_cast<const u16 *>(d_table);
     p.max_len = (u32)max_codeword_length;
-    p.out = d_out;
-    p.n_out = n_out;
     p.ticket = reinterpret_cast<u32 *>(d_scratch);
     p.desc = reinterpret_cast<cuhd::TileDesc *>(reinterpret_cast<char *>(d_scratch) + 128);
-    p.num_subtiles = cuhd::subtiles_for(v, n_units);
     const u32 all_pieces = cuhd::pieces_for(v, n_units);
     if (end_piece > all_pieces) end_piece = all_pieces;
     if (first_piece >= end_piece) return B200LC_OK;
     p.num_pieces = (u32)end_piece;
     p.first_piece = (u32)first_piece;
-    p.tma_tiles = 0;
-    if ((reinterpret_cast<uintptr_t>(d_units) & 15) == 0 && n_units >= 4)
-        p.tma_tiles = (u32)min((u64)p.num_subtiles, (u64)(n_units - 4) / (u64)(v.T * v.S));
 
     if (first_piece == 0)
         B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128 + all_pieces * sizeof(cuhd::TileDesc), stream));
@@ -764,5 +828,112 @@ extern "C" int b200lc_cuhd_decode_progress_async(const void *d_scratch, size_t e
         reinterpret_cast<const cuhd::TileDesc *>(reinterpret_cast<const char *>(d_scratch) + 128);
     B200LC_CUDA_TRY(cudaMemcpyAsync(h_symbols, &desc[end_piece - 1].incl, sizeof(u64),
                                     cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+    return B200LC_OK;
+}
+
+// ------------------------------------------------------------------------------------ batch
+// Many independent streams that share one code table, decoded by ONE launch: pieces of all
+// streams are handed out through the same ticket counter and the look-back of a piece stops at
+// the first piece of its stream (the same idea as the block segments of the radix sort).
+namespace {
+struct BatchPlan {
+    const cuhd::Variant *v;
+    std::vector<cuhd::StreamView> views;   // non-empty streams only
+    u64 pieces;
+    size_t desc_off, views_off, map_off, total;
+};
+
+static int plan_batch(const uint32_t *d_units, uint8_t *d_out, const b200lc_cuhd_stream *h, size_t n,
+                      BatchPlan &bp)
+{
+    u64 total_units = 0;
+    for (size_t i = 0; i < n; ++i) total_units += h[i].n_units;
+    // piece length from the total size, like pick_variant does for one stream
+    bp.v = &cuhd::kVariants[4];
+    if (getenv("B200LC_CUHD_VARIANT")) bp.v = &cuhd::variant();
+    else {
+        const u64 want = (u64)num_sms() * 4;
+        for (int k = 0; k < 4; ++k) {
+            const cuhd::Variant &v = cuhd::kVariants[k];
+            u64 pieces = 0;
+            for (size_t i = 0; i < n; ++i)
+                if (h[i].n_units && h[i].n_out) pieces += cuhd::pieces_for(v, h[i].n_units);
+            if (pieces >= want) { bp.v = &v; break; }
+        }
+    }
+    bp.views.clear();
+    bp.pieces = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (h[i].n_units == 0 || h[i].n_out == 0) continue;
+        if (h[i].n_units >= (1ull << 40)) return B200LC_ERR_UNSUPPORTED;
+        bp.views.push_back(cuhd::make_view(*bp.v, d_units + h[i].unit_offset, h[i].n_units,
+                                           d_out + h[i].out_offset, h[i].n_out, (u32)bp.pieces));
+        bp.pieces += cuhd::pieces_for(*bp.v, h[i].n_units);
+    }
+    if (bp.pieces >= (1ull << 31)) return B200LC_ERR_UNSUPPORTED;
+    auto up = [](size_t x) { return (x + 127) & ~size_t(127); };
+    bp.desc_off = 128;
+    bp.views_off = bp.desc_off + up(bp.pieces * sizeof(cuhd::TileDesc));
+    bp.map_off = bp.views_off + up(bp.views.size() * sizeof(cuhd::StreamView));
+    bp.total = bp.map_off + up(bp.pieces * 4);
+    (void)total_units;
+    return B200LC_OK;
+}
+}  // namespace
+
+extern "C" size_t b200lc_cuhd_decode_batch_scratch_bytes(const b200lc_cuhd_stream *h_streams, size_t n_streams)
+{
+    if (!h_streams) return 0;
+    // sized for the variant with the shortest pieces so that the answer does not depend on tuning
+    const cuhd::Variant &v = cuhd::kVariants[4];
+    u64 pieces = 0;
+    for (size_t i = 0; i < n_streams; ++i) pieces += cuhd::pieces_for(v, h_streams[i].n_units);
+    auto up = [](size_t x) { return (x + 127) & ~size_t(127); };
+    return 128 + up(pieces * sizeof(cuhd::TileDesc)) + up(n_streams * sizeof(cuhd::StreamView)) + up(pieces * 4) + 256;
+}
+
+extern "C" int b200lc_cuhd_decode_batch(const uint32_t *d_units, uint8_t *d_out,
+                                        const b200lc_cuhd_stream *h_streams, size_t n_streams,
+                                        const void *d_table, int max_codeword_length, void *d_scratch,
+                                        size_t scratch_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (max_codeword_length < 1 || max_codeword_length > 13) return B200LC_ERR_UNSUPPORTED;
+    if (n_streams == 0) return B200LC_OK;
+    if (!d_units || !d_out || !h_streams || !d_table || !d_scratch) return B200LC_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
+    BatchPlan bp;
+    int rc = plan_batch(d_units, d_out, h_streams, n_streams, bp);
+    if (rc) return rc;
+    if (bp.pieces == 0) return B200LC_OK;
+    if (scratch_bytes < bp.total) return B200LC_ERR_SCRATCH;
+    const cuhd::Variant &v = *bp.v;
+    const size_t smem = v.smem_fixed + (size_t(5) << max_codeword_length);
+    B200LC_CUDA_TRY(cudaFuncSetAttribute(v.kern_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.kern_batch, v.T + 32, smem));
+    if (occ < 1) return B200LC_ERR_CUDA;
+    char *base = reinterpret_cast<char *>(d_scratch);
+    cuhd::StreamView *d_views = reinterpret_cast<cuhd::StreamView *>(base + bp.views_off);
+    u32 *d_map = reinterpret_cast<u32 *>(base + bp.map_off);
+    B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, bp.views_off, stream));      // ticket + descriptors
+    // the views come from pageable host memory: this copy returns once they have been staged
+    B200LC_CUDA_TRY(cudaMemcpyAsync(d_views, bp.views.data(), bp.views.size() * sizeof(cuhd::StreamView),
+                                    cudaMemcpyHostToDevice, stream));
+    cuhd::piece_stream_kernel<<<(u32)((bp.pieces + 255) / 256), 256, 0, stream>>>(d_views, (u32)bp.views.size(),
+                                                                                  (u32)bp.pieces, d_map);
+    cuhd::DecodeParams p;
+    p.one = bp.views[0];
+    p.streams = d_views;
+    p.piece_stream = d_map;
+    p.lut = reinterpret_cast<const u16 *>(d_table);
+    p.max_len = (u32)max_codeword_length;
+    p.ticket = reinterpret_cast<u32 *>(d_scratch);
+    p.desc = reinterpret_cast<cuhd::TileDesc *>(base + bp.desc_off);
+    p.num_pieces = (u32)bp.pieces;
+    p.first_piece = 0;
+    const u32 grid = (u32)min((u64)bp.pieces, (u64)num_sms() * (u64)occ);
+    v.kern_batch<<<grid, v.T + 32, smem, stream>>>(p);
+    B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }

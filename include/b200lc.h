@@ -74,6 +74,21 @@ int b200lc_cuhd_decode_pieces(const uint32_t *d_units, size_t n_units, uint8_t *
 int b200lc_cuhd_decode_progress_async(const void *d_scratch, size_t end_piece,
                                       uint64_t *h_symbols, void *stream);
 
+/* Batch: many independent streams that share ONE code table (e.g. the blocks of a buffer packed
+ * separately for random access), decoded by one launch.  Stream i occupies
+ * d_units[unit_offset .. unit_offset + n_units) and decodes to d_out[out_offset .. out_offset + n_out);
+ * its codes start at bit 0 of its first unit.  unit_offset % 4 == 0 lets the stream use TMA bulk
+ * copies (any offset works).  The stream descriptors are HOST memory; everything else as above.
+ * Scratch: b200lc_cuhd_decode_batch_scratch_bytes(), 128-byte aligned.  Asynchronous once the
+ * descriptors have been staged. */
+typedef struct b200lc_cuhd_stream {
+    uint64_t unit_offset, n_units, out_offset, n_out;
+} b200lc_cuhd_stream;
+size_t b200lc_cuhd_decode_batch_scratch_bytes(const b200lc_cuhd_stream *h_streams, size_t n_streams);
+int b200lc_cuhd_decode_batch(const uint32_t *d_units, uint8_t *d_out, const b200lc_cuhd_stream *h_streams,
+                             size_t n_streams, const void *d_table, int max_codeword_length,
+                             void *d_scratch, size_t scratch_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * CUHD-format encoder side: replaces the sequential CPU stages of the
  * reference's demo (cuhd-icpp/src/demo.cc:90-107).

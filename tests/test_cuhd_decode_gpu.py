@@ -174,3 +174,70 @@ def test_session_round_trip_host_buffers(n, pinned):
     sess.decode(h_units, nu + 1, h_lut, h_out, 11)   # scratch reuse across calls
     sess.close()
     assert np.array_equal(h_out.numpy(), data)
+
+
+# ------------------------------------------------------------------------------------------ batch
+DEV = "cuda:0"
+
+
+def _encode_blocks(data, sizes, align_units=4):
+    """Blocks of `data` packed separately with ONE shared table; returns (units tensor, streams
+    array, lut tensor).  Each stream starts at a multiple of align_units units."""
+    d = torch.from_numpy(data).to(DEV)
+    hist = b200lc.histogram_u8(d).cpu().numpy()
+    hist = np.maximum(hist, 1)                      # every symbol gets a code: blocks share the table
+    code, length, lut = b200lc.cuhd_build_table(hist)
+    d_code = torch.from_numpy(code.view(np.int32)).to(DEV)
+    d_len = torch.from_numpy(length).to(DEV)
+    parts, streams, uoff, ooff = [], [], 0, 0
+    for n in sizes:
+        if n == 0:
+            streams.append((uoff, 0, ooff, 0))
+            continue
+        enc = b200lc.cuhd_encode(d[ooff:ooff + n], d_code, d_len)
+        nu = enc.n_units
+        parts.append(enc.units[:nu])
+        pad = (-nu) % align_units if align_units > 1 else 0
+        if pad:
+            parts.append(torch.zeros(pad, dtype=torch.int32, device=DEV))
+        streams.append((uoff, nu, ooff, n))
+        uoff += nu + pad
+        ooff += n
+    units = torch.cat(parts + [torch.zeros(8, dtype=torch.int32, device=DEV)])
+    return units, np.array(streams, np.uint64), torch.from_numpy(lut).to(DEV), code, length, lut
+
+
+@pytest.mark.parametrize("sizes,align", [
+    ([1 << 20] * 8, 4),                                  # equal blocks (config 5 shape)
+    ([65536] * 64, 4),
+    ([1, 2, 3, 100, 4097, 0, 70001, 1 << 20, 5, 300000], 4),   # ragged, an empty stream in the middle
+    ([12345, 54321, 99999, 1 << 18], 1),                 # streams at arbitrary unit offsets (no TMA)
+    ([3 << 20, 1000, 1 << 21], 4),                       # long + short mixed: look-back stops per stream
+])
+def test_batch_decode_equals_per_stream_oracle(sizes, align):
+    total = sum(sizes)
+    data = O.zipf_bytes(total, 1.1, seed=total % 1000)
+    units, streams, d_lut, code, length, lut = _encode_blocks(data, sizes, align)
+    out = torch.full((total + 64,), 0xEE, dtype=torch.uint8, device=DEV)
+    b200lc.cuhd_decode_batch(units, out, streams, d_lut)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:total], data)
+    assert (got[total:] == 0xEE).all()                   # nothing written past the last stream
+    # oracle decode of two of the streams from their own units
+    hu = units.cpu().numpy().view(np.uint32)
+    for (uo, nu, oo, n) in streams[[0, len(streams) - 1]]:
+        if n:
+            exp, cnt = O.cuhd_oracle_decode(hu[int(uo):int(uo + nu) + 1].copy(), lut, int(n))
+            assert cnt == n and np.array_equal(exp, data[int(oo):int(oo + n)])
+
+
+def test_batch_decode_many_small_streams_one_launch():
+    # 2048 streams of 16 KiB: far more streams than CTAs, one piece each
+    sizes = [16384] * 2048
+    total = sum(sizes)
+    data = O.zipf_bytes(total, 1.3, seed=11)
+    units, streams, d_lut, *_ = _encode_blocks(data, sizes, 4)
+    out = torch.empty(total, dtype=torch.uint8, device=DEV)
+    b200lc.cuhd_decode_batch(units, out, streams, d_lut)
+    assert np.array_equal(out.cpu().numpy(), data)

@@ -120,6 +120,56 @@ def point_cuhd(data, block, dev):
     return enc_ms, dec_ms, comp, ok
 
 
+def point_cuhd_batch(data, block, dev):
+    """Blocks of `block` symbols packed separately with ONE shared code table and decoded by one
+    launch of b200lc_cuhd_decode_batch (look-back stops at block boundaries).  The blocks are
+    packed with per-block encoder calls on 8 CUDA streams."""
+    n = data.numel()
+    nstreams = n // block
+    L = pkg.lib()
+    hist = np.maximum(pkg.histogram_u8(data).cpu().numpy(), 1)
+    code, length, lut = pkg.cuhd_build_table(hist)
+    d_code, d_len = torch.from_numpy(code.view(np.int32)).to(dev), torch.from_numpy(length).to(dev)
+    d_lut = torch.from_numpy(lut).to(dev)
+    ucap = ((block * 11 + 31) // 32 + 2 + 3) // 4 * 4
+    units = torch.zeros(nstreams * ucap, dtype=torch.int32, device=dev)
+    streams = np.zeros((nstreams, 4), np.uint64)
+    escr = torch.empty(L.b200lc_cuhd_encode_scratch_bytes(block), dtype=torch.uint8, device=dev)
+    comp = 0
+    for s in range(nstreams):
+        enc = pkg.cuhd_encode(data[s * block:(s + 1) * block], d_code, d_len, units=units[s * ucap:(s + 1) * ucap],
+                              scratch=escr)
+        streams[s] = (s * ucap, enc.n_units, s * block, block)
+        comp += enc.n_units * 4
+    lanes = min(NSTREAMS, nstreams)
+    cstreams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+    bits = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(lanes)]
+    escrs = [torch.empty(L.b200lc_cuhd_encode_scratch_bytes(block), dtype=torch.uint8, device=dev) for _ in range(lanes)]
+
+    def enc_all():
+        main = torch.cuda.current_stream()
+        pkg.histogram_u8(data)
+        start = torch.cuda.Event()
+        start.record(main)
+        for st in cstreams:
+            st.wait_event(start)
+        for s in range(nstreams):
+            k = s % lanes
+            with torch.cuda.stream(cstreams[k]):
+                pkg.cuhd_encode(data[s * block:(s + 1) * block], d_code, d_len, units=units[s * ucap:(s + 1) * ucap],
+                                total_bits=bits[k], scratch=escrs[k], sync=False, stream=cstreams[k])
+        for st in cstreams:
+            main.wait_stream(st)
+
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    dscr = torch.empty(L.b200lc_cuhd_decode_batch_scratch_bytes(streams.ctypes.data, nstreams) + 256,
+                       dtype=torch.uint8, device=dev)
+    enc_ms = timeit(enc_all, iters=3, warm=1)
+    dec_ms = timeit(lambda: pkg.cuhd_decode_batch(units, out, streams, d_lut, scratch=dscr), iters=3, warm=1)
+    torch.cuda.synchronize()
+    return enc_ms, dec_ms, comp, bool(torch.equal(out, data))
+
+
 def point_culzss(data, block, dev):
     n = data.numel()
     nbuf = n // block
@@ -183,7 +233,7 @@ def point_cudpp(data, block, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mib", type=int, default=256)
-    ap.add_argument("--paths", default="cuhd,culzss,cudpp")
+    ap.add_argument("--paths", default="cuhd,cuhd_batch,culzss,cudpp")
     ap.add_argument("--blocks", default="65536,262144,1048576,4194304")
     ap.add_argument("--entropies", default="1,2,3,4,5,6,7,8")
     ap.add_argument("--md", default=None)
@@ -191,7 +241,7 @@ def main():
     dev = torch.device("cuda:0")
     rows = []
     for path in args.paths.split(","):
-        fn = {"cuhd": point_cuhd, "culzss": point_culzss, "cudpp": point_cudpp}[path]
+        fn = {"cuhd": point_cuhd, "cuhd_batch": point_cuhd_batch, "culzss": point_culzss, "cudpp": point_cudpp}[path]
         total = (args.mib if path != "cudpp" else min(args.mib, 128)) * MIB
         for H in [float(x) for x in args.entropies.split(",")]:
             data = gen(total, H, dev, seed=1000 + int(H * 10), lo_sym=1 if path == "cudpp" else 0)
