@@ -52,6 +52,10 @@ def lib():
     L.b200lc_cuhd_encode_scratch_bytes.argtypes = [sz]
     L.b200lc_cuhd_encode.restype = i32
     L.b200lc_cuhd_encode.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, sz, vp]
+    L.b200lc_cuhd_encode_blocks_scratch_bytes.restype = sz
+    L.b200lc_cuhd_encode_blocks_scratch_bytes.argtypes = [sz, sz]
+    L.b200lc_cuhd_encode_blocks.restype = i32
+    L.b200lc_cuhd_encode_blocks.argtypes = [vp, sz, sz, vp, vp, vp, sz, vp, vp, sz, vp]
     L.b200lc_cuhd_encode_overflowed.restype = i32
     L.b200lc_cuhd_encode_overflowed.argtypes = [vp, vp]
     L.b200lc_cuhd_session_create.restype = i32
@@ -233,6 +237,31 @@ def cuhd_encode(data, code, length, units_cap=None, stream=None, scratch=None, u
     bits = int(total_bits.item())
     n_units = (bits + 31) // 32
     return CuhdEncoded(units[: min(n_units + 1, units_cap)], n_units, bits)
+
+
+def cuhd_encode_blocks(data, block, code, length, unit_stride=None, units=None, block_bits=None,
+                       scratch=None, stream=None):
+    """Pack blocks of `block` symbols of a cuda uint8 tensor as independent streams with one
+    dictionary in one launch.  Returns (units int32 [nblocks * unit_stride], block_bits int64
+    [nblocks], unit_stride).  Asynchronous."""
+    import torch
+    L = lib()
+    n = data.numel()
+    nblocks = (n + block - 1) // block
+    if unit_stride is None:
+        unit_stride = ((block * 13 + 31) // 32 + 2 + 3) // 4 * 4
+    if units is None:
+        units = torch.empty(nblocks * unit_stride, dtype=torch.int32, device=data.device)
+    if block_bits is None:
+        block_bits = torch.zeros(nblocks, dtype=torch.int64, device=data.device)
+    need = L.b200lc_cuhd_encode_blocks_scratch_bytes(n, block)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=data.device)
+    check(L.b200lc_cuhd_encode_blocks(data.data_ptr(), n, block, code.data_ptr(), length.data_ptr(),
+                                      units.data_ptr(), unit_stride, block_bits.data_ptr(),
+                                      scratch.data_ptr(), scratch.numel(), _stream_ptr(stream)),
+          "b200lc_cuhd_encode_blocks")
+    return units, block_bits, unit_stride
 
 
 class CuhdSession:

@@ -50,10 +50,39 @@ struct EncParams {
     u32 *overflow;              // device flag, set if out_cap_units was too small
     EncDesc *desc;
     u32 *ticket;
-    u32 num_subtiles;
     u32 num_pieces;
-    u32 tma_tiles;       // leading sub-tiles that one TMA bulk copy can fetch (0: unaligned input)
+    // Blocks: the input is cut into blocks of block_syms symbols (one block = the whole input for
+    // a plain call), each packed as an independent stream that starts at bit 0 of
+    // out + block * unit_stride.  Pieces never straddle blocks; a block has pieces_per_block of them.
+    u64 block_syms;
+    u64 unit_stride;
+    u32 pieces_per_block;
+    u32 aligned;         // input base and block_syms are multiples of 16: TMA bulk copies allowed
+    u64 *block_bits;     // [blocks] stream bits of every block (nullptr for a plain call)
 };
+
+// What a piece needs to know about its block.
+struct BlockView {
+    const u8 *in;        // first symbol of the block
+    u64 n;               // symbols in the block
+    u32 *out;
+    u32 block, lp;       // block number, piece number inside the block
+    u32 num_subtiles, tma_tiles, last_lp;
+};
+__device__ __forceinline__ BlockView block_view(const EncParams &p, u32 piece)
+{
+    BlockView v;
+    v.block = piece / p.pieces_per_block;
+    v.lp = piece - v.block * p.pieces_per_block;
+    const u64 first = (u64)v.block * p.block_syms;
+    v.in = p.in + first;
+    v.n = min(p.block_syms, p.n - first);
+    v.out = p.out + (u64)v.block * p.unit_stride;
+    v.num_subtiles = (u32)((v.n + kTileSyms - 1) / kTileSyms);
+    v.tma_tiles = p.aligned ? (u32)(v.n / kTileSyms) : 0u;
+    v.last_lp = (v.num_subtiles + kNSub - 1) / kNSub - 1;
+    return v;
+}
 
 struct EncSmem {
     __align__(16) u8 in[2][kTileSyms];
@@ -88,32 +117,35 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
     }
     __syncthreads();
 
-    auto tma_ok = [&](u32 g) -> bool {
-        return g < p.tma_tiles;
+    auto tma_ok = [&](const BlockView &v, u32 g) -> bool {
+        return g < v.tma_tiles;
     };
-    auto issue_load = [&](u32 g, u32 buf) {
-        if (g < p.num_subtiles && tma_ok(g)) {
+    auto issue_load = [&](const BlockView &v, u32 g, u32 buf) {
+        if (g < v.num_subtiles && tma_ok(v, g)) {
             mbar_expect_tx(&sm.bar[buf], kTileSyms);
-            tma_load_1d(sm.in[buf], p.in + (u64)g * kTileSyms, kTileSyms, &sm.bar[buf]);
+            tma_load_1d(sm.in[buf], v.in + (u64)g * kTileSyms, kTileSyms, &sm.bar[buf]);
         }
     };
     if (tid == 0) {
         const u32 t0 = atomicAdd(p.ticket, 1u);
         sm.next_piece = t0;
-        if (t0 < p.num_pieces) issue_load(t0 * kNSub, 0);
+        if (t0 < p.num_pieces) {
+            const BlockView v0 = block_view(p, t0);
+            issue_load(v0, v0.lp * kNSub, 0);
+        }
     }
     __syncthreads();
 
     u32 step = 0, phase0 = 0, phase1 = 0;
-    auto acquire_input = [&](u32 g, u32 tile_n) {
+    auto acquire_input = [&](const BlockView &v, u32 g, u32 tile_n) {
         const u32 buf = step & 1;
-        if (tma_ok(g)) {
+        if (tma_ok(v, g)) {
             if (buf == 0) { mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
             else          { mbar_wait(&sm.bar[1], phase1); phase1 ^= 1; }
         } else {
             const u64 first = (u64)g * kTileSyms;
             for (u32 i = tid; i < kTileSyms; i += kThreads)
-                sm.in[buf][i] = i < tile_n ? p.in[first + i] : (u8)0;
+                sm.in[buf][i] = i < tile_n ? v.in[first + i] : (u8)0;
             fence_proxy_async();
             __syncthreads();
         }
@@ -122,21 +154,21 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
     while (true) {
         const u32 piece = sm.next_piece;
         if (piece >= p.num_pieces) break;
-        const u32 g0 = piece * kNSub;
-        const u32 nsub = min((u32)kNSub, p.num_subtiles - g0);
+        const BlockView V = block_view(p, piece);
+        const u32 g0 = V.lp * kNSub;                 // sub-tile numbers are local to the block
+        const u32 nsub = min((u32)kNSub, V.num_subtiles - g0);
 
         auto prefetch = [&](u32 pass, u32 c) {
             if (tid != 0) return;
-            u32 g;
-            if (c + 1 < nsub) g = g0 + c + 1;
-            else if (pass == 0) g = g0;
+            if (c + 1 < nsub) issue_load(V, g0 + c + 1, (step & 1) ^ 1);
+            else if (pass == 0) issue_load(V, g0, (step & 1) ^ 1);
             else {
                 const u32 np = atomicAdd(p.ticket, 1u);
                 sm.next_piece = np;
                 if (np >= p.num_pieces) return;
-                g = np * kNSub;
+                const BlockView vn = block_view(p, np);
+                issue_load(vn, vn.lp * kNSub, (step & 1) ^ 1);
             }
-            issue_load(g, (step & 1) ^ 1);
         };
         // code|len of the thread's 16 symbols; returns their bit count.  Full tiles (all but the
         // very last one) take the path without end-of-input selects.
@@ -185,8 +217,8 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
         u32 my_piece_bits = 0;   // per-thread partial over all sub-tiles (<= 16*16*13 bits)
         for (u32 c = 0; c < nsub; ++c) {
             const u64 first = (u64)(g0 + c) * kTileSyms;
-            const u32 tile_n = (u32)min((u64)kTileSyms, p.n - first);
-            acquire_input(g0 + c, tile_n);
+            const u32 tile_n = (u32)min((u64)kTileSyms, V.n - first);
+            acquire_input(V, g0 + c, tile_n);
             prefetch(0, c);
             const u32 bits = count_bits(step & 1, tile_n);
             my_piece_bits += bits;
@@ -230,20 +262,21 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             }
             u64 base = 0;
             u32 prev_tail = 0;
-            if (piece > 0) {
-                // warp-wide look-back: lane i inspects piece (k - i)
+            const int first_of_block = (int)(piece - V.lp);
+            if (V.lp > 0) {
+                // warp-wide look-back: lane i inspects piece (k - i); it stops at the block's first piece
                 int k = (int)piece - 1;
                 bool done = false;
                 bool first_batch = true;
                 while (!done) {
                     const int idx = k - (int)lane;
                     u64 a = 0, in = 0;
-                    if (idx >= 0) {
+                    if (idx >= first_of_block) {
                         in = ld_acquire_u64(&p.desc[idx].incl);
                         if (!(in & kValid)) a = ld_acquire_u64(&p.desc[idx].agg);
                     }
-                    const bool has_incl = idx >= 0 && (in & kValid);
-                    const bool has_any = idx < 0 || has_incl || (a & kValid);
+                    const bool has_incl = idx >= first_of_block && (in & kValid);
+                    const bool has_any = idx < first_of_block || has_incl || (a & kValid);
                     const u32 incl_mask = __ballot_sync(0xffffffffu, has_incl);
                     const u32 any_mask = __ballot_sync(0xffffffffu, has_any);
                     // usable prefix of lanes: all ready up to (and including) the first inclusive
@@ -254,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
                         continue;  // somebody not ready yet: poll again
                     }
                     u64 contrib = 0;
-                    if (lane < first_incl && idx >= 0) contrib = (a & ~kValid) >> 31;
+                    if (lane < first_incl && idx >= first_of_block) contrib = (a & ~kValid) >> 31;
                     if (lane == first_incl) contrib = in & ~kValid;
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
@@ -269,7 +302,7 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
                         prev_tail = (u32)__shfl_sync(0xffffffffu, pa, 0) & 0x7fffffffu;
                         first_batch = false;
                     }
-                    if (first_incl < 32 || k - 32 < 0) done = true;
+                    if (first_incl < 32 || k - 32 < first_of_block) done = true;
                     k -= 32;
                 }
             }
@@ -289,11 +322,11 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             const u32 r0 = (u32)(base & 31);
             if (r0) carry = (sm.prev_tail & ((1u << r0) - 1)) << (32 - r0);
         }
-        const bool last_piece = piece == p.num_pieces - 1;
+        const bool last_piece = V.lp == V.last_lp;        // of its block
         for (u32 c = 0; c < nsub; ++c) {
             const u64 first = (u64)(g0 + c) * kTileSyms;
-            const u32 tile_n = (u32)min((u64)kTileSyms, p.n - first);
-            acquire_input(g0 + c, tile_n);
+            const u32 tile_n = (u32)min((u64)kTileSyms, V.n - first);
+            acquire_input(V, g0 + c, tile_n);
             prefetch(1, c);
             u32 e[kSyms];
             const u32 my_bits = lookup(step & 1, tile_n, e);
@@ -350,7 +383,7 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             if (w0 + nwords > p.out_cap_units) {
                 if (tid == 0) atomicExch(p.overflow, 1u);
             } else {
-                u32 *g = p.out + w0;
+                u32 *g = V.out + w0;
                 const u32 head = min(nwords, (4u - salign) & 3u);
                 const u32 nvec = (nwords - head) >> 2;
                 const u32 tail0 = head + (nvec << 2);
@@ -360,7 +393,8 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
                 for (u32 i = tid; i < nvec; i += kThreads) gv[i] = sv[i];
                 if (tid < nwords - tail0) g[tail0 + tid] = sm.stage[salign + tail0 + tid];
                 if (last_tile && tid == 0) {
-                    *p.total_bits = base + total;
+                    if (p.block_bits) p.block_bits[V.block] = base + total;
+                    else *p.total_bits = base + total;
                     if (w0 + nwords < p.out_cap_units) g[nwords] = 0;  // the reference's pad unit
                 }
             }
@@ -466,9 +500,12 @@ extern "C" int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t 
     p.ticket = reinterpret_cast<u32 *>(d_scratch);
     p.overflow = reinterpret_cast<u32 *>(d_scratch) + 1;
     p.desc = reinterpret_cast<cuhd_enc::EncDesc *>(reinterpret_cast<char *>(d_scratch) + 256);
-    p.num_subtiles = cuhd_enc::subtiles_for(n);
     p.num_pieces = cuhd_enc::pieces_for(n);
-    p.tma_tiles = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 ? (u32)(n / cuhd_enc::kTileSyms) : 0u;
+    p.block_syms = n;
+    p.unit_stride = 0;
+    p.pieces_per_block = p.num_pieces;
+    p.aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
+    p.block_bits = nullptr;
 
     static int occ = 0;
     if (!occ) {
@@ -476,6 +513,58 @@ extern "C" int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t 
             &occ, cuhd_enc::cuhd_encode_kernel, cuhd_enc::kThreads, 0));
         if (occ < 1) return B200LC_ERR_CUDA;
     }
+    const u32 grid = (u32)min((u64)p.num_pieces, (u64)num_sms() * (u64)occ);
+    cuhd_enc::cuhd_encode_kernel<<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}
+
+// Blocks of block_symbols symbols packed as independent streams with one dictionary, one launch.
+extern "C" size_t b200lc_cuhd_encode_blocks_scratch_bytes(size_t n, size_t block_symbols)
+{
+    if (block_symbols == 0) return 0;
+    const size_t blocks = (n + block_symbols - 1) / block_symbols;
+    return 256 + blocks * (size_t)cuhd_enc::pieces_for(block_symbols) * sizeof(cuhd_enc::EncDesc);
+}
+
+extern "C" int b200lc_cuhd_encode_blocks(const uint8_t *d_in, size_t n, size_t block_symbols,
+                                         const uint32_t *d_code_of_symbol, const uint8_t *d_len_of_symbol,
+                                         uint32_t *d_units, size_t unit_stride, uint64_t *d_block_bits,
+                                         void *d_scratch, size_t scratch_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_code_of_symbol || !d_len_of_symbol || !d_units || !d_block_bits || !d_scratch) return B200LC_ERR_ARG;
+    if (n == 0) return B200LC_OK;
+    if (!d_in || block_symbols == 0 || (unit_stride & 3)) return B200LC_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_units) & 15) return B200LC_ERR_ARG;
+    const size_t need = b200lc_cuhd_encode_blocks_scratch_bytes(n, block_symbols);
+    if (scratch_bytes < need) return B200LC_ERR_SCRATCH;
+    const u64 blocks = (n + block_symbols - 1) / block_symbols;
+    const u64 ppb = cuhd_enc::pieces_for(block_symbols);
+    if (blocks * ppb >= (1ull << 31)) return B200LC_ERR_UNSUPPORTED;
+    B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, need, stream));
+    cuhd_enc::EncParams p;
+    p.in = d_in;
+    p.n = n;
+    p.code_of_symbol = d_code_of_symbol;
+    p.len_of_symbol = d_len_of_symbol;
+    p.out = d_units;
+    p.out_cap_units = unit_stride;
+    p.total_bits = nullptr;
+    p.ticket = reinterpret_cast<u32 *>(d_scratch);
+    p.overflow = reinterpret_cast<u32 *>(d_scratch) + 1;
+    p.desc = reinterpret_cast<cuhd_enc::EncDesc *>(reinterpret_cast<char *>(d_scratch) + 256);
+    p.num_pieces = (u32)(blocks * ppb);
+    p.block_syms = block_symbols;
+    p.unit_stride = unit_stride;
+    p.pieces_per_block = (u32)ppb;
+    p.aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && block_symbols % 16 == 0;
+    p.block_bits = d_block_bits;
+    int occ = 0;
+    B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cuhd_enc::cuhd_encode_kernel,
+                                                                  cuhd_enc::kThreads, 0));
+    if (occ < 1) return B200LC_ERR_CUDA;
     const u32 grid = (u32)min((u64)p.num_pieces, (u64)num_sms() * (u64)occ);
     cuhd_enc::cuhd_encode_kernel<<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());

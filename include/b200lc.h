@@ -123,6 +123,19 @@ int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t *d_code_of_
                        void *stream);
 int b200lc_cuhd_encode_overflowed(const void *d_scratch, void *stream);
 
+/* Blocks: d_in[n] is cut into blocks of block_symbols symbols (the last one may be shorter) and
+ * every block is packed as an independent stream with the same dictionary, all by one launch:
+ * block b starts at bit 0 of d_units + b * unit_stride (unit_stride a multiple of 4, at least
+ * the block's units + 1 for the pad unit), d_block_bits[b] receives its number of stream bits.
+ * These are the streams b200lc_cuhd_decode_batch takes (unit_offset = b * unit_stride,
+ * n_units = ceil(bits / 32)).  block_symbols % 16 == 0 lets the blocks use TMA bulk copies.
+ * Asynchronous; b200lc_cuhd_encode_overflowed() reports a unit_stride that was too small. */
+size_t b200lc_cuhd_encode_blocks_scratch_bytes(size_t n, size_t block_symbols);
+int b200lc_cuhd_encode_blocks(const uint8_t *d_in, size_t n, size_t block_symbols,
+                              const uint32_t *d_code_of_symbol, const uint8_t *d_len_of_symbol,
+                              uint32_t *d_units, size_t unit_stride, uint64_t *d_block_bits,
+                              void *d_scratch, size_t scratch_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host-buffer session for the CUHD path: the reference demo's flow around the decoder
  * (cuhd-icpp/src/demo.cc:122-168: device buffers, H2D of table + stream, decode, D2H) and around

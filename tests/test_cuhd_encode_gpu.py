@@ -92,3 +92,34 @@ def test_encode_unaligned_input_base():
     enc = b200lc.cuhd_encode(view, c, l)
     got = enc.units.cpu().numpy().view(np.uint32)
     assert np.array_equal(got[: want.size], want)
+
+
+# ------------------------------------------------------------------------------------------ blocks
+@pytest.mark.parametrize("n,block", [(1 << 22, 1 << 20), (1 << 21, 65536), (300000, 65536), (1000, 4096),
+                                     (5 * 131072 + 77, 131072), (3 * 200000, 200000), (7 * 50001, 50001)])
+def test_encode_blocks_equals_per_block_encode_and_round_trips_through_batch_decode(n, block):
+    DEVB = "cuda:0"
+    data = O.zipf_bytes(n, 1.1, seed=n % 997)
+    d = torch.from_numpy(data).to(DEVB)
+    hist = np.maximum(np.bincount(data, minlength=256), 1)
+    code, length, lut = b200lc.cuhd_build_table(hist)
+    d_code = torch.from_numpy(code.view(np.int32)).to(DEVB)
+    d_len = torch.from_numpy(length).to(DEVB)
+    units, bits, stride = b200lc.cuhd_encode_blocks(d, block, d_code, d_len)
+    torch.cuda.synchronize()
+    hb = bits.cpu().numpy()
+    hu = units.cpu().numpy().view(np.uint32)
+    nblocks = (n + block - 1) // block
+    streams = np.zeros((nblocks, 4), np.uint64)
+    for b in range(nblocks):
+        part = data[b * block:(b + 1) * block]
+        want, _ = O.cuhd_oracle_encode(part, code, length)
+        wbits = int(length[part].astype(np.int64).sum())
+        assert int(hb[b]) == wbits, b
+        nu = (wbits + 31) // 32
+        assert np.array_equal(hu[b * stride: b * stride + nu], want[:nu]), b
+        assert hu[b * stride + nu] == 0                      # the reference's pad unit
+        streams[b] = (b * stride, nu, b * block, part.size)
+    out = torch.empty(n, dtype=torch.uint8, device=DEVB)
+    b200lc.cuhd_decode_batch(units, out, streams, torch.from_numpy(lut).to(DEVB))
+    assert np.array_equal(out.cpu().numpy(), data)

@@ -121,9 +121,9 @@ def point_cuhd(data, block, dev):
 
 
 def point_cuhd_batch(data, block, dev):
-    """Blocks of `block` symbols packed separately with ONE shared code table and decoded by one
-    launch of b200lc_cuhd_decode_batch (look-back stops at block boundaries).  The blocks are
-    packed with per-block encoder calls on 8 CUDA streams."""
+    """Blocks of `block` symbols packed as independent streams with ONE shared code table by one
+    launch of b200lc_cuhd_encode_blocks and decoded by one launch of b200lc_cuhd_decode_batch
+    (look-backs stop at block boundaries)."""
     n = data.numel()
     nstreams = n // block
     L = pkg.lib()
@@ -131,40 +131,25 @@ def point_cuhd_batch(data, block, dev):
     code, length, lut = pkg.cuhd_build_table(hist)
     d_code, d_len = torch.from_numpy(code.view(np.int32)).to(dev), torch.from_numpy(length).to(dev)
     d_lut = torch.from_numpy(lut).to(dev)
-    ucap = ((block * 11 + 31) // 32 + 2 + 3) // 4 * 4
-    units = torch.zeros(nstreams * ucap, dtype=torch.int32, device=dev)
-    streams = np.zeros((nstreams, 4), np.uint64)
-    escr = torch.empty(L.b200lc_cuhd_encode_scratch_bytes(block), dtype=torch.uint8, device=dev)
-    comp = 0
-    for s in range(nstreams):
-        enc = pkg.cuhd_encode(data[s * block:(s + 1) * block], d_code, d_len, units=units[s * ucap:(s + 1) * ucap],
-                              scratch=escr)
-        streams[s] = (s * ucap, enc.n_units, s * block, block)
-        comp += enc.n_units * 4
-    lanes = min(NSTREAMS, nstreams)
-    cstreams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
-    bits = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(lanes)]
-    escrs = [torch.empty(L.b200lc_cuhd_encode_scratch_bytes(block), dtype=torch.uint8, device=dev) for _ in range(lanes)]
+    units, bits, stride = pkg.cuhd_encode_blocks(data, block, d_code, d_len)
+    escr = torch.empty(L.b200lc_cuhd_encode_blocks_scratch_bytes(n, block), dtype=torch.uint8, device=dev)
 
     def enc_all():
-        main = torch.cuda.current_stream()
         pkg.histogram_u8(data)
-        start = torch.cuda.Event()
-        start.record(main)
-        for st in cstreams:
-            st.wait_event(start)
-        for s in range(nstreams):
-            k = s % lanes
-            with torch.cuda.stream(cstreams[k]):
-                pkg.cuhd_encode(data[s * block:(s + 1) * block], d_code, d_len, units=units[s * ucap:(s + 1) * ucap],
-                                total_bits=bits[k], scratch=escrs[k], sync=False, stream=cstreams[k])
-        for st in cstreams:
-            main.wait_stream(st)
+        pkg.cuhd_encode_blocks(data, block, d_code, d_len, unit_stride=stride, units=units, block_bits=bits,
+                               scratch=escr)
 
+    enc_ms = timeit(enc_all, iters=3, warm=1)
+    nu = (bits.cpu().numpy().astype(np.int64) + 31) // 32
+    streams = np.zeros((nstreams, 4), np.uint64)
+    streams[:, 0] = np.arange(nstreams, dtype=np.uint64) * np.uint64(stride)
+    streams[:, 1] = nu.astype(np.uint64)
+    streams[:, 2] = np.arange(nstreams, dtype=np.uint64) * np.uint64(block)
+    streams[:, 3] = block
+    comp = int(nu.sum()) * 4
     out = torch.empty(n, dtype=torch.uint8, device=dev)
     dscr = torch.empty(L.b200lc_cuhd_decode_batch_scratch_bytes(streams.ctypes.data, nstreams) + 256,
                        dtype=torch.uint8, device=dev)
-    enc_ms = timeit(enc_all, iters=3, warm=1)
     dec_ms = timeit(lambda: pkg.cuhd_decode_batch(units, out, streams, d_lut, scratch=dscr), iters=3, warm=1)
     torch.cuda.synchronize()
     return enc_ms, dec_ms, comp, bool(torch.equal(out, data))
