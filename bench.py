@@ -106,6 +106,23 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def profiled_traffic(mib):
+    """DRAM bytes per launch of the decode kernel (dram__bytes_read.sum + dram__bytes_write.sum) from
+    the committed `ncu --set full` capture of the same workload (profiles/, 1 GiB only), else None."""
+    if mib != 1024:
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r01_cuhd_decode_ncu_full_summary.txt")
+    try:
+        total = 0.0
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[-1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[-2]]
+        return (total or None), "profiles/r01_cuhd_decode_ncu_full_summary.txt"
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -318,6 +335,7 @@ def run_ours(args, rank, world, local_rank):
         return
 
     peak, peak_src = measured_peak()
+    traffic, traffic_src = profiled_traffic(args.mib)
     n_units = state["n_units"]
     dec_bytes = 4 * n_units + n + (2 << MAX_LEN)          # algorithmic bytes of one decode launch
     dec_gbs = dec_bytes / (dec_mean * 1e-3) / 1e9
@@ -346,8 +364,8 @@ def run_ours(args, rank, world, local_rank):
         "encode_gbs": world * n / (enc_mean * 1e-3) / 1e9,
         "decode_gbs": world * n / (dec_mean * 1e-3) / 1e9,
         "roofline": {"kernel": "cuhd_decode_kernel", "bound": "hbm", "achieved": dec_gbs,
-                     "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak, "traffic": None,
-                     "peak_source": peak_src,
+                     "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak, "traffic": traffic,
+                     "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes": dec_bytes, "launch_ms": dec_mean},
         "e2e": {"value": world * n / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
