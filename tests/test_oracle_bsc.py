@@ -6,7 +6,17 @@ import pytest
 
 import oracle_lib as O
 
-pytestmark = pytest.mark.skipif(not O.have_ref("bsc"), reason="oracle/_ref/libref_bsc.so not built")
+import os
+
+needs_ref = pytest.mark.skipif(not O.have_ref("bsc"), reason="oracle/_ref/libref_bsc.so not built")
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["bsc_zipf", "bsc_binary"])
+def test_oracle_matches_golden_from_reference_divbwt(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))       # written by tools/make_golden.py from the reference
+    u, p, idx = O.bsc_oracle_bwt_encode(g["data"])
+    assert p == int(g["primary"]) and np.array_equal(u, g["U"]) and np.array_equal(idx, g["indexes"])
 
 
 def _cases():
@@ -25,6 +35,7 @@ def _cases():
     }
 
 
+@needs_ref
 @pytest.mark.parametrize("name", list(_cases().keys()))
 def test_oracle_equals_reference_divbwt(name):
     data = _cases()[name]

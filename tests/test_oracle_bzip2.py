@@ -105,3 +105,15 @@ def test_code_lengths_oracle_equals_reference_hbMakeCodeLengths():
         ref(b.ctypes.data_as(C.c_void_p), freq.ctypes.data_as(C.c_void_p), alpha, 17)
         assert np.array_equal(a, b), (trial, alpha)
         assert a.max() <= 17 and a.min() >= 1
+
+
+@pytest.mark.parametrize("name", ["bzip2_text", "bzip2_zipf"])
+def test_back_end_oracle_matches_golden_from_reference(name):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))   # tools/make_golden.py
+    block, ptr = g["block"], g["ptr"]
+    mtfv, freq, used = O.bzip2_oracle_mtf_rle(block, ptr)
+    assert used == int(g["n_in_use"]) and np.array_equal(mtfv, g["mtfv"]) and np.array_equal(freq, g["freq"])
+    bits, nbits, lens, sel, groups = O.bzip2_oracle_send_mtf(mtfv, freq, O.bzip2_in_use(block), used)
+    assert nbits == int(g["nbits"]) and np.array_equal(bits, g["bits"]) and np.array_equal(sel, g["selector"])
+    assert np.array_equal(lens[:groups, : used + 2], g["lens"][:groups, : used + 2])

@@ -6,6 +6,9 @@
   cuhd_binom.npz   : same for the reference demo's binomial byte distribution (demo.cc.ori:54-63)
   culzss_quant.npz : reference aftercompression_wrapper output for a 64 KiB quant-code buffer
   culzss_text.npz  : same for 64 KiB of the bundled pg1661.txt
+  bsc_*.npz        : reference bsc_bwt_encode (divbwt): U, primary index, secondary indexes
+  bzip2_*.npz      : reference generateMTFValues + sendMTFValues on a sorted block: mtfv, mtfFreq,
+                     code lengths, selectors, bit string
 """
 import os
 import sys
@@ -57,8 +60,28 @@ def cudpp(name, data):
                         tree_head=np.int64(head.value), offsets=offs, words=words)
 
 
+def bsc(name, data):
+    u, p, idx = O.bsc_ref_bwt_encode(data)
+    np.savez_compressed(os.path.join(OUT, name), data=data, U=u, primary=np.int64(p), indexes=idx)
+
+
+def bzip2(name, block):
+    n = block.size
+    ptr = np.zeros(n, np.uint32)
+    O.oracle().bzip2_oracle_rotation_order(block, n, ptr)       # any correct rotation order
+    mtfv, freq, used = O.bzip2_ref_mtf_rle(block, ptr)
+    bits, nbits, lens, sel = O.bzip2_ref_send_mtf(mtfv, freq, O.bzip2_in_use(block), used)
+    np.savez_compressed(os.path.join(OUT, name), block=block, ptr=ptr, mtfv=mtfv, freq=freq,
+                        n_in_use=np.int64(used), bits=bits, nbits=np.int64(nbits), lens=lens, selector=sel)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    bsc("bsc_zipf.npz", O.zipf_bytes(70001, 1.3, seed=3))
+    bsc("bsc_binary.npz", np.random.default_rng(5).integers(0, 2, 20000, dtype=np.uint8))
+    bzip2("bzip2_text.npz", np.frombuffer((b"it was the best of times, it was the worst of times, " * 600)[:30000],
+                                          np.uint8).copy())
+    bzip2("bzip2_zipf.npz", O.zipf_bytes(40000, 1.5, seed=4))
     cudpp("cudpp_zipf.npz", O.cudpp_block(32768, "zipf", seed=1))
     cudpp("cudpp_text.npz", O.cudpp_block(32768, "text", seed=2))
     cuhd("cuhd_zipf.npz", O.zipf_bytes(20000, 1.1, seed=12345))
