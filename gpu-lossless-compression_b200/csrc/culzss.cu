@@ -554,8 +554,19 @@ __global__ void __launch_bounds__(kDecWarps * 32) culzss_decode_kernel(
                 const u32 off = get(fp++);
                 const u32 a = (w - off) & 127;      // distance from source slot to write slot
                 if ((a == 0 || a >= len) && len <= 64 && w + len <= kPacket) {
-                    // source slots are not overwritten before they are read: forward copy
-                    for (u32 k = 0; k < len; ++k) row[(w + k) & 127] = row[(off + k) & 127];
+                    // source slots are not overwritten before they are read: forward copy, four
+                    // bytes per step (two aligned ring words funnel-shifted to the source offset;
+                    // a step only overwrites slots whose source bytes earlier steps have consumed)
+                    const u32 *row32 = reinterpret_cast<const u32 *>(row);
+                    for (u32 k = 0; k < len; k += 4) {
+                        const u32 s = (off + k) & 127, i0 = s >> 2;
+                        const u32 x = __funnelshift_r(row32[i0], row32[(i0 + 1) & 31], 8 * (s & 3));
+                        const u32 d = w + k;
+                        row[d & 127] = (u8)x;
+                        if (k + 1 < len) row[(d + 1) & 127] = (u8)(x >> 8);
+                        if (k + 2 < len) row[(d + 2) & 127] = (u8)(x >> 16);
+                        if (k + 3 < len) row[(d + 3) & 127] = (u8)(x >> 24);
+                    }
                     w += len;
                 } else {
                     // general case exactly as the reference (gpu_decompress.cu:220-236):
