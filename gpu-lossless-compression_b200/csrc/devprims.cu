@@ -6,9 +6,10 @@
 //   * one kernel per pass ("one sweep"): a CTA takes a tile of 4096 pairs through a ticket,
 //     stages it into shared memory with two 1-D TMA bulk copies, ranks the keys warp by warp
 //     (match.any on the digit: peers of a digit share one counter update, which keeps the sort
-//     stable), publishes the tile's 256 digit counts, resolves the counts of all earlier tiles
-//     of its segment by a decoupled look-back (one thread per digit), reorders the tile in
-//     shared memory and writes every digit run to its final place with coalesced stores.
+//     stable), publishes the tile's 256 digit counts right away, reorders the tile in shared
+//     memory, and only then resolves the counts of all earlier tiles of its segment by a
+//     decoupled look-back (one thread per digit; by now their counts have had time to land)
+//     and writes every digit run to its final place with coalesced stores.
 //     Keys and values cross HBM once per pass in each direction.
 //   * segments (independent BWT blocks) never exchange elements: tiles do not straddle segment
 //     boundaries and the look-back stops at the first tile of a segment, so the block number
