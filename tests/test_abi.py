@@ -55,3 +55,24 @@ def test_errors_without_gpu_are_loud():
     assert lib.b200lc_cuhd_decode(None, 10, None, 10, None, 11, None, 0, None) == b200lc.ERR_ARG
     assert lib.b200lc_cuhd_decode(None, 10, None, 10, None, 20, None, 0, None) == b200lc.ERR_UNSUPPORTED
     assert lib.b200lc_culzss_encode_batch(None, 1, 4096, None, 0, None, None, 0, None) == b200lc.ERR_ARG
+
+
+def test_new_entry_points_reject_bad_arguments_before_touching_cuda():
+    lib = b200lc.lib()
+    E = b200lc
+    where = ctypes.c_int(0)
+    assert lib.b200lc_sort_pairs_u64(None, None, None, None, 10, 0, 0, 48, None, 0, None, ctypes.byref(where)) == E.ERR_ARG
+    assert lib.b200lc_sort_pairs_u32(None, None, None, None, 0, 0, 0, 32, None, 0, None, ctypes.byref(where)) == E.OK   # nothing to sort
+    assert lib.b200lc_exclusive_sum_u32(None, None, 10, None, 0, None) == E.ERR_ARG
+    assert lib.b200lc_cuhd_decode_batch(None, None, None, 3, None, 11, None, 0, None) == E.ERR_ARG
+    assert lib.b200lc_cuhd_decode_batch(None, None, None, 3, None, 14, None, 0, None) == E.ERR_UNSUPPORTED
+    assert lib.b200lc_cuhd_encode_blocks(None, 100, 0, None, None, None, 0, None, None, 0, None) == E.ERR_ARG
+    assert lib.b200lc_bzip2_mtf_rle(None, None, 10, None, None, None, None, None) == E.ERR_ARG
+    nb = ctypes.c_ulonglong(0)
+    assert lib.b200lc_bzip2_send_mtf_values(None, 10, None, None, 4, None, 0, ctypes.byref(nb), None, None) == E.ERR_ARG
+    assert lib.bsc_bwt_encode(None, 10, None, None, 0) == -1          # LIBBSC_BAD_PARAMETER (libbsc.h:52)
+    assert lib.b200lc_sort_scratch_bytes(1 << 20, 1 << 18) > (1 << 20) // 4096 * 1024
+    # scratch sizes are pure host arithmetic
+    st = (ctypes.c_uint64 * 8)(0, 1000, 0, 4000, 1000, 2000, 4000, 8000)
+    assert lib.b200lc_cuhd_decode_batch_scratch_bytes(st, 2) >= 128 + 2 * 64
+    assert lib.b200lc_cuhd_encode_blocks_scratch_bytes(1 << 20, 1 << 16) >= 256 + 16 * 16
