@@ -846,8 +846,6 @@ struct BatchPlan {
 static int plan_batch(const uint32_t *d_units, uint8_t *d_out, const b200lc_cuhd_stream *h, size_t n,
                       BatchPlan &bp)
 {
-    u64 total_units = 0;
-    for (size_t i = 0; i < n; ++i) total_units += h[i].n_units;
     // piece length from the total size, like pick_variant does for one stream
     bp.v = &cuhd::kVariants[4];
     if (getenv("B200LC_CUHD_VARIANT")) bp.v = &cuhd::variant();
@@ -876,7 +874,6 @@ static int plan_batch(const uint32_t *d_units, uint8_t *d_out, const b200lc_cuhd
     bp.views_off = bp.desc_off + up(bp.pieces * sizeof(cuhd::TileDesc));
     bp.map_off = bp.views_off + up(bp.views.size() * sizeof(cuhd::StreamView));
     bp.total = bp.map_off + up(bp.pieces * 4);
-    (void)total_units;
     return B200LC_OK;
 }
 }  // namespace
