@@ -235,14 +235,17 @@ def run_ours(args, rank, world, local_rank):
     enc_scratch = torch.empty(L.b200lc_cuhd_encode_scratch_bytes(n), dtype=torch.uint8, device=dev)
     dec_scratch = torch.empty(L.b200lc_cuhd_decode_scratch_bytes(units_cap), dtype=torch.uint8,
                               device=dev)
+    piece_hist = torch.empty(max(1, L.b200lc_cuhd_piece_hist_bytes(n) // 4), dtype=torch.int32, device=dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     state = {}
 
     def step(timed):
-        """hist -> table -> pack -> decode, all on `stream`; returns (enc_ms, dec_ms) if timed."""
+        """hist (+ per-piece histograms) -> table -> one-pass pack -> decode, all on `stream`;
+        returns (enc_ms, dec_ms) if timed."""
         if timed:
             ev[0].record(stream)
-        pkg.check(L.b200lc_histogram_u8(data.data_ptr(), n, hist.data_ptr(), sp), "hist")
+        pkg.check(L.b200lc_histogram_u8_pieces(data.data_ptr(), n, hist.data_ptr(), piece_hist.data_ptr(), sp),
+                  "hist")
         h_hist.copy_(hist, non_blocking=True)
         stream.synchronize()                      # the code table is built on the host
         pkg.check(L.b200lc_cuhd_build_table(h_hist.data_ptr(), MAX_LEN, h_code.data_ptr(),
@@ -250,9 +253,10 @@ def run_ours(args, rank, world, local_rank):
         d_code.copy_(h_code, non_blocking=True)
         d_len.copy_(h_len, non_blocking=True)
         d_lut.copy_(h_lut, non_blocking=True)
-        pkg.check(L.b200lc_cuhd_encode(data.data_ptr(), n, d_code.data_ptr(), d_len.data_ptr(),
-                                       units.data_ptr(), units_cap, bits.data_ptr(),
-                                       enc_scratch.data_ptr(), enc_scratch.numel(), sp), "encode")
+        pkg.check(L.b200lc_cuhd_encode_planned(data.data_ptr(), n, d_code.data_ptr(), d_len.data_ptr(),
+                                               piece_hist.data_ptr(), units.data_ptr(), units_cap,
+                                               bits.data_ptr(), enc_scratch.data_ptr(), enc_scratch.numel(),
+                                               sp), "encode")
         n_units = L.b200lc_cuhd_compressed_units(h_hist.data_ptr(), h_len.data_ptr()) + 1
         if timed:
             ev[1].record(stream)
@@ -370,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": world * n / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "b200lc_cuhd_session_encode + b200lc_cuhd_session_decode, pinned host buffers"},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 6 * args.steps,   # piece histograms, their reduction, piece bits, plan, pack, decode
         "clocks": clocks,
     }
     if cpu:

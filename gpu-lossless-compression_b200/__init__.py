@@ -56,6 +56,12 @@ def lib():
     L.b200lc_cuhd_encode_blocks_scratch_bytes.argtypes = [sz, sz]
     L.b200lc_cuhd_encode_blocks.restype = i32
     L.b200lc_cuhd_encode_blocks.argtypes = [vp, sz, sz, vp, vp, vp, sz, vp, vp, sz, vp]
+    L.b200lc_cuhd_piece_hist_bytes.restype = sz
+    L.b200lc_cuhd_piece_hist_bytes.argtypes = [sz]
+    L.b200lc_histogram_u8_pieces.restype = i32
+    L.b200lc_histogram_u8_pieces.argtypes = [vp, sz, vp, vp, vp]
+    L.b200lc_cuhd_encode_planned.restype = i32
+    L.b200lc_cuhd_encode_planned.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp, vp, sz, vp]
     L.b200lc_cuhd_encode_overflowed.restype = i32
     L.b200lc_cuhd_encode_overflowed.argtypes = [vp, vp]
     L.b200lc_cuhd_session_create.restype = i32
@@ -206,7 +212,7 @@ class CuhdEncoded:
 
 
 def cuhd_encode(data, code, length, units_cap=None, stream=None, scratch=None, units=None,
-                total_bits=None, sync=True):
+                total_bits=None, sync=True, piece_hist=None):
     """Pack a cuda uint8 tensor with the dictionary (code, length: cuda int32[256] / uint8[256]).
 
     With sync=True (default) the bit count is read back and the unit tensor is trimmed to
@@ -226,10 +232,16 @@ def cuhd_encode(data, code, length, units_cap=None, stream=None, scratch=None, u
     need = L.b200lc_cuhd_encode_scratch_bytes(n)
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty(need, dtype=torch.uint8, device=data.device)
-    check(L.b200lc_cuhd_encode(data.data_ptr(), n, code.data_ptr(), length.data_ptr(),
-                               units.data_ptr(), units_cap, total_bits.data_ptr(),
-                               scratch.data_ptr(), scratch.numel(), _stream_ptr(stream)),
-          "b200lc_cuhd_encode")
+    if piece_hist is not None:      # one-pass packer on the piece histograms of histogram_u8_pieces
+        check(L.b200lc_cuhd_encode_planned(data.data_ptr(), n, code.data_ptr(), length.data_ptr(),
+                                           piece_hist.data_ptr(), units.data_ptr(), units_cap,
+                                           total_bits.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                           _stream_ptr(stream)), "b200lc_cuhd_encode_planned")
+    else:
+        check(L.b200lc_cuhd_encode(data.data_ptr(), n, code.data_ptr(), length.data_ptr(),
+                                   units.data_ptr(), units_cap, total_bits.data_ptr(),
+                                   scratch.data_ptr(), scratch.numel(), _stream_ptr(stream)),
+              "b200lc_cuhd_encode")
     if not sync:
         return CuhdEncoded(units, None, total_bits)
     check(L.b200lc_cuhd_encode_overflowed(scratch.data_ptr(), _stream_ptr(stream)),
@@ -237,6 +249,19 @@ def cuhd_encode(data, code, length, units_cap=None, stream=None, scratch=None, u
     bits = int(total_bits.item())
     n_units = (bits + 31) // 32
     return CuhdEncoded(units[: min(n_units + 1, units_cap)], n_units, bits)
+
+
+def histogram_u8_pieces(data, piece_hist=None, stream=None):
+    """-> (hist int64[256], piece_hist int32[pieces * 256]) for cuhd_encode(..., piece_hist=...)."""
+    import torch
+    L = lib()
+    n = data.numel()
+    hist = torch.empty(256, dtype=torch.int64, device=data.device)
+    if piece_hist is None:
+        piece_hist = torch.empty(max(1, L.b200lc_cuhd_piece_hist_bytes(n) // 4), dtype=torch.int32, device=data.device)
+    check(L.b200lc_histogram_u8_pieces(data.data_ptr(), n, hist.data_ptr(), piece_hist.data_ptr(),
+                                       _stream_ptr(stream)), "b200lc_histogram_u8_pieces")
+    return hist, piece_hist
 
 
 def cuhd_encode_blocks(data, block, code, length, unit_stride=None, units=None, block_bits=None,

@@ -59,6 +59,7 @@ struct EncParams {
     u32 pieces_per_block;
     u32 aligned;         // input base and block_syms are multiples of 16: TMA bulk copies allowed
     u64 *block_bits;     // [blocks] stream bits of every block (nullptr for a plain call)
+    const u64 *base_bits;   // PLANNED: bit offset of every piece, known before the launch
 };
 
 // What a piece needs to know about its block.
@@ -100,6 +101,11 @@ struct EncSmem {
     u32 tail_bits[2];
 };
 
+// PLANNED: the bit offset of every piece is an input (computed from per-piece histograms and the
+// code lengths, see b200lc_cuhd_encode_planned), so the counting pass and the look-back disappear.
+// Without the predecessor's tail a piece cannot complete the word it shares with its neighbour:
+// both sides OR their bits into that word, which the planning kernel has zeroed.
+template <bool PLANNED>
 __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p)
 {
     __shared__ EncSmem sm;
@@ -213,6 +219,13 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             return bits;
         };
 
+        if (PLANNED) {
+            if (tid == 0) {
+                sm.base_bits = p.base_bits[piece];
+                sm.prev_tail = 0;
+            }
+            __syncthreads();
+        } else {
         // ================================================================ pass A: bit count
         u32 my_piece_bits = 0;   // per-thread partial over all sub-tiles (<= 16*16*13 bits)
         for (u32 c = 0; c < nsub; ++c) {
@@ -313,6 +326,7 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             }
         }
         __syncthreads();
+        }   // !PLANNED
 
         // ================================================================ pass B: pack + write
         u64 base = sm.base_bits;                 // running global bit offset
@@ -379,19 +393,30 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             __syncthreads();
             // the partial last word travels to the next sub-tile of this piece
             carry = sm.stage[salign + (tile_bits >> 5)];
+            if (PLANNED && c == nsub - 1 && !last_piece && (tile_bits & 31) && tid == 0) {
+                // ... or, at the end of a planned piece, is ORed into the word shared with the successor
+                const u64 idx = w0 + (tile_bits >> 5);
+                if (idx < p.out_cap_units) atomicOr(&V.out[idx], carry);
+                else atomicExch(p.overflow, 1u);
+            }
 
             if (w0 + nwords > p.out_cap_units) {
                 if (tid == 0) atomicExch(p.overflow, 1u);
             } else {
                 u32 *g = V.out + w0;
-                const u32 head = min(nwords, (4u - salign) & 3u);
-                const u32 nvec = (nwords - head) >> 2;
+                // a planned piece shares its first word with its predecessor: OR instead of store
+                const u32 skip = (PLANNED && c == 0 && r != 0 && nwords > 0) ? 1u : 0u;
+                if (skip && tid == 0) atomicOr(g, sm.stage[salign]);
+                const u32 sa = salign + skip, nw = nwords - skip;
+                u32 *gs = g + skip;
+                const u32 head = min(nw, (4u - (sa & 3u)) & 3u);
+                const u32 nvec = (nw - head) >> 2;
                 const u32 tail0 = head + (nvec << 2);
-                if (tid < head) g[tid] = sm.stage[salign + tid];
-                const uint4 *sv = reinterpret_cast<const uint4 *>(&sm.stage[salign + head]);
-                uint4 *gv = reinterpret_cast<uint4 *>(g + head);
+                if (tid < head) gs[tid] = sm.stage[sa + tid];
+                const uint4 *sv = reinterpret_cast<const uint4 *>(&sm.stage[sa + head]);
+                uint4 *gv = reinterpret_cast<uint4 *>(gs + head);
                 for (u32 i = tid; i < nvec; i += kThreads) gv[i] = sv[i];
-                if (tid < nwords - tail0) g[tail0 + tid] = sm.stage[salign + tail0 + tid];
+                if (tid < nw - tail0) gs[tail0 + tid] = sm.stage[sa + tail0 + tid];
                 if (last_tile && tid == 0) {
                     if (p.block_bits) p.block_bits[V.block] = base + total;
                     else *p.total_bits = base + total;
@@ -402,6 +427,96 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
             __syncthreads();   // staging + input buffer hand-over
             ++step;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------- planning
+// One 256-bin histogram per piece (kPieceSyms symbols), one CTA per piece.
+__global__ void __launch_bounds__(256) piece_hist_kernel(const u8 *__restrict__ in, u64 n, u32 *__restrict__ piece_hist)
+{
+    __shared__ u32 sh[8][256];
+    const u32 tid = threadIdx.x, warp = tid >> 5;
+    for (u32 i = tid; i < 8 * 256; i += 256) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const u64 first = (u64)blockIdx.x * kPieceSyms;
+    const u32 cnt = (u32)min((u64)kPieceSyms, n - first);
+    const uint4 *v = reinterpret_cast<const uint4 *>(in + first);      // piece starts are 16-byte aligned
+    for (u32 i = tid; i < (cnt >> 4); i += 256) {
+        const uint4 x = v[i];
+        const u32 w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            atomicAdd(&sh[warp][w[q] & 0xff], 1u);
+            atomicAdd(&sh[warp][(w[q] >> 8) & 0xff], 1u);
+            atomicAdd(&sh[warp][(w[q] >> 16) & 0xff], 1u);
+            atomicAdd(&sh[warp][w[q] >> 24], 1u);
+        }
+    }
+    for (u32 i = (cnt & ~15u) + tid; i < cnt; i += 256) atomicAdd(&sh[warp][in[first + i]], 1u);
+    __syncthreads();
+    u32 s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sh[w][tid];
+    piece_hist[(u64)blockIdx.x * 256 + tid] = s;
+}
+
+// column sums of the piece histograms -> the 64-bit histogram of the whole input
+__global__ void __launch_bounds__(256) hist_reduce_kernel(const u32 *__restrict__ piece_hist, u32 pieces,
+                                                          unsigned long long *__restrict__ hist)
+{
+    unsigned long long s = 0;
+    for (u32 p = blockIdx.x; p < pieces; p += gridDim.x) s += piece_hist[(u64)p * 256 + threadIdx.x];
+    if (s) atomicAdd(&hist[threadIdx.x], s);
+}
+
+// bits of every piece = <its histogram, code lengths>; one warp per piece
+__global__ void __launch_bounds__(256) piece_bits_kernel(const u32 *__restrict__ piece_hist, u32 pieces,
+                                                         const u8 *__restrict__ len_of_symbol,
+                                                         u64 *__restrict__ piece_bits)
+{
+    const u32 piece = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (piece >= pieces) return;
+    u32 s = 0;
+    for (u32 k = lane; k < 256; k += 32) s += piece_hist[(u64)piece * 256 + k] * (u32)len_of_symbol[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) piece_bits[piece] = s;
+}
+
+// exclusive scan of the piece bits (in place), zeroing of every word two pieces share, capacity check
+__global__ void __launch_bounds__(1024) plan_kernel(u64 *__restrict__ bits, u32 pieces, u32 *__restrict__ out,
+                                                    u64 out_cap_units, u32 *__restrict__ overflow)
+{
+    __shared__ u64 ws[32];
+    __shared__ u64 s_carry;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (u32 lo = 0; lo < pieces; lo += 1024) {
+        const u32 i = lo + tid;
+        const u64 v = i < pieces ? bits[i] : 0;
+        u64 incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (u32)d) incl += t;
+        }
+        if (lane == 31) ws[warp] = incl;
+        __syncthreads();
+        u64 pre = s_carry;
+        for (u32 w = 0; w < warp; ++w) pre += ws[w];
+        const u64 base = pre + incl - v;
+        if (i < pieces) {
+            bits[i] = base;
+            if (i > 0 && (base & 31)) {
+                if ((base >> 5) < out_cap_units) out[base >> 5] = 0;
+                else atomicExch(overflow, 1u);
+            }
+            if (i == pieces - 1 && ((base + v + 31) >> 5) > out_cap_units) atomicExch(overflow, 1u);
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = base + v;
+        __syncthreads();
     }
 }
 
@@ -506,15 +621,92 @@ extern "C" int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t 
     p.pieces_per_block = p.num_pieces;
     p.aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
     p.block_bits = nullptr;
+    p.base_bits = nullptr;
 
     static int occ = 0;
     if (!occ) {
         B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &occ, cuhd_enc::cuhd_encode_kernel, cuhd_enc::kThreads, 0));
+            &occ, cuhd_enc::cuhd_encode_kernel<false>, cuhd_enc::kThreads, 0));
         if (occ < 1) return B200LC_ERR_CUDA;
     }
     const u32 grid = (u32)min((u64)p.num_pieces, (u64)num_sms() * (u64)occ);
-    cuhd_enc::cuhd_encode_kernel<<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
+    cuhd_enc::cuhd_encode_kernel<false><<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}
+
+// Histogram that also keeps one 256-bin histogram per piece for b200lc_cuhd_encode_planned.
+extern "C" size_t b200lc_cuhd_piece_hist_bytes(size_t n)
+{
+    return (size_t)cuhd_enc::pieces_for(n) * 256 * sizeof(u32);
+}
+
+extern "C" int b200lc_histogram_u8_pieces(const uint8_t *d_in, size_t n, uint64_t *d_hist,
+                                          uint32_t *d_piece_hist, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_hist || !d_piece_hist || (n && !d_in)) return B200LC_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_in) & 15) return B200LC_ERR_ARG;
+    B200LC_CUDA_TRY(cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint64_t), stream));
+    if (n == 0) return B200LC_OK;
+    const u32 pieces = cuhd_enc::pieces_for(n);
+    cuhd_enc::piece_hist_kernel<<<pieces, 256, 0, stream>>>(d_in, n, d_piece_hist);
+    cuhd_enc::hist_reduce_kernel<<<min(pieces, 64u), 256, 0, stream>>>(
+        d_piece_hist, pieces, reinterpret_cast<unsigned long long *>(d_hist));
+    B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}
+
+// b200lc_cuhd_encode with the piece histograms of b200lc_histogram_u8_pieces: same stream, one pass.
+extern "C" int b200lc_cuhd_encode_planned(const uint8_t *d_in, size_t n, const uint32_t *d_code_of_symbol,
+                                          const uint8_t *d_len_of_symbol, const uint32_t *d_piece_hist,
+                                          uint32_t *d_units, size_t units_cap, uint64_t *d_total_bits,
+                                          void *d_scratch, size_t scratch_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_code_of_symbol || !d_len_of_symbol || !d_piece_hist || !d_units || !d_total_bits || !d_scratch)
+        return B200LC_ERR_ARG;
+    if (n && !d_in) return B200LC_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_scratch) & 127) || (reinterpret_cast<uintptr_t>(d_units) & 15) ||
+        (reinterpret_cast<uintptr_t>(d_in) & 15))
+        return B200LC_ERR_ARG;
+    const size_t need = b200lc_cuhd_encode_scratch_bytes(n);
+    if (scratch_bytes < need) return B200LC_ERR_SCRATCH;
+    B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 256, stream));
+    if (n == 0) {
+        B200LC_CUDA_TRY(cudaMemsetAsync(d_total_bits, 0, sizeof(uint64_t), stream));
+        return B200LC_OK;
+    }
+    cuhd_enc::EncParams p;
+    p.in = d_in;
+    p.n = n;
+    p.code_of_symbol = d_code_of_symbol;
+    p.len_of_symbol = d_len_of_symbol;
+    p.out = d_units;
+    p.out_cap_units = units_cap;
+    p.total_bits = d_total_bits;
+    p.ticket = reinterpret_cast<u32 *>(d_scratch);
+    p.overflow = reinterpret_cast<u32 *>(d_scratch) + 1;
+    p.desc = nullptr;
+    p.num_pieces = cuhd_enc::pieces_for(n);
+    p.block_syms = n;
+    p.unit_stride = 0;
+    p.pieces_per_block = p.num_pieces;
+    p.aligned = 1;
+    p.block_bits = nullptr;
+    u64 *base_bits = reinterpret_cast<u64 *>(reinterpret_cast<char *>(d_scratch) + 256);
+    p.base_bits = base_bits;
+    cuhd_enc::piece_bits_kernel<<<(p.num_pieces + 7) / 8, 256, 0, stream>>>(d_piece_hist, p.num_pieces,
+                                                                            d_len_of_symbol, base_bits);
+    cuhd_enc::plan_kernel<<<1, 1024, 0, stream>>>(base_bits, p.num_pieces, d_units, units_cap, p.overflow);
+    static int occ = 0;
+    if (!occ) {
+        B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cuhd_enc::cuhd_encode_kernel<true>,
+                                                                      cuhd_enc::kThreads, 0));
+        if (occ < 1) return B200LC_ERR_CUDA;
+    }
+    const u32 grid = (u32)min((u64)p.num_pieces, (u64)num_sms() * (u64)occ);
+    cuhd_enc::cuhd_encode_kernel<true><<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }
@@ -561,12 +753,13 @@ extern "C" int b200lc_cuhd_encode_blocks(const uint8_t *d_in, size_t n, size_t b
     p.pieces_per_block = (u32)ppb;
     p.aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && block_symbols % 16 == 0;
     p.block_bits = d_block_bits;
+    p.base_bits = nullptr;
     int occ = 0;
-    B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cuhd_enc::cuhd_encode_kernel,
+    B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cuhd_enc::cuhd_encode_kernel<false>,
                                                                   cuhd_enc::kThreads, 0));
     if (occ < 1) return B200LC_ERR_CUDA;
     const u32 grid = (u32)min((u64)p.num_pieces, (u64)num_sms() * (u64)occ);
-    cuhd_enc::cuhd_encode_kernel<<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
+    cuhd_enc::cuhd_encode_kernel<false><<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }

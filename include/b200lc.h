@@ -123,6 +123,19 @@ int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t *d_code_of_
                        void *stream);
 int b200lc_cuhd_encode_overflowed(const void *d_scratch, void *stream);
 
+/* One-pass variant for callers that run the histogram anyway: b200lc_histogram_u8_pieces also keeps
+ * one 256-bin histogram per 128 KiB piece (d_piece_hist, b200lc_cuhd_piece_hist_bytes(n) bytes);
+ * with them and the code lengths b200lc_cuhd_encode_planned knows the bit offset of every piece
+ * before it starts, so the packer's counting pass and its look-back disappear.  Same arguments,
+ * same output and same overflow reporting as b200lc_cuhd_encode.  Asynchronous. */
+size_t b200lc_cuhd_piece_hist_bytes(size_t n);
+int b200lc_histogram_u8_pieces(const uint8_t *d_in, size_t n, uint64_t *d_hist, uint32_t *d_piece_hist,
+                               void *stream);
+int b200lc_cuhd_encode_planned(const uint8_t *d_in, size_t n, const uint32_t *d_code_of_symbol,
+                               const uint8_t *d_len_of_symbol, const uint32_t *d_piece_hist,
+                               uint32_t *d_units, size_t units_cap, uint64_t *d_total_bits,
+                               void *d_scratch, size_t scratch_bytes, void *stream);
+
 /* Blocks: d_in[n] is cut into blocks of block_symbols symbols (the last one may be shorter) and
  * every block is packed as an independent stream with the same dictionary, all by one launch:
  * block b starts at bit 0 of d_units + b * unit_stride (unit_stride a multiple of 4, at least

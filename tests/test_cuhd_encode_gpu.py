@@ -123,3 +123,33 @@ def test_encode_blocks_equals_per_block_encode_and_round_trips_through_batch_dec
     out = torch.empty(n, dtype=torch.uint8, device=DEVB)
     b200lc.cuhd_decode_batch(units, out, streams, torch.from_numpy(lut).to(DEVB))
     assert np.array_equal(out.cpu().numpy(), data)
+
+
+# ------------------------------------------------------------------------------------------ planned
+@pytest.mark.parametrize("n", [2, 100, 8193, 131072, 131073, 5 * 131072, (1 << 22) + 77, (1 << 24) + 12345])
+@pytest.mark.parametrize("alpha", [1.1, 3.0])
+def test_planned_encode_is_identical_to_the_two_pass_encode(n, alpha):
+    data = O.zipf_bytes(n, alpha, seed=n % 991)
+    d = torch.from_numpy(data).to(DEV)
+    hist, ph = b200lc.histogram_u8_pieces(d)
+    assert np.array_equal(hist.cpu().numpy(), np.bincount(data, minlength=256))
+    code, length, lut = b200lc.cuhd_build_table(hist.cpu().numpy())
+    d_code = torch.from_numpy(code.view(np.int32)).to(DEV)
+    d_len = torch.from_numpy(length).to(DEV)
+    a = b200lc.cuhd_encode(d, d_code, d_len)
+    b = b200lc.cuhd_encode(d, d_code, d_len, piece_hist=ph)
+    assert a.bits == b.bits and a.n_units == b.n_units
+    assert torch.equal(a.units[: a.n_units + 1], b.units[: b.n_units + 1])       # incl. the pad unit
+    out = b200lc.cuhd_decode(b.units, n, torch.from_numpy(lut).to(DEV))
+    assert np.array_equal(out.cpu().numpy(), data)
+
+
+def test_planned_encode_reports_overflow():
+    n = 1 << 20
+    data = O.zipf_bytes(n, 1.1, seed=5)
+    d = torch.from_numpy(data).to(DEV)
+    hist, ph = b200lc.histogram_u8_pieces(d)
+    code, length, _ = b200lc.cuhd_build_table(hist.cpu().numpy())
+    with pytest.raises(b200lc.B200LCError):
+        b200lc.cuhd_encode(d, torch.from_numpy(code.view(np.int32)).to(DEV), torch.from_numpy(length).to(DEV),
+                           units_cap=1000, piece_hist=ph)
