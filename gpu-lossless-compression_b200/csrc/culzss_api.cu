@@ -280,7 +280,13 @@ extern "C" int b200lc_culzss_decompress_container(const uint8_t *h_in, size_t n,
     if (out_bytes > cap) return B200LC_ERR_OVERFLOW;
     std::vector<u64> offs(nb + 1);
     offs[0] = 0;
-    for (size_t b = 0; b < nb; ++b) offs[b + 1] = hdr[2 + b];
+    for (size_t b = 0; b < nb; ++b) {
+        offs[b + 1] = hdr[2 + b];
+        // cumulative ends must grow, by at most the worst-case size of one stored buffer
+        // (aftercomp's test lets the payload pass buf_length by one token group, then the trailer)
+        if (offs[b + 1] <= offs[b] || offs[b + 1] - offs[b] > kBuf + 2 * (kBuf / 4096) + 6 + 32)
+            return B200LC_ERR_ARG;
+    }
     u8 *d_comp = nullptr, *d_out = nullptr;
     u64 *d_offs = nullptr;
     void *d_scratch = nullptr;

@@ -76,3 +76,30 @@ def test_new_entry_points_reject_bad_arguments_before_touching_cuda():
     st = (ctypes.c_uint64 * 8)(0, 1000, 0, 4000, 1000, 2000, 4000, 8000)
     assert lib.b200lc_cuhd_decode_batch_scratch_bytes(st, 2) >= 128 + 2 * 64
     assert lib.b200lc_cuhd_encode_blocks_scratch_bytes(1 << 20, 1 << 16) >= 256 + 16 * 16
+
+
+def test_culzss_container_header_is_validated_before_touching_cuda():
+    """u32 nblocks, u32 padding, u32 cumulative_end[nblocks] (cuda-lzss-cluster/culzss.c:220,243-264):
+    non-increasing ends, a buffer larger than the worst case, a truncated payload and an output
+    buffer that is too small are all rejected on the host."""
+    import numpy as np
+    lib = b200lc.lib()
+    lib.b200lc_culzss_decompress_container.restype = ctypes.c_int
+    lib.b200lc_culzss_decompress_container.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                                       ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    out = np.zeros(4 << 20, dtype=np.uint8)
+    got = ctypes.c_size_t(0)
+
+    def run(words, payload_bytes, cap=out.nbytes):
+        buf = np.concatenate([np.asarray(words, dtype=np.uint32).view(np.uint8),
+                              np.zeros(payload_bytes, dtype=np.uint8)])
+        return lib.b200lc_culzss_decompress_container(buf.ctypes.data, buf.nbytes, out.ctypes.data, cap,
+                                                      ctypes.byref(got))
+
+    assert run([2, 0, 1000, 1000], 1000) == b200lc.ERR_ARG          # second buffer is empty
+    assert run([2, 0, 2000, 1000], 2000) == b200lc.ERR_ARG          # ends go backwards
+    assert run([1, 0, (1 << 20) + 4096], (1 << 20) + 4096) == b200lc.ERR_ARG   # larger than any stored buffer
+    assert run([2, 0, 1000, 2000], 1500) == b200lc.ERR_ARG          # payload truncated
+    assert run([0, 0], 0) == b200lc.ERR_ARG                         # no buffers
+    assert run([1, 1 << 20, 1000], 1000) == b200lc.ERR_ARG          # padding of a whole buffer
+    assert run([2, 0, 1000, 2000], 2000, cap=1 << 20) == b200lc.ERR_OVERFLOW
