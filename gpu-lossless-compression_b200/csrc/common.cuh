@@ -33,18 +33,26 @@ enum {
         }                                                                             \
     } while (0)
 
+// Kernel attributes, occupancy and the SM count belong to the CURRENT device, and one process may
+// drive several devices (cudaSetDevice between calls): every cached value is kept per device.
+constexpr int kMaxDevices = 64;
+inline int device_slot()        // index into a per-device cache, -1 = do not cache
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    return dev;
+}
+
 inline int num_sms()
 {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = B200LC_NUM_SMS_FALLBACK;
-    }
-    return cached;
+    static int cached[kMaxDevices] = {0};
+    const int slot = device_slot();
+    if (slot >= 0 && cached[slot]) return cached[slot];
+    int n = 0;
+    if (slot < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, slot) != cudaSuccess || n <= 0)
+        return B200LC_NUM_SMS_FALLBACK;
+    cached[slot] = n;
+    return n;
 }
 
 #ifdef __CUDACC__

@@ -760,15 +760,15 @@ static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t
     if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
 
     const size_t smem = v.smem_fixed + (size_t(5) << max_codeword_length);
-    static int occ_table[cuhd::kNumVariants][14] = {{0}};
-    int *occ_cache = occ_table[&v - cuhd::kVariants];
-    if (!occ_cache[max_codeword_length]) {
+    static int occ_table[kMaxDevices][cuhd::kNumVariants][14] = {{{0}}};
+    const int slot = device_slot();
+    int occ = slot >= 0 ? occ_table[slot][&v - cuhd::kVariants][max_codeword_length] : 0;
+    if (!occ) {
         B200LC_CUDA_TRY(cudaFuncSetAttribute(v.kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
-        int occ = 0;
         B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.kern, v.T + 32, smem));
         if (occ < 1) return B200LC_ERR_CUDA;
-        occ_cache[max_codeword_length] = occ;
+        if (slot >= 0) occ_table[slot][&v - cuhd::kVariants][max_codeword_length] = occ;
     }
     cuhd::DecodeParams p;
     p.one = cuhd::make_view(v, d_units, n_units, d_out, n_out, 0);
@@ -789,7 +789,7 @@ static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t
     else
         B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128, stream));   // ticket only
     const u32 grid = (u32)min((u64)(end_piece - first_piece),
-                              (u64)num_sms() * (u64)occ_cache[max_codeword_length]);
+                              (u64)num_sms() * (u64)occ);
     v.kern<<<grid, v.T + 32, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;

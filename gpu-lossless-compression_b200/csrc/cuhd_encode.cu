@@ -623,11 +623,14 @@ extern "C" int b200lc_cuhd_encode(const uint8_t *d_in, size_t n, const uint32_t 
     p.block_bits = nullptr;
     p.base_bits = nullptr;
 
-    static int occ = 0;
+    static int occ_dev[kMaxDevices] = {0};
+    const int slot = device_slot();
+    int occ = slot >= 0 ? occ_dev[slot] : 0;
     if (!occ) {
         B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &occ, cuhd_enc::cuhd_encode_kernel<false>, cuhd_enc::kThreads, 0));
         if (occ < 1) return B200LC_ERR_CUDA;
+        if (slot >= 0) occ_dev[slot] = occ;
     }
     const u32 grid = (u32)min((u64)p.num_pieces, (u64)num_sms() * (u64)occ);
     cuhd_enc::cuhd_encode_kernel<false><<<grid, cuhd_enc::kThreads, 0, stream>>>(p);
@@ -699,11 +702,14 @@ extern "C" int b200lc_cuhd_encode_planned(const uint8_t *d_in, size_t n, const u
     cuhd_enc::piece_bits_kernel<<<(p.num_pieces + 7) / 8, 256, 0, stream>>>(d_piece_hist, p.num_pieces,
                                                                             d_len_of_symbol, base_bits);
     cuhd_enc::plan_kernel<<<1, 1024, 0, stream>>>(base_bits, p.num_pieces, d_units, units_cap, p.overflow);
-    static int occ = 0;
+    static int occ_dev[kMaxDevices] = {0};
+    const int slot = device_slot();
+    int occ = slot >= 0 ? occ_dev[slot] : 0;
     if (!occ) {
         B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cuhd_enc::cuhd_encode_kernel<true>,
                                                                       cuhd_enc::kThreads, 0));
         if (occ < 1) return B200LC_ERR_CUDA;
+        if (slot >= 0) occ_dev[slot] = occ;
     }
     const u32 grid = (u32)min((u64)p.num_pieces, (u64)num_sms() * (u64)occ);
     cuhd_enc::cuhd_encode_kernel<true><<<grid, cuhd_enc::kThreads, 0, stream>>>(p);

@@ -304,12 +304,13 @@ int sort_pairs(K *keys_a, K *keys_b, u32 *vals_a, u32 *vals_b, u64 n, u64 seg_le
     u32 *status = reinterpret_cast<u32 *>(base + L.status);
     u32 *hist = reinterpret_cast<u32 *>(base + L.hist);
 
-    static bool attr_done = false;
+    static bool attr_done[kMaxDevices] = {false};
+    const int slot = device_slot();
     const size_t smem = sizeof(SortSmem<K>);
-    if (!attr_done) {
+    if (slot < 0 || !attr_done[slot]) {
         B200LC_CUDA_TRY(cudaFuncSetAttribute(sort_onesweep_kernel<K>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        if (slot >= 0) attr_done[slot] = true;
     }
 
     B200LC_CUDA_TRY(cudaMemsetAsync(hist, 0, L.nseg * passes * 1024, stream));
