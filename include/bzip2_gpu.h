@@ -24,6 +24,8 @@
 #ifndef B200LC_BZIP2_GPU_H_
 #define B200LC_BZIP2_GPU_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 int gpuBlockSort(unsigned char *block, unsigned int *order, unsigned int *orderFirstSort,
                  unsigned int *orderSecondSort, unsigned int *orderFirstSortRank, int blockSize,

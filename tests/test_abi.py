@@ -103,3 +103,20 @@ def test_culzss_container_header_is_validated_before_touching_cuda():
     assert run([0, 0], 0) == b200lc.ERR_ARG                         # no buffers
     assert run([1, 1 << 20, 1000], 1000) == b200lc.ERR_ARG          # padding of a whole buffer
     assert run([2, 0, 1000, 2000], 2000, cap=1 << 20) == b200lc.ERR_OVERFLOW
+
+
+def test_public_headers_compile_standalone():
+    """Every header under include/ is self-contained: C99 for the C-ABI ones, C++ for the one that
+    keeps the reference's C++ linkage (bzip2_gpu.h) and for the CUHD class mirror."""
+    inc = os.path.join(ROOT, "include")
+    for h in sorted(glob.glob(os.path.join(inc, "*.h"))):
+        name = os.path.basename(h)
+        for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
+            r = subprocess.run(["gcc", std, "-Wall", "-Werror", "-I", inc, "-x", lang, "-fsyntax-only", "-"],
+                               input='#include "%s"\n' % name, capture_output=True, text=True)
+            assert r.returncode == 0, "%s as %s:\n%s" % (name, lang, r.stderr)
+    for h in sorted(glob.glob(os.path.join(inc, "cuhd_compat", "*.h"))):
+        r = subprocess.run(["g++", "-std=c++14", "-I", inc, "-I", os.path.join(inc, "cuhd_compat"),
+                            "-I", "/usr/local/cuda/include", "-x", "c++", "-fsyntax-only", "-"],
+                           input='#include "%s"\n' % os.path.basename(h), capture_output=True, text=True)
+        assert r.returncode == 0, "%s:\n%s" % (h, r.stderr)
