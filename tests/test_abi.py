@@ -120,3 +120,15 @@ def test_public_headers_compile_standalone():
                             "-I", "/usr/local/cuda/include", "-x", "c++", "-fsyntax-only", "-"],
                            input='#include "%s"\n' % os.path.basename(h), capture_output=True, text=True)
         assert r.returncode == 0, "%s:\n%s" % (h, r.stderr)
+
+
+def test_cudpp_header_matches_the_reference_abi(tmp_path):
+    """Enumerator values, CUDPPConfiguration layout and the handle type of include/cudpp.h equal what
+    the reference's cudpp-inpar/include/cudpp.h gives a C++ caller (golden: tools/make_abi_golden.sh)."""
+    exe = str(tmp_path / "dump")
+    r = subprocess.run(["g++", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "cudpp_enum_dump.cc"), "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ours = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert ours == open(os.path.join(ROOT, "tests", "golden", "cudpp_abi.txt")).read()
