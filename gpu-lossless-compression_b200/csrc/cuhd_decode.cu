@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "cuhd_walks.cuh"
 #include "../../include/b200lc.h"
 
 namespace b200lc {
@@ -83,92 +84,6 @@ struct DecodeParams {
     u32 num_pieces;      // pieces [first_piece, num_pieces) are decoded by this launch
     u32 first_piece;
 };
-
-// ---------------------------------------------------------------------------------- walks
-// Round 0: decode the subsequence from bit 0, remember every codeword start.
-template <int S>
-__device__ __forceinline__ void walk_record(const u32 (&u)[S + 1], const u8 *tab, u32 shift,
-                                            u32 (&m)[S], u32 &end, u32 &cnt)
-{
-    u32 at = 0, c = 0;
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-        const u32 cur = u[j], nxt = u[j + 1];
-        u32 mj = 0;
-        while (at < 32) {
-            mj |= 0x80000000u >> at;
-            const u32 w = __funnelshift_l(nxt, cur, at);
-            at += tab[w >> shift];
-        }
-        m[j] = mj;
-        c += __popc(mj);
-        at -= 32;
-    }
-    end = at;
-    cnt = c;
-}
-
-// Decode from entry state `a` until the walk lands on a codeword start of the recorded path
-// (then the rest of the subsequence is the recorded path: end = e0) or runs off the end.
-// No early return: a lane that has merged idles through the remaining unit loops so that the
-// warp reconverges after every unit (an early exit makes the lanes run the later loops one at
-// a time -- measured: 52% of all issued instructions at 1 active thread).
-template <int S>
-__device__ __forceinline__ void walk_merge(const u32 (&u)[S + 1], const u32 (&m)[S], u32 a, u32 e0,
-                                           const u8 *tab, u32 shift, u32 &end, u32 &cnt)
-{
-    u32 at = a, k = 0, rest = 0;
-    bool done = false;
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-        const u32 cur = u[j], nxt = u[j + 1], mj = m[j];
-        if (done) {
-            rest += __popc(mj);
-        } else {
-            while (at < 32) {
-                const u32 bit = 0x80000000u >> at;
-                if (mj & bit) {
-                    rest = __popc(mj & (bit | (bit - 1)));
-                    done = true;
-                    break;
-                }
-                const u32 w = __funnelshift_l(nxt, cur, at);
-                at += tab[w >> shift];
-                ++k;
-            }
-            if (!done) at -= 32;
-        }
-    }
-    end = done ? e0 : at;
-    cnt = k + rest;
-}
-
-// Write pass: decode from the true entry state, symbol i of this subsequence goes to dst[i].
-// Table entries carry TWO symbols when the window holds two whole codewords: bits 0..7 first
-// symbol, 8..15 second symbol, 16..23 bits consumed, bit 31 = second symbol present.  A second
-// symbol that starts beyond this subsequence is also the next subsequence's first symbol: it is
-// stored twice with the same value at the same position (or beyond the tile, where nothing is
-// copied out).  With CHECK, only tile-local positions in [lo, hi) are stored (staging-window
-// overflow path).
-template <int S, bool CHECK>
-__device__ __forceinline__ void walk_write(const u32 (&u)[S + 1], const u32 *tab, u32 shift, u32 a,
-                                           u8 *dst, u32 pos, u32 lo, u32 hi)
-{
-    u32 at = a;
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-        const u32 cur = u[j], nxt = u[j + 1];
-        while (at < 32) {
-            const u32 w = __funnelshift_l(nxt, cur, at);
-            const u32 e = tab[w >> shift];
-            if (!CHECK || (pos >= lo && pos < hi)) dst[pos] = (u8)e;
-            if ((int)e < 0 && (!CHECK || (pos + 1 >= lo && pos + 1 < hi))) dst[pos + 1] = (u8)(e >> 8);
-            pos += 1 + (e >> 31);
-            at += (e >> 16) & 0xffu;
-        }
-        at -= 32;
-    }
-}
 
 // ---------------------------------------------------------------------------------- kernel
 // Work decomposition: subsequence = S units (one thread), sub-tile = T subsequences (one TMA

@@ -1,0 +1,218 @@
+// The per-thread decode walks and the shared-memory table entries of the CUHD decoder
+// (cuhd_decode.cu), kept in a header that also compiles for the host so that the CPU test
+// tests/c/cuhd_walks_host.cc can run them against a bit-serial decode without a GPU.
+// Decode contract: SURVEY.md appendix A.1 (cuhd-icpp/src/cuhd_gpu_decoder.cu:16-143).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B200LC_HD __host__ __device__ __forceinline__
+#else
+#define B200LC_HD inline
+#endif
+
+namespace b200lc {
+namespace cuhd {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+
+// (hi:lo) << s, upper word; (hi:lo) >> s, lower word; s in 0..31
+B200LC_HD u32 fsl(u32 lo, u32 hi, u32 s)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    s &= 31;
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+B200LC_HD u32 fsr(u32 lo, u32 hi, u32 s)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    s &= 31;
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+B200LC_HD u32 popc32(u32 x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return (u32)__builtin_popcount(x);
+#endif
+}
+B200LC_HD u32 clz32(u32 x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz(x);
+#else
+    return x ? (u32)__builtin_clz(x) : 32u;
+#endif
+}
+
+// ---------------------------------------------------------------------------------- tables
+// Length of the first codeword of window `i` (the next L stream bits).  A zero-length entry
+// (unused prefix of an incomplete code) would stall the reference forever; it is mapped to
+// length 1 here so that garbage input still terminates.
+B200LC_HD u32 first_len(const u16 *lut, u32 i, u32 L)
+{
+    u32 len = lut[i] & 0xffu;
+    if (len == 0 || len > L) len = 1;
+    return len;
+}
+
+// Write-pass entry: bits 0..7 first symbol, 8..15 second symbol, 16..23 bits consumed, bit 31 =
+// second symbol present (the window holds two whole codewords).
+B200LC_HD u32 write_entry(const u16 *lut, u32 i, u32 L)
+{
+    const u32 e0 = lut[i];
+    const u32 len0 = first_len(lut, i, L);
+    const u32 i1 = (i << len0) & ((1u << L) - 1);
+    const u32 e1 = lut[i1];
+    const u32 len1 = first_len(lut, i1, L);
+    u32 entry = (e0 >> 8) | (len0 << 16);
+    if (len0 + len1 <= L) entry = (e0 >> 8) | (e1 & 0xff00u) | ((len0 + len1) << 16) | 0x80000000u;
+    return entry;
+}
+
+// Pass-A entry that covers EVERY whole codeword inside the window: bits 0..3 = bits consumed
+// (1..13), bit 16-o = a codeword starts at offset o (o = 1..12; offset 0 always starts one).
+// A codeword at offset o is known to be whole iff its length <= L - o: the window is
+// zero-filled beyond L bits, and a prefix code is decided by the codeword's own bits.
+B200LC_HD u16 multi_entry(const u16 *lut, u32 i, u32 L)
+{
+    const u32 mask = (1u << L) - 1;
+    u32 o = first_len(lut, i, L);
+    u32 e = 0;
+    while (o < L) {
+        const u32 len = first_len(lut, (i << o) & mask, L);
+        if (o + len > L) break;
+        e |= 1u << (16 - o);
+        o += len;
+    }
+    return (u16)(e | o);
+}
+
+// ---------------------------------------------------------------------------------- walks
+// Round 0: decode the subsequence from bit 0, remember every codeword start.
+template <int S>
+B200LC_HD void walk_record(const u32 (&u)[S + 1], const u8 *tab, u32 shift, u32 (&m)[S], u32 &end,
+                           u32 &cnt)
+{
+    u32 at = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1];
+        u32 mj = 0;
+        while (at < 32) {
+            mj |= 0x80000000u >> at;
+            const u32 w = fsl(nxt, cur, at);
+            at += tab[w >> shift];
+        }
+        m[j] = mj;
+        c += popc32(mj);
+        at -= 32;
+    }
+    end = at;
+    cnt = c;
+}
+
+// Same result as walk_record from multi_entry() tables: one lookup advances over all whole
+// codewords of the window (~1.8 on Zipf(1.1) data), i.e. half the dependent lookups.  Starts
+// that fall into the next unit travel in `carry` and seed its mask; a step of the last unit may
+// run past the first codeword of the next subsequence, so the exit state is the first start
+// at or after the boundary, not where the walk stopped.
+template <int S>
+B200LC_HD void walk_record_multi(const u32 (&u)[S + 1], const u16 *mtab, u32 shift, u32 (&m)[S],
+                                 u32 &end, u32 &cnt)
+{
+    u32 at = 0, c = 0, carry = 0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1];
+        u32 mj = carry;
+        carry = 0;
+        while (at < 32) {
+            const u32 w = fsl(nxt, cur, at);
+            const u32 e = mtab[w >> shift];
+            const u32 E = 0x80000000u | ((e & 0xfff0u) << 15);
+            mj |= E >> at;
+            carry |= fsr(0u, E, at);
+            at += e & 15u;
+        }
+        m[j] = mj;
+        c += popc32(mj);
+        at -= 32;
+    }
+    end = carry ? clz32(carry) : at;
+    cnt = c;
+}
+
+// Decode from entry state `a` until the walk lands on a codeword start of the recorded path
+// (then the rest of the subsequence is the recorded path: end = e0) or runs off the end.
+// No early return: a lane that has merged idles through the remaining unit loops so that the
+// warp reconverges after every unit (an early exit makes the lanes run the later loops one at
+// a time -- measured: 52% of all issued instructions at 1 active thread).
+template <int S>
+B200LC_HD void walk_merge(const u32 (&u)[S + 1], const u32 (&m)[S], u32 a, u32 e0, const u8 *tab,
+                          u32 shift, u32 &end, u32 &cnt)
+{
+    u32 at = a, k = 0, rest = 0;
+    bool done = false;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1], mj = m[j];
+        if (done) {
+            rest += popc32(mj);
+        } else {
+            while (at < 32) {
+                const u32 bit = 0x80000000u >> at;
+                if (mj & bit) {
+                    rest = popc32(mj & (bit | (bit - 1)));
+                    done = true;
+                    break;
+                }
+                const u32 w = fsl(nxt, cur, at);
+                at += tab[w >> shift];
+                ++k;
+            }
+            if (!done) at -= 32;
+        }
+    }
+    end = done ? e0 : at;
+    cnt = k + rest;
+}
+
+// Write pass: decode from the true entry state, symbol i of this subsequence goes to dst[i].
+// Table entries carry TWO symbols when the window holds two whole codewords: bits 0..7 first
+// symbol, 8..15 second symbol, 16..23 bits consumed, bit 31 = second symbol present.  A second
+// symbol that starts beyond this subsequence is also the next subsequence's first symbol: it is
+// stored twice with the same value at the same position (or beyond the tile, where nothing is
+// copied out).  With CHECK, only tile-local positions in [lo, hi) are stored (staging-window
+// overflow path).
+template <int S, bool CHECK>
+B200LC_HD void walk_write(const u32 (&u)[S + 1], const u32 *tab, u32 shift, u32 a, u8 *dst, u32 pos,
+                          u32 lo, u32 hi)
+{
+    u32 at = a;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1];
+        while (at < 32) {
+            const u32 w = fsl(nxt, cur, at);
+            const u32 e = tab[w >> shift];
+            if (!CHECK || (pos >= lo && pos < hi)) dst[pos] = (u8)e;
+            if ((int)e < 0 && (!CHECK || (pos + 1 >= lo && pos + 1 < hi))) dst[pos + 1] = (u8)(e >> 8);
+            pos += 1 + (e >> 31);
+            at += (e >> 16) & 0xffu;
+        }
+        at -= 32;
+    }
+}
+
+}  // namespace cuhd
+}  // namespace b200lc

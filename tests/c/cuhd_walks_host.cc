@@ -1,0 +1,182 @@
+// CPU check of the CUHD decoder's per-thread walks (gpu-lossless-compression_b200/csrc/cuhd_walks.cuh,
+// compiled for the host) against a bit-serial decode through the flat LUT -- the decode contract
+// of cuhd-icpp/src/cuhd_gpu_decoder.cu:16-143.  Test infrastructure.
+//   walk_record / walk_record_multi : codeword-start masks, exit state, symbol count from bit 0
+//   walk_merge                      : entry state a -> (exit state, count) via the recorded path
+//   walk_write                      : symbols from the true entry state (two-symbol entries)
+// Usage: cuhd_walks_host [seed] [rounds]; exit code 0 = all equal.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <random>
+#include <vector>
+
+#include "cuhd_walks.cuh"
+
+using namespace b200lc::cuhd;
+
+static const int S = 8;
+
+// random complete prefix code with lengths <= L over `nsym` symbols -> flat LUT {len, sym}
+static std::vector<u16> random_lut(std::mt19937_64 &rng, u32 L, u32 nsym, bool complete)
+{
+    // split leaves of a binary tree at random until nsym leaves, depth limited to L
+    std::vector<u32> depth(1, 0);
+    while (depth.size() < nsym) {
+        std::vector<size_t> cand;
+        for (size_t i = 0; i < depth.size(); ++i)
+            if (depth[i] < L) cand.push_back(i);
+        if (cand.empty()) break;
+        // bias towards splitting shallow leaves sometimes, deep leaves other times
+        size_t pick = cand[rng() % cand.size()];
+        if (rng() % 3 == 0) pick = *std::min_element(cand.begin(), cand.end(), [&](size_t a, size_t b) { return depth[a] < depth[b]; });
+        const u32 d = depth[pick] + 1;
+        depth[pick] = d;
+        depth.push_back(d);
+    }
+    std::sort(depth.begin(), depth.end());
+    std::vector<u16> lut(size_t(1) << L, 0);   // 0 = unused prefix
+    u32 code = 0, prev = depth[0];
+    std::vector<u32> syms(depth.size());
+    for (size_t i = 0; i < syms.size(); ++i) syms[i] = (u32)(rng() & 0xff);
+    for (size_t i = 0; i < depth.size(); ++i) {
+        const u32 len = depth[i];
+        code <<= (len - prev);
+        prev = len;
+        if (!(complete == false && i + 1 == depth.size() && depth.size() > 1)) {   // incomplete: drop the last code
+            if (len == 0) {   // single leaf: the encoder gives it the code 0 of length 1
+                for (size_t j = 0; j < lut.size() / 2; ++j) lut[j] = (u16)(1 | (syms[i] << 8));
+            } else {
+                const u32 first = code << (L - len);
+                for (u32 j = 0; j < (1u << (L - len)); ++j) lut[first + j] = (u16)(len | (syms[i] << 8));
+            }
+        }
+        ++code;
+    }
+    return lut;
+}
+
+struct Serial {
+    std::vector<u32> starts;   // bit positions of codeword starts in [a, 32*S)
+    std::vector<u8> syms;
+    u32 end;                   // first start at or after 32*S, minus 32*S
+};
+
+static u32 window(const u32 *u, u32 bit, u32 L)
+{
+    const u32 j = bit >> 5, o = bit & 31;
+    const u32 w = o ? (u[j] << o) | (u[j + 1] >> (32 - o)) : u[j];
+    return w >> (32 - L);
+}
+
+static Serial serial_decode(const u32 *u, const std::vector<u16> &lut, u32 L, u32 a)
+{
+    Serial r;
+    u32 at = a;
+    while (at < 32u * S) {
+        const u32 i = window(u, at, L);
+        u32 len = lut[i] & 0xff;
+        if (len == 0 || len > L) len = 1;
+        r.starts.push_back(at);
+        r.syms.push_back((u8)(lut[i] >> 8));
+        at += len;
+    }
+    r.end = at - 32u * S;
+    return r;
+}
+
+int main(int argc, char **argv)
+{
+    const unsigned long long seed = argc > 1 ? strtoull(argv[1], 0, 10) : 1;
+    const int rounds = argc > 2 ? atoi(argv[2]) : 300;
+    std::mt19937_64 rng(seed);
+    long checked = 0, multi_steps = 0, single_steps = 0;
+    for (int round = 0; round < rounds; ++round) {
+        const u32 L = 1 + (u32)(rng() % 13);                        // 1..13
+        const u32 max_sym = std::min<u32>(256, 1u << L);
+        const u32 nsym = 1 + (u32)(rng() % max_sym);
+        const bool complete = rng() % 4 != 0;
+        const std::vector<u16> lut = random_lut(rng, L, nsym, complete);
+        const u32 shift = 32 - L;
+        std::vector<u8> ltab(size_t(1) << L);
+        std::vector<u16> mtab(size_t(1) << L);
+        std::vector<u32> wtab(size_t(1) << L);
+        for (u32 i = 0; i < (1u << L); ++i) {
+            ltab[i] = (u8)first_len(lut.data(), i, L);
+            mtab[i] = multi_entry(lut.data(), i, L);
+            wtab[i] = write_entry(lut.data(), i, L);
+        }
+        for (int sub = 0; sub < 64; ++sub) {
+            u32 u[S + 2];
+            const int kind = (int)(rng() % 5);
+            for (int j = 0; j < S + 2; ++j) {
+                u32 x = (u32)rng();
+                if (kind == 1) x &= (u32)rng() & (u32)rng();        // sparse ones: long runs of the all-zero code
+                if (kind == 2) x |= (u32)rng() | (u32)rng();        // dense ones
+                if (kind == 3) x = 0;
+                if (kind == 4) x = 0xffffffffu;
+                u[j] = x;
+            }
+            u32 un[S + 1];
+            memcpy(un, u, sizeof(un));
+            // --- walk_record vs serial from bit 0
+            const Serial s0 = serial_decode(u, lut, L, 0);
+            u32 m[S], e0 = 0, c0 = 0;
+            walk_record<S>(un, ltab.data(), shift, m, e0, c0);
+            u32 want[S] = {0};
+            for (u32 b : s0.starts) want[b >> 5] |= 0x80000000u >> (b & 31);
+            if (memcmp(m, want, sizeof(m)) || e0 != s0.end || c0 != s0.starts.size()) {
+                printf("walk_record mismatch: seed %llu round %d sub %d L %u\n", seed, round, sub, L);
+                return 1;
+            }
+            single_steps += c0;
+            // --- walk_record_multi == walk_record
+            u32 mm[S], e1 = 0, c1 = 0;
+            walk_record_multi<S>(un, mtab.data(), shift, mm, e1, c1);
+            if (memcmp(mm, m, sizeof(m)) || e1 != e0 || c1 != c0) {
+                printf("walk_record_multi mismatch: seed %llu round %d sub %d L %u (end %u/%u cnt %u/%u)\n",
+                       seed, round, sub, L, e1, e0, c1, c0);
+                return 1;
+            }
+            for (u32 at = 0; at < 32u * S;) { at += mtab[window(u, at, L)] & 15u; ++multi_steps; }
+            // --- walk_merge / walk_write for every entry state
+            for (u32 a = 0; a < L; ++a) {
+                const Serial sa = serial_decode(u, lut, L, a);
+                u32 ne = 0, nc = 0;
+                walk_merge<S>(un, m, a, e0, ltab.data(), shift, ne, nc);
+                if (ne != sa.end || nc != sa.starts.size()) {
+                    printf("walk_merge mismatch: seed %llu round %d sub %d L %u a %u (end %u/%u cnt %u/%zu)\n",
+                           seed, round, sub, L, a, ne, sa.end, nc, sa.starts.size());
+                    return 1;
+                }
+                // walk_write may store one symbol past the subsequence (the successor's first)
+                std::vector<u8> dst(sa.syms.size() + 40, 0xEE), chk(sa.syms.size() + 40, 0xEE);
+                walk_write<S, false>(un, wtab.data(), shift, a, dst.data() + 8, 0, 0, 0);
+                if (memcmp(dst.data() + 8, sa.syms.data(), sa.syms.size())) {
+                    printf("walk_write mismatch: seed %llu round %d sub %d L %u a %u\n", seed, round, sub, L, a);
+                    return 1;
+                }
+                for (int q = 0; q < 8; ++q)
+                    if (dst[q] != 0xEE) { printf("walk_write wrote before dst\n"); return 1; }
+                // CHECK variant: only positions in [lo, hi) are stored
+                const u32 lo = sa.syms.size() / 3, hi = std::max<u32>(lo, (u32)(2 * sa.syms.size() / 3));
+                walk_write<S, true>(un, wtab.data(), shift, a, chk.data() + 8, 0, lo, hi);
+                for (u32 q = 0; q < sa.syms.size() + 32; ++q) {
+                    const u8 expect = (q >= lo && q < hi && q < sa.syms.size()) ? sa.syms[q] : (u8)0xEE;
+                    if (q >= sa.syms.size() && q >= lo && q < hi) continue;   // the duplicate of the successor's first symbol
+                    if (chk[8 + q] != expect) {
+                        printf("walk_write<CHECK> mismatch: seed %llu round %d sub %d L %u a %u q %u\n",
+                               seed, round, sub, L, a, q);
+                        return 1;
+                    }
+                }
+                ++checked;
+            }
+        }
+    }
+    printf("ok: %ld (subsequence, entry state) cases; %.2f symbols per multi-symbol lookup\n", checked,
+           multi_steps ? (double)single_steps / (double)multi_steps : 0.0);
+    return 0;
+}
