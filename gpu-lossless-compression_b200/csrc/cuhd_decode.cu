@@ -118,7 +118,9 @@ struct SmemLayout {
 // compiler keeps in uniform registers -- reading the same numbers from shared memory instead cost
 // 8 % on C2); BATCH = true: the view of each piece's stream is fetched from global memory into
 // shared memory by the thread that claims the piece.
-template <int S, int T, int NSUB, int CAP, bool BATCH>
+// PAM = true (opt-in, B200LC_CUHD_PASSA=multi): pass A walks with multi-symbol 16-bit entries
+// (walk_record_multi) from a third table behind the byte table.
+template <int S, int T, int NSUB, int CAP, bool BATCH, bool PAM = false>
 __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams p)
 {
     using Smem = SmemLayout<S, T, NSUB, CAP>;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     u32 *tab = reinterpret_cast<u32 *>(smem_raw + ((sizeof(Smem) + 127) & ~size_t(127)));
     u8 *ltab = reinterpret_cast<u8 *>(tab + (size_t(1) << p.max_len));   // lengths only: 1 byte per entry
+    // PAM only: a third table behind ltab, u16 per entry, all whole codewords of the window
 
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31;
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
         if (len0 + len1 <= L) entry = (e0 >> 8) | (e1 & 0xff00u) | ((len0 + len1) << 16) | 0x80000000u;
         tab[i] = entry;
         ltab[i] = (u8)len0;
+        if constexpr (PAM) reinterpret_cast<u16 *>(ltab + (size_t(1) << L))[i] = multi_entry(p.lut, i, L);
     }
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
@@ -238,7 +242,8 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
         // and the chain would crawl through it one subsequence per round.
         auto resolve_subtile = [&](u32 entry, bool keep_masks, u32 real) {
             if (worker) {
-                walk_record<S>(u, ltab, shift, m, e0, c0);
+                if constexpr (PAM) walk_record_multi<S>(u, reinterpret_cast<const u16 *>(ltab + (size_t(1) << L)), shift, m, e0, c0);
+                else walk_record<S>(u, ltab, shift, m, e0, c0);
                 sm.end[tid] = (u8)e0;
                 if (keep_masks) {
 #pragma unroll
@@ -558,10 +563,13 @@ struct Variant {
     int S, T, NSUB, CAP;
     void (*kern)(const DecodeParams);
     void (*kern_batch)(const DecodeParams);
+    void (*kern_pam)(const DecodeParams);         // multi-symbol pass A (opt-in)
+    void (*kern_batch_pam)(const DecodeParams);
     size_t smem_fixed;
 };
 #define B200LC_VARIANT(S_, T_, N_, C_) \
     { S_, T_, N_, C_, cuhd_decode_kernel<S_, T_, N_, C_, false>, cuhd_decode_kernel<S_, T_, N_, C_, true>, \
+      cuhd_decode_kernel<S_, T_, N_, C_, false, true>, cuhd_decode_kernel<S_, T_, N_, C_, true, true>, \
       ((sizeof(SmemLayout<S_, T_, N_, C_>) + 127) & ~size_t(127)) }
 static const Variant kVariants[] = {
     B200LC_VARIANT(8, 256, 16, 16384),   // default for long streams: 407 GB/s of output on C2 (B200, round 1)
@@ -584,6 +592,23 @@ static const Variant &variant()
         if (v < 0 || v >= kNumVariants) v = 0;
     }
     return kVariants[v];
+}
+
+// B200LC_CUHD_PASSA=multi selects the kernels whose pass A advances over every whole codeword of
+// the window per lookup (tuning switch; the default is the single-symbol byte table).
+static bool pass_a_multi()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("B200LC_CUHD_PASSA");
+        v = (e && e[0] == 'm') ? 1 : 0;
+    }
+    return v == 1;
+}
+// dynamic shared memory: fixed layout + write table (4 B) + byte lengths (1 B) [+ multi table (2 B)]
+static size_t smem_bytes(const Variant &v, int L, bool pam)
+{
+    return v.smem_fixed + (size_t(pam ? 7 : 5) << L);
 }
 
 // One-shot decodes pick the piece length by stream size: a piece is decoded by one CTA, two
@@ -674,14 +699,16 @@ static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t
     if (scratch_bytes < need) return B200LC_ERR_SCRATCH;
     if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
 
-    const size_t smem = v.smem_fixed + (size_t(5) << max_codeword_length);
+    const bool pam = cuhd::pass_a_multi();
+    void (*const kern)(const cuhd::DecodeParams) = pam ? v.kern_pam : v.kern;
+    const size_t smem = cuhd::smem_bytes(v, max_codeword_length, pam);
     static int occ_table[kMaxDevices][cuhd::kNumVariants][14] = {{{0}}};
     const int slot = device_slot();
     int occ = slot >= 0 ? occ_table[slot][&v - cuhd::kVariants][max_codeword_length] : 0;
     if (!occ) {
-        B200LC_CUDA_TRY(cudaFuncSetAttribute(v.kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B200LC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
-        B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.kern, v.T + 32, smem));
+        B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, v.T + 32, smem));
         if (occ < 1) return B200LC_ERR_CUDA;
         if (slot >= 0) occ_table[slot][&v - cuhd::kVariants][max_codeword_length] = occ;
     }
@@ -705,7 +732,7 @@ static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t
         B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128, stream));   // ticket only
     const u32 grid = (u32)min((u64)(end_piece - first_piece),
                               (u64)num_sms() * (u64)occ);
-    v.kern<<<grid, v.T + 32, smem, stream>>>(p);
+    kern<<<grid, v.T + 32, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }
@@ -820,10 +847,12 @@ extern "C" int b200lc_cuhd_decode_batch(const uint32_t *d_units, uint8_t *d_out,
     if (bp.pieces == 0) return B200LC_OK;
     if (scratch_bytes < bp.total) return B200LC_ERR_SCRATCH;
     const cuhd::Variant &v = *bp.v;
-    const size_t smem = v.smem_fixed + (size_t(5) << max_codeword_length);
-    B200LC_CUDA_TRY(cudaFuncSetAttribute(v.kern_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool pam = cuhd::pass_a_multi();
+    void (*const kern_batch)(const cuhd::DecodeParams) = pam ? v.kern_batch_pam : v.kern_batch;
+    const size_t smem = cuhd::smem_bytes(v, max_codeword_length, pam);
+    B200LC_CUDA_TRY(cudaFuncSetAttribute(kern_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.kern_batch, v.T + 32, smem));
+    B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_batch, v.T + 32, smem));
     if (occ < 1) return B200LC_ERR_CUDA;
     char *base = reinterpret_cast<char *>(d_scratch);
     cuhd::StreamView *d_views = reinterpret_cast<cuhd::StreamView *>(base + bp.views_off);
@@ -845,7 +874,7 @@ extern "C" int b200lc_cuhd_decode_batch(const uint32_t *d_units, uint8_t *d_out,
     p.num_pieces = (u32)bp.pieces;
     p.first_piece = 0;
     const u32 grid = (u32)min((u64)bp.pieces, (u64)num_sms() * (u64)occ);
-    v.kern_batch<<<grid, v.T + 32, smem, stream>>>(p);
+    kern_batch<<<grid, v.T + 32, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }

@@ -79,8 +79,10 @@ B200LC_HD u32 write_entry(const u16 *lut, u32 i, u32 L)
     return entry;
 }
 
-// Pass-A entry that covers EVERY whole codeword inside the window: bits 0..3 = bits consumed
-// (1..13), bit 16-o = a codeword starts at offset o (o = 1..12; offset 0 always starts one).
+// Pass-A entry that covers EVERY whole codeword inside the window: bits 12..15 = bits consumed
+// (1..13), bit 12-o = a codeword starts at offset o (o = 1..12; offset 0 always starts one), so
+// that `entry << 19` puts the start of offset o at bit 31-o and drops the bit count (its lowest
+// bit lands on bit 31, which is set anyway).
 // A codeword at offset o is known to be whole iff its length <= L - o: the window is
 // zero-filled beyond L bits, and a prefix code is decided by the codeword's own bits.
 B200LC_HD u16 multi_entry(const u16 *lut, u32 i, u32 L)
@@ -91,10 +93,10 @@ B200LC_HD u16 multi_entry(const u16 *lut, u32 i, u32 L)
     while (o < L) {
         const u32 len = first_len(lut, (i << o) & mask, L);
         if (o + len > L) break;
-        e |= 1u << (16 - o);
+        e |= 1u << (12 - o);
         o += len;
     }
-    return (u16)(e | o);
+    return (u16)(e | (o << 12));
 }
 
 // ---------------------------------------------------------------------------------- walks
@@ -139,10 +141,10 @@ B200LC_HD void walk_record_multi(const u32 (&u)[S + 1], const u16 *mtab, u32 shi
         while (at < 32) {
             const u32 w = fsl(nxt, cur, at);
             const u32 e = mtab[w >> shift];
-            const u32 E = 0x80000000u | ((e & 0xfff0u) << 15);
+            const u32 E = 0x80000000u | (e << 19);
             mj |= E >> at;
             carry |= fsr(0u, E, at);
-            at += e & 15u;
+            at += e >> 12;
         }
         m[j] = mj;
         c += popc32(mj);

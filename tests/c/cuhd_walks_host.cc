@@ -140,7 +140,7 @@ int main(int argc, char **argv)
                        seed, round, sub, L, e1, e0, c1, c0);
                 return 1;
             }
-            for (u32 at = 0; at < 32u * S;) { at += mtab[window(u, at, L)] & 15u; ++multi_steps; }
+            for (u32 at = 0; at < 32u * S;) { at += mtab[window(u, at, L)] >> 12; ++multi_steps; }
             // --- walk_merge / walk_write for every entry state
             for (u32 a = 0; a < L; ++a) {
                 const Serial sa = serial_decode(u, lut, L, a);
