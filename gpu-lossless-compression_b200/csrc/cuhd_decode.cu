@@ -118,9 +118,15 @@ struct SmemLayout {
 // compiler keeps in uniform registers -- reading the same numbers from shared memory instead cost
 // 8 % on C2); BATCH = true: the view of each piece's stream is fetched from global memory into
 // shared memory by the thread that claims the piece.
-// PAM = true (opt-in, B200LC_CUHD_PASSA=multi): pass A walks with multi-symbol 16-bit entries
-// (walk_record_multi) from a third table behind the byte table.
-template <int S, int T, int NSUB, int CAP, bool BATCH, bool PAM = false>
+// VAR: opt-in tuning switches (0 = the kernels every round-1 GPU test ran).
+//   bit 0 (B200LC_CUHD_PASSA=multi): pass A walks with multi-symbol 16-bit entries
+//         (walk_record_multi) from a third table behind the byte table;
+//   bit 1 (B200LC_CUHD_WRITE=2): write-table layout 2 + running store pointer (walk_write2).
+// Each switch alone compiles to the default's 56 registers; both together take 67 (3 CTAs/SM
+// instead of 4) -- a register cap on that instantiation has to wait for a GPU to check it: every
+// way of attaching one (minimum-blocks hint, __maxnreg__, body as a device function) also changed
+// the code of the default kernel.
+template <int S, int T, int NSUB, int CAP, bool BATCH, int VAR = 0>
 __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams p)
 {
     using Smem = SmemLayout<S, T, NSUB, CAP>;
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
     u8 *ltab = reinterpret_cast<u8 *>(tab + (size_t(1) << p.max_len));   // lengths only: 1 byte per entry
     // PAM only: a third table behind ltab, u16 per entry, all whole codewords of the window
 
+    constexpr bool PAM = (VAR & 1) != 0, W2 = (VAR & 2) != 0;
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31;
     const bool worker = tid < T;
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
         if (len1 == 0 || len1 > L) len1 = 1;
         u32 entry = (e0 >> 8) | (len0 << 16);
         if (len0 + len1 <= L) entry = (e0 >> 8) | (e1 & 0xff00u) | ((len0 + len1) << 16) | 0x80000000u;
+        if constexpr (W2) entry = (entry & 0xffffu) | ((entry >> 31) << 16) | (((entry >> 16) & 0xffu) << 24);
         tab[i] = entry;
         ltab[i] = (u8)len0;
         if constexpr (PAM) reinterpret_cast<u16 *>(ltab + (size_t(1) << L))[i] = multi_entry(p.lut, i, L);
@@ -525,7 +533,12 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
                     const u32 lo = w0, hi = w0 + wlen;
                     if (pre < hi && pre + my_cnt > lo) {
                         u8 *dst = sm.stage + ((int)sh - (int)w0);
-                        if (pre >= lo && pre + my_cnt <= hi)
+                        if constexpr (W2) {
+                            if (pre >= lo && pre + my_cnt <= hi)
+                                walk_write2<S, false>(u, tab, shift, my_start, dst, pre, lo, hi);
+                            else
+                                walk_write2<S, true>(u, tab, shift, my_start, dst, pre, lo, hi);
+                        } else if (pre >= lo && pre + my_cnt <= hi)
                             walk_write<S, false>(u, tab, shift, my_start, dst, pre, lo, hi);
                         else
                             walk_write<S, true>(u, tab, shift, my_start, dst, pre, lo, hi);
@@ -561,15 +574,16 @@ __global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams 
 // tuning runs.
 struct Variant {
     int S, T, NSUB, CAP;
-    void (*kern)(const DecodeParams);
-    void (*kern_batch)(const DecodeParams);
-    void (*kern_pam)(const DecodeParams);         // multi-symbol pass A (opt-in)
-    void (*kern_batch_pam)(const DecodeParams);
+    void (*kern[4])(const DecodeParams);          // indexed by the opt-in switches VAR (0 = default)
+    void (*kern_batch[4])(const DecodeParams);
     size_t smem_fixed;
 };
 #define B200LC_VARIANT(S_, T_, N_, C_) \
-    { S_, T_, N_, C_, cuhd_decode_kernel<S_, T_, N_, C_, false>, cuhd_decode_kernel<S_, T_, N_, C_, true>, \
-      cuhd_decode_kernel<S_, T_, N_, C_, false, true>, cuhd_decode_kernel<S_, T_, N_, C_, true, true>, \
+    { S_, T_, N_, C_, \
+      { cuhd_decode_kernel<S_, T_, N_, C_, false, 0>, cuhd_decode_kernel<S_, T_, N_, C_, false, 1>, \
+        cuhd_decode_kernel<S_, T_, N_, C_, false, 2>, cuhd_decode_kernel<S_, T_, N_, C_, false, 3> }, \
+      { cuhd_decode_kernel<S_, T_, N_, C_, true, 0>, cuhd_decode_kernel<S_, T_, N_, C_, true, 1>, \
+        cuhd_decode_kernel<S_, T_, N_, C_, true, 2>, cuhd_decode_kernel<S_, T_, N_, C_, true, 3> }, \
       ((sizeof(SmemLayout<S_, T_, N_, C_>) + 127) & ~size_t(127)) }
 static const Variant kVariants[] = {
     B200LC_VARIANT(8, 256, 16, 16384),   // default for long streams: 407 GB/s of output on C2 (B200, round 1)
@@ -594,21 +608,21 @@ static const Variant &variant()
     return kVariants[v];
 }
 
-// B200LC_CUHD_PASSA=multi selects the kernels whose pass A advances over every whole codeword of
-// the window per lookup (tuning switch; the default is the single-symbol byte table).
-static bool pass_a_multi()
+// Opt-in tuning switches (template parameter VAR of the kernel): B200LC_CUHD_PASSA=multi -> bit 0,
+// B200LC_CUHD_WRITE=2 -> bit 1.  Read once per process; the default is 0.
+static int tuning_switches()
 {
     static int v = -1;
     if (v < 0) {
-        const char *e = getenv("B200LC_CUHD_PASSA");
-        v = (e && e[0] == 'm') ? 1 : 0;
+        const char *a = getenv("B200LC_CUHD_PASSA"), *w = getenv("B200LC_CUHD_WRITE");
+        v = ((a && a[0] == 'm') ? 1 : 0) | ((w && w[0] == '2') ? 2 : 0);
     }
-    return v == 1;
+    return v;
 }
 // dynamic shared memory: fixed layout + write table (4 B) + byte lengths (1 B) [+ multi table (2 B)]
-static size_t smem_bytes(const Variant &v, int L, bool pam)
+static size_t smem_bytes(const Variant &v, int L, int var)
 {
-    return v.smem_fixed + (size_t(pam ? 7 : 5) << L);
+    return v.smem_fixed + (size_t((var & 1) ? 7 : 5) << L);
 }
 
 // One-shot decodes pick the piece length by stream size: a piece is decoded by one CTA, two
@@ -699,9 +713,9 @@ static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t
     if (scratch_bytes < need) return B200LC_ERR_SCRATCH;
     if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
 
-    const bool pam = cuhd::pass_a_multi();
-    void (*const kern)(const cuhd::DecodeParams) = pam ? v.kern_pam : v.kern;
-    const size_t smem = cuhd::smem_bytes(v, max_codeword_length, pam);
+    const int var = cuhd::tuning_switches();
+    void (*const kern)(const cuhd::DecodeParams) = v.kern[var];
+    const size_t smem = cuhd::smem_bytes(v, max_codeword_length, var);
     static int occ_table[kMaxDevices][cuhd::kNumVariants][14] = {{{0}}};
     const int slot = device_slot();
     int occ = slot >= 0 ? occ_table[slot][&v - cuhd::kVariants][max_codeword_length] : 0;
@@ -847,9 +861,9 @@ extern "C" int b200lc_cuhd_decode_batch(const uint32_t *d_units, uint8_t *d_out,
     if (bp.pieces == 0) return B200LC_OK;
     if (scratch_bytes < bp.total) return B200LC_ERR_SCRATCH;
     const cuhd::Variant &v = *bp.v;
-    const bool pam = cuhd::pass_a_multi();
-    void (*const kern_batch)(const cuhd::DecodeParams) = pam ? v.kern_batch_pam : v.kern_batch;
-    const size_t smem = cuhd::smem_bytes(v, max_codeword_length, pam);
+    const int var = cuhd::tuning_switches();
+    void (*const kern_batch)(const cuhd::DecodeParams) = v.kern_batch[var];
+    const size_t smem = cuhd::smem_bytes(v, max_codeword_length, var);
     B200LC_CUDA_TRY(cudaFuncSetAttribute(kern_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_batch, v.T + 32, smem));

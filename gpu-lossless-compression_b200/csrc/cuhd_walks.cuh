@@ -79,6 +79,15 @@ B200LC_HD u32 write_entry(const u16 *lut, u32 i, u32 L)
     return entry;
 }
 
+// Write-pass entry, layout 2 (opt-in): bits 0..7 first symbol, 8..15 second symbol, bit 16 =
+// second symbol present, bits 24..31 = bits consumed -- `at += e >> 24` is one instruction
+// (shift-and-add) where layout 1 needs shift, mask and add.
+B200LC_HD u32 write_entry2(const u16 *lut, u32 i, u32 L)
+{
+    const u32 e = write_entry(lut, i, L);
+    return (e & 0xffffu) | ((e >> 31) << 16) | (((e >> 16) & 0xffu) << 24);
+}
+
 // Pass-A entry that covers EVERY whole codeword inside the window: bits 12..15 = bits consumed
 // (1..13), bit 12-o = a codeword starts at offset o (o = 1..12; offset 0 always starts one), so
 // that `entry << 19` puts the start of offset o at bit 31-o and drops the bit count (its lowest
@@ -211,6 +220,36 @@ B200LC_HD void walk_write(const u32 (&u)[S + 1], const u32 *tab, u32 shift, u32 
             if ((int)e < 0 && (!CHECK || (pos + 1 >= lo && pos + 1 < hi))) dst[pos + 1] = (u8)(e >> 8);
             pos += 1 + (e >> 31);
             at += (e >> 16) & 0xffu;
+        }
+        at -= 32;
+    }
+}
+
+// Write pass on write_entry2() tables with a running store pointer instead of base + position.
+template <int S, bool CHECK>
+B200LC_HD void walk_write2(const u32 (&u)[S + 1], const u32 *tab, u32 shift, u32 a, u8 *dst, u32 pos,
+                           u32 lo, u32 hi)
+{
+    u32 at = a;
+    u8 *q = dst + pos;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1];
+        while (at < 32) {
+            const u32 w = fsl(nxt, cur, at);
+            const u32 e = tab[w >> shift];
+            const bool two = (e & 0x10000u) != 0;
+            if (CHECK) {
+                const u32 at_pos = (u32)(q - dst);
+                if (at_pos >= lo && at_pos < hi) q[0] = (u8)e;
+                if (two && at_pos + 1 >= lo && at_pos + 1 < hi) q[1] = (u8)(e >> 8);
+            } else {
+                q[0] = (u8)e;
+                if (two) q[1] = (u8)(e >> 8);
+            }
+            q += 1;
+            if (two) q += 1;
+            at += e >> 24;
         }
         at -= 32;
     }

@@ -3,7 +3,7 @@
 // of cuhd-icpp/src/cuhd_gpu_decoder.cu:16-143.  Test infrastructure.
 //   walk_record / walk_record_multi : codeword-start masks, exit state, symbol count from bit 0
 //   walk_merge                      : entry state a -> (exit state, count) via the recorded path
-//   walk_write                      : symbols from the true entry state (two-symbol entries)
+//   walk_write / walk_write2        : symbols from the true entry state (two-symbol entries, both layouts)
 // Usage: cuhd_walks_host [seed] [rounds]; exit code 0 = all equal.
 #include <stdio.h>
 #include <stdlib.h>
@@ -102,11 +102,12 @@ int main(int argc, char **argv)
         const u32 shift = 32 - L;
         std::vector<u8> ltab(size_t(1) << L);
         std::vector<u16> mtab(size_t(1) << L);
-        std::vector<u32> wtab(size_t(1) << L);
+        std::vector<u32> wtab(size_t(1) << L), wtab2(size_t(1) << L);
         for (u32 i = 0; i < (1u << L); ++i) {
             ltab[i] = (u8)first_len(lut.data(), i, L);
             mtab[i] = multi_entry(lut.data(), i, L);
             wtab[i] = write_entry(lut.data(), i, L);
+            wtab2[i] = write_entry2(lut.data(), i, L);
         }
         for (int sub = 0; sub < 64; ++sub) {
             u32 u[S + 2];
@@ -160,9 +161,21 @@ int main(int argc, char **argv)
                 }
                 for (int q = 0; q < 8; ++q)
                     if (dst[q] != 0xEE) { printf("walk_write wrote before dst\n"); return 1; }
+                // layout 2 stores exactly the same bytes
+                std::vector<u8> dst2(dst.size(), 0xEE), chk2(dst.size(), 0xEE);
+                walk_write2<S, false>(un, wtab2.data(), shift, a, dst2.data() + 8, 0, 0, 0);
+                if (dst2 != dst) {
+                    printf("walk_write2 mismatch: seed %llu round %d sub %d L %u a %u\n", seed, round, sub, L, a);
+                    return 1;
+                }
                 // CHECK variant: only positions in [lo, hi) are stored
                 const u32 lo = sa.syms.size() / 3, hi = std::max<u32>(lo, (u32)(2 * sa.syms.size() / 3));
                 walk_write<S, true>(un, wtab.data(), shift, a, chk.data() + 8, 0, lo, hi);
+                walk_write2<S, true>(un, wtab2.data(), shift, a, chk2.data() + 8, 0, lo, hi);
+                if (chk2 != chk) {
+                    printf("walk_write2<CHECK> mismatch: seed %llu round %d sub %d L %u a %u\n", seed, round, sub, L, a);
+                    return 1;
+                }
                 for (u32 q = 0; q < sa.syms.size() + 32; ++q) {
                     const u8 expect = (q >= lo && q < hi && q < sa.syms.size()) ? sa.syms[q] : (u8)0xEE;
                     if (q >= sa.syms.size() && q >= lo && q < hi) continue;   // the duplicate of the successor's first symbol

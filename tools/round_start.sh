@@ -13,4 +13,4 @@ ncu --set full --clock-control none --import-source on -k regex:cuhd_decode_kern
     python tools/bench_paths.py cuhd --mib 1024 > gpurun_out/rs_ncu_dec.log 2>&1
 B200LC_CUHD_PASSA=multi ncu --set full --clock-control none --import-source on -k regex:cuhd_decode_kernel -c 1 -f \
     -o gpurun_out/rs_dec_multi python tools/bench_paths.py cuhd --mib 1024 > gpurun_out/rs_ncu_dec_multi.log 2>&1
-tail -2 gpurun_out/rs_pytest.log; cat gpurun_out/rs_bench.json; grep -h '"path": "cuhd"' gpurun_out/rs_variants.log
+tail -2 gpurun_out/rs_pytest.log; cat gpurun_out/rs_bench.json; grep -h -e "===" -e "\"path\": \"cuhd\"" gpurun_out/rs_variants.log
