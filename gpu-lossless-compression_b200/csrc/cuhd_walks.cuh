@@ -133,7 +133,7 @@ B200LC_HD void walk_record(const u32 (&u)[S + 1], const u8 *tab, u32 shift, u32 
 }
 
 // Same result as walk_record from multi_entry() tables: one lookup advances over all whole
-// codewords of the window (~1.8 on Zipf(1.1) data), i.e. half the dependent lookups.  Starts
+// codewords of the window (1.64 on the C2 code), i.e. 0.6x the dependent lookups.  Starts
 // that fall into the next unit travel in `carry` and seed its mask; a step of the last unit may
 // run past the first codeword of the next subsequence, so the exit state is the first start
 // at or after the boundary, not where the walk stopped.
