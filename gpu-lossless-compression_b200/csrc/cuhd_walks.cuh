@@ -65,6 +65,13 @@ B200LC_HD u32 first_len(const u16 *lut, u32 i, u32 L)
     return len;
 }
 
+// {length, symbol} of the first codeword with the length made safe: low byte = first_len(),
+// high byte = symbol (the layout of the caller's LUT itself).
+B200LC_HD u16 len_sym_entry(const u16 *lut, u32 i, u32 L)
+{
+    return (u16)((lut[i] & 0xff00u) | first_len(lut, i, L));
+}
+
 // Write-pass entry: bits 0..7 first symbol, 8..15 second symbol, 16..23 bits consumed, bit 31 =
 // second symbol present (the window holds two whole codewords).
 B200LC_HD u32 write_entry(const u16 *lut, u32 i, u32 L)
@@ -252,6 +259,89 @@ B200LC_HD void walk_write2(const u32 (&u)[S + 1], const u32 *tab, u32 shift, u32
             at += e >> 24;
         }
         at -= 32;
+    }
+}
+
+// ------------------------------------------------------------------- decode-once building blocks
+// (not used by the kernel yet.)  Pass A that also keeps the symbols of the
+// path from bit 0 in a per-subsequence slot, so that the write pass becomes a copy:
+//   symbols(entry state a) = the k symbols walk_merge_skip() steps over before it lands on the
+//                            recorded path  +  slot[skip .. c0)
+// with k + (c0 - skip) = the count walk_merge reports.  A subsequence with more than SLOT symbols
+// on its recorded path reports overflow and is decoded by the second walk as today.
+template <int S, int SLOT>
+B200LC_HD bool walk_record_sym(const u32 (&u)[S + 1], const u16 *tab, u32 shift, u32 (&m)[S], u32 &end,
+                               u32 &cnt, u8 *slot)
+{
+    u32 at = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1];
+        u32 mj = 0;
+        while (at < 32) {
+            mj |= 0x80000000u >> at;
+            const u32 w = fsl(nxt, cur, at);
+            const u32 e = tab[w >> shift];          // {u8 len, u8 symbol} of the first codeword
+            if (c < (u32)SLOT) slot[c] = (u8)(e >> 8);
+            ++c;
+            at += e & 0xffu;
+        }
+        m[j] = mj;
+        at -= 32;
+    }
+    end = at;
+    cnt = c;
+    return c <= (u32)SLOT;
+}
+
+// walk_merge that also reports where the recorded path takes over: `k` symbols are decoded from
+// entry state a before the walk lands on recorded start number `skip` (skip = c0 when it never
+// lands: then all k symbols are the subsequence's own and the slot is not used).
+template <int S>
+B200LC_HD void walk_merge_skip(const u32 (&u)[S + 1], const u32 (&m)[S], u32 a, u32 e0, u32 c0,
+                               const u8 *ltab, u32 shift, u32 &end, u32 &k_out, u32 &skip_out)
+{
+    u32 at = a, k = 0, before = 0;
+    bool done = false;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1], mj = m[j];
+        if (!done) {
+            while (at < 32) {
+                const u32 bit = 0x80000000u >> at;
+                if (mj & bit) {
+                    before += popc32(mj & ~(bit | (bit - 1)));   // recorded starts in front of the landing bit
+                    done = true;
+                    break;
+                }
+                const u32 w = fsl(nxt, cur, at);
+                at += ltab[w >> shift];
+                ++k;
+            }
+            if (!done) { at -= 32; before += popc32(mj); }
+        }
+    }
+    end = done ? e0 : at;
+    k_out = k;
+    skip_out = done ? before : c0;
+}
+
+// The k symbols in front of the landing point, decoded again from entry state a (k is 1-3 on
+// real data: the walks re-synchronise within a few codewords).
+template <int S>
+B200LC_HD void walk_emit(const u32 (&u)[S + 1], const u16 *tab, u32 shift, u32 a, u32 k, u8 *dst)
+{
+    u32 at = a, i = 0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1];
+        while (at < 32 && i < k) {
+            const u32 w = fsl(nxt, cur, at);
+            const u32 e = tab[w >> shift];
+            dst[i++] = (u8)(e >> 8);
+            at += e & 0xffu;
+        }
+        at -= 32;      // only meaningful while i < k
     }
 }
 

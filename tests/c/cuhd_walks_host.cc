@@ -3,8 +3,10 @@
 // of cuhd-icpp/src/cuhd_gpu_decoder.cu:16-143.  Test infrastructure.
 //   walk_record / walk_record_multi : codeword-start masks, exit state, symbol count from bit 0
 //   walk_merge                      : entry state a -> (exit state, count) via the recorded path
+//   walk_record_sym / walk_merge_skip / walk_emit : decode-once building blocks
 //   walk_write / walk_write2        : symbols from the true entry state (two-symbol entries, both layouts)
 // Usage: cuhd_walks_host [seed] [rounds]; exit code 0 = all equal.
+//        cuhd_walks_host stream <lut.bin> <units.bin> <L>   (statistics of a real stream)
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -87,12 +89,71 @@ static Serial serial_decode(const u32 *u, const std::vector<u16> &lut, u32 L, u3
     return r;
 }
 
+// Statistics of a real stream (LUT file: u16[1 << L], units file: u32[]), every subsequence entered
+// in its true state: how many symbols the merge walk decodes before the recorded path takes over,
+// how many subsequences never land on it, how full the symbol slots get.  Also checks the
+// decode-once composition against the serial decode of the whole stream.
+static int stream_stats(const char *lut_path, const char *units_path, u32 L)
+{
+    std::vector<u16> lut(size_t(1) << L);
+    FILE *f = fopen(lut_path, "rb");
+    if (!f || fread(lut.data(), 2, lut.size(), f) != lut.size()) { printf("cannot read %s\n", lut_path); return 2; }
+    fclose(f);
+    f = fopen(units_path, "rb");
+    if (!f) { printf("cannot read %s\n", units_path); return 2; }
+    std::vector<u32> units;
+    u32 buf[4096];
+    size_t got;
+    while ((got = fread(buf, 4, 4096, f)) > 0) units.insert(units.end(), buf, buf + got);
+    fclose(f);
+    const size_t nsub = units.size() / S;
+    units.resize((nsub + 1) * S + 2, 0);
+    const u32 shift = 32 - L;
+    std::vector<u8> ltab(size_t(1) << L);
+    std::vector<u16> stab(size_t(1) << L);
+    for (u32 i = 0; i < (1u << L); ++i) {
+        ltab[i] = (u8)first_len(lut.data(), i, L);
+        stab[i] = len_sym_entry(lut.data(), i, L);
+    }
+    u32 entry = 0;
+    unsigned long long k_sum = 0, never = 0, symbols = 0, over64 = 0, over48 = 0, k_max = 0, k_hist[6] = {0};
+    for (size_t q = 0; q < nsub; ++q) {
+        u32 un[S + 1];
+        memcpy(un, &units[q * S], sizeof(un));
+        u32 m[S], e0, c0, ne, k, skip;
+        u8 slot[32 * S];
+        walk_record_sym<S, 32 * S>(un, stab.data(), shift, m, e0, c0, slot);
+        walk_merge_skip<S>(un, m, entry, e0, c0, ltab.data(), shift, ne, k, skip);
+        const Serial sa = serial_decode(un, lut, L, entry);
+        std::vector<u8> out(k + 8);
+        walk_emit<S>(un, stab.data(), shift, entry, k, out.data());
+        out.resize(k);
+        out.insert(out.end(), slot + skip, slot + c0);
+        if (out != sa.syms || ne != sa.end) { printf("decode-once mismatch at subsequence %zu\n", q); return 1; }
+        k_sum += k; symbols += out.size();
+        if (skip == c0 && k) ++never;
+        if (c0 > 64) ++over64;
+        if (c0 > 48) ++over48;
+        if (k > k_max) k_max = k;
+        ++k_hist[k < 5 ? k : 5];
+        entry = ne;
+    }
+    printf("subsequences %zu, symbols %llu (%.1f per subsequence)\n", nsub, symbols, (double)symbols / nsub);
+    printf("own symbols before the recorded path takes over: mean %.3f, max %llu; k=0..4,5+: %.3f %.3f %.3f %.3f %.3f %.3f\n",
+           (double)k_sum / nsub, k_max, (double)k_hist[0] / nsub, (double)k_hist[1] / nsub, (double)k_hist[2] / nsub,
+           (double)k_hist[3] / nsub, (double)k_hist[4] / nsub, (double)k_hist[5] / nsub);
+    printf("never land on the recorded path: %.5f; recorded path longer than 64 symbols: %.5f, than 48: %.5f\n",
+           (double)never / nsub, (double)over64 / nsub, (double)over48 / nsub);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 4 && !strcmp(argv[1], "stream")) return stream_stats(argv[2], argv[3], (u32)atoi(argv[4]));
     const unsigned long long seed = argc > 1 ? strtoull(argv[1], 0, 10) : 1;
     const int rounds = argc > 2 ? atoi(argv[2]) : 300;
     std::mt19937_64 rng(seed);
-    long checked = 0, multi_steps = 0, single_steps = 0;
+    long checked = 0, multi_steps = 0, single_steps = 0, fix_symbols = 0, fix_cases = 0;
     for (int round = 0; round < rounds; ++round) {
         const u32 L = 1 + (u32)(rng() % 13);                        // 1..13
         const u32 max_sym = std::min<u32>(256, 1u << L);
@@ -101,11 +162,12 @@ int main(int argc, char **argv)
         const std::vector<u16> lut = random_lut(rng, L, nsym, complete);
         const u32 shift = 32 - L;
         std::vector<u8> ltab(size_t(1) << L);
-        std::vector<u16> mtab(size_t(1) << L);
+        std::vector<u16> mtab(size_t(1) << L), stab(size_t(1) << L);
         std::vector<u32> wtab(size_t(1) << L), wtab2(size_t(1) << L);
         for (u32 i = 0; i < (1u << L); ++i) {
             ltab[i] = (u8)first_len(lut.data(), i, L);
             mtab[i] = multi_entry(lut.data(), i, L);
+            stab[i] = len_sym_entry(lut.data(), i, L);
             wtab[i] = write_entry(lut.data(), i, L);
             wtab2[i] = write_entry2(lut.data(), i, L);
         }
@@ -142,6 +204,20 @@ int main(int argc, char **argv)
                 return 1;
             }
             for (u32 at = 0; at < 32u * S;) { at += mtab[window(u, at, L)] >> 12; ++multi_steps; }
+            // --- decode-once building blocks: the recorded path with its symbols
+            u32 ms[S], e2 = 0, c2 = 0;
+            u8 slot[32 * S];
+            const bool fits = walk_record_sym<S, 32 * S>(un, stab.data(), shift, ms, e2, c2, slot);
+            if (!fits || memcmp(ms, m, sizeof(m)) || e2 != e0 || c2 != c0 || memcmp(slot, s0.syms.data(), c0)) {
+                printf("walk_record_sym mismatch: seed %llu round %d sub %d L %u\n", seed, round, sub, L);
+                return 1;
+            }
+            u8 small_slot[16];
+            u32 ms2[S];
+            if (walk_record_sym<S, 16>(un, stab.data(), shift, ms2, e2, c2, small_slot) != (c0 <= 16)) {
+                printf("walk_record_sym overflow flag wrong: seed %llu round %d sub %d\n", seed, round, sub);
+                return 1;
+            }
             // --- walk_merge / walk_write for every entry state
             for (u32 a = 0; a < L; ++a) {
                 const Serial sa = serial_decode(u, lut, L, a);
@@ -151,6 +227,22 @@ int main(int argc, char **argv)
                     printf("walk_merge mismatch: seed %llu round %d sub %d L %u a %u (end %u/%u cnt %u/%zu)\n",
                            seed, round, sub, L, a, ne, sa.end, nc, sa.starts.size());
                     return 1;
+                }
+                // decode once: k own symbols, then the recorded ones from `skip` on
+                {
+                    u32 ne2 = 0, k = 0, skip = 0;
+                    walk_merge_skip<S>(un, m, a, e0, c0, ltab.data(), shift, ne2, k, skip);
+                    std::vector<u8> got(k + 8, 0xEE);
+                    walk_emit<S>(un, stab.data(), shift, a, k, got.data());
+                    got.resize(k);
+                    got.insert(got.end(), slot + skip, slot + c0);
+                    if (ne2 != sa.end || got != sa.syms) {
+                        printf("decode-once mismatch: seed %llu round %d sub %d L %u a %u (k %u skip %u c0 %u, %zu/%zu symbols)\n",
+                               seed, round, sub, L, a, k, skip, c0, got.size(), sa.syms.size());
+                        return 1;
+                    }
+                    fix_symbols += k;
+                    fix_cases += 1;
                 }
                 // walk_write may store one symbol past the subsequence (the successor's first)
                 std::vector<u8> dst(sa.syms.size() + 40, 0xEE), chk(sa.syms.size() + 40, 0xEE);
@@ -189,7 +281,9 @@ int main(int argc, char **argv)
             }
         }
     }
-    printf("ok: %ld (subsequence, entry state) cases; %.2f symbols per multi-symbol lookup\n", checked,
-           multi_steps ? (double)single_steps / (double)multi_steps : 0.0);
+    printf("ok: %ld (subsequence, entry state) cases; %.2f symbols per multi-symbol lookup; "
+           "%.2f symbols decoded before the recorded path takes over\n", checked,
+           multi_steps ? (double)single_steps / (double)multi_steps : 0.0,
+           fix_cases ? (double)fix_symbols / (double)fix_cases : 0.0);
     return 0;
 }
