@@ -43,6 +43,10 @@ inline int device_slot()        // index into a per-device cache, -1 = do not ca
     return dev;
 }
 
+// cudaDeviceReset (resetGPU in culzss_api.cu) destroys the context and with it every kernel
+// attribute: caches of "attribute already set" remember the epoch they were filled in.
+unsigned &context_epoch();      // defined in version.cpp; bumped by resetGPU
+
 inline int num_sms()
 {
     static int cached[kMaxDevices] = {0};

@@ -1,27 +1,34 @@
 // Self-synchronising canonical-Huffman decode for sm_100a  (hot path 3).
 //
 // Replaces the reference's 4 phases / 6 kernels / host do-while
-// (cuhd-icpp/src/cuhd_gpu_decoder.cu:145-523) with ONE persistent kernel:
+// (cuhd-icpp/src/cuhd_gpu_decoder.cu:145-523) with ONE persistent kernel.  Round-2 formulation
+// (round 1: CTA-wide sub-tiles, codeword-start masks and merge walks, 11 CTA barriers per 8 KiB;
+// DESIGN.md section 3.1 keeps the history):
 //
-//   * the compressed stream is cut into subsequences of S units (S*32 bits) and tiles of T
-//     subsequences; each CTA pulls tiles from a ticket counter and stages the next tile's units
-//     into shared memory with a 1-D TMA bulk copy (cp.async.bulk + mbarrier) while it works on
-//     the current one;
-//   * round 0: every thread decodes its subsequence from bit 0 and records the bit positions of
-//     all codeword starts it saw (S registers of mask) -- this replaces phase 1's "decode the
-//     whole next subsequence again and compare the last codeword" (:188-231) by an exact
-//     merge test against the mask, so resynchronisation costs a few symbols, not a subsequence;
-//   * the tile's effect on the decoder state is published as a FUNCTION of the entry state
-//     (bit offset 0..L-1 of the first codeword): end state and symbol count for every entry
-//     state that provably merges.  Tiles are chained with a decoupled look-back over those
-//     function tables, which replaces phase 2's host loop + D2H flag copies (:458-495) and
-//     phase 3's three passes over the 16-byte sync points (:498-509);
-//   * the write pass re-decodes from the now known entry state into a shared-memory staging
-//     buffer and leaves with 16-byte coalesced stores instead of phase 4's per-thread byte
-//     stores (:101-105).
+//   * subsequence = S units = 32 bytes = one lane; warp-step = 32 subsequences = 1 KiB;
+//     segment = K consecutive warp-steps handled by ONE warp; piece = kWarps segments handled
+//     by one CTA between two look-backs.  Pieces are handed out through a ticket counter.
+//   * pass A (per warp, no CTA barrier): every lane walks its subsequence from bit 0 with
+//     multi-codeword lookups that advance the bit position AND the codeword count with one add
+//     (walk_count in cuhd_walks.cuh); entry states are then chained through the warp with
+//     shuffles, and a lane whose entry state is not 0 walks once more from the true state.  This
+//     replaces phase 1's "decode the next subsequence again until the sync point repeats"
+//     (:188-231).  The exit state of a step is the exact entry state of the warp's next step.
+//   * the entry state of a segment (and of a piece) is GUESSED from a walk over the subsequence
+//     in front of it (a path from bit 0 re-synchronises within a subsequence with probability
+//     > 0.999 on real data) and VERIFIED against the predecessor's exit state: inside the CTA
+//     after pass A, between pieces by the look-back.  A wrong guess is repaired by re-running
+//     pass A of that segment with the true state.  This replaces phase 2's host loop with D2H
+//     flag copies (:458-495).
+//   * pieces are chained by a warp-wide decoupled look-back over 16-byte descriptors
+//     {assumed entry state, exit state, symbols}; a chain of aggregates is usable when every
+//     link's assumed entry state equals its predecessor's exit state.  Replaces phase 3's three
+//     passes over 16-byte sync points (:498-509).
+//   * pass B (per warp): decode from the now known entry states with two-symbol table entries
+//     into a per-warp shared-memory staging buffer and leave with aligned 16-byte streaming
+//     stores; phase 4 wrote single bytes (:101-105).
 //
-// HBM traffic is therefore units-in + symbols-out + 64 B of descriptor per tile; the
-// reference's 20 B of sync-point state per 16 B of input is gone.
+// HBM traffic: units in (pass B re-reads them through L2) + symbols out + 16 B per piece.
 //
 // Decode contract (bit-exact with the reference): out[i] = symbol of
 // the i-th codeword when reading the stream MSB-first from bit 0 of unit 0 through the flat LUT
@@ -37,26 +44,25 @@
 namespace b200lc {
 namespace cuhd {
 
-constexpr u32 kMaxStates = 16;       // entry states 0..L-1, L <= 13 supported
-constexpr int kAltMaxSub = 8;        // entry-state walks give up after this many subsequences
-constexpr u64 kInclValid = 1ull << 63;
+constexpr int S = 8;                      // units per subsequence
+constexpr int kWarps = 8;                 // warps per CTA = segments per piece
+constexpr int kThreads = kWarps * 32;
+constexpr u32 kStageBytes = 2560;         // per-warp output staging
+constexpr u32 kWin = kStageBytes - 32;    // symbols staged per round (<= 15 carried bytes + 1 duplicate fit)
+constexpr u32 kMultiBits = 13;            // window of the counting table (>= L)
+
+constexpr u64 kValid = 1ull << 63;
 constexpr u64 kCountMask = (1ull << 56) - 1;
 
-// One 64-byte descriptor per tile, three independently readable parts:
-//   incl : bit 63 valid | bits 56..59 exit state | bits 0..55 symbols that start before the next tile
-//   agg  : bit 63 valid | bits 56..59 exit state E of every entry state that merges |
-//          bits 40..55 mask of entry states that merge | bits 0..31 symbols for entry state 0
-//   d[a] : symbols for entry state a minus symbols for entry state 0 (valid if mask bit a)
-// By construction every merging entry state leaves the tile in the same state E, so a chain of
-// tiles is traversable from aggregates alone whenever E of tile t-1 is in the mask of tile t.
-struct __align__(64) TileDesc {
-    u64 incl;
+// One 16-byte descriptor per piece:
+//   agg : bit 63 valid | bits 56..59 ASSUMED entry state A | bits 48..51 exit state X |
+//         bits 0..31 symbols T -- X and T hold if the piece is entered in state A
+//   incl: bit 63 valid | bits 56..59 true exit state | bits 0..55 symbols that start before the
+//         next piece of the stream (inclusive over all earlier pieces)
+struct __align__(16) PieceDesc {
     u64 agg;
-    short d[kMaxStates];
-    u8 pad[16];
+    u64 incl;
 };
-static_assert(sizeof(TileDesc) == 64, "descriptor is 64 bytes");
-constexpr u64 kAggValid = 1ull << 63;
 
 // One independent bit stream (codes start at bit 0 of its first unit, entry state 0) and the
 // range of pieces that decodes it.  A single-stream call carries its view inside the kernel
@@ -68,9 +74,7 @@ struct StreamView {
     u8 *out;
     u64 n_out;
     u32 first_piece;     // global number of the stream's first piece
-    u32 num_subtiles;
-    u32 tma_tiles;       // leading sub-tiles (+ 4 lookahead units) that one TMA bulk copy can fetch
-    u32 pad;
+    u32 aligned;         // units pointer is 16-byte aligned: lanes fetch their 32 bytes with two 16-byte loads
 };
 
 struct DecodeParams {
@@ -79,523 +83,392 @@ struct DecodeParams {
     const u32 *piece_stream;      // batch: stream number of every piece
     const u16 *lut;      // {u8 num_bits, u8 symbol} little-endian pairs
     u32 max_len;         // L
-    TileDesc *desc;
+    u32 multi_bits;      // LM: window of the counting table, L <= LM <= 15
+    PieceDesc *desc;
     u32 *ticket;
     u32 num_pieces;      // pieces [first_piece, num_pieces) are decoded by this launch
     u32 first_piece;
 };
 
-// ---------------------------------------------------------------------------------- kernel
-// Work decomposition: subsequence = S units (one thread), sub-tile = T subsequences (one TMA
-// transfer, T*S*4 bytes), piece = NSUB sub-tiles handled by one CTA between two look-backs.
-template <int S, int T, int NSUB, int CAP>
+template <int K>
 struct SmemLayout {
-    static constexpr int kTileUnits = T * S + 4;  // + one 16-byte lookahead
-    u32 in[2][kTileUnits];
-    union {
-        __align__(16) u8 stage[CAP + 16];   // pass B: output staging
-        u32 masks[T * S];                   // pass A, sub-tile 0: codeword-start masks of the paths from bit 0
-    };
-    u32 pre[T + 1];          // sub-tile 0 only: exclusive prefix of resolved symbol counts
-    u16 saved[NSUB][T];      // pass A result per subsequence: entry state << 12 | symbol count
-    u32 sub_total[NSUB];     // pass A symbols per sub-tile
-    u8 sub_entry[NSUB];      // pass A entry / exit state per sub-tile
-    u8 sub_exit[NSUB];
-    u32 warp_sums[T / 32];
-    u8 end[T];               // resolved exit state of every subsequence of the current sub-tile
-    u8 wexit[2][T / 32];     // exit state of each warp's last lane, double-buffered by resolution round
-    u8 onpath[T];            // sub-tile 0 only: resolved path ends on the recorded path
-    u64 bar[2];
+    u16 saved[kWarps][K][32];               // pass A result per subsequence: entry state << 12 | symbols
+    __align__(16) u8 stage[kWarps][kStageBytes];
+    // per segment, double-buffered by piece parity: assumed entry state, exit state, symbols
+    u32 wt[2][kWarps];
+    u8 wa[2][kWarps];
+    u8 wx[2][kWarps];
     u64 base;
-    StreamView view[2];      // stream of the current piece / of the piece being prefetched (by piece parity)
     u32 next_piece;
-    u32 total;
-    u32 astar;
-    u32 known;
+    u32 true_entry;
+    u32 redo;
+    StreamView view[2];                     // batch: stream of the current / the next piece (by piece parity)
 };
 
-// BATCH = false: one stream, its view comes from the kernel parameters (warp-uniform values the
-// compiler keeps in uniform registers -- reading the same numbers from shared memory instead cost
-// 8 % on C2); BATCH = true: the view of each piece's stream is fetched from global memory into
-// shared memory by the thread that claims the piece.
-// VAR: opt-in tuning switches (0 = the kernels every round-1 GPU test ran).
-//   bit 0 (B200LC_CUHD_PASSA=multi): pass A walks with multi-symbol 16-bit entries
-//         (walk_record_multi) from a third table behind the byte table;
-//   bit 1 (B200LC_CUHD_WRITE=2): write-table layout 2 + running store pointer (walk_write2).
-// Each switch alone compiles to the default's 56 registers; both together take 67 (3 CTAs/SM
-// instead of 4) -- a register cap on that instantiation has to wait for a GPU to check it: every
-// way of attaching one (minimum-blocks hint, __maxnreg__, body as a device function) also changed
-// the code of the default kernel.
-template <int S, int T, int NSUB, int CAP, bool BATCH, int VAR = 0>
-__global__ void __launch_bounds__(T + 32) cuhd_decode_kernel(const DecodeParams p)
+__device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v)
 {
-    using Smem = SmemLayout<S, T, NSUB, CAP>;
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------- kernel
+// MINB: minimum resident CTAs per SM the register allocation is bounded for (4: 64 registers,
+// 5: 48 registers with a few spilled loop variables; B200LC_CUHD_MINB=5 selects the latter).
+template <int K, bool BATCH, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const DecodeParams p)
+{
+    using Smem = SmemLayout<K>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    u32 *tab = reinterpret_cast<u32 *>(smem_raw + ((sizeof(Smem) + 127) & ~size_t(127)));
-    u8 *ltab = reinterpret_cast<u8 *>(tab + (size_t(1) << p.max_len));   // lengths only: 1 byte per entry
-    // PAM only: a third table behind ltab, u16 per entry, all whole codewords of the window
+    const u32 L = p.max_len, LM = p.multi_bits;
+    u32 *wtab = reinterpret_cast<u32 *>(smem_raw + ((sizeof(Smem) + 127) & ~size_t(127)));   // write pass: two symbols
+    u8 *mtab = reinterpret_cast<u8 *>(wtab + (size_t(1) << L));                              // counting: <= 3 codewords
+    u8 *stab = mtab + (size_t(1) << LM);                                                      // counting: 1 codeword
 
-    constexpr bool PAM = (VAR & 1) != 0, W2 = (VAR & 2) != 0;
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31;
-    const bool worker = tid < T;
-    const u32 L = p.max_len;
-    const u32 shift = 32 - L;
-    constexpr u32 kTileUnits = Smem::kTileUnits;
-    constexpr u32 kTileBytes = kTileUnits * 4;
+    const u32 warp = tid >> 5;
+    const u32 shift = 32 - L, shift_m = 32 - LM;
 
-    // LUT -> shared memory: two-symbol entries for the write pass (see walk_write) + a byte table
-    // of first-codeword lengths for the counting passes.  A zero-length entry (unused prefix of an
-    // incomplete code) would stall the reference forever; it is mapped to length 1 here so that
-    // garbage input still terminates.
-    for (u32 i = tid; i < (1u << L); i += blockDim.x) {
-        const u32 e0 = p.lut[i];
-        u32 len0 = e0 & 0xffu;
-        if (len0 == 0 || len0 > L) len0 = 1;
-        const u32 e1 = p.lut[(i << len0) & ((1u << L) - 1)];
-        u32 len1 = e1 & 0xffu;
-        if (len1 == 0 || len1 > L) len1 = 1;
-        u32 entry = (e0 >> 8) | (len0 << 16);
-        if (len0 + len1 <= L) entry = (e0 >> 8) | (e1 & 0xff00u) | ((len0 + len1) << 16) | 0x80000000u;
-        if constexpr (W2) entry = (entry & 0xffffu) | ((entry >> 31) << 16) | (((entry >> 16) & 0xffu) << 24);
-        tab[i] = entry;
-        ltab[i] = (u8)len0;
-        if constexpr (PAM) reinterpret_cast<u16 *>(ltab + (size_t(1) << L))[i] = multi_entry(p.lut, i, L);
+    // LUT -> shared-memory tables.  A zero-length entry (unused prefix of an incomplete code)
+    // would stall the reference forever; first_len() maps it to length 1 so that garbage input
+    // still terminates.
+    for (u32 i = tid; i < (1u << L); i += kThreads) {
+        wtab[i] = write_entry2(p.lut, i, L);
+        stab[i] = count_entry(p.lut, i, L, L, 1);
     }
-    if (tid == 0) {
-        mbar_init(&sm.bar[0], 1);
-        mbar_init(&sm.bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    // the stream a piece belongs to
-    auto view_of = [&](u32 piece) -> StreamView {
-        return p.streams[p.piece_stream[piece]];
-    };
-    // sub-tile index g (inside its stream) -> can it be fetched by one TMA bulk copy?
-    auto tma_ok = [&](const StreamView &v, u32 g) -> bool {
-        return g < v.tma_tiles;
-    };
-    auto issue_load = [&](const StreamView &v, u32 g, u32 buf) {  // one thread
-        if (g < v.num_subtiles && tma_ok(v, g)) {
-            mbar_expect_tx(&sm.bar[buf], kTileBytes);
-            tma_load_1d(sm.in[buf], v.units + (u64)g * (T * S), kTileBytes, &sm.bar[buf]);
-        }
-    };
+    for (u32 i = tid; i < (1u << LM); i += kThreads) mtab[i] = count_entry(p.lut, i, L, LM, 3);
 
     if (tid == 0) {
         const u32 t0 = p.first_piece + atomicAdd(p.ticket, 1u);
         sm.next_piece = t0;
-        if (t0 < p.num_pieces) {
-            if (BATCH) {
-                sm.view[0] = view_of(t0);
-                issue_load(sm.view[0], (t0 - sm.view[0].first_piece) * NSUB, 0);
-            } else {
-                issue_load(p.one, t0 * NSUB, 0);
-            }
-        }
+        if (BATCH && t0 < p.num_pieces) sm.view[0] = p.streams[p.piece_stream[t0]];
     }
     __syncthreads();
-    u32 turn = 0;               // pieces this CTA has started: its view is sm.view[turn & 1]
 
-    u32 step = 0;               // buffer = step & 1
-    u32 phase0 = 0, phase1 = 0;
-
-    // wait for (or synchronously load) sub-tile g into buffer (step & 1)
-    auto acquire_input = [&](const StreamView &v, u32 g) {
-        const u32 buf = step & 1;
-        if (tma_ok(v, g)) {
-            if (buf == 0) { mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
-            else          { mbar_wait(&sm.bar[1], phase1); phase1 ^= 1; }
-        } else {
-            const u64 first = (u64)g * (T * S);
-            for (u32 i = tid; i < kTileUnits; i += blockDim.x) {
-                const u64 idx = first + i;
-                sm.in[buf][i] = idx < v.n_units ? v.units[idx] : 0u;
-            }
-            fence_proxy_async();
-            __syncthreads();
-        }
-    };
-
-    while (true) {
+    for (u32 turn = 0;; ++turn) {
         const u32 piece = sm.next_piece;
         if (piece >= p.num_pieces) break;
-        const StreamView &V = BATCH ? sm.view[turn & 1] : p.one;
+        const u32 par = turn & 1;
+        const StreamView &V = BATCH ? sm.view[par] : p.one;
+        const bool aligned = V.aligned != 0;
         const u32 lp = piece - V.first_piece;          // piece number inside its stream
-        const u32 g0 = lp * NSUB;
-        const u32 nsub = min((u32)NSUB, V.num_subtiles - g0);
+        constexpr u32 kSegSubs = (u32)K * 32;          // subsequences per segment
+        constexpr u32 kSegUnits = kSegSubs * S;
+        // Everything below is indexed relative to my segment with 32-bit numbers: its units
+        // (seg_units[0 .. seg_rem), zero beyond), its subsequences (seg_subs of them hold units).
+        const u64 seg_first_unit = ((u64)lp * kWarps + warp) * (u64)kSegUnits;
+        const u32 *const seg_units = V.units + seg_first_unit;
+        const u32 seg_rem = seg_first_unit >= V.n_units ? 0u : (u32)min(V.n_units - seg_first_unit, (u64)0x7fffff00u);
+        const u32 seg_subs = min(kSegSubs, (seg_rem + S - 1) / S);
+        // segments of this piece that hold stream units (the stream's last piece may have fewer)
+        const u32 real_segs = (u32)min((u64)kWarps, (V.n_units - (u64)lp * (kWarps * kSegUnits) + (kSegUnits - 1)) / (u64)kSegUnits);
 
-        u32 u[S + 1], m[S];
-        u32 e0 = 0, c0 = 0;
-        u32 my_start = 0, my_end = 0, my_cnt = 0;
-        u32 pre = 0;
-
-        auto load_units = [&](u32 buf) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(&sm.in[buf][tid * S]);
+        // the S units of my segment's subsequence `sub` (may be -1: the one in front of the
+        // segment) plus one lookahead unit
+        auto load_units = [&](int sub, u32 (&u)[S + 1]) {
+            const int first = sub * S;
+            if (aligned && first + S + 1 <= (int)seg_rem) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(seg_units + first);
 #pragma unroll
-            for (int q = 0; q < S / 4; ++q) {
-                const uint4 v = src[q];
-                u[4 * q + 0] = v.x; u[4 * q + 1] = v.y; u[4 * q + 2] = v.z; u[4 * q + 3] = v.w;
-            }
-            u[S] = sm.in[buf][tid * S + S];
-        };
-        // Round 0 + chain resolution of the current sub-tile for entry state `entry`.
-        // Leaves my_start / my_end / my_cnt per worker and sm.end[] = resolved exit states.
-        // Only the first `real` subsequences hold stream units; the rest of the last sub-tile is
-        // zero padding whose symbols lie beyond n_out.  Their entry states are not resolved: a
-        // run of zeros never re-synchronises when the all-zero codeword is longer than one bit,
-        // and the chain would crawl through it one subsequence per round.
-        auto resolve_subtile = [&](u32 entry, bool keep_masks, u32 real) {
-            if (worker) {
-                if constexpr (PAM) walk_record_multi<S>(u, reinterpret_cast<const u16 *>(ltab + (size_t(1) << L)), shift, m, e0, c0);
-                else walk_record<S>(u, ltab, shift, m, e0, c0);
-                sm.end[tid] = (u8)e0;
-                if (keep_masks) {
+                for (int q = 0; q < S / 4; ++q) {
+                    const uint4 v = __ldg(src + q);
+                    u[4 * q + 0] = v.x; u[4 * q + 1] = v.y; u[4 * q + 2] = v.z; u[4 * q + 3] = v.w;
+                }
+                u[S] = __ldg(seg_units + first + S);
+            } else {
 #pragma unroll
-                    for (int j = 0; j < S; ++j) sm.masks[tid * S + j] = m[j];
-                }
-            }
-            if (worker && lane == 31) sm.wexit[1][tid >> 5] = (u8)e0;
-            __syncthreads();   // tentative exit states (paths from bit 0) visible
-            my_start = 0;
-            my_end = e0;
-            my_cnt = c0;
-            // Fixed point of "entry state = exit state of the predecessor".  Inside a warp the
-            // chain is followed with shuffles (no CTA barrier); between warps through wexit[]:
-            // in round r a warp starts from what its left neighbour's last lane published in
-            // round r-1 and publishes its own exit state for round r+1.  Another CTA round runs
-            // only if some warp published a different state than before -- rare, because nearly
-            // every subsequence ends on the recorded path whatever its entry.
-            u32 evaluated = 0;   // entry state for which my_end / my_cnt currently hold
-            for (u32 round = 0;; ++round) {
-                bool pub_changed = false;
-                if (worker) {
-                    const u32 rd = (round + 1) & 1, wr = round & 1, wid = tid >> 5;
-                    const u32 warp_in = tid == 0 ? entry : (lane == 0 ? (u32)sm.wexit[rd][wid - 1] : 0u);
-                    while (true) {
-                        u32 sv = __shfl_up_sync(0xffffffffu, my_end, 1);
-                        if (lane == 0) sv = warp_in;
-                        my_start = sv;
-                        const bool eval = sv != evaluated && tid < real;
-                        bool changed = false;
-                        if (eval) {
-                            u32 ne, nc;
-                            walk_merge<S>(u, m, sv, e0, ltab, shift, ne, nc);
-                            changed = ne != my_end;
-                            my_end = ne;
-                            my_cnt = nc;
-                            evaluated = sv;
-                        }
-                        if (!__any_sync(0xffffffffu, changed)) break;
-                    }
-                    sm.end[tid] = (u8)my_end;
-                    if (lane == 31) {
-                        pub_changed = my_end != (u32)sm.wexit[rd][wid];
-                        sm.wexit[wr][wid] = (u8)my_end;
-                    }
-                }
-                if (!__syncthreads_or(pub_changed)) break;
-            }
-        };
-        // exclusive scan of my_cnt over the workers -> pre, sm.total
-        auto block_scan = [&]() {
-            u32 incl = 0;
-            if (worker) {
-                incl = warp_incl_scan(my_cnt);
-                if (lane == 31) sm.warp_sums[tid >> 5] = incl;
-            }
-            __syncthreads();
-            if (tid < 32) {
-                u32 v = tid < T / 32 ? sm.warp_sums[tid] : 0u;
-                const u32 s = warp_incl_scan(v);
-                if (tid < T / 32) sm.warp_sums[tid] = s - v;
-                if (tid == T / 32 - 1) sm.total = s;
-            }
-            __syncthreads();
-            if (worker) pre = sm.warp_sums[tid >> 5] + incl - my_cnt;
-        };
-        // prefetch the sub-tile of the NEXT step into the other buffer (one thread)
-        auto prefetch = [&](u32 pass, u32 c) {
-            if (tid != 0) return;
-            if (c + 1 < nsub) issue_load(V, g0 + c + 1, (step & 1) ^ 1);
-            else if (pass == 0) issue_load(V, g0, (step & 1) ^ 1);
-            else {
-                const u32 np = p.first_piece + atomicAdd(p.ticket, 1u);
-                sm.next_piece = np;
-                if (np >= p.num_pieces) return;
-                if (BATCH) {
-                    StreamView &vn = sm.view[(turn + 1) & 1];
-                    vn = view_of(np);
-                    issue_load(vn, (np - vn.first_piece) * NSUB, (step & 1) ^ 1);
-                } else {
-                    issue_load(p.one, np * NSUB, (step & 1) ^ 1);
-                }
+                for (int j = 0; j <= S; ++j) u[j] = first + j < (int)seg_rem ? __ldg(seg_units + first + j) : 0u;
             }
         };
 
-        // number of subsequences of sub-tile g that start inside the stream
-        const u64 total_subseq = (V.n_units + S - 1) / S;
-        auto real_subseq = [&](u32 g) -> u32 {
-            const u64 s0 = (u64)g * T;
-            return s0 >= total_subseq ? 0u : (u32)min((u64)T, total_subseq - s0);
+        // entry state of my segment, guessed: the path from bit 0 of the subsequence in front of it
+        auto guess_entry = [&]() -> u32 {
+            if (seg_first_unit == 0 || seg_rem == 0) return 0u;
+            u32 e = 0, c = 0;
+            if (lane == 31) {
+                u32 u[S + 1];
+                load_units(-1, u);
+                walk_count<S>(u, mtab, shift_m, stab, shift, 0u, e, c);
+            }
+            return __shfl_sync(0xffffffffu, e, 31);
         };
 
-        // ================================================================ pass A: states + counts
-        u32 entry = 0;
-        u32 piece_total = 0;
-        int dl = 0;            // alt warp: symbols(entry state lane) - symbols(entry state 0)
-        bool known = false;
-        for (u32 c = 0; c < nsub; ++c) {
-            acquire_input(V, g0 + c);
-            prefetch(0, c);
-            const u32 buf = step & 1;
-            if (worker) load_units(buf);
-            resolve_subtile(entry, c == 0, real_subseq(g0 + c));
-            block_scan();
-            if (worker) {
-                sm.saved[c][tid] = (u16)((my_start << 12) | my_cnt);
-                if (c == 0) {
-                    sm.pre[tid] = pre;
-                    sm.onpath[tid] = my_end == e0;
-                    if (tid == T - 1) sm.pre[T] = pre + my_cnt;
+        // pass A of my segment entered in state `entry`: saved[], exit state, symbols
+        auto segment_pass_a = [&](u32 entry, u32 &exit_state, u32 &symbols) {
+            u32 entry_in = entry, my_total = 0;
+            for (u32 step = 0; step * 32 < seg_subs; ++step) {
+                const u32 sub = step * 32 + lane;
+                const bool real = sub < seg_subs;
+                u32 u[S + 1];
+                u32 my_end = 0, my_cnt = 0, my_start = 0, evaluated = 0;
+                if (real) {
+                    load_units((int)sub, u);
+                    walk_count<S>(u, mtab, shift_m, stab, shift, 0u, my_end, my_cnt);
                 }
-                if (tid == T - 1) {
-                    sm.sub_entry[c] = (u8)entry;
-                    sm.sub_exit[c] = (u8)my_end;
-                    sm.sub_total[c] = sm.total;
+                // Fixed point of "entry state = exit state of the predecessor", followed through
+                // the warp with shuffles.  Nearly every subsequence leaves in the same state
+                // whatever its entry state, so the second round changes nothing and ends the loop.
+                for (;;) {
+                    u32 sv = __shfl_up_sync(0xffffffffu, my_end, 1);
+                    if (lane == 0) sv = entry_in;
+                    my_start = sv;
+                    const bool need = real && sv != evaluated;
+                    if (!__any_sync(0xffffffffu, need)) break;
+                    bool changed = false;
+                    if (need) {
+                        u32 ne, nc;
+                        walk_count<S>(u, mtab, shift_m, stab, shift, sv, ne, nc);
+                        changed = ne != my_end;
+                        my_end = ne;
+                        my_cnt = nc;
+                        evaluated = sv;
+                    }
+                    if (!__any_sync(0xffffffffu, changed)) break;
                 }
+                sm.saved[warp][step][lane] = (u16)((my_start << 12) | my_cnt);
+                my_total += my_cnt;
+                // lane 31's exit state enters the next step (if lane 31 is padding beyond the
+                // stream, nothing real follows)
+                entry_in = __shfl_sync(0xffffffffu, my_end, 31);
             }
-            piece_total += sm.total;
-            entry = sm.end[T - 1];
-            if (c == 0) {
-                __syncthreads();
-                // The piece as a function of its entry state `lane`: walk from bit `lane` of the
-                // first subsequence until the walk lands on the resolved path (usually within a
-                // few symbols); from there on the piece behaves as for entry state 0.
-                if (!worker) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) my_total += __shfl_xor_sync(0xffffffffu, my_total, d);
+            exit_state = entry_in;
+            symbols = my_total;
+        };
+
+        // ================================================================ pass A + piece chaining
+        // Evaluation rounds: (re)run pass A where a segment was entered in another state than its
+        // predecessor left, first against the guessed entry state of the piece, then -- after the
+        // look-back -- against the true one.  Normally: one pass A per warp, two checks, no repair.
+        {
+            u32 my_entry = guess_entry();
+            bool run = true, claimed = false, have_true = false;
+            u32 entry0 = 0;
+            for (;;) {
+                if (run) {
+                    u32 x, t;
+                    segment_pass_a(my_entry, x, t);
                     if (lane == 0) {
-                        known = true;
-                    } else if (lane < L) {
-                        u32 at = lane, own = 0;
-                        for (u32 sq = 0; sq < (u32)min(T, kAltMaxSub); ++sq) {
-                            u32 au[S + 1], am[S];
+                        sm.wa[par][warp] = (u8)my_entry;
+                        sm.wx[par][warp] = (u8)x;
+                        sm.wt[par][warp] = t;
+                    }
+                }
+                __syncthreads();
+                if (!claimed) {
+                    claimed = true;
+                    if (tid == 0) {          // claim the next piece (every thread has read `piece`)
+                        const u32 np = p.first_piece + atomicAdd(p.ticket, 1u);
+                        sm.next_piece = np;
+                        if (BATCH && np < p.num_pieces) sm.view[par ^ 1] = p.streams[p.piece_stream[np]];
+                    }
+                }
+                // first segment that was entered in another state than its predecessor left
+                if (!have_true) entry0 = sm.wa[par][0];
+                u32 wbad = kWarps, ebad = 0;
 #pragma unroll
-                            for (int j = 0; j <= S; ++j) au[j] = sm.in[buf][sq * S + j];
-                            const bool onp = sm.onpath[sq];
+                for (int w = kWarps - 1; w >= 0; --w) {
+                    const u32 e_in = w == 0 ? entry0 : (u32)sm.wx[par][w - 1];
+                    if ((u32)w < real_segs && (u32)sm.wa[par][w] != e_in) { wbad = (u32)w; ebad = e_in; }
+                }
+                if (wbad < (u32)kWarps) {
+                    run = warp == wbad;
+                    my_entry = ebad;
+                    __syncthreads();         // everyone has read wa / wx before segment wbad rewrites them
+                    continue;
+                }
+                if (have_true) break;
+
+                // ------------------------------------------------------------ publish + look-back
+                if (warp == 0) {
+                    const u32 A = entry0, X = sm.wx[par][real_segs - 1];
+                    u32 T = lane < (u32)kWarps ? sm.wt[par][lane] : 0u;
 #pragma unroll
-                            for (int j = 0; j < S; ++j) am[j] = onp ? sm.masks[sq * S + j] : 0u;
-                            const u32 rend = sm.end[sq];
-                            u32 ne, nc;
-                            walk_merge<S>(au, am, at, rend, ltab, shift, ne, nc);
-                            own += nc;
-                            if (ne == rend) {
-                                dl = (int)own - (int)sm.pre[sq + 1];
-                                known = dl >= -32768 && dl <= 32767;
+                    for (int d = 16; d > 0; d >>= 1) T += __shfl_xor_sync(0xffffffffu, T, d);
+                    PieceDesc *d = &p.desc[piece];
+                    u32 astar = A;
+                    u64 base = 0;
+                    if (lp == 0) {
+                        // first piece of its stream: entry state 0 is exact (guess_entry returned 0)
+                        if (lane == 0) st_release_u64(&d->incl, kValid | ((u64)X << 56) | (u64)T);
+                    } else {
+                        if (lane == 0)
+                            st_release_u64(&d->agg, kValid | ((u64)A << 56) | ((u64)X << 48) | (u64)T);
+                        // warp-wide look-back: lane i inspects piece k - i; windows overlap by one so
+                        // that every traversed piece sees the exit state of its predecessor.
+                        int k = (int)piece - 1;
+                        u64 acc = 0;
+                        bool first = true;
+                        u32 carried = 0;   // exit state assumed for the overlap piece by the previous window
+                        while (true) {
+                            const int idx = k - (int)lane;
+                            const bool in = idx >= (int)V.first_piece;
+                            u64 G = 0, I = 0;
+                            if (in) {
+                                I = ld_acquire_u64(&p.desc[idx].incl);
+                                G = ld_acquire_u64(&p.desc[idx].agg);
+                            }
+                            const bool has_incl = (I & kValid) != 0;
+                            const u32 incl_mask = __ballot_sync(0xffffffffu, has_incl);
+                            const u32 pl = incl_mask ? (u32)__ffs(incl_mask) - 1 : 32u;
+                            const bool ready = !in || has_incl || (G & kValid) != 0;
+                            const u32 ready_mask = __ballot_sync(0xffffffffu, ready);
+                            const u32 need = pl >= 32 ? 0xffffffffu : ((1u << pl) - 1);
+                            if ((ready_mask & need) != need) {
+                                __nanosleep(100);
+                                continue;
+                            }
+                            const u32 prov = has_incl ? (u32)(I >> 56) & 0xfu : (u32)(G >> 48) & 0xfu;
+                            if (!first && __shfl_sync(0xffffffffu, prov, 0) != carried) {
+                                // the overlap piece left in another state than assumed: start over
+                                k = (int)piece - 1;
+                                acc = 0;
+                                first = true;
+                                continue;
+                            }
+                            const u32 pin = __shfl_down_sync(0xffffffffu, prov, 1);   // exit state of the predecessor
+                            const u32 nl = min(pl, 31u);   // lanes [0, nl) are traversed in this window
+                            bool link = true;
+                            u32 c = 0;
+                            if (lane < nl) {
+                                link = ((u32)(G >> 56) & 0xfu) == pin;
+                                c = (u32)G;
+                            }
+                            if (!__all_sync(0xffffffffu, link)) {
+                                __nanosleep(200);   // a piece on the way was entered in another state than
+                                continue;           // it assumed: it will publish its own inclusive state
+                            }
+                            u64 sum = c;
+#pragma unroll
+                            for (int dd = 16; dd > 0; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
+                            acc += sum;
+                            if (first) {
+                                astar = __shfl_sync(0xffffffffu, prov, 0);
+                                first = false;
+                            }
+                            if (pl < 32) {
+                                base = (__shfl_sync(0xffffffffu, I, pl) & kCountMask) + acc;
                                 break;
                             }
-                            at = ne;
+                            carried = __shfl_sync(0xffffffffu, prov, 31);
+                            k -= 31;
                         }
+                        if (lane == 0 && astar == A)
+                            st_release_u64(&d->incl, kValid | ((u64)X << 56) | (base + (u64)T));
+                    }
+                    if (lane == 0) {
+                        sm.base = base;
+                        sm.true_entry = astar;
+                        sm.redo = astar != A;
                     }
                 }
+                __syncthreads();
+                have_true = true;
+                entry0 = sm.true_entry;
+                run = false;
             }
-            __syncthreads();   // buffer hand-over, sm.end / sm.total reuse
-            ++step;
-        }
-
-        // ================================================================ publish + look-back
-        if (!worker) {
-            const u32 total0 = piece_total;
-            const u32 exit0 = entry;
-            const u32 known_mask = __ballot_sync(0xffffffffu, known) & 0xffffu;
-            TileDesc *d = &p.desc[piece];
-            u32 astar = 0;
-            u64 base = 0;
-            if (lp == 0) {
-                if (lane == 0) st_release_u64(&d->incl, kInclValid | ((u64)exit0 << 56) | total0);
-            } else {
-                if (lane < kMaxStates) d->d[lane] = (short)(known ? dl : 0);
-                __threadfence();
-                __syncwarp();
-                if (lane == 0)
-                    st_release_u64(&d->agg, kAggValid | ((u64)exit0 << 56) |
-                                                ((u64)known_mask << 40) | total0);
-
-                // warp-wide look-back: lane i inspects piece k - i; windows overlap by one so
-                // that every traversed piece sees the exit state of its predecessor.
-                int k = (int)piece - 1;
-                u64 acc = 0;
-                bool first = true;
-                u32 carried = 0;   // exit state assumed for the overlap piece by the previous window
-                while (true) {
-                    const int idx = k - (int)lane;
-                    u64 A = 0, I = 0;
-                    if (idx >= (int)V.first_piece) {
-                        I = ld_acquire_u64(&p.desc[idx].incl);
-                        A = ld_acquire_u64(&p.desc[idx].agg);
-                    }
-                    const bool has_incl = (I & kInclValid) != 0;
-                    const u32 incl_mask = __ballot_sync(0xffffffffu, has_incl);
-                    const u32 pl = incl_mask ? (u32)__ffs(incl_mask) - 1 : 32u;
-                    const bool agg_ok = idx < (int)V.first_piece || (A & kAggValid) != 0;
-                    const u32 agg_mask = __ballot_sync(0xffffffffu, agg_ok);
-                    const u32 need = pl >= 32 ? 0xffffffffu : ((1u << pl) - 1);
-                    if ((agg_mask & need) != need) {
-                        __nanosleep(100);
-                        continue;
-                    }
-                    const u32 prov = has_incl ? (u32)(I >> 56) & 0xfu : (u32)(A >> 56) & 0xfu;
-                    if (!first && __shfl_sync(0xffffffffu, prov, 0) != carried) {
-                        // the overlap piece left in another state than assumed: start over
-                        k = (int)piece - 1;
-                        acc = 0;
-                        first = true;
-                        continue;
-                    }
-                    const u32 in = __shfl_down_sync(0xffffffffu, prov, 1);
-                    const u32 nl = min(pl, 31u);   // lanes [0, nl) are traversed in this window
-                    bool ok = true;
-                    u32 c = 0;
-                    if (lane < nl) {
-                        ok = ((u32)(A >> 40) >> in) & 1u;
-                        if (ok) c = (u32)((int)(u32)A + (int)__ldcg(&p.desc[idx].d[in]));
-                    }
-                    if (!__all_sync(0xffffffffu, ok)) {
-                        __nanosleep(200);   // a piece on the way must publish its own inclusive state
-                        continue;
-                    }
-                    u64 sum = c;
-#pragma unroll
-                    for (int dd = 16; dd > 0; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
-                    acc += sum;
-                    if (first) {
-                        astar = __shfl_sync(0xffffffffu, prov, 0);
-                        first = false;
-                    }
-                    if (pl < 32) {
-                        base = (__shfl_sync(0xffffffffu, I, pl) & kCountMask) + acc;
-                        break;
-                    }
-                    carried = __shfl_sync(0xffffffffu, prov, 31);
-                    k -= 31;
-                }
-                // inclusive state of this piece, if its entry state merges
-                const bool my_known = (known_mask >> astar) & 1u;
-                const int my_d = __shfl_sync(0xffffffffu, dl, astar);
-                if (lane == 0 && my_known)
-                    st_release_u64(&d->incl, kInclValid | ((u64)exit0 << 56) |
-                                                 (base + (u64)((int)total0 + my_d)));
-                if (lane == 0) sm.known = my_known;
-            }
-            if (lane == 0) {
-                sm.astar = astar;
-                sm.base = base;
-                if (lp == 0) sm.known = 1;
+            if (sm.redo && tid == 0) {
+                // the piece was entered in another state than guessed: its inclusive state comes late
+                u64 T = 0;
+                for (int w = 0; w < kWarps; ++w) T += sm.wt[par][w];
+                st_release_u64(&p.desc[piece].incl,
+                               kValid | ((u64)sm.wx[par][real_segs - 1] << 56) | (sm.base + T));
             }
         }
-        __syncthreads();
 
         // ================================================================ pass B: decode + write
-        u32 entry_true = sm.astar;
-        u64 base_run = sm.base;
-        const bool publish_late = !sm.known;
-        for (u32 c = 0; c < nsub; ++c) {
-            acquire_input(V, g0 + c);
-            prefetch(1, c);
-            const u32 buf = step & 1;
-            if (worker) load_units(buf);
-            u32 exit_state;
-            if (entry_true != sm.sub_entry[c]) {
-                // entry state differs from what pass A assumed (always for sub-tile 0 when the
-                // piece's entry state is not 0): redo states + counts for this sub-tile
-                resolve_subtile(entry_true, false, real_subseq(g0 + c));
-                exit_state = sm.end[T - 1];
-            } else {
-                if (worker) {
-                    const u32 sv = sm.saved[c][tid];
-                    my_start = sv >> 12;
-                    my_cnt = sv & 0xfffu;
-                }
-                exit_state = sm.sub_exit[c];
-            }
-            block_scan();
-            const u32 total = sm.total;
-
-            u64 tile_cnt = 0;
-            if (base_run < V.n_out) tile_cnt = min((u64)total, V.n_out - base_run);
-            for (u32 w0 = 0; w0 < tile_cnt; w0 += CAP) {
-                const u32 wlen = (u32)min((u64)CAP, tile_cnt - w0);
-                u8 *g = V.out + base_run + w0;
-                const u32 sh = (u32)(reinterpret_cast<uintptr_t>(g) & 15u);
-                if (worker) {
-                    const u32 lo = w0, hi = w0 + wlen;
-                    if (pre < hi && pre + my_cnt > lo) {
-                        u8 *dst = sm.stage + ((int)sh - (int)w0);
-                        if constexpr (W2) {
+        if (seg_subs) {
+            u64 gstart = sm.base;                    // output index of my segment's first symbol
+            for (u32 w = 0; w < warp; ++w) gstart += sm.wt[par][w];
+            if (gstart < V.n_out) {
+                u8 *const stage = sm.stage[warp];
+                // stage[0] corresponds to the 16-byte aligned output address optr; of the staged
+                // bytes only those at [lo_ok, hi_ok) relative to optr are mine and inside the output
+                u32 lo_ok = (u32)((reinterpret_cast<uintptr_t>(V.out) + gstart) & 15u);
+                u8 *optr = V.out + gstart - lo_ok;
+                u32 hi_ok = (u32)min(V.n_out - gstart + lo_ok, (u64)0x7fffff00u);
+                u32 fill = lo_ok;
+                auto flush_vectors = [&]() {       // whole 16-byte vectors of stage[0, fill) leave; the rest moves to the front
+                    const u32 nvec = fill >> 4;
+                    for (u32 i = lane; i < nvec; i += 32) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(stage + 16 * i);
+                        if (16 * i >= lo_ok && 16 * i + 16 <= hi_ok) {
+                            st_stream_v4(optr + 16 * i, v);
+                        } else {
+                            for (u32 b = 16 * i; b < 16 * i + 16; ++b)
+                                if (b >= lo_ok && b < hi_ok) optr[b] = stage[b];
+                        }
+                    }
+                    const u32 tail = fill & 15u;
+                    u8 keep = 0;
+                    if (lane < tail) keep = stage[16 * nvec + lane];
+                    __syncwarp();
+                    if (lane < tail) stage[lane] = keep;
+                    __syncwarp();
+                    optr += 16 * nvec;
+                    lo_ok = lo_ok > 16 * nvec ? lo_ok - 16 * nvec : 0u;
+                    hi_ok = hi_ok > 16 * nvec ? hi_ok - 16 * nvec : 0u;
+                    fill = tail;
+                };
+                for (u32 step = 0; step * 32 < seg_subs; ++step) {
+                    if (fill >= hi_ok) break;      // the rest lies beyond the output
+                    const u32 sub = step * 32 + lane;
+                    u32 u[S + 1];
+                    if (sub < seg_subs) load_units((int)sub, u);
+                    const u32 sv = sm.saved[warp][step][lane];
+                    const u32 my_start = sv >> 12, my_cnt = sv & 0xfffu;
+                    const u32 incl = warp_incl_scan(my_cnt);
+                    const u32 pre = incl - my_cnt;
+                    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+                    for (u32 lo = 0; lo < total; lo += kWin) {
+                        const u32 hi = min(total, lo + kWin);
+                        // symbol at step-local position q goes to dst[q]
+                        u8 *dst = stage + ((int)fill - (int)lo);
+                        if (pre < hi && pre + my_cnt > lo) {
                             if (pre >= lo && pre + my_cnt <= hi)
-                                walk_write2<S, false>(u, tab, shift, my_start, dst, pre, lo, hi);
+                                walk_write2<S, false>(u, wtab, shift, my_start, dst, pre, lo, hi);
                             else
-                                walk_write2<S, true>(u, tab, shift, my_start, dst, pre, lo, hi);
-                        } else if (pre >= lo && pre + my_cnt <= hi)
-                            walk_write<S, false>(u, tab, shift, my_start, dst, pre, lo, hi);
-                        else
-                            walk_write<S, true>(u, tab, shift, my_start, dst, pre, lo, hi);
+                                walk_write2<S, true>(u, wtab, shift, my_start, dst, pre, lo, hi);
+                        }
+                        __syncwarp();
+                        fill += hi - lo;
+                        flush_vectors();
                     }
                 }
-                __syncthreads();
-                const u32 head = min(wlen, (16u - sh) & 15u);
-                const u32 nvec = (wlen - head) >> 4;
-                const u32 tail0 = head + (nvec << 4);
-                if (tid < head) g[tid] = sm.stage[sh + tid];
-                const uint4 *sv = reinterpret_cast<const uint4 *>(sm.stage + sh + head);
-                uint4 *gv = reinterpret_cast<uint4 *>(g + head);
-                for (u32 i = tid; i < nvec; i += blockDim.x) gv[i] = sv[i];
-                if (tid < wlen - tail0) g[tail0 + tid] = sm.stage[sh + tail0 + tid];
-                __syncthreads();
+                // the segment's last partial vector
+                for (u32 i = lane; i < fill; i += 32)
+                    if (i >= lo_ok && i < hi_ok) optr[i] = stage[i];
+                __syncwarp();
             }
-            base_run += total;
-            entry_true = exit_state;
-            __syncthreads();   // buffer hand-over, sm.total / sm.end reuse
-            ++step;
         }
-        if (publish_late && tid == 0)
-            st_release_u64(&p.desc[piece].incl,
-                           kInclValid | ((u64)entry_true << 56) | base_run);
-        __syncthreads();
-        ++turn;
     }
 }
 
 // ---------------------------------------------------------------------------------- host
-// Kernel variants (subsequence units S, subsequences per sub-tile T, sub-tiles per piece NSUB,
-// staging bytes CAP).  Variant 0 is the default; B200LC_CUHD_VARIANT selects another one for
-// tuning runs.
+// Kernel variants differ in K = warp-steps per segment, i.e. in the piece length
+// (kWarps * K KiB of stream).  B200LC_CUHD_VARIANT pins one for tuning runs.
 struct Variant {
-    int S, T, NSUB, CAP;
-    void (*kern[4])(const DecodeParams);          // indexed by the opt-in switches VAR (0 = default)
-    void (*kern_batch[4])(const DecodeParams);
+    int K;
+    void (*kern[2])(const DecodeParams);         // [MINB == 5]
+    void (*kern_batch[2])(const DecodeParams);
     size_t smem_fixed;
 };
-#define B200LC_VARIANT(S_, T_, N_, C_) \
-    { S_, T_, N_, C_, \
-      { cuhd_decode_kernel<S_, T_, N_, C_, false, 0>, cuhd_decode_kernel<S_, T_, N_, C_, false, 1>, \
-        cuhd_decode_kernel<S_, T_, N_, C_, false, 2>, cuhd_decode_kernel<S_, T_, N_, C_, false, 3> }, \
-      { cuhd_decode_kernel<S_, T_, N_, C_, true, 0>, cuhd_decode_kernel<S_, T_, N_, C_, true, 1>, \
-        cuhd_decode_kernel<S_, T_, N_, C_, true, 2>, cuhd_decode_kernel<S_, T_, N_, C_, true, 3> }, \
-      ((sizeof(SmemLayout<S_, T_, N_, C_>) + 127) & ~size_t(127)) }
+#define B200LC_VARIANT(K_) \
+    { K_, { cuhd_decode_kernel<K_, false, 4>, cuhd_decode_kernel<K_, false, 5> }, \
+      { cuhd_decode_kernel<K_, true, 4>, cuhd_decode_kernel<K_, true, 5> }, \
+      ((sizeof(SmemLayout<K_>) + 127) & ~size_t(127)) }
 static const Variant kVariants[] = {
-    B200LC_VARIANT(8, 256, 16, 16384),   // default for long streams: 407 GB/s of output on C2 (B200, round 1)
-    B200LC_VARIANT(8, 256, 8, 16384),    // shorter pieces for shorter streams (see pick_variant)
-    B200LC_VARIANT(8, 256, 4, 16384),
-    B200LC_VARIANT(8, 256, 2, 16384),
-    B200LC_VARIANT(8, 256, 1, 16384),
-    B200LC_VARIANT(8, 256, 32, 16384),   // tuning points: 333
-    B200LC_VARIANT(8, 128, 16, 8192),    // 375
-    B200LC_VARIANT(4, 256, 32, 12288),   // 279
+    B200LC_VARIANT(16),   // 128 KiB pieces: default for long streams
+    B200LC_VARIANT(8),    // shorter pieces for shorter streams (see pick_variant)
+    B200LC_VARIANT(4),
+    B200LC_VARIANT(2),
+    B200LC_VARIANT(1),
+    B200LC_VARIANT(32),   // tuning point
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kSmallest = 4;   // index of the variant with the shortest pieces
 
 static const Variant &variant()
 {
@@ -608,50 +481,57 @@ static const Variant &variant()
     return kVariants[v];
 }
 
-// Opt-in tuning switches (template parameter VAR of the kernel): B200LC_CUHD_PASSA=multi -> bit 0,
-// B200LC_CUHD_WRITE=2 -> bit 1.  Read once per process; the default is 0.
-static int tuning_switches()
+static int minb_index()
 {
     static int v = -1;
     if (v < 0) {
-        const char *a = getenv("B200LC_CUHD_PASSA"), *w = getenv("B200LC_CUHD_WRITE");
-        v = ((a && a[0] == 'm') ? 1 : 0) | ((w && w[0] == '2') ? 2 : 0);
+        const char *e = getenv("B200LC_CUHD_MINB");
+        v = (e && atoi(e) == 5) ? 1 : 0;
     }
     return v;
 }
-// dynamic shared memory: fixed layout + write table (4 B) + byte lengths (1 B) [+ multi table (2 B)]
-static size_t smem_bytes(const Variant &v, int L, int var)
+
+static u32 multi_bits(int L)
 {
-    return v.smem_fixed + (size_t((var & 1) ? 7 : 5) << L);
+    static int lm = -1;
+    if (lm < 0) {
+        const char *e = getenv("B200LC_CUHD_MULTI_BITS");
+        lm = e ? atoi(e) : (int)kMultiBits;
+        if (lm < 1 || lm > 15) lm = (int)kMultiBits;
+    }
+    return (u32)(lm > L ? lm : L);
 }
 
-// One-shot decodes pick the piece length by stream size: a piece is decoded by one CTA, two
-// passes over NSUB sub-tiles back to back (~5 us each), so a stream with fewer pieces than the
-// GPU has CTA slots is latency-bound by its piece length.  Halve it until the pieces fill the
-// machine (variants 0..4 differ only in NSUB).  B200LC_CUHD_VARIANT pins one variant.
-static const Variant &pick_variant(u64 n_units)
+// dynamic shared memory: fixed layout + write table (4 B per entry) + counting tables (1 B each)
+static size_t smem_bytes(const Variant &v, int L)
+{
+    return v.smem_fixed + (size_t(5) << L) + (size_t(1) << multi_bits(L));
+}
+
+static u64 piece_units(const Variant &v) { return (u64)kWarps * v.K * 32 * S; }
+
+static u32 pieces_for(const Variant &v, u64 n_units)
+{
+    return (u32)((n_units + piece_units(v) - 1) / piece_units(v));
+}
+
+// One-shot decodes pick the piece length by stream size: a piece is decoded by one CTA in two
+// passes over K warp-steps, so a stream with fewer pieces than the GPU has CTA slots is
+// latency-bound by its piece length.  Halve it until the pieces fill the machine.
+static const Variant &pick_variant_for(u64 pieces_at_k1)
 {
     if (getenv("B200LC_CUHD_VARIANT")) return variant();
     const u64 want = (u64)num_sms() * 4;
-    for (int i = 0; i < 4; ++i) {
-        const Variant &v = kVariants[i];
-        const u64 sub = ((n_units + v.S - 1) / v.S + v.T - 1) / v.T;
-        if ((sub + v.NSUB - 1) / v.NSUB >= want) return v;
-    }
-    return kVariants[4];
+    for (int i = 0; i < kSmallest; ++i)
+        if (pieces_at_k1 / (u64)kVariants[i].K >= want) return kVariants[i];
+    return kVariants[kSmallest];
+}
+static const Variant &pick_variant(u64 n_units)
+{
+    return pick_variant_for(pieces_for(kVariants[kSmallest], n_units));
 }
 
-static u32 subtiles_for(const Variant &v, u64 n_units)
-{
-    const u64 nsub = (n_units + v.S - 1) / v.S;
-    return (u32)((nsub + v.T - 1) / v.T);
-}
-static u32 pieces_for(const Variant &v, u64 n_units)
-{
-    return (subtiles_for(v, n_units) + v.NSUB - 1) / v.NSUB;
-}
-
-static StreamView make_view(const Variant &v, const u32 *units, u64 n_units, u8 *out, u64 n_out, u32 first_piece)
+static StreamView make_view(const u32 *units, u64 n_units, u8 *out, u64 n_out, u32 first_piece)
 {
     StreamView s;
     s.units = units;
@@ -659,12 +539,46 @@ static StreamView make_view(const Variant &v, const u32 *units, u64 n_units, u8 
     s.out = out;
     s.n_out = n_out;
     s.first_piece = first_piece;
-    s.num_subtiles = subtiles_for(v, n_units);
-    s.tma_tiles = 0;
-    if ((reinterpret_cast<uintptr_t>(units) & 15) == 0 && n_units >= 4)
-        s.tma_tiles = (u32)min((u64)s.num_subtiles, (u64)(n_units - 4) / (u64)(v.T * v.S));
-    s.pad = 0;
+    s.aligned = (reinterpret_cast<uintptr_t>(units) & 15) == 0 ? 1u : 0u;
     return s;
+}
+
+// The dynamic shared-memory limit is an attribute of the KERNEL (not of the table width it is
+// launched with): raise it whenever a launch needs more than the largest value set so far on this
+// device, and keep the occupancy that goes with each (kernel, table width).  Both are forgotten
+// when the context epoch changes (cudaDeviceReset in resetGPU, culzss_api.cu).
+struct KernelCache {
+    unsigned epoch;
+    size_t smem_set[kNumVariants][2];
+    int occ[kNumVariants][2][16];
+    size_t occ_smem[kNumVariants][2][16];
+};
+static KernelCache g_cache[kMaxDevices];
+
+static int prepare_kernel(const Variant &v, bool batch, int L, size_t smem, int *occ_out)
+{
+    void (*const kern)(const DecodeParams) = batch ? v.kern_batch[minb_index()] : v.kern[minb_index()];
+    const int slot = device_slot();
+    const int vi = (int)(&v - kVariants), bi = batch ? 1 : 0;
+    KernelCache local = KernelCache();
+    KernelCache &kc = slot >= 0 ? g_cache[slot] : local;
+    if (kc.epoch != context_epoch()) {
+        kc = KernelCache();
+        kc.epoch = context_epoch();
+    }
+    if (smem > kc.smem_set[vi][bi]) {
+        B200LC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kc.smem_set[vi][bi] = smem;
+    }
+    int occ = kc.occ_smem[vi][bi][L] == smem ? kc.occ[vi][bi][L] : 0;
+    if (!occ) {
+        B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+        if (occ < 1) return B200LC_ERR_CUDA;
+        kc.occ[vi][bi][L] = occ;
+        kc.occ_smem[vi][bi][L] = smem;
+    }
+    *occ_out = occ;
+    return B200LC_OK;
 }
 
 // batch: stream number of every piece (views are sorted by first_piece)
@@ -689,12 +603,7 @@ using namespace b200lc;
 extern "C" size_t b200lc_cuhd_decode_scratch_bytes(size_t n_units)
 {
     // sized for the variant with the smallest pieces so that the answer does not depend on tuning
-    size_t worst = 0;
-    for (int i = 0; i < cuhd::kNumVariants; ++i) {
-        const size_t n = cuhd::pieces_for(cuhd::kVariants[i], n_units);
-        if (n > worst) worst = n;
-    }
-    return 128 + worst * sizeof(cuhd::TileDesc);
+    return 128 + (size_t)cuhd::pieces_for(cuhd::kVariants[cuhd::kSmallest], n_units) * sizeof(cuhd::PieceDesc) + 128;
 }
 
 // Decodes pieces [first_piece, end_piece) of the stream.  The descriptors of earlier pieces must
@@ -713,27 +622,19 @@ static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t
     if (scratch_bytes < need) return B200LC_ERR_SCRATCH;
     if (reinterpret_cast<uintptr_t>(d_scratch) & 127) return B200LC_ERR_ARG;
 
-    const int var = cuhd::tuning_switches();
-    void (*const kern)(const cuhd::DecodeParams) = v.kern[var];
-    const size_t smem = cuhd::smem_bytes(v, max_codeword_length, var);
-    static int occ_table[kMaxDevices][cuhd::kNumVariants][14] = {{{0}}};
-    const int slot = device_slot();
-    int occ = slot >= 0 ? occ_table[slot][&v - cuhd::kVariants][max_codeword_length] : 0;
-    if (!occ) {
-        B200LC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-        B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, v.T + 32, smem));
-        if (occ < 1) return B200LC_ERR_CUDA;
-        if (slot >= 0) occ_table[slot][&v - cuhd::kVariants][max_codeword_length] = occ;
-    }
+    const size_t smem = cuhd::smem_bytes(v, max_codeword_length);
+    int occ = 0;
+    const int rc = cuhd::prepare_kernel(v, false, max_codeword_length, smem, &occ);
+    if (rc) return rc;
     cuhd::DecodeParams p;
-    p.one = cuhd::make_view(v, d_units, n_units, d_out, n_out, 0);
+    p.one = cuhd::make_view(d_units, n_units, d_out, n_out, 0);
     p.streams = nullptr;
     p.piece_stream = nullptr;
     p.lut = reinterpret_cast<const u16 *>(d_table);
     p.max_len = (u32)max_codeword_length;
+    p.multi_bits = cuhd::multi_bits(max_codeword_length);
     p.ticket = reinterpret_cast<u32 *>(d_scratch);
-    p.desc = reinterpret_cast<cuhd::TileDesc *>(reinterpret_cast<char *>(d_scratch) + 128);
+    p.desc = reinterpret_cast<cuhd::PieceDesc *>(reinterpret_cast<char *>(d_scratch) + 128);
     const u32 all_pieces = cuhd::pieces_for(v, n_units);
     if (end_piece > all_pieces) end_piece = all_pieces;
     if (first_piece >= end_piece) return B200LC_OK;
@@ -741,12 +642,11 @@ static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t
     p.first_piece = (u32)first_piece;
 
     if (first_piece == 0)
-        B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128 + all_pieces * sizeof(cuhd::TileDesc), stream));
+        B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128 + all_pieces * sizeof(cuhd::PieceDesc), stream));
     else
         B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128, stream));   // ticket only
-    const u32 grid = (u32)min((u64)(end_piece - first_piece),
-                              (u64)num_sms() * (u64)occ);
-    kern<<<grid, v.T + 32, smem, stream>>>(p);
+    const u32 grid = (u32)min((u64)(end_piece - first_piece), (u64)num_sms() * (u64)occ);
+    v.kern[cuhd::minb_index()]<<<grid, cuhd::kThreads, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }
@@ -761,8 +661,7 @@ extern "C" int b200lc_cuhd_decode(const uint32_t *d_units, size_t n_units, uint8
 
 extern "C" size_t b200lc_cuhd_decode_piece_units(void)
 {
-    const cuhd::Variant &v = cuhd::variant();
-    return (size_t)v.S * v.T * v.NSUB;
+    return (size_t)cuhd::piece_units(cuhd::variant());
 }
 
 extern "C" int b200lc_cuhd_decode_pieces(const uint32_t *d_units, size_t n_units, uint8_t *d_out,
@@ -780,8 +679,8 @@ extern "C" int b200lc_cuhd_decode_progress_async(const void *d_scratch, size_t e
                                                  uint64_t *h_symbols, void *stream_)
 {
     if (!d_scratch || !h_symbols || end_piece == 0) return B200LC_ERR_ARG;
-    const cuhd::TileDesc *desc =
-        reinterpret_cast<const cuhd::TileDesc *>(reinterpret_cast<const char *>(d_scratch) + 128);
+    const cuhd::PieceDesc *desc =
+        reinterpret_cast<const cuhd::PieceDesc *>(reinterpret_cast<const char *>(d_scratch) + 128);
     B200LC_CUDA_TRY(cudaMemcpyAsync(h_symbols, &desc[end_piece - 1].incl, sizeof(u64),
                                     cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
     return B200LC_OK;
@@ -803,31 +702,23 @@ static int plan_batch(const uint32_t *d_units, uint8_t *d_out, const b200lc_cuhd
                       BatchPlan &bp)
 {
     // piece length from the total size, like pick_variant does for one stream
-    bp.v = &cuhd::kVariants[4];
-    if (getenv("B200LC_CUHD_VARIANT")) bp.v = &cuhd::variant();
-    else {
-        const u64 want = (u64)num_sms() * 4;
-        for (int k = 0; k < 4; ++k) {
-            const cuhd::Variant &v = cuhd::kVariants[k];
-            u64 pieces = 0;
-            for (size_t i = 0; i < n; ++i)
-                if (h[i].n_units && h[i].n_out) pieces += cuhd::pieces_for(v, h[i].n_units);
-            if (pieces >= want) { bp.v = &v; break; }
-        }
-    }
+    u64 small_pieces = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (h[i].n_units && h[i].n_out) small_pieces += cuhd::pieces_for(cuhd::kVariants[cuhd::kSmallest], h[i].n_units);
+    bp.v = &cuhd::pick_variant_for(small_pieces);
     bp.views.clear();
     bp.pieces = 0;
     for (size_t i = 0; i < n; ++i) {
         if (h[i].n_units == 0 || h[i].n_out == 0) continue;
         if (h[i].n_units >= (1ull << 40)) return B200LC_ERR_UNSUPPORTED;
-        bp.views.push_back(cuhd::make_view(*bp.v, d_units + h[i].unit_offset, h[i].n_units,
+        bp.views.push_back(cuhd::make_view(d_units + h[i].unit_offset, h[i].n_units,
                                            d_out + h[i].out_offset, h[i].n_out, (u32)bp.pieces));
         bp.pieces += cuhd::pieces_for(*bp.v, h[i].n_units);
     }
     if (bp.pieces >= (1ull << 31)) return B200LC_ERR_UNSUPPORTED;
     auto up = [](size_t x) { return (x + 127) & ~size_t(127); };
     bp.desc_off = 128;
-    bp.views_off = bp.desc_off + up(bp.pieces * sizeof(cuhd::TileDesc));
+    bp.views_off = bp.desc_off + up(bp.pieces * sizeof(cuhd::PieceDesc));
     bp.map_off = bp.views_off + up(bp.views.size() * sizeof(cuhd::StreamView));
     bp.total = bp.map_off + up(bp.pieces * 4);
     return B200LC_OK;
@@ -838,11 +729,11 @@ extern "C" size_t b200lc_cuhd_decode_batch_scratch_bytes(const b200lc_cuhd_strea
 {
     if (!h_streams) return 0;
     // sized for the variant with the shortest pieces so that the answer does not depend on tuning
-    const cuhd::Variant &v = cuhd::kVariants[4];
+    const cuhd::Variant &v = cuhd::kVariants[cuhd::kSmallest];
     u64 pieces = 0;
     for (size_t i = 0; i < n_streams; ++i) pieces += cuhd::pieces_for(v, h_streams[i].n_units);
     auto up = [](size_t x) { return (x + 127) & ~size_t(127); };
-    return 128 + up(pieces * sizeof(cuhd::TileDesc)) + up(n_streams * sizeof(cuhd::StreamView)) + up(pieces * 4) + 256;
+    return 128 + up(pieces * sizeof(cuhd::PieceDesc)) + up(n_streams * sizeof(cuhd::StreamView)) + up(pieces * 4) + 256;
 }
 
 extern "C" int b200lc_cuhd_decode_batch(const uint32_t *d_units, uint8_t *d_out,
@@ -861,13 +752,10 @@ extern "C" int b200lc_cuhd_decode_batch(const uint32_t *d_units, uint8_t *d_out,
     if (bp.pieces == 0) return B200LC_OK;
     if (scratch_bytes < bp.total) return B200LC_ERR_SCRATCH;
     const cuhd::Variant &v = *bp.v;
-    const int var = cuhd::tuning_switches();
-    void (*const kern_batch)(const cuhd::DecodeParams) = v.kern_batch[var];
-    const size_t smem = cuhd::smem_bytes(v, max_codeword_length, var);
-    B200LC_CUDA_TRY(cudaFuncSetAttribute(kern_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = cuhd::smem_bytes(v, max_codeword_length);
     int occ = 0;
-    B200LC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_batch, v.T + 32, smem));
-    if (occ < 1) return B200LC_ERR_CUDA;
+    rc = cuhd::prepare_kernel(v, true, max_codeword_length, smem, &occ);
+    if (rc) return rc;
     char *base = reinterpret_cast<char *>(d_scratch);
     cuhd::StreamView *d_views = reinterpret_cast<cuhd::StreamView *>(base + bp.views_off);
     u32 *d_map = reinterpret_cast<u32 *>(base + bp.map_off);
@@ -883,12 +771,13 @@ extern "C" int b200lc_cuhd_decode_batch(const uint32_t *d_units, uint8_t *d_out,
     p.piece_stream = d_map;
     p.lut = reinterpret_cast<const u16 *>(d_table);
     p.max_len = (u32)max_codeword_length;
+    p.multi_bits = cuhd::multi_bits(max_codeword_length);
     p.ticket = reinterpret_cast<u32 *>(d_scratch);
-    p.desc = reinterpret_cast<cuhd::TileDesc *>(base + bp.desc_off);
+    p.desc = reinterpret_cast<cuhd::PieceDesc *>(base + bp.desc_off);
     p.num_pieces = (u32)bp.pieces;
     p.first_piece = 0;
     const u32 grid = (u32)min((u64)bp.pieces, (u64)num_sms() * (u64)occ);
-    kern_batch<<<grid, v.T + 32, smem, stream>>>(p);
+    v.kern_batch[cuhd::minb_index()]<<<grid, cuhd::kThreads, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }

@@ -262,6 +262,70 @@ B200LC_HD void walk_write2(const u32 (&u)[S + 1], const u32 *tab, u32 shift, u32
     }
 }
 
+// --------------------------------------------------------------------------- counting walk
+// Round-2 pass A: no codeword-start masks.  One byte per window of LM >= L bits:
+//   bits 0..3  bits consumed by the first n whole codewords of the window, n = 1..3
+//   bits 6..7  n
+// so that `acc += entry` advances the bit position (bits 0..5 of acc, < 64 inside a unit) and the
+// codeword count (bits 6 and up) with ONE add, and the funnel shift takes its amount from the low
+// five bits of the same register.  A codeword at offset o of the window is whole iff
+// o + length <= LM (the bits beyond the window are unknown; a prefix code is decided by the
+// codeword's own bits).  n is capped at 3 (two bits); the cap `max_n` = 1 gives the single-step
+// table used near the end of a subsequence.
+B200LC_HD u8 count_entry(const u16 *lut, u32 i, u32 L, u32 LM, u32 max_n)
+{
+    const u32 wmask = (1u << LM) - 1;
+    u32 o = 0, n = 0;
+    while (n < max_n) {
+        const u32 idx = ((i << o) & wmask) >> (LM - L);
+        const u32 len = first_len(lut, idx, L);
+        if (n && o + len > LM) break;
+        o += len;
+        ++n;
+        if (o >= LM) break;
+    }
+    return (u8)(o | (n << 6));
+}
+
+// Exit state and codeword count of the subsequence entered at bit `a` (0 <= a < 32).
+// Contract (same as walk_record / walk_merge): cnt = codewords that START in [a, 32 S),
+// end = first codeword start at or after 32 S, minus 32 S.  Multi-codeword lookups (mtab, window
+// LM bits: shift_m = 32 - LM) are taken while every codeword they cover starts inside the
+// subsequence, i.e. while the position is <= 32 S - LM; the last few bits are walked one codeword
+// at a time (stab: count_entry(.., max_n = 1) on the L-bit window, shift = 32 - L).
+template <int S>
+B200LC_HD void walk_count(const u32 (&u)[S + 1], const u8 *mtab, u32 shift_m, const u8 *stab, u32 shift,
+                          u32 a, u32 &end, u32 &cnt)
+{
+    u32 acc = a, c = 0;
+#pragma unroll
+    for (int j = 0; j < S - 1; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1];
+        while (!(acc & 32u)) {
+            const u32 w = fsl(nxt, cur, acc);
+            acc += mtab[w >> shift_m];
+        }
+        c += acc >> 6;
+        acc = (acc & 63u) - 32u;
+    }
+    {
+        const u32 cur = u[S - 1], nxt = u[S];
+        const u32 lim = shift_m;                       // 32 - LM
+        while ((acc & 63u) <= lim) {
+            const u32 w = fsl(nxt, cur, acc);
+            acc += mtab[w >> shift_m];
+        }
+        while (!(acc & 32u)) {
+            const u32 w = fsl(nxt, cur, acc);
+            acc += stab[w >> shift];
+        }
+        c += acc >> 6;
+        acc = (acc & 63u) - 32u;
+    }
+    end = acc;
+    cnt = c;
+}
+
 // ------------------------------------------------------------------- decode-once building blocks
 // (not used by the kernel yet.)  Pass A that also keeps the symbols of the
 // path from bit 0 in a per-subsequence slot, so that the write pass becomes a copy:

@@ -632,13 +632,13 @@ extern "C" int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size
     u8 *lastg = reinterpret_cast<u8 *>(sizes) + ((npk * 2 + 255) & ~u64(255));
     u32 *pkoff = reinterpret_cast<u32 *>(lastg + ((npk + 255) & ~u64(255)));
 
-    static bool attr_done[kMaxDevices] = {false};
+    static unsigned attr_done[kMaxDevices] = {0};   // context epoch the attribute was set in
     const int slot = device_slot();
-    if (slot < 0 || !attr_done[slot]) {
+    if (slot < 0 || attr_done[slot] != context_epoch()) {
         B200LC_CUDA_TRY(cudaFuncSetAttribute(lzss::culzss_encode_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(lzss::EncSmem)));
-        if (slot >= 0) attr_done[slot] = true;
+        if (slot >= 0) attr_done[slot] = context_epoch();
     }
     const u32 grid = (u32)min(npk, (u64)num_sms() * 64);
     lzss::culzss_encode_kernel<<<grid, 128, sizeof(lzss::EncSmem), stream>>>(d_in, npk, tmp, sizes, lastg);

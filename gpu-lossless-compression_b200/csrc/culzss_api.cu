@@ -75,6 +75,7 @@ extern "C" void resetGPU(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     cudaDeviceReset();
+    ++context_epoch();          // kernel attributes set in the old context are gone
     g_init = false;
     for (int i = 0; i < kGroups; ++i) {
         g_streams[i] = nullptr;

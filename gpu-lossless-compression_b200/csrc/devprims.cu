@@ -304,13 +304,13 @@ int sort_pairs(K *keys_a, K *keys_b, u32 *vals_a, u32 *vals_b, u64 n, u64 seg_le
     u32 *status = reinterpret_cast<u32 *>(base + L.status);
     u32 *hist = reinterpret_cast<u32 *>(base + L.hist);
 
-    static bool attr_done[kMaxDevices] = {false};
+    static unsigned attr_done[kMaxDevices] = {0};   // context epoch the attribute was set in
     const int slot = device_slot();
     const size_t smem = sizeof(SortSmem<K>);
-    if (slot < 0 || !attr_done[slot]) {
+    if (slot < 0 || attr_done[slot] != context_epoch()) {
         B200LC_CUDA_TRY(cudaFuncSetAttribute(sort_onesweep_kernel<K>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (slot >= 0) attr_done[slot] = true;
+        if (slot >= 0) attr_done[slot] = context_epoch();
     }
 
     B200LC_CUDA_TRY(cudaMemsetAsync(hist, 0, L.nseg * passes * 1024, stream));

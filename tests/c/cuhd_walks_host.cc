@@ -171,6 +171,13 @@ int main(int argc, char **argv)
             wtab[i] = write_entry(lut.data(), i, L);
             wtab2[i] = write_entry2(lut.data(), i, L);
         }
+        const u32 LMs[3] = {L, std::max<u32>(L, 13), 15};
+        std::vector<u8> ctab[3], stab1(size_t(1) << L);
+        for (int t = 0; t < 3; ++t) {
+            ctab[t].resize(size_t(1) << LMs[t]);
+            for (u32 i = 0; i < (1u << LMs[t]); ++i) ctab[t][i] = count_entry(lut.data(), i, L, LMs[t], 3);
+        }
+        for (u32 i = 0; i < (1u << L); ++i) stab1[i] = count_entry(lut.data(), i, L, L, 1);
         for (int sub = 0; sub < 64; ++sub) {
             u32 u[S + 2];
             const int kind = (int)(rng() % 5);
@@ -222,6 +229,16 @@ int main(int argc, char **argv)
             for (u32 a = 0; a < L; ++a) {
                 const Serial sa = serial_decode(u, lut, L, a);
                 u32 ne = 0, nc = 0;
+                // round-2 counting walk (no masks), every table width
+                for (int t = 0; t < 3; ++t) {
+                    u32 we = 99, wc = 99;
+                    walk_count<S>(un, ctab[t].data(), 32 - LMs[t], stab1.data(), shift, a, we, wc);
+                    if (we != sa.end || wc != sa.starts.size()) {
+                        printf("walk_count mismatch: seed %llu round %d sub %d L %u LM %u a %u (end %u/%u cnt %u/%zu)\n",
+                               seed, round, sub, L, LMs[t], a, we, sa.end, wc, sa.starts.size());
+                        return 1;
+                    }
+                }
                 walk_merge<S>(un, m, a, e0, ltab.data(), shift, ne, nc);
                 if (ne != sa.end || nc != sa.starts.size()) {
                     printf("walk_merge mismatch: seed %llu round %d sub %d L %u a %u (end %u/%u cnt %u/%zu)\n",

@@ -82,6 +82,32 @@ def test_other_table_widths(max_len):
     _run(O.zipf_bytes(300000, 1.1, seed=max_len), max_len=max_len, use_ref=False)
 
 
+def test_table_width_order_13_11_13():
+    # the dynamic shared-memory limit is a kernel attribute: a narrower table after a wider one
+    # must not lower it (round-1 ADVICE: 13 -> 11 -> 13 failed with a cached occupancy)
+    d = O.zipf_bytes(200000, 1.1, seed=21)
+    for max_len in (13, 11, 13, 9, 13):
+        _run(d, max_len=max_len, use_ref=False)
+
+
+def test_zero_runs_with_two_bit_code_do_not_resynchronise():
+    # symbol 0 dominates and gets a short all-zero codeword: long runs of it keep a wrong entry
+    # state alive, so guesses fail and the repair rounds (segment + piece level) must run
+    rng = np.random.default_rng(8)
+    d = np.zeros(3 << 20, np.uint8)
+    idx = rng.integers(0, d.size, d.size // 7)
+    d[idx] = rng.integers(1, 7, idx.size, dtype=np.uint8)
+    d[1 << 20:(1 << 20) + 400000] = 0
+    _run(d, use_ref=False)
+
+
+def test_fixed_3bit_codes_large_never_resynchronise():
+    # as test_fixed_3bit_codes_never_resynchronise but over many pieces: every guess of a segment
+    # or piece entry state is wrong two times out of three
+    rng = np.random.default_rng(9)
+    _run(rng.integers(0, 8, 3 << 20, dtype=np.uint8), use_ref=False)
+
+
 def test_without_pad_unit_and_unaligned_base():
     d = O.zipf_bytes(500000, 1.1, seed=11)
     _run(d, drop_pad=True)
