@@ -92,17 +92,19 @@ struct DecodeParams {
 
 template <int K>
 struct SmemLayout {
-    u16 saved[kWarps][K][32];               // pass A result per subsequence: entry state << 12 | symbols
+    // Two pieces are in flight per CTA (pass A of piece n runs before pass B of piece n - 1), and a
+    // warp may run ahead of its CTA by most of an iteration: per-piece state is indexed by
+    // turn % 2 where only the owning warp touches it (saved) and by turn % 3 where others read it.
+    u16 saved[2][kWarps][K][32];            // pass A result per subsequence: entry state << 12 | symbols
     __align__(16) u8 stage[kWarps][kStageBytes];
-    // per segment, double-buffered by piece parity: assumed entry state, exit state, symbols
-    u32 wt[2][kWarps];
-    u8 wa[2][kWarps];
-    u8 wx[2][kWarps];
+    u32 wt[3][kWarps];                      // per segment: symbols,
+    u8 wa[3][kWarps];                       //   assumed entry state,
+    u8 wx[3][kWarps];                       //   exit state
     u64 base;
     u32 next_piece;
     u32 true_entry;
     u32 redo;
-    StreamView view[2];                     // batch: stream of the current / the next piece (by piece parity)
+    StreamView view[3];                     // batch: stream of the piece of each turn
 };
 
 __device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v)
@@ -111,9 +113,202 @@ __device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v)
                  : "memory");
 }
 
+// The tables in shared memory.  The walks must be inlined into the kernel with table addresses the
+// compiler can see are warp-uniform shared-memory addresses (LDS [R + UR + imm]: 6 instructions
+// per lookup step); handing them to a __noinline__ function made them generic pointers (LD +
+// 64-bit arithmetic, +19 % instructions measured), and offsets from a namespace-scope shared
+// array still cost one IADD3 per step.  Hence ONE inlined call site for pass A in the kernel.
+struct Tables {
+    const u32 *wtab;     // write pass: two symbols per entry, window L bits
+    const u8 *mtab;      // counting: <= 3 codewords per entry, window LM bits
+    const u8 *stab;      // counting: 1 codeword per entry, window L bits
+    u32 shift, shift_m;  // 32 - L, 32 - LM
+};
+
+// My warp's segment of a piece, indexed with 32-bit numbers relative to its first unit: units
+// seg_units[0 .. seg_rem) (zero beyond), seg_subs subsequences that hold units.
+struct Segment {
+    const u32 *seg_units;
+    u32 seg_rem, seg_subs;
+    bool aligned, stream_start;
+};
+
+template <int K>
+__device__ __forceinline__ Segment make_segment(const StreamView &V, u32 lp, u32 warp)
+{
+    constexpr u32 kSegUnits = (u32)K * 32 * S;
+    Segment g;
+    const u64 first_unit = ((u64)lp * kWarps + warp) * (u64)kSegUnits;
+    g.seg_units = V.units + first_unit;
+    g.seg_rem = first_unit >= V.n_units ? 0u : (u32)min(V.n_units - first_unit, (u64)0x7fffff00u);
+    g.seg_subs = min((u32)K * 32, (g.seg_rem + S - 1) / S);
+    g.aligned = V.aligned != 0;
+    g.stream_start = first_unit == 0;
+    return g;
+}
+
+// segments of piece lp that hold stream units (the stream's last piece may have fewer)
+template <int K>
+__device__ __forceinline__ u32 real_segments(const StreamView &V, u32 lp)
+{
+    constexpr u32 kSegUnits = (u32)K * 32 * S;
+    return (u32)min((u64)kWarps, (V.n_units - (u64)lp * (kWarps * kSegUnits) + (kSegUnits - 1)) / (u64)kSegUnits);
+}
+
+// the S units of the segment's subsequence `sub` (may be -1: the one in front of the segment)
+// plus one lookahead unit
+__device__ __forceinline__ void load_units(const Segment &g, int sub, u32 (&u)[S + 1])
+{
+    const int first = sub * S;
+    if (g.aligned && first + S + 1 <= (int)g.seg_rem) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g.seg_units + first);
+#pragma unroll
+        for (int q = 0; q < S / 4; ++q) {
+            const uint4 v = __ldg(src + q);
+            u[4 * q + 0] = v.x; u[4 * q + 1] = v.y; u[4 * q + 2] = v.z; u[4 * q + 3] = v.w;
+        }
+        u[S] = __ldg(g.seg_units + first + S);
+    } else {
+#pragma unroll
+        for (int j = 0; j <= S; ++j) u[j] = first + j < (int)g.seg_rem ? __ldg(g.seg_units + first + j) : 0u;
+    }
+}
+
+// Pass A of one segment entered in state `entry` (entry > 15: guess it from the path from bit 0 of
+// the subsequence in front of the segment).  Fills saved[step][lane] = entry state << 12 | symbols
+// of every subsequence; returns assumed entry state | exit state << 8 | symbols << 32.
+template <int K>
+__device__ __forceinline__ u64 segment_pass_a(const Segment &g, const Tables &tb, u32 entry, u16 (*saved)[32])
+{
+    const u8 *const mtab = tb.mtab, *const stab = tb.stab;
+    const u32 lane = threadIdx.x & 31;
+    if (entry > 15) {
+        entry = 0;
+        if (!g.stream_start && g.seg_rem) {
+            u32 e = 0, c = 0;
+            if (lane == 31) {
+                u32 u[S + 1];
+                load_units(g, -1, u);
+                walk_count<S>(u, mtab, tb.shift_m, stab, tb.shift, 0u, e, c);
+            }
+            entry = __shfl_sync(0xffffffffu, e, 31);
+        }
+    }
+    u32 entry_in = entry, my_total = 0;
+    for (u32 step = 0; step * 32 < g.seg_subs; ++step) {
+        const u32 sub = step * 32 + lane;
+        const bool real = sub < g.seg_subs;
+        u32 u[S + 1];
+        u32 my_end = 0, my_cnt = 0, my_start = 0, evaluated = 0;
+        if (real) {
+            load_units(g, (int)sub, u);
+            walk_count<S>(u, mtab, tb.shift_m, stab, tb.shift, 0u, my_end, my_cnt);
+        }
+        // Fixed point of "entry state = exit state of the predecessor", followed through the
+        // warp with shuffles.  Nearly every subsequence leaves in the same state whatever its
+        // entry state, so the second round changes nothing and ends the loop.
+        for (;;) {
+            u32 sv = __shfl_up_sync(0xffffffffu, my_end, 1);
+            if (lane == 0) sv = entry_in;
+            my_start = sv;
+            const bool need = real && sv != evaluated;
+            if (!__any_sync(0xffffffffu, need)) break;
+            bool changed = false;
+            if (need) {
+                u32 ne, nc;
+                walk_count<S>(u, mtab, tb.shift_m, stab, tb.shift, sv, ne, nc);
+                changed = ne != my_end;
+                my_end = ne;
+                my_cnt = nc;
+                evaluated = sv;
+            }
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        saved[step][lane] = (u16)((my_start << 12) | my_cnt);
+        my_total += my_cnt;
+        // lane 31's exit state enters the next step (if lane 31 is padding beyond the stream,
+        // nothing real follows)
+        entry_in = __shfl_sync(0xffffffffu, my_end, 31);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_total += __shfl_xor_sync(0xffffffffu, my_total, d);
+    return (u64)(entry | (entry_in << 8)) | ((u64)my_total << 32);
+}
+
+// Pass B of one segment: decode from the saved entry states, stage, store.  gstart = output
+// index of the segment's first symbol.
+template <int K>
+__device__ __forceinline__ void segment_pass_b(const Segment &g, const Tables &tb, const u16 (*saved)[32],
+                                               u8 *stage, u8 *out, u64 n_out, u64 gstart)
+{
+    const u32 lane = threadIdx.x & 31;
+    if (g.seg_subs == 0 || gstart >= n_out) return;
+    // stage[0] corresponds to the 16-byte aligned output address optr; of the staged bytes only
+    // those at [lo_ok, hi_ok) relative to optr are mine and inside the output
+    u32 lo_ok = (u32)((reinterpret_cast<uintptr_t>(out) + gstart) & 15u);
+    u8 *optr = out + gstart - lo_ok;
+    u32 hi_ok = (u32)min(n_out - gstart + lo_ok, (u64)0x7fffff00u);
+    u32 fill = lo_ok;
+    for (u32 step = 0; step * 32 < g.seg_subs; ++step) {
+        if (fill >= hi_ok) break;      // the rest lies beyond the output
+        const u32 sub = step * 32 + lane;
+        u32 u[S + 1];
+        if (sub < g.seg_subs) load_units(g, (int)sub, u);
+        const u32 sv = saved[step][lane];
+        const u32 my_start = sv >> 12, my_cnt = sv & 0xfffu;
+        const u32 incl = warp_incl_scan(my_cnt);
+        const u32 pre = incl - my_cnt;
+        const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        for (u32 lo = 0; lo < total; lo += kWin) {
+            const u32 hi = min(total, lo + kWin);
+            // symbol at step-local position q goes to dst[q]
+            u8 *dst = stage + ((int)fill - (int)lo);
+            if (pre < hi && pre + my_cnt > lo) {
+                if (pre >= lo && pre + my_cnt <= hi)
+                    walk_write2<S, false>(u, tb.wtab, tb.shift, my_start, dst, pre, lo, hi);
+                else
+                    walk_write2<S, true>(u, tb.wtab, tb.shift, my_start, dst, pre, lo, hi);
+            }
+            __syncwarp();
+            fill += hi - lo;
+            // whole 16-byte vectors of stage[0, fill) leave; the rest moves to the front
+            const u32 nvec = fill >> 4;
+            for (u32 i = lane; i < nvec; i += 32) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(stage + 16 * i);
+                if (16 * i >= lo_ok && 16 * i + 16 <= hi_ok) {
+                    st_stream_v4(optr + 16 * i, v);
+                } else {
+                    for (u32 b = 16 * i; b < 16 * i + 16; ++b)
+                        if (b >= lo_ok && b < hi_ok) optr[b] = stage[b];
+                }
+            }
+            const u32 tail = fill & 15u;
+            u8 keep = 0;
+            if (lane < tail) keep = stage[16 * nvec + lane];
+            __syncwarp();
+            if (lane < tail) stage[lane] = keep;
+            __syncwarp();
+            optr += 16 * nvec;
+            lo_ok = lo_ok > 16 * nvec ? lo_ok - 16 * nvec : 0u;
+            hi_ok = hi_ok > 16 * nvec ? hi_ok - 16 * nvec : 0u;
+            fill = tail;
+        }
+    }
+    // the segment's last partial vector
+    for (u32 i = lane; i < fill; i += 32)
+        if (i >= lo_ok && i < hi_ok) optr[i] = stage[i];
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------- kernel
 // MINB: minimum resident CTAs per SM the register allocation is bounded for (4: 64 registers,
 // 5: 48 registers with a few spilled loop variables; B200LC_CUHD_MINB=5 selects the latter).
+//
+// Software pipeline over the pieces a CTA claims: iteration n runs pass A of piece n, publishes
+// its aggregate, and only then chains piece n - 1 (look-back) and runs its pass B.  By that
+// time the predecessors of piece n - 1 have long published theirs, so the look-back neither
+// waits nor spins (measured without the pipeline: 13 % of all issued instructions were
+// look-back polls and 16 % of the stall samples sat on the barrier behind them).
 template <int K, bool BATCH, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const DecodeParams p)
 {
@@ -121,14 +316,13 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const u32 L = p.max_len, LM = p.multi_bits;
-    u32 *wtab = reinterpret_cast<u32 *>(smem_raw + ((sizeof(Smem) + 127) & ~size_t(127)));   // write pass: two symbols
-    u8 *mtab = reinterpret_cast<u8 *>(wtab + (size_t(1) << L));                              // counting: <= 3 codewords
-    u8 *stab = mtab + (size_t(1) << LM);                                                      // counting: 1 codeword
+    u32 *wtab = reinterpret_cast<u32 *>(smem_raw + ((sizeof(Smem) + 127) & ~size_t(127)));
+    u8 *mtab = reinterpret_cast<u8 *>(wtab + (size_t(1) << L));
+    u8 *stab = mtab + (size_t(1) << LM);
 
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31;
     const u32 warp = tid >> 5;
-    const u32 shift = 32 - L, shift_m = 32 - LM;
 
     // LUT -> shared-memory tables.  A zero-length entry (unused prefix of an incomplete code)
     // would stall the reference forever; first_len() maps it to length 1 so that garbage input
@@ -138,6 +332,9 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
         stab[i] = count_entry(p.lut, i, L, L, 1);
     }
     for (u32 i = tid; i < (1u << LM); i += kThreads) mtab[i] = count_entry(p.lut, i, L, LM, 3);
+    Tables tb;
+    tb.wtab = wtab; tb.mtab = mtab; tb.stab = stab;
+    tb.shift = 32 - L; tb.shift_m = 32 - LM;
 
     if (tid == 0) {
         const u32 t0 = p.first_piece + atomicAdd(p.ticket, 1u);
@@ -146,161 +343,44 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
     }
     __syncthreads();
 
+    bool have_prev = false;
+    u32 ppiece = 0;
     for (u32 turn = 0;; ++turn) {
         const u32 piece = sm.next_piece;
-        if (piece >= p.num_pieces) break;
-        const u32 par = turn & 1;
-        const StreamView &V = BATCH ? sm.view[par] : p.one;
-        const bool aligned = V.aligned != 0;
-        const u32 lp = piece - V.first_piece;          // piece number inside its stream
-        constexpr u32 kSegSubs = (u32)K * 32;          // subsequences per segment
-        constexpr u32 kSegUnits = kSegSubs * S;
-        // Everything below is indexed relative to my segment with 32-bit numbers: its units
-        // (seg_units[0 .. seg_rem), zero beyond), its subsequences (seg_subs of them hold units).
-        const u64 seg_first_unit = ((u64)lp * kWarps + warp) * (u64)kSegUnits;
-        const u32 *const seg_units = V.units + seg_first_unit;
-        const u32 seg_rem = seg_first_unit >= V.n_units ? 0u : (u32)min(V.n_units - seg_first_unit, (u64)0x7fffff00u);
-        const u32 seg_subs = min(kSegSubs, (seg_rem + S - 1) / S);
-        // segments of this piece that hold stream units (the stream's last piece may have fewer)
-        const u32 real_segs = (u32)min((u64)kWarps, (V.n_units - (u64)lp * (kWarps * kSegUnits) + (kSegUnits - 1)) / (u64)kSegUnits);
+        const bool have_cur = piece < p.num_pieces;
+        if (!have_cur && !have_prev) break;
 
-        // the S units of my segment's subsequence `sub` (may be -1: the one in front of the
-        // segment) plus one lookahead unit
-        auto load_units = [&](int sub, u32 (&u)[S + 1]) {
-            const int first = sub * S;
-            if (aligned && first + S + 1 <= (int)seg_rem) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(seg_units + first);
-#pragma unroll
-                for (int q = 0; q < S / 4; ++q) {
-                    const uint4 v = __ldg(src + q);
-                    u[4 * q + 0] = v.x; u[4 * q + 1] = v.y; u[4 * q + 2] = v.z; u[4 * q + 3] = v.w;
-                }
-                u[S] = __ldg(seg_units + first + S);
-            } else {
-#pragma unroll
-                for (int j = 0; j <= S; ++j) u[j] = first + j < (int)seg_rem ? __ldg(seg_units + first + j) : 0u;
-            }
-        };
+        // Two evaluation jobs per iteration, ONE copy of the code (see Tables):
+        //   job 0: pass A of the piece of this turn against guessed entry states, then publish;
+        //   job 1: chain the piece of the previous turn (look-back); if it was entered in another
+        //          state than guessed (rare), repair its pass A against the true state.
+#pragma unroll 1
+        for (u32 job = 0; job < 2; ++job) {
+            if (job == 0 ? !have_cur : !have_prev) continue;
+            const u32 t = turn - job;
+            const u32 b3 = t % 3, b2 = t & 1;
+            const u32 jpiece = job == 0 ? piece : ppiece;
+            const StreamView &V = BATCH ? sm.view[b3] : p.one;
+            const u32 lp = jpiece - V.first_piece;
+            const u32 real_segs = real_segments<K>(V, lp);
+            bool first = job == 0;
+            u32 true_entry = 0;
 
-        // entry state of my segment, guessed: the path from bit 0 of the subsequence in front of it
-        auto guess_entry = [&]() -> u32 {
-            if (seg_first_unit == 0 || seg_rem == 0) return 0u;
-            u32 e = 0, c = 0;
-            if (lane == 31) {
-                u32 u[S + 1];
-                load_units(-1, u);
-                walk_count<S>(u, mtab, shift_m, stab, shift, 0u, e, c);
-            }
-            return __shfl_sync(0xffffffffu, e, 31);
-        };
-
-        // pass A of my segment entered in state `entry`: saved[], exit state, symbols
-        auto segment_pass_a = [&](u32 entry, u32 &exit_state, u32 &symbols) {
-            u32 entry_in = entry, my_total = 0;
-            for (u32 step = 0; step * 32 < seg_subs; ++step) {
-                const u32 sub = step * 32 + lane;
-                const bool real = sub < seg_subs;
-                u32 u[S + 1];
-                u32 my_end = 0, my_cnt = 0, my_start = 0, evaluated = 0;
-                if (real) {
-                    load_units((int)sub, u);
-                    walk_count<S>(u, mtab, shift_m, stab, shift, 0u, my_end, my_cnt);
-                }
-                // Fixed point of "entry state = exit state of the predecessor", followed through
-                // the warp with shuffles.  Nearly every subsequence leaves in the same state
-                // whatever its entry state, so the second round changes nothing and ends the loop.
-                for (;;) {
-                    u32 sv = __shfl_up_sync(0xffffffffu, my_end, 1);
-                    if (lane == 0) sv = entry_in;
-                    my_start = sv;
-                    const bool need = real && sv != evaluated;
-                    if (!__any_sync(0xffffffffu, need)) break;
-                    bool changed = false;
-                    if (need) {
-                        u32 ne, nc;
-                        walk_count<S>(u, mtab, shift_m, stab, shift, sv, ne, nc);
-                        changed = ne != my_end;
-                        my_end = ne;
-                        my_cnt = nc;
-                        evaluated = sv;
-                    }
-                    if (!__any_sync(0xffffffffu, changed)) break;
-                }
-                sm.saved[warp][step][lane] = (u16)((my_start << 12) | my_cnt);
-                my_total += my_cnt;
-                // lane 31's exit state enters the next step (if lane 31 is padding beyond the
-                // stream, nothing real follows)
-                entry_in = __shfl_sync(0xffffffffu, my_end, 31);
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) my_total += __shfl_xor_sync(0xffffffffu, my_total, d);
-            exit_state = entry_in;
-            symbols = my_total;
-        };
-
-        // ================================================================ pass A + piece chaining
-        // Evaluation rounds: (re)run pass A where a segment was entered in another state than its
-        // predecessor left, first against the guessed entry state of the piece, then -- after the
-        // look-back -- against the true one.  Normally: one pass A per warp, two checks, no repair.
-        {
-            u32 my_entry = guess_entry();
-            bool run = true, claimed = false, have_true = false;
-            u32 entry0 = 0;
-            for (;;) {
-                if (run) {
-                    u32 x, t;
-                    segment_pass_a(my_entry, x, t);
-                    if (lane == 0) {
-                        sm.wa[par][warp] = (u8)my_entry;
-                        sm.wx[par][warp] = (u8)x;
-                        sm.wt[par][warp] = t;
-                    }
-                }
-                __syncthreads();
-                if (!claimed) {
-                    claimed = true;
-                    if (tid == 0) {          // claim the next piece (every thread has read `piece`)
-                        const u32 np = p.first_piece + atomicAdd(p.ticket, 1u);
-                        sm.next_piece = np;
-                        if (BATCH && np < p.num_pieces) sm.view[par ^ 1] = p.streams[p.piece_stream[np]];
-                    }
-                }
-                // first segment that was entered in another state than its predecessor left
-                if (!have_true) entry0 = sm.wa[par][0];
-                u32 wbad = kWarps, ebad = 0;
-#pragma unroll
-                for (int w = kWarps - 1; w >= 0; --w) {
-                    const u32 e_in = w == 0 ? entry0 : (u32)sm.wx[par][w - 1];
-                    if ((u32)w < real_segs && (u32)sm.wa[par][w] != e_in) { wbad = (u32)w; ebad = e_in; }
-                }
-                if (wbad < (u32)kWarps) {
-                    run = warp == wbad;
-                    my_entry = ebad;
-                    __syncthreads();         // everyone has read wa / wx before segment wbad rewrites them
-                    continue;
-                }
-                if (have_true) break;
-
-                // ------------------------------------------------------------ publish + look-back
+            if (job == 1) {
+                // ------------------------------------------------------------ look-back
                 if (warp == 0) {
-                    const u32 A = entry0, X = sm.wx[par][real_segs - 1];
-                    u32 T = lane < (u32)kWarps ? sm.wt[par][lane] : 0u;
+                    const u32 A = sm.wa[b3][0], X = sm.wx[b3][real_segs - 1];
+                    u32 T = lane < (u32)kWarps ? sm.wt[b3][lane] : 0u;
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) T += __shfl_xor_sync(0xffffffffu, T, d);
-                    PieceDesc *d = &p.desc[piece];
                     u32 astar = A;
                     u64 base = 0;
-                    if (lp == 0) {
-                        // first piece of its stream: entry state 0 is exact (guess_entry returned 0)
-                        if (lane == 0) st_release_u64(&d->incl, kValid | ((u64)X << 56) | (u64)T);
-                    } else {
-                        if (lane == 0)
-                            st_release_u64(&d->agg, kValid | ((u64)A << 56) | ((u64)X << 48) | (u64)T);
-                        // warp-wide look-back: lane i inspects piece k - i; windows overlap by one so
-                        // that every traversed piece sees the exit state of its predecessor.
-                        int k = (int)piece - 1;
+                    if (lp != 0) {
+                        // warp-wide look-back: lane i inspects piece k - i; windows overlap by one
+                        // so that every traversed piece sees the exit state of its predecessor.
+                        int k = (int)jpiece - 1;
                         u64 acc = 0;
-                        bool first = true;
+                        bool fresh = true;
                         u32 carried = 0;   // exit state assumed for the overlap piece by the previous window
                         while (true) {
                             const int idx = k - (int)lane;
@@ -317,15 +397,15 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
                             const u32 ready_mask = __ballot_sync(0xffffffffu, ready);
                             const u32 need = pl >= 32 ? 0xffffffffu : ((1u << pl) - 1);
                             if ((ready_mask & need) != need) {
-                                __nanosleep(100);
+                                __nanosleep(200);
                                 continue;
                             }
                             const u32 prov = has_incl ? (u32)(I >> 56) & 0xfu : (u32)(G >> 48) & 0xfu;
-                            if (!first && __shfl_sync(0xffffffffu, prov, 0) != carried) {
+                            if (!fresh && __shfl_sync(0xffffffffu, prov, 0) != carried) {
                                 // the overlap piece left in another state than assumed: start over
-                                k = (int)piece - 1;
+                                k = (int)jpiece - 1;
                                 acc = 0;
-                                first = true;
+                                fresh = true;
                                 continue;
                             }
                             const u32 pin = __shfl_down_sync(0xffffffffu, prov, 1);   // exit state of the predecessor
@@ -337,16 +417,16 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
                                 c = (u32)G;
                             }
                             if (!__all_sync(0xffffffffu, link)) {
-                                __nanosleep(200);   // a piece on the way was entered in another state than
+                                __nanosleep(400);   // a piece on the way was entered in another state than
                                 continue;           // it assumed: it will publish its own inclusive state
                             }
                             u64 sum = c;
 #pragma unroll
                             for (int dd = 16; dd > 0; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
                             acc += sum;
-                            if (first) {
+                            if (fresh) {
                                 astar = __shfl_sync(0xffffffffu, prov, 0);
-                                first = false;
+                                fresh = false;
                             }
                             if (pl < 32) {
                                 base = (__shfl_sync(0xffffffffu, I, pl) & kCountMask) + acc;
@@ -356,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
                             k -= 31;
                         }
                         if (lane == 0 && astar == A)
-                            st_release_u64(&d->incl, kValid | ((u64)X << 56) | (base + (u64)T));
+                            st_release_u64(&p.desc[jpiece].incl, kValid | ((u64)X << 56) | (base + (u64)T));
                     }
                     if (lane == 0) {
                         sm.base = base;
@@ -365,84 +445,89 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
                     }
                 }
                 __syncthreads();
-                have_true = true;
-                entry0 = sm.true_entry;
-                run = false;
+                if (!sm.redo) continue;
+                true_entry = sm.true_entry;
             }
-            if (sm.redo && tid == 0) {
-                // the piece was entered in another state than guessed: its inclusive state comes late
+
+            // ---------------------------------------------------------------- evaluation rounds
+            // (Re)run pass A where a segment was entered in another state than its predecessor
+            // left.  Normally (job 0): one pass A per warp, one check, no repair.
+            {
+                const Segment g = make_segment<K>(V, lp, warp);
+                bool run = first;
+                u32 my_entry = 0xffu;     // guess
+                for (;;) {
+                    if (run) {
+                        const u64 r = segment_pass_a<K>(g, tb, my_entry, sm.saved[b2][warp]);
+                        if (lane == 0) {
+                            sm.wa[b3][warp] = (u8)(r & 0xffu);
+                            sm.wx[b3][warp] = (u8)((r >> 8) & 0xffu);
+                            sm.wt[b3][warp] = (u32)(r >> 32);
+                        }
+                    }
+                    __syncthreads();
+                    if (first) {
+                        first = false;
+                        if (tid == 0) {      // claim the next piece (every thread has read sm.next_piece)
+                            const u32 np = p.first_piece + atomicAdd(p.ticket, 1u);
+                            sm.next_piece = np;
+                            if (BATCH && np < p.num_pieces) sm.view[(t + 1) % 3] = p.streams[p.piece_stream[np]];
+                        }
+                    }
+                    // first segment that was entered in another state than its predecessor left
+                    const u32 entry0 = job == 1 ? true_entry : (u32)sm.wa[b3][0];
+                    u32 wbad = kWarps, ebad = 0;
+#pragma unroll
+                    for (int w = kWarps - 1; w >= 0; --w) {
+                        const u32 e_in = w == 0 ? entry0 : (u32)sm.wx[b3][w - 1];
+                        if ((u32)w < real_segs && (u32)sm.wa[b3][w] != e_in) { wbad = (u32)w; ebad = e_in; }
+                    }
+                    if (wbad >= (u32)kWarps) break;
+                    run = warp == wbad;
+                    my_entry = ebad;
+                    __syncthreads();         // everyone has read wa / wx before segment wbad rewrites them
+                }
+            }
+
+            // ---------------------------------------------------------------- publish
+            if (job == 0) {
+                // the first piece of a stream is entered in state 0 exactly -> inclusive state;
+                // any other piece -> aggregate under its guessed entry state
+                if (warp == 0) {
+                    const u32 A = sm.wa[b3][0], X = sm.wx[b3][real_segs - 1];
+                    u32 T = lane < (u32)kWarps ? sm.wt[b3][lane] : 0u;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) T += __shfl_xor_sync(0xffffffffu, T, d);
+                    if (lane == 0) {
+                        if (lp == 0) st_release_u64(&p.desc[jpiece].incl, kValid | ((u64)X << 56) | (u64)T);
+                        else st_release_u64(&p.desc[jpiece].agg, kValid | ((u64)A << 56) | ((u64)X << 48) | (u64)T);
+                    }
+                }
+                // sm.next_piece was rewritten behind the barrier of the evaluation; the barrier
+                // behind the look-back orders that against the read at the top of the loop --
+                // except when there is no previous piece
+                if (!have_prev) __syncthreads();
+            } else if (tid == 0) {
+                // the repaired piece's inclusive state comes late
                 u64 T = 0;
-                for (int w = 0; w < kWarps; ++w) T += sm.wt[par][w];
-                st_release_u64(&p.desc[piece].incl,
-                               kValid | ((u64)sm.wx[par][real_segs - 1] << 56) | (sm.base + T));
+                for (int w = 0; w < kWarps; ++w) T += sm.wt[b3][w];
+                st_release_u64(&p.desc[jpiece].incl,
+                               kValid | ((u64)sm.wx[b3][real_segs - 1] << 56) | (sm.base + T));
             }
         }
 
-        // ================================================================ pass B: decode + write
-        if (seg_subs) {
+        // ================================================================ pass B of piece `turn - 1`
+        if (have_prev) {
+            const u32 pt = turn - 1, pb3 = pt % 3, pb2 = pt & 1;
+            const StreamView &V = BATCH ? sm.view[pb3] : p.one;
+            const u32 lp = ppiece - V.first_piece;
             u64 gstart = sm.base;                    // output index of my segment's first symbol
-            for (u32 w = 0; w < warp; ++w) gstart += sm.wt[par][w];
-            if (gstart < V.n_out) {
-                u8 *const stage = sm.stage[warp];
-                // stage[0] corresponds to the 16-byte aligned output address optr; of the staged
-                // bytes only those at [lo_ok, hi_ok) relative to optr are mine and inside the output
-                u32 lo_ok = (u32)((reinterpret_cast<uintptr_t>(V.out) + gstart) & 15u);
-                u8 *optr = V.out + gstart - lo_ok;
-                u32 hi_ok = (u32)min(V.n_out - gstart + lo_ok, (u64)0x7fffff00u);
-                u32 fill = lo_ok;
-                auto flush_vectors = [&]() {       // whole 16-byte vectors of stage[0, fill) leave; the rest moves to the front
-                    const u32 nvec = fill >> 4;
-                    for (u32 i = lane; i < nvec; i += 32) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(stage + 16 * i);
-                        if (16 * i >= lo_ok && 16 * i + 16 <= hi_ok) {
-                            st_stream_v4(optr + 16 * i, v);
-                        } else {
-                            for (u32 b = 16 * i; b < 16 * i + 16; ++b)
-                                if (b >= lo_ok && b < hi_ok) optr[b] = stage[b];
-                        }
-                    }
-                    const u32 tail = fill & 15u;
-                    u8 keep = 0;
-                    if (lane < tail) keep = stage[16 * nvec + lane];
-                    __syncwarp();
-                    if (lane < tail) stage[lane] = keep;
-                    __syncwarp();
-                    optr += 16 * nvec;
-                    lo_ok = lo_ok > 16 * nvec ? lo_ok - 16 * nvec : 0u;
-                    hi_ok = hi_ok > 16 * nvec ? hi_ok - 16 * nvec : 0u;
-                    fill = tail;
-                };
-                for (u32 step = 0; step * 32 < seg_subs; ++step) {
-                    if (fill >= hi_ok) break;      // the rest lies beyond the output
-                    const u32 sub = step * 32 + lane;
-                    u32 u[S + 1];
-                    if (sub < seg_subs) load_units((int)sub, u);
-                    const u32 sv = sm.saved[warp][step][lane];
-                    const u32 my_start = sv >> 12, my_cnt = sv & 0xfffu;
-                    const u32 incl = warp_incl_scan(my_cnt);
-                    const u32 pre = incl - my_cnt;
-                    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-                    for (u32 lo = 0; lo < total; lo += kWin) {
-                        const u32 hi = min(total, lo + kWin);
-                        // symbol at step-local position q goes to dst[q]
-                        u8 *dst = stage + ((int)fill - (int)lo);
-                        if (pre < hi && pre + my_cnt > lo) {
-                            if (pre >= lo && pre + my_cnt <= hi)
-                                walk_write2<S, false>(u, wtab, shift, my_start, dst, pre, lo, hi);
-                            else
-                                walk_write2<S, true>(u, wtab, shift, my_start, dst, pre, lo, hi);
-                        }
-                        __syncwarp();
-                        fill += hi - lo;
-                        flush_vectors();
-                    }
-                }
-                // the segment's last partial vector
-                for (u32 i = lane; i < fill; i += 32)
-                    if (i >= lo_ok && i < hi_ok) optr[i] = stage[i];
-                __syncwarp();
-            }
+            for (u32 w = 0; w < warp; ++w) gstart += sm.wt[pb3][w];
+            const Segment g = make_segment<K>(V, lp, warp);
+            segment_pass_b<K>(g, tb, sm.saved[pb2][warp], sm.stage[warp], V.out, V.n_out, gstart);
         }
+        have_prev = have_cur;
+        ppiece = piece;
     }
 }
 
