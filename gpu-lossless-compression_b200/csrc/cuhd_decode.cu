@@ -174,71 +174,70 @@ __device__ __forceinline__ void load_units(const Segment &g, int sub, u32 (&u)[S
     }
 }
 
-// Pass A of one segment entered in state `entry` (entry > 15: guess it from the path from bit 0 of
-// the subsequence in front of the segment).  Fills saved[step][lane] = entry state << 12 | symbols
-// of every subsequence; returns assumed entry state | exit state << 8 | symbols << 32.
+// Pass A of one segment entered in state `entry` (entry > 15: guess it).  Fills
+// saved[subsequence] = entry state << 12 | symbols; returns assumed entry state of the segment |
+// exit state << 8 | symbols << 32.
+//
+// Lane l owns the CHUNK of K consecutive subsequences [l K, (l + 1) K) and walks them one after
+// the other: the exit state of one is the exact entry state of the next, so every subsequence is
+// walked ONCE (lanes on consecutive subsequences had to walk from bit 0 first and again from the
+// true state: 1.83 walks per subsequence on C2).  Only the entry state of a chunk is a guess --
+// the path from bit 0 of the subsequence in front of it, one extra walk per K -- and it is
+// verified against the exit state of the lane before; a lane that guessed wrong walks its chunk
+// again (0.03 % of the guesses on C2).  The lanes read 32-byte sectors 32 K bytes apart: every
+// sector is still fetched once.
 template <int K>
-__device__ __forceinline__ u64 segment_pass_a(const Segment &g, const Tables &tb, u32 entry, u16 (*saved)[32])
+__device__ __forceinline__ u64 segment_pass_a(const Segment &g, const Tables &tb, u32 entry, u16 *saved)
 {
     const u8 *const mtab = tb.mtab, *const stab = tb.stab;
     const u32 lane = threadIdx.x & 31;
-    if (entry > 15) {
-        entry = 0;
-        if (!g.stream_start && g.seg_rem) {
-            u32 e = 0, c = 0;
-            if (lane == 31) {
-                u32 u[S + 1];
-                load_units(g, -1, u);
-                walk_count<S>(u, mtab, tb.shift_m, stab, tb.shift, 0u, e, c);
-            }
-            entry = __shfl_sync(0xffffffffu, e, 31);
-        }
+    if (g.seg_subs == 0) {
+        const u32 e = entry > 15 ? 0u : entry;
+        return (u64)(e | (e << 8));
     }
-    u32 entry_in = entry, my_total = 0;
-    for (u32 step = 0; step * 32 < g.seg_subs; ++step) {
-        const u32 sub = step * 32 + lane;
-        const bool real = sub < g.seg_subs;
-        u32 u[S + 1];
-        u32 my_end = 0, my_cnt = 0, my_start = 0, evaluated = 0;
-        if (real) {
-            load_units(g, (int)sub, u);
-            walk_count<S>(u, mtab, tb.shift_m, stab, tb.shift, 0u, my_end, my_cnt);
-        }
-        // Fixed point of "entry state = exit state of the predecessor", followed through the
-        // warp with shuffles.  Nearly every subsequence leaves in the same state whatever its
-        // entry state, so the second round changes nothing and ends the loop.
-        for (;;) {
-            u32 sv = __shfl_up_sync(0xffffffffu, my_end, 1);
-            if (lane == 0) sv = entry_in;
-            my_start = sv;
-            const bool need = real && sv != evaluated;
-            if (!__any_sync(0xffffffffu, need)) break;
-            bool changed = false;
-            if (need) {
-                u32 ne, nc;
-                walk_count<S>(u, mtab, tb.shift_m, stab, tb.shift, sv, ne, nc);
-                changed = ne != my_end;
-                my_end = ne;
-                my_cnt = nc;
-                evaluated = sv;
+    const u32 first_sub = lane * K;
+    const bool chunk_real = first_sub < g.seg_subs;
+    u32 my_entry = 0;
+    if (chunk_real && (lane > 0 || (entry > 15 && !g.stream_start))) {
+        u32 u[S + 1], c;
+        load_units(g, (int)first_sub - 1, u);
+        walk_count<S>(u, mtab, tb.shift_m, stab, tb.shift, 0u, my_entry, c);
+    }
+    if (lane == 0 && entry <= 15) my_entry = entry;
+    const u32 seg_entry = __shfl_sync(0xffffffffu, my_entry, 0);
+    u32 my_exit = 0, my_total = 0;
+    bool active = chunk_real;
+    for (;;) {
+        if (active) {
+            u32 e = my_entry;
+            my_total = 0;
+#pragma unroll 1
+            for (u32 sub = first_sub; sub < first_sub + K && sub < g.seg_subs; ++sub) {
+                u32 u[S + 1], ne, nc;
+                load_units(g, (int)sub, u);
+                walk_count<S>(u, mtab, tb.shift_m, stab, tb.shift, e, ne, nc);
+                saved[sub] = (u16)((e << 12) | nc);
+                my_total += nc;
+                e = ne;
             }
-            if (!__any_sync(0xffffffffu, changed)) break;
+            my_exit = e;
         }
-        saved[step][lane] = (u16)((my_start << 12) | my_cnt);
-        my_total += my_cnt;
-        // lane 31's exit state enters the next step (if lane 31 is padding beyond the stream,
-        // nothing real follows)
-        entry_in = __shfl_sync(0xffffffffu, my_end, 31);
+        // every chunk must have been entered in the state the chunk before it left
+        const u32 prev_exit = __shfl_up_sync(0xffffffffu, my_exit, 1);
+        active = chunk_real && lane > 0 && prev_exit != my_entry;
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) my_entry = prev_exit;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) my_total += __shfl_xor_sync(0xffffffffu, my_total, d);
-    return (u64)(entry | (entry_in << 8)) | ((u64)my_total << 32);
+    const u32 exit_state = __shfl_sync(0xffffffffu, my_exit, (g.seg_subs - 1) / K);
+    return (u64)(seg_entry | (exit_state << 8)) | ((u64)my_total << 32);
 }
 
 // Pass B of one segment: decode from the saved entry states, stage, store.  gstart = output
 // index of the segment's first symbol.
 template <int K>
-__device__ __forceinline__ void segment_pass_b(const Segment &g, const Tables &tb, const u16 (*saved)[32],
+__device__ __forceinline__ void segment_pass_b(const Segment &g, const Tables &tb, const u16 *saved,
                                                u8 *stage, u8 *out, u64 n_out, u64 gstart)
 {
     const u32 lane = threadIdx.x & 31;
@@ -254,7 +253,7 @@ __device__ __forceinline__ void segment_pass_b(const Segment &g, const Tables &t
         const u32 sub = step * 32 + lane;
         u32 u[S + 1];
         if (sub < g.seg_subs) load_units(g, (int)sub, u);
-        const u32 sv = saved[step][lane];
+        const u32 sv = saved[sub];
         const u32 my_start = sv >> 12, my_cnt = sv & 0xfffu;
         const u32 incl = warp_incl_scan(my_cnt);
         const u32 pre = incl - my_cnt;
@@ -458,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
                 u32 my_entry = 0xffu;     // guess
                 for (;;) {
                     if (run) {
-                        const u64 r = segment_pass_a<K>(g, tb, my_entry, sm.saved[b2][warp]);
+                        const u64 r = segment_pass_a<K>(g, tb, my_entry, &sm.saved[b2][warp][0][0]);
                         if (lane == 0) {
                             sm.wa[b3][warp] = (u8)(r & 0xffu);
                             sm.wx[b3][warp] = (u8)((r >> 8) & 0xffu);
@@ -524,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
             u64 gstart = sm.base;                    // output index of my segment's first symbol
             for (u32 w = 0; w < warp; ++w) gstart += sm.wt[pb3][w];
             const Segment g = make_segment<K>(V, lp, warp);
-            segment_pass_b<K>(g, tb, sm.saved[pb2][warp], sm.stage[warp], V.out, V.n_out, gstart);
+            segment_pass_b<K>(g, tb, &sm.saved[pb2][warp][0][0], sm.stage[warp], V.out, V.n_out, gstart);
         }
         have_prev = have_cur;
         ppiece = piece;
