@@ -24,9 +24,11 @@
 //     {assumed entry state, exit state, symbols}; a chain of aggregates is usable when every
 //     link's assumed entry state equals its predecessor's exit state.  Replaces phase 3's three
 //     passes over 16-byte sync points (:498-509).
-//   * pass B (per warp): decode from the now known entry states with two-symbol table entries
-//     into a per-warp shared-memory staging buffer and leave with aligned 16-byte streaming
-//     stores; phase 4 wrote single bytes (:101-105).
+//   * pass B (per warp): decode from the now known entry states with three-symbol table entries;
+//     a lane packs its symbols into 32-bit words in a register and stores words into a per-warp
+//     shared-memory staging buffer (walk_write3 in cuhd_walks.cuh: byte stores were 44 % of all
+//     shared-memory wavefronts); the buffer leaves with aligned 16-byte streaming stores.
+//     Phase 4 wrote single bytes to global memory (:101-105).
 //
 // HBM traffic: units in (pass B re-reads them through L2) + symbols out + 16 B per piece.
 //
@@ -45,11 +47,11 @@ namespace b200lc {
 namespace cuhd {
 
 constexpr int S = 8;                      // units per subsequence
-constexpr int kWarps = 8;                 // warps per CTA = segments per piece
-constexpr int kThreads = kWarps * 32;
-constexpr u32 kStageBytes = 2560;         // per-warp output staging
-constexpr u32 kWin = kStageBytes - 32;    // symbols staged per round (<= 15 carried bytes + 1 duplicate fit)
-constexpr u32 kMultiBits = 13;            // window of the counting table (>= L)
+constexpr int kWarps = 16;                // warps per CTA = segments per piece (two CTAs per SM share
+constexpr int kThreads = kWarps * 32;     //   the SM: the 32 KiB write table is paid twice, not four times)
+constexpr u32 kStageBytes = 2048;         // per-warp output staging
+constexpr u32 kWin = kStageBytes - 32;    // symbols staged per round (<= 15 carried bytes fit in front)
+constexpr u32 kMultiBits = 13;            // window of the counting table and of the write table (>= L)
 
 constexpr u64 kValid = 1ull << 63;
 constexpr u64 kCountMask = (1ull << 56) - 1;
@@ -83,7 +85,7 @@ struct DecodeParams {
     const u32 *piece_stream;      // batch: stream number of every piece
     const u16 *lut;      // {u8 num_bits, u8 symbol} little-endian pairs
     u32 max_len;         // L
-    u32 multi_bits;      // LM: window of the counting table, L <= LM <= 15
+    u32 multi_bits;      // LM: window of the counting table and of the write table, L <= LM <= 15
     PieceDesc *desc;
     u32 *ticket;
     u32 num_pieces;      // pieces [first_piece, num_pieces) are decoded by this launch
@@ -119,7 +121,7 @@ __device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v)
 // 64-bit arithmetic, +19 % instructions measured), and offsets from a namespace-scope shared
 // array still cost one IADD3 per step.  Hence ONE inlined call site for pass A in the kernel.
 struct Tables {
-    const u32 *wtab;     // write pass: two symbols per entry, window L bits
+    const u32 *wtab;     // write pass: <= 3 symbols per entry, window LM bits (write_entry3)
     const u8 *mtab;      // counting: <= 3 codewords per entry, window LM bits
     const u8 *stab;      // counting: 1 codeword per entry, window L bits
     u32 shift, shift_m;  // 32 - L, 32 - LM
@@ -253,21 +255,29 @@ __device__ __forceinline__ void segment_pass_b(const Segment &g, const Tables &t
         const u32 sub = step * 32 + lane;
         u32 u[S + 1];
         if (sub < g.seg_subs) load_units(g, (int)sub, u);
-        const u32 sv = saved[sub];
+        const u32 sv = sub < g.seg_subs ? (u32)saved[sub] : 0u;
         const u32 my_start = sv >> 12, my_cnt = sv & 0xfffu;
         const u32 incl = warp_incl_scan(my_cnt);
         const u32 pre = incl - my_cnt;
         const u32 total = __shfl_sync(0xffffffffu, incl, 31);
         for (u32 lo = 0; lo < total; lo += kWin) {
             const u32 hi = min(total, lo + kWin);
-            // symbol at step-local position q goes to dst[q]
-            u8 *dst = stage + ((int)fill - (int)lo);
-            if (pre < hi && pre + my_cnt > lo) {
-                if (pre >= lo && pre + my_cnt <= hi)
-                    walk_write2<S, false>(u, tb.wtab, tb.shift, my_start, dst, pre, lo, hi);
-                else
-                    walk_write2<S, true>(u, tb.wtab, tb.shift, my_start, dst, pre, lo, hi);
-            }
+            // symbol at step-local position q goes to stage[fill - lo + q]
+            const bool mine = my_cnt != 0 && pre < hi && pre + my_cnt > lo;
+            const bool fast = mine && pre >= lo && pre + my_cnt <= hi;
+            const u32 d0 = fill + pre - lo;
+            u32 pend = 0;
+            if (fast)
+                pend = walk_write3<S>(u, tb.wtab, tb.shift_m, my_start, my_cnt, stage, d0,
+                                      walk_write3_head(stage, d0, fill));
+            __syncwarp();
+            // bytes that share a word with a neighbour's first word, and the rare lane that
+            // straddles the window, come after the word stores
+            if (fast)
+                walk_write3_tail(stage, d0, my_cnt, pend);
+            else if (mine)
+                walk_write3_bytes<S>(u, tb.wtab, tb.shift_m, my_start, my_cnt, stage + ((int)fill - (int)lo),
+                                     pre, lo, hi);
             __syncwarp();
             fill += hi - lo;
             // whole 16-byte vectors of stage[0, fill) leave; the rest moves to the front
@@ -300,23 +310,22 @@ __device__ __forceinline__ void segment_pass_b(const Segment &g, const Tables &t
 }
 
 // ---------------------------------------------------------------------------------- kernel
-// MINB: minimum resident CTAs per SM the register allocation is bounded for (4: 64 registers,
-// 5: 48 registers with a few spilled loop variables; B200LC_CUHD_MINB=5 selects the latter).
+// Two CTAs of 16 warps per SM (64 registers per thread).
 //
 // Software pipeline over the pieces a CTA claims: iteration n runs pass A of piece n, publishes
 // its aggregate, and only then chains piece n - 1 (look-back) and runs its pass B.  By that
 // time the predecessors of piece n - 1 have long published theirs, so the look-back neither
 // waits nor spins (measured without the pipeline: 13 % of all issued instructions were
 // look-back polls and 16 % of the stall samples sat on the barrier behind them).
-template <int K, bool BATCH, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const DecodeParams p)
+template <int K, bool BATCH>
+__global__ void __launch_bounds__(kThreads, 2) cuhd_decode_kernel(const DecodeParams p)
 {
     using Smem = SmemLayout<K>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const u32 L = p.max_len, LM = p.multi_bits;
     u32 *wtab = reinterpret_cast<u32 *>(smem_raw + ((sizeof(Smem) + 127) & ~size_t(127)));
-    u8 *mtab = reinterpret_cast<u8 *>(wtab + (size_t(1) << L));
+    u8 *mtab = reinterpret_cast<u8 *>(wtab + (size_t(1) << LM));
     u8 *stab = mtab + (size_t(1) << LM);
 
     const u32 tid = threadIdx.x;
@@ -326,11 +335,12 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
     // LUT -> shared-memory tables.  A zero-length entry (unused prefix of an incomplete code)
     // would stall the reference forever; first_len() maps it to length 1 so that garbage input
     // still terminates.
-    for (u32 i = tid; i < (1u << L); i += kThreads) {
-        wtab[i] = write_entry2(p.lut, i, L);
-        stab[i] = count_entry(p.lut, i, L, L, 1);
+    for (u32 i = tid; i < (1u << L); i += kThreads) stab[i] = count_entry(p.lut, i, L, L, 1);
+    for (u32 i = tid; i < (1u << LM); i += kThreads) {
+        const u32 e = write_entry3(p.lut, i, L, LM);
+        wtab[i] = e;
+        mtab[i] = (u8)(e >> 24);       // == count_entry(p.lut, i, L, LM, 3)
     }
-    for (u32 i = tid; i < (1u << LM); i += kThreads) mtab[i] = count_entry(p.lut, i, L, LM, 3);
     Tables tb;
     tb.wtab = wtab; tb.mtab = mtab; tb.stab = stab;
     tb.shift = 32 - L; tb.shift_m = 32 - LM;
@@ -535,24 +545,23 @@ __global__ void __launch_bounds__(kThreads, MINB) cuhd_decode_kernel(const Decod
 // (kWarps * K KiB of stream).  B200LC_CUHD_VARIANT pins one for tuning runs.
 struct Variant {
     int K;
-    void (*kern[2])(const DecodeParams);         // [MINB == 5]
-    void (*kern_batch[2])(const DecodeParams);
+    void (*kern)(const DecodeParams);
+    void (*kern_batch)(const DecodeParams);
     size_t smem_fixed;
 };
 #define B200LC_VARIANT(K_) \
-    { K_, { cuhd_decode_kernel<K_, false, 4>, cuhd_decode_kernel<K_, false, 5> }, \
-      { cuhd_decode_kernel<K_, true, 4>, cuhd_decode_kernel<K_, true, 5> }, \
+    { K_, cuhd_decode_kernel<K_, false>, cuhd_decode_kernel<K_, true>, \
       ((sizeof(SmemLayout<K_>) + 127) & ~size_t(127)) }
 static const Variant kVariants[] = {
-    B200LC_VARIANT(16),   // 128 KiB pieces: default for long streams
-    B200LC_VARIANT(8),    // shorter pieces for shorter streams (see pick_variant)
-    B200LC_VARIANT(4),
+    B200LC_VARIANT(8),    // 128 KiB pieces: default for long streams (16: 1.68 ms, 8: 1.60 ms, 4: 1.72 ms on C2)
+    B200LC_VARIANT(4),    // shorter pieces for shorter streams (see pick_variant)
     B200LC_VARIANT(2),
     B200LC_VARIANT(1),
-    B200LC_VARIANT(32),   // tuning point
+    B200LC_VARIANT(16),   // tuning points
+    B200LC_VARIANT(32),
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kSmallest = 4;   // index of the variant with the shortest pieces
+constexpr int kSmallest = 3;   // index of the variant with the shortest pieces
 
 static const Variant &variant()
 {
@@ -563,16 +572,6 @@ static const Variant &variant()
         if (v < 0 || v >= kNumVariants) v = 0;
     }
     return kVariants[v];
-}
-
-static int minb_index()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("B200LC_CUHD_MINB");
-        v = (e && atoi(e) == 5) ? 1 : 0;
-    }
-    return v;
 }
 
 static u32 multi_bits(int L)
@@ -589,7 +588,7 @@ static u32 multi_bits(int L)
 // dynamic shared memory: fixed layout + write table (4 B per entry) + counting tables (1 B each)
 static size_t smem_bytes(const Variant &v, int L)
 {
-    return v.smem_fixed + (size_t(5) << L) + (size_t(1) << multi_bits(L));
+    return v.smem_fixed + (size_t(5) << multi_bits(L)) + (size_t(1) << L);
 }
 
 static u64 piece_units(const Variant &v) { return (u64)kWarps * v.K * 32 * S; }
@@ -605,7 +604,7 @@ static u32 pieces_for(const Variant &v, u64 n_units)
 static const Variant &pick_variant_for(u64 pieces_at_k1)
 {
     if (getenv("B200LC_CUHD_VARIANT")) return variant();
-    const u64 want = (u64)num_sms() * 4;
+    const u64 want = (u64)num_sms() * 2;
     for (int i = 0; i < kSmallest; ++i)
         if (pieces_at_k1 / (u64)kVariants[i].K >= want) return kVariants[i];
     return kVariants[kSmallest];
@@ -633,15 +632,15 @@ static StreamView make_view(const u32 *units, u64 n_units, u8 *out, u64 n_out, u
 // when the context epoch changes (cudaDeviceReset in resetGPU, culzss_api.cu).
 struct KernelCache {
     unsigned epoch;
-    size_t smem_set[kNumVariants][2];
-    int occ[kNumVariants][2][16];
+    size_t smem_set[kNumVariants][2];           // [variant][batch]
+    int occ[kNumVariants][2][16];               // [variant][batch][L]
     size_t occ_smem[kNumVariants][2][16];
 };
 static KernelCache g_cache[kMaxDevices];
 
 static int prepare_kernel(const Variant &v, bool batch, int L, size_t smem, int *occ_out)
 {
-    void (*const kern)(const DecodeParams) = batch ? v.kern_batch[minb_index()] : v.kern[minb_index()];
+    void (*const kern)(const DecodeParams) = batch ? v.kern_batch : v.kern;
     const int slot = device_slot();
     const int vi = (int)(&v - kVariants), bi = batch ? 1 : 0;
     KernelCache local = KernelCache();
@@ -730,7 +729,7 @@ static int decode_pieces(const cuhd::Variant &v, const uint32_t *d_units, size_t
     else
         B200LC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 128, stream));   // ticket only
     const u32 grid = (u32)min((u64)(end_piece - first_piece), (u64)num_sms() * (u64)occ);
-    v.kern[cuhd::minb_index()]<<<grid, cuhd::kThreads, smem, stream>>>(p);
+    v.kern<<<grid, cuhd::kThreads, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }
@@ -861,7 +860,7 @@ extern "C" int b200lc_cuhd_decode_batch(const uint32_t *d_units, uint8_t *d_out,
     p.num_pieces = (u32)bp.pieces;
     p.first_piece = 0;
     const u32 grid = (u32)min((u64)bp.pieces, (u64)num_sms() * (u64)occ);
-    v.kern_batch[cuhd::minb_index()]<<<grid, cuhd::kThreads, smem, stream>>>(p);
+    v.kern_batch<<<grid, cuhd::kThreads, smem, stream>>>(p);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }

@@ -326,6 +326,141 @@ B200LC_HD void walk_count(const u32 (&u)[S + 1], const u8 *mtab, u32 shift_m, co
     cnt = c;
 }
 
+// ------------------------------------------------------------------- packed write pass
+// Round-2 pass B.  One u32 per window of LW >= L bits:
+//   bits  0..23  the symbols of the first n whole codewords of the window (n = 1..3, absent = 0)
+//   bits 24..27  bits consumed by them          } the top byte is count_entry(.., LW, 3): one
+//   bits 30..31  n                              } shift-and-add advances the position
+// The lane packs its symbols into 32-bit words in a register and stores WORDS into the staging
+// buffer (one conflict-prone shared-memory store per four symbols instead of one per symbol):
+//   pow = 1 << 8 k, k = bytes pending in buf;   (hi : lo) = symbols * pow + buf   (one IMAD.WIDE)
+//   pow' = rotl(pow, 8 n); it wraps (pow' < pow) exactly when the word is full: store lo, keep hi.
+B200LC_HD u32 write_entry3(const u16 *lut, u32 i, u32 L, u32 LW)
+{
+    const u32 wmask = (1u << LW) - 1;
+    u32 o = 0, n = 0, syms = 0;
+    while (n < 3) {
+        const u32 idx = ((i << o) & wmask) >> (LW - L);
+        const u32 len = first_len(lut, idx, L);
+        if (n && o + len > LW) break;
+        syms |= (u32)(lut[idx] >> 8) << (8 * n);
+        o += len;
+        ++n;
+        if (o >= LW) break;
+    }
+    return syms | (o << 24) | (n << 30);
+}
+
+B200LC_HD u32 rotl32(u32 x, u32 s) { return fsl(x, x, s); }
+
+// Phase 1 of the packed write: the `cnt` symbols of the subsequence entered at bit `a` go to
+// stage[d0 .. d0 + cnt) (stage 4-byte aligned).  Stores every word that fills up, INCLUDING the
+// first one whose bytes below d0 are zero -- they belong to the lanes in front, which hold them
+// back as pending bytes and store them in phase 2 (walk_write3_tail) after a warp barrier.
+// Exactly cnt symbols are emitted: the last lookups of the subsequence are clamped, so that no
+// word of the successor is touched.  buf0 = bytes already in front of d0 in its word that nobody
+// will store again (bytes carried over from the previous staging round), else 0.  Returns the
+// pending bytes (word (d0 + cnt) >> 2).
+template <int S>
+B200LC_HD u32 walk_write3(const u32 (&u)[S + 1], const u32 *tab3, u32 shift_w, u32 a, u32 cnt, u8 *stage,
+                          u32 d0, u32 buf0)
+{
+    u32 acc = a, buf = buf0;
+    u32 pow = 1u << (8 * (d0 & 3u));
+    const u32 wo0 = d0 & ~3u;
+    u32 wo = wo0;                                      // byte offset of the word being filled
+#define B200LC_EMIT3(e, syms, r)                                           \
+    {                                                                      \
+        const unsigned long long prod = (unsigned long long)(syms) * pow;  \
+        const u32 lo = (u32)prod | buf;                                    \
+        const u32 pow2 = rotl32(pow, (r));                                 \
+        buf = lo;                                                          \
+        if (pow2 < pow) {                                                  \
+            *reinterpret_cast<u32 *>(stage + wo) = lo;                     \
+            wo += 4;                                                       \
+            buf = (u32)(prod >> 32);                                       \
+        }                                                                  \
+        pow = pow2;                                                        \
+    }
+#pragma unroll
+    for (int j = 0; j < S - 1; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1];
+        while (!(acc & 32u)) {
+            const u32 w = fsl(nxt, cur, acc);
+            const u32 e = tab3[w >> shift_w];
+            acc += e >> 24;
+            B200LC_EMIT3(e, e & 0xffffffu, (e >> 27) & 0x18u)
+        }
+        acc = (acc & 63u) - 32u;
+    }
+    {
+        const u32 cur = u[S - 1], nxt = u[S];
+        const u32 lim = shift_w;                       // 32 - LW: every codeword of the window starts inside
+        while ((acc & 63u) <= lim) {
+            const u32 w = fsl(nxt, cur, acc);
+            const u32 e = tab3[w >> shift_w];
+            acc += e >> 24;
+            B200LC_EMIT3(e, e & 0xffffffu, (e >> 27) & 0x18u)
+        }
+        const u32 k = (31u - clz32(pow)) >> 3;
+        u32 rem = cnt - ((wo - wo0) + k - (d0 & 3u));
+        while ((int)rem > 0 && !(acc & 32u)) {
+            const u32 w = fsl(nxt, cur, acc);
+            const u32 e = tab3[w >> shift_w];
+            acc += e >> 24;
+            u32 n = e >> 30;
+            if (n > rem) n = rem;
+            rem -= n;
+            const u32 syms = e & (0xffffffu >> (24u - 8u * n));
+            B200LC_EMIT3(e, syms, 8u * n)
+        }
+    }
+#undef B200LC_EMIT3
+    return buf;
+}
+
+// buf0 for walk_write3: stage[0, fill) are final bytes of earlier rounds.
+B200LC_HD u32 walk_write3_head(const u8 *stage, u32 d0, u32 fill)
+{
+    const u32 w0 = d0 & ~3u;
+    return w0 < fill ? *reinterpret_cast<const u32 *>(stage + w0) & ((1u << (8 * (d0 & 3u))) - 1u) : 0u;
+}
+
+// Phase 2: the pending bytes of word (d0 + cnt) >> 2 that are this lane's own.
+B200LC_HD void walk_write3_tail(u8 *stage, u32 d0, u32 cnt, u32 buf)
+{
+    const u32 end = d0 + cnt, w0 = end & ~3u;
+#pragma unroll
+    for (u32 i = 0; i < 3; ++i) {
+        const u32 p = w0 + i;
+        if (p >= d0 && p < end) stage[p] = (u8)(buf >> (8 * i));
+    }
+}
+
+// The same symbols one byte at a time, only positions in [lo, hi) stored: symbol i of the
+// subsequence goes to dst[pos + i].  For the rare lane that straddles a staging window.
+template <int S>
+B200LC_HD void walk_write3_bytes(const u32 (&u)[S + 1], const u32 *tab3, u32 shift_w, u32 a, u32 cnt, u8 *dst,
+                                 u32 pos, u32 lo, u32 hi)
+{
+    u32 acc = a, done = 0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const u32 cur = u[j], nxt = u[j + 1];
+        while (!(acc & 32u) && done < cnt) {
+            const u32 w = fsl(nxt, cur, acc);
+            const u32 e = tab3[w >> shift_w];
+            acc += e >> 24;
+            const u32 n = e >> 30;
+            for (u32 t = 0; t < n && done < cnt; ++t, ++done) {
+                const u32 p = pos + done;
+                if (p >= lo && p < hi) dst[p] = (u8)(e >> (8 * t));
+            }
+        }
+        acc = (acc & 63u) - 32u;
+    }
+}
+
 // ------------------------------------------------------------------- decode-once building blocks
 // (not used by the kernel yet.)  Pass A that also keeps the symbols of the
 // path from bit 0 in a per-subsequence slot, so that the write pass becomes a copy:

@@ -298,8 +298,110 @@ int main(int argc, char **argv)
             }
         }
     }
-    printf("ok: %ld (subsequence, entry state) cases; %.2f symbols per multi-symbol lookup; "
-           "%.2f symbols decoded before the recorded path takes over\n", checked,
+    // --- packed write pass (walk_write3): a warp of 32 consecutive subsequences staged in two
+    // phases, lanes visited in random order inside each phase (no ordering between lanes may be
+    // assumed on the GPU), staging window and carried bytes as in segment_pass_b
+    long warps = 0;
+    for (int round = 0; round < rounds; ++round) {
+        const u32 L = 1 + (u32)(rng() % 13);
+        const u32 LW = std::max<u32>(L, (u32)(rng() % 3 == 0 ? L : 11 + rng() % 4));
+        const u32 nsym = 1 + (u32)(rng() % std::min<u32>(256, 1u << L));
+        const std::vector<u16> lut = random_lut(rng, L, nsym, rng() % 4 != 0);
+        std::vector<u32> tab3(size_t(1) << LW);
+        std::vector<u8> ctab(size_t(1) << LW), stab1(size_t(1) << L);
+        for (u32 i = 0; i < (1u << LW); ++i) {
+            tab3[i] = write_entry3(lut.data(), i, L, LW);
+            ctab[i] = count_entry(lut.data(), i, L, LW, 3);
+            if ((tab3[i] >> 24) != ctab[i]) { printf("write_entry3 top byte != count_entry\n"); return 1; }
+        }
+        for (u32 i = 0; i < (1u << L); ++i) stab1[i] = count_entry(lut.data(), i, L, L, 1);
+        for (int rep = 0; rep < 4; ++rep) {
+            const int nl = 1 + (int)(rng() % 32);
+            std::vector<u32> units((size_t)nl * S + 2);
+            const int kind = (int)(rng() % 4);
+            for (auto &x : units) {
+                x = (u32)rng();
+                if (kind == 1) x &= (u32)rng() & (u32)rng();
+                if (kind == 2) x |= (u32)rng() | (u32)rng();
+            }
+            // serial decode of the whole range from a random entry state
+            u32 entry[33], cnt[33], pre[33];
+            std::vector<u8> all;
+            entry[0] = (u32)(rng() % L);
+            pre[0] = 0;
+            for (int l = 0; l < nl; ++l) {
+                const Serial sa = serial_decode(&units[(size_t)l * S], lut, L, entry[l]);
+                cnt[l] = (u32)sa.syms.size();
+                all.insert(all.end(), sa.syms.begin(), sa.syms.end());
+                entry[l + 1] = sa.end;
+                pre[l + 1] = pre[l] + cnt[l];
+                u32 un[S + 1], we, wc;
+                memcpy(un, &units[(size_t)l * S], sizeof(un));
+                walk_count<S>(un, ctab.data(), 32 - LW, stab1.data(), 32 - L, entry[l], we, wc);
+                if (we != sa.end || wc != cnt[l]) { printf("walk_count (LW table) mismatch\n"); return 1; }
+            }
+            const u32 total = pre[nl];
+            const u32 win = 64 + (u32)(rng() % 2500);
+            u32 fill = (u32)(rng() % 16);
+            std::vector<u8> out;
+            std::vector<u8> stage(16 + win + 64, 0xEE);
+            std::vector<u8> carried(fill);
+            for (auto &c : carried) c = (u8)rng();
+            memcpy(stage.data(), carried.data(), fill);
+            for (u32 lo = 0; lo < total; lo += win) {
+                const u32 hi = std::min(total, lo + win);
+                int order[32];
+                for (int l = 0; l < nl; ++l) order[l] = l;
+                u32 pend[32] = {0};
+                bool fast[32] = {false}, mine[32] = {false};
+                std::shuffle(order, order + nl, rng);
+                for (int t = 0; t < nl; ++t) {
+                    const int l = order[t];
+                    mine[l] = pre[l] < hi && pre[l] + cnt[l] > lo;
+                    fast[l] = mine[l] && pre[l] >= lo && pre[l] + cnt[l] <= hi;
+                    if (!fast[l]) continue;
+                    u32 un[S + 1];
+                    memcpy(un, &units[(size_t)l * S], sizeof(un));
+                    const u32 d0 = fill + pre[l] - lo;
+                    pend[l] = walk_write3<S>(un, tab3.data(), 32 - LW, entry[l], cnt[l], stage.data(), d0,
+                                             walk_write3_head(stage.data(), d0, fill));
+                }
+                std::shuffle(order, order + nl, rng);
+                for (int t = 0; t < nl; ++t) {
+                    const int l = order[t];
+                    u32 un[S + 1];
+                    memcpy(un, &units[(size_t)l * S], sizeof(un));
+                    if (fast[l]) walk_write3_tail(stage.data(), fill + pre[l] - lo, cnt[l], pend[l]);
+                    else if (mine[l])
+                        walk_write3_bytes<S>(un, tab3.data(), 32 - LW, entry[l], cnt[l],
+                                             stage.data() + ((int)fill - (int)lo), pre[l], lo, hi);
+                }
+                fill += hi - lo;
+                for (u32 q = fill; q < stage.size(); ++q)
+                    if (q >= ((fill + 3) & ~3u) && stage[q] != 0xEE) { printf("packed write stored beyond the window\n"); return 1; }
+                const u32 nvec = fill >> 4;
+                out.insert(out.end(), stage.begin(), stage.begin() + 16 * nvec);
+                const u32 tail = fill & 15u;
+                std::vector<u8> keep(stage.begin() + 16 * nvec, stage.begin() + 16 * nvec + tail);
+                std::fill(stage.begin(), stage.end(), (u8)0xEE);
+                memcpy(stage.data(), keep.data(), tail);
+                fill = tail;
+            }
+            out.insert(out.end(), stage.begin(), stage.begin() + fill);
+            std::vector<u8> want(carried);
+            want.insert(want.end(), all.begin(), all.end());
+            if (out != want) {
+                size_t q = 0;
+                while (q < out.size() && q < want.size() && out[q] == want[q]) ++q;
+                printf("packed write mismatch: seed %llu round %d L %u LW %u lanes %d win %u at byte %zu of %zu\n",
+                       seed, round, L, LW, nl, win, q, want.size());
+                return 1;
+            }
+            ++warps;
+        }
+    }
+    printf("ok: %ld (subsequence, entry state) cases; %ld packed-write warps; %.2f symbols per multi-symbol lookup; "
+           "%.2f symbols decoded before the recorded path takes over\n", checked, warps,
            multi_steps ? (double)single_steps / (double)multi_steps : 0.0,
            fix_cases ? (double)fix_symbols / (double)fix_cases : 0.0);
     return 0;
