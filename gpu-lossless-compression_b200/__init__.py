@@ -500,7 +500,7 @@ def sort_pairs(keys, vals, seg_len=0, begin_bit=0, end_bit=None, stream=None):
     fn = L.b200lc_sort_pairs_u64 if wide else L.b200lc_sort_pairs_u32
     check(fn(keys.data_ptr(), kb.data_ptr(), vals.data_ptr(), vb.data_ptr(), n, seg_len, begin_bit,
              end_bit, scratch.data_ptr(), scratch.numel(), _stream_ptr(stream), C.byref(where)), "sort_pairs")
-    torch.cuda.current_stream().synchronize()
+    (stream if stream is not None else torch.cuda.current_stream()).synchronize()   # scratch dies here
     return (kb, vb) if where.value else (keys, vals)
 
 
@@ -514,7 +514,7 @@ def scan_u32(x, kind="exclusive_sum", out=None, stream=None):
     scratch = torch.empty(L.b200lc_scan_scratch_bytes(n) + 256, dtype=torch.uint8, device=x.device)
     fn = L.b200lc_exclusive_sum_u32 if kind == "exclusive_sum" else L.b200lc_inclusive_max_u32
     check(fn(x.data_ptr(), out.data_ptr(), n, scratch.data_ptr(), scratch.numel(), _stream_ptr(stream)), kind)
-    torch.cuda.current_stream().synchronize()
+    (stream if stream is not None else torch.cuda.current_stream()).synchronize()   # scratch dies here
     return out
 
 

@@ -105,9 +105,18 @@ extern "C" CUDPPResult cudppPlan(const CUDPPHandle cudppHandle, CUDPPHandle *pla
     if (!cudppHandle || cudppHandle == CUDPP_INVALID_HANDLE || m->magic != kMgrMagic)
         return CUDPP_ERROR_INVALID_HANDLE;
     if (config.algorithm != CUDPP_COMPRESS && config.algorithm != CUDPP_BWT &&
-        config.algorithm != CUDPP_MTF && config.algorithm != CUDPP_SA)
+        config.algorithm != CUDPP_MTF && config.algorithm != CUDPP_SA && config.algorithm != CUDPP_SORT_RADIX)
         return CUDPP_ERROR_ILLEGAL_CONFIGURATION;
-    if (config.datatype != CUDPP_UCHAR || n == 0) return CUDPP_ERROR_ILLEGAL_CONFIGURATION;
+    if (n == 0) return CUDPP_ERROR_ILLEGAL_CONFIGURATION;
+    if (config.algorithm == CUDPP_SORT_RADIX) {
+        // the sort the reference's own test decodes its BWT with (test_compress.cpp:318-344):
+        // unsigned char or unsigned int keys, with or without unsigned int values
+        if (config.datatype != CUDPP_UCHAR && config.datatype != CUDPP_UINT) return CUDPP_ERROR_ILLEGAL_CONFIGURATION;
+        if (!(config.options & (CUDPP_OPTION_KEYS_ONLY | CUDPP_OPTION_KEY_VALUE_PAIRS)) || n >= (size_t(1) << 30))
+            return CUDPP_ERROR_ILLEGAL_CONFIGURATION;
+    } else if (config.datatype != CUDPP_UCHAR) {
+        return CUDPP_ERROR_ILLEGAL_CONFIGURATION;
+    }
     Plan *p = new (std::nothrow) Plan();
     if (!p) return CUDPP_ERROR_INSUFFICIENT_RESOURCES;
     p->magic = kPlanMagic;
@@ -116,6 +125,9 @@ extern "C" CUDPPResult cudppPlan(const CUDPPHandle cudppHandle, CUDPPHandle *pla
     switch (config.algorithm) {
         case CUDPP_COMPRESS: p->scratch_bytes = b200lc_cudpp_compress_scratch_bytes(1, n); break;
         case CUDPP_MTF: p->scratch_bytes = b200lc_mtf_scratch_bytes(1, n); break;
+        case CUDPP_SORT_RADIX:   // sort scratch + keys A/B + values A/B
+            p->scratch_bytes = ((b200lc_sort_scratch_bytes(n, 0) + 255) & ~size_t(255)) + 4 * ((n * 4 + 255) & ~size_t(255));
+            break;
         default: p->scratch_bytes = b200lc_bwt_scratch_bytes(1, n); break;
     }
     if (cudaMalloc(&p->scratch, p->scratch_bytes + 512) != cudaSuccess) {
@@ -205,4 +217,57 @@ extern "C" CUDPPResult cudppSuffixArray(CUDPPHandle planHandle, unsigned char *d
     if (numElements == 0 || numElements > p->n) return CUDPP_ERROR_ILLEGAL_CONFIGURATION;
     int rc = b200lc_suffix_array_batch(d_str, 1, numElements, d_keys_sa, p->scratch, p->scratch_bytes, nullptr);
     return rc == B200LC_OK ? CUDPP_SUCCESS : CUDPP_ERROR_UNKNOWN;
+}
+
+// ============================================================================ cudppRadixSort
+namespace {
+__global__ void widen_keys_kernel(const unsigned char *__restrict__ in, u32 *__restrict__ out, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void narrow_keys_kernel(const u32 *__restrict__ in, unsigned char *__restrict__ out, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (unsigned char)in[i];
+}
+}  // namespace
+
+// Stable ascending radix sort of numElements keys (and their values) in place, on the default
+// stream (cudpp-inpar/include/cudpp.h:256-259; dispatch cudpp.cpp `cudppRadixSort`).  The keys
+// travel through the one-sweep sort of devprims.cu as 32-bit words (8 or 32 key bits sorted).
+extern "C" CUDPPResult cudppRadixSort(const CUDPPHandle planHandle, void *d_keys, void *d_values,
+                                      size_t numElements)
+{
+    CUDPPResult dev = check_device();
+    if (dev != CUDPP_SUCCESS) return dev;
+    Plan *p = plan_of(planHandle);
+    if (!p) return CUDPP_ERROR_INVALID_HANDLE;
+    if (p->config.algorithm != CUDPP_SORT_RADIX) return CUDPP_ERROR_INVALID_PLAN;
+    const bool pairs = (p->config.options & CUDPP_OPTION_KEY_VALUE_PAIRS) != 0;
+    if (numElements > p->n || !d_keys || (pairs && !d_values)) return CUDPP_ERROR_ILLEGAL_CONFIGURATION;
+    if (numElements == 0) return CUDPP_SUCCESS;
+    const size_t n = numElements;
+    const size_t sort_bytes = (b200lc_sort_scratch_bytes(p->n, 0) + 255) & ~size_t(255);
+    const size_t arr = (p->n * 4 + 255) & ~size_t(255);
+    char *base = reinterpret_cast<char *>(p->scratch);
+    u32 *ka = reinterpret_cast<u32 *>(base + sort_bytes), *kb = reinterpret_cast<u32 *>(base + sort_bytes + arr);
+    u32 *va = reinterpret_cast<u32 *>(base + sort_bytes + 2 * arr), *vb = reinterpret_cast<u32 *>(base + sort_bytes + 3 * arr);
+    const bool bytes = p->config.datatype == CUDPP_UCHAR;
+    const u32 grid = (u32)((n + 255) / 256);
+    if (bytes) widen_keys_kernel<<<grid, 256>>>(static_cast<const unsigned char *>(d_keys), ka, n);
+    else if (cudaMemcpyAsync(ka, d_keys, n * 4, cudaMemcpyDeviceToDevice, 0) != cudaSuccess) return CUDPP_ERROR_UNKNOWN;
+    if (pairs) {
+        if (cudaMemcpyAsync(va, d_values, n * 4, cudaMemcpyDeviceToDevice, 0) != cudaSuccess) return CUDPP_ERROR_UNKNOWN;
+    } else if (cudaMemsetAsync(va, 0, n * 4, 0) != cudaSuccess) {
+        return CUDPP_ERROR_UNKNOWN;
+    }
+    int in_b = 0;
+    const int rc = b200lc_sort_pairs_u32(ka, kb, va, vb, n, 0, 0, bytes ? 8 : 32, base, sort_bytes, nullptr, &in_b);
+    if (rc != B200LC_OK) return CUDPP_ERROR_UNKNOWN;
+    const u32 *ks = in_b ? kb : ka, *vs = in_b ? vb : va;
+    if (bytes) narrow_keys_kernel<<<grid, 256>>>(ks, static_cast<unsigned char *>(d_keys), n);
+    else if (cudaMemcpyAsync(d_keys, ks, n * 4, cudaMemcpyDeviceToDevice, 0) != cudaSuccess) return CUDPP_ERROR_UNKNOWN;
+    if (pairs && cudaMemcpyAsync(d_values, vs, n * 4, cudaMemcpyDeviceToDevice, 0) != cudaSuccess) return CUDPP_ERROR_UNKNOWN;
+    return cudaGetLastError() == cudaSuccess ? CUDPP_SUCCESS : CUDPP_ERROR_UNKNOWN;
 }

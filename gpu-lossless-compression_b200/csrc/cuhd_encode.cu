@@ -660,6 +660,40 @@ extern "C" int b200lc_histogram_u8_pieces(const uint8_t *d_in, size_t n, uint64_
     return B200LC_OK;
 }
 
+// The same in two steps for callers whose input arrives in chunks (b200lc_cuhd_session_encode):
+// pieces [first_piece, end_piece) of the n-symbol buffer, then the reduction of all of them.
+extern "C" size_t b200lc_cuhd_piece_symbols(void) { return (size_t)cuhd_enc::kPieceSyms; }
+
+extern "C" int b200lc_histogram_u8_pieces_part(const uint8_t *d_in, size_t n, size_t first_piece,
+                                               size_t end_piece, uint32_t *d_piece_hist, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_piece_hist || !d_in) return B200LC_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_in) & 15) return B200LC_ERR_ARG;
+    const size_t pieces = cuhd_enc::pieces_for(n);
+    if (end_piece > pieces) end_piece = pieces;
+    if (first_piece >= end_piece) return B200LC_OK;
+    const size_t lo = first_piece * (size_t)cuhd_enc::kPieceSyms;
+    cuhd_enc::piece_hist_kernel<<<(u32)(end_piece - first_piece), 256, 0, stream>>>(
+        d_in + lo, n - lo, d_piece_hist + first_piece * 256);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}
+
+extern "C" int b200lc_histogram_u8_pieces_finish(const uint32_t *d_piece_hist, size_t n, uint64_t *d_hist,
+                                                 void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_hist || !d_piece_hist) return B200LC_ERR_ARG;
+    B200LC_CUDA_TRY(cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint64_t), stream));
+    if (n == 0) return B200LC_OK;
+    const u32 pieces = cuhd_enc::pieces_for(n);
+    cuhd_enc::hist_reduce_kernel<<<min(pieces, 64u), 256, 0, stream>>>(
+        d_piece_hist, pieces, reinterpret_cast<unsigned long long *>(d_hist));
+    B200LC_CUDA_TRY(cudaGetLastError());
+    return B200LC_OK;
+}
+
 // b200lc_cuhd_encode with the piece histograms of b200lc_histogram_u8_pieces: same stream, one pass.
 extern "C" int b200lc_cuhd_encode_planned(const uint8_t *d_in, size_t n, const uint32_t *d_code_of_symbol,
                                           const uint8_t *d_len_of_symbol, const uint32_t *d_piece_hist,

@@ -21,6 +21,7 @@ struct b200lc_cuhd_session {
     u32 *d_units = nullptr;
     u8 *d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    u32 *d_piece_hist = nullptr;   // one 256-bin histogram per encoder piece
     u8 *d_small = nullptr;   // [0,2048) hist | [2048,3072) code | [3072,3328) len | [4096,..) lut | total_bits
     u64 *h_small = nullptr;  // pinned: hist[256] + total_bits + kMaxChunks progress words
     cudaStream_t h2d = nullptr, d2h = nullptr;   // copy streams of the pipelined decode
@@ -47,6 +48,7 @@ extern "C" int b200lc_cuhd_session_create(size_t max_symbols, b200lc_cuhd_sessio
     if (e == cudaSuccess) e = cudaMalloc(&s->d_units, s->max_units * sizeof(u32));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, s->scratch_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_small, kSmallBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_piece_hist, b200lc_cuhd_piece_hist_bytes(max_symbols) + 1024);
     if (e == cudaSuccess) e = cudaHostAlloc(&s->h_small, (257 + kMaxChunks) * sizeof(u64), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking);
@@ -67,6 +69,7 @@ extern "C" int b200lc_cuhd_session_destroy(b200lc_cuhd_session *s)
     cudaFree(s->d_units);
     cudaFree(s->d_scratch);
     cudaFree(s->d_small);
+    cudaFree(s->d_piece_hist);
     if (s->h_small) cudaFreeHost(s->h_small);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->h2d) cudaStreamDestroy(s->h2d);
@@ -76,7 +79,11 @@ extern "C" int b200lc_cuhd_session_destroy(b200lc_cuhd_session *s)
     return B200LC_OK;
 }
 
-// host symbols -> host stream units + dictionary + LUT.  Synchronous.
+// host symbols -> host stream units + dictionary + LUT.  Synchronous.  Pipelined like the decode
+// below: the symbols go up in chunks on one copy engine while the per-piece histograms of the
+// chunks that have arrived are computed; the dictionary is built on the host from their sum; the
+// one-pass packer (b200lc_cuhd_encode_planned) needs no counting pass because the piece histograms
+// and the code lengths give the bit offset of every piece.
 extern "C" int b200lc_cuhd_session_encode(b200lc_cuhd_session *s, const uint8_t *h_in, size_t n,
                                           int max_len, uint32_t *h_units, size_t units_cap,
                                           size_t *n_units, uint32_t *h_code_of_symbol,
@@ -91,9 +98,26 @@ extern "C" int b200lc_cuhd_session_encode(b200lc_cuhd_session *s, const uint8_t 
     u8 *d_len = s->d_small + 3072;
     u64 *d_bits = reinterpret_cast<u64 *>(s->d_small + 4096 + (size_t(2) << 13));
 
-    B200LC_CUDA_TRY(cudaMemcpyAsync(s->d_symbols, h_in, n, cudaMemcpyHostToDevice, s->stream));
-    int rc = b200lc_histogram_u8(s->d_symbols, n, d_hist, s->stream);
-    if (rc) return rc;
+    const size_t ps = b200lc_cuhd_piece_symbols();
+    size_t chunk = (kChunkBytesMin * 4 / ps) * ps;           // 32 MiB, a whole number of pieces
+    while ((n + chunk - 1) / chunk > kMaxChunks) chunk *= 2;
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    while (s->events.size() < 2 * nchunks) {
+        cudaEvent_t ev;
+        B200LC_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        s->events.push_back(ev);
+    }
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t lo = k * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        B200LC_CUDA_TRY(cudaMemcpyAsync(s->d_symbols + lo, h_in + lo, hi - lo, cudaMemcpyHostToDevice, s->h2d));
+        B200LC_CUDA_TRY(cudaEventRecord(s->events[k], s->h2d));
+        B200LC_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->events[k], 0));
+        const int rc = b200lc_histogram_u8_pieces_part(s->d_symbols, n, lo / ps, (hi + ps - 1) / ps,
+                                                       s->d_piece_hist, s->stream);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+    }
+    int rc = b200lc_histogram_u8_pieces_finish(s->d_piece_hist, n, d_hist, s->stream);
+    if (rc) { cudaDeviceSynchronize(); return rc; }
     B200LC_CUDA_TRY(cudaMemcpyAsync(s->h_small, d_hist, 256 * sizeof(u64), cudaMemcpyDeviceToHost,
                                     s->stream));
     B200LC_CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -105,8 +129,8 @@ extern "C" int b200lc_cuhd_session_encode(b200lc_cuhd_session *s, const uint8_t 
     B200LC_CUDA_TRY(cudaMemcpyAsync(d_code, h_code_of_symbol, 256 * sizeof(u32),
                                     cudaMemcpyHostToDevice, s->stream));
     B200LC_CUDA_TRY(cudaMemcpyAsync(d_len, h_len_of_symbol, 256, cudaMemcpyHostToDevice, s->stream));
-    rc = b200lc_cuhd_encode(s->d_symbols, n, d_code, d_len, s->d_units, s->max_units, d_bits,
-                            s->d_scratch, s->scratch_bytes, s->stream);
+    rc = b200lc_cuhd_encode_planned(s->d_symbols, n, d_code, d_len, s->d_piece_hist, s->d_units, s->max_units,
+                                    d_bits, s->d_scratch, s->scratch_bytes, s->stream);
     if (rc) return rc;
     B200LC_CUDA_TRY(cudaMemcpyAsync(h_units, s->d_units, (units + 1) * sizeof(u32),
                                     cudaMemcpyDeviceToHost, s->stream));

@@ -131,6 +131,13 @@ int b200lc_cuhd_encode_overflowed(const void *d_scratch, void *stream);
 size_t b200lc_cuhd_piece_hist_bytes(size_t n);
 int b200lc_histogram_u8_pieces(const uint8_t *d_in, size_t n, uint64_t *d_hist, uint32_t *d_piece_hist,
                                void *stream);
+/* The same in two steps for input that arrives in chunks: the histograms of pieces
+ * [first_piece, end_piece) (a piece = b200lc_cuhd_piece_symbols() symbols of d_in[n]) as soon as
+ * their symbols are resident, then the reduction of all pieces into d_hist[256]. */
+size_t b200lc_cuhd_piece_symbols(void);
+int b200lc_histogram_u8_pieces_part(const uint8_t *d_in, size_t n, size_t first_piece, size_t end_piece,
+                                    uint32_t *d_piece_hist, void *stream);
+int b200lc_histogram_u8_pieces_finish(const uint32_t *d_piece_hist, size_t n, uint64_t *d_hist, void *stream);
 int b200lc_cuhd_encode_planned(const uint8_t *d_in, size_t n, const uint32_t *d_code_of_symbol,
                                const uint8_t *d_len_of_symbol, const uint32_t *d_piece_hist,
                                uint32_t *d_units, size_t units_cap, uint64_t *d_total_bits,

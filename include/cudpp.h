@@ -8,7 +8,8 @@
  * against the reference header links against libb200lc.so unchanged.
  *
  * Implemented algorithms: CUDPP_COMPRESS, CUDPP_BWT, CUDPP_MTF, CUDPP_SA with datatype
- * CUDPP_UCHAR.  cudppPlan with any other algorithm returns CUDPP_ERROR_ILLEGAL_CONFIGURATION
+ * CUDPP_UCHAR, and CUDPP_SORT_RADIX (unsigned char / unsigned int keys) for the reference test's
+ * own decoder.  cudppPlan with any other algorithm returns CUDPP_ERROR_ILLEGAL_CONFIGURATION
  * (those primitives are outside the hot path).
  *
  * All data pointers are DEVICE pointers owned by the caller; plans own their scratch
@@ -115,6 +116,12 @@ CUDPPResult_t cudppMoveToFrontTransform(CUDPPHandle planHandle, unsigned char *d
  * positions in sorted order. */
 CUDPPResult_t cudppSuffixArray(CUDPPHandle planHandle, unsigned char *d_str,
                                unsigned int *d_keys_sa, size_t numElements);
+/* cudpp.h:256-259: stable ascending radix sort in place, plan algorithm CUDPP_SORT_RADIX with
+ * datatype CUDPP_UCHAR or CUDPP_UINT and CUDPP_OPTION_KEYS_ONLY or CUDPP_OPTION_KEY_VALUE_PAIRS
+ * (values: unsigned int).  This is the sort the reference's own compress test decodes its BWT
+ * with (apps/cudpp_testrig/test_compress.cpp:318-344), so the unmodified testrig links against
+ * libb200lc.so alone. */
+CUDPPResult_t cudppRadixSort(const CUDPPHandle planHandle, void *d_keys, void *d_values, size_t numElements);
 
 #ifdef __cplusplus
 }

@@ -159,12 +159,29 @@ def cuhd_oracle_lut(code, length, max_len=11):
 
 # ---------------------------------------------------------------------------- generators
 def zipf_bytes(n, alpha=1.1, seed=12345, nsym=256):
-    """Synthetic C2 input: symbol k with P ~ 1/(k+1)^alpha, inverse-CDF sampling."""
+    """Synthetic C2 input: symbol k with P ~ 1/(k+1)^alpha, inverse-CDF sampling:
+    out[i] = min(searchsorted(cdf, u[i]), nsym - 1), u = Generator(MT19937(seed)).random(n).
+    Evaluated in chunks through a 65536-bucket table of the inverse CDF (a bucket that lies inside
+    one symbol's interval needs no search) -- same values as the plain formula, 10x faster, so that
+    the full 1 GiB input can be produced inside a test."""
     rng = np.random.Generator(np.random.MT19937(seed))
     p = 1.0 / np.arange(1, nsym + 1, dtype=np.float64) ** alpha
     cdf = np.cumsum(p / p.sum())
-    u = rng.random(n)
-    return np.minimum(np.searchsorted(cdf, u), nsym - 1).astype(np.uint8)
+    edges = np.arange(65537, dtype=np.float64) / 65536.0
+    lo = np.searchsorted(cdf, edges[:-1])
+    hi = np.searchsorted(cdf, np.nextafter(edges[1:], 0.0))
+    direct = np.minimum(lo, nsym - 1).astype(np.uint8)
+    ambiguous = lo != hi
+    out = np.empty(n, np.uint8)
+    step = 1 << 24
+    for at in range(0, n, step):
+        u = rng.random(min(step, n - at))
+        b = (u * 65536.0).astype(np.int32)
+        part = direct[b]
+        m = ambiguous[b]
+        part[m] = np.minimum(np.searchsorted(cdf, u[m]), nsym - 1).astype(np.uint8)
+        out[at:at + part.size] = part
+    return out
 
 
 def limited_lengths(hist, max_len=11):

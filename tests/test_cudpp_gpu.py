@@ -212,6 +212,58 @@ def test_cudpp_named_entry_points():
     assert L.cudppDestroy(mgr) == 0
 
 
+@pytest.mark.parametrize("n", [1, 1000, MIB, MIB + 5])
+def test_cudpp_radix_sort_is_the_sort_of_the_reference_tests_decoder(n):
+    """cudppRadixSort as apps/cudpp_testrig/test_compress.cpp:318-344 calls it: plan
+    {CUDPP_SORT_RADIX, CUDPP_UCHAR, KEY_VALUE_PAIRS}, keys = the BWT bytes, values = 0..n-1; the
+    sorted values are the permutation the test walks from the BWT index.  Stable, in place."""
+    L = b200lc.lib()
+
+    class Config(C.Structure):
+        _fields_ = [("algorithm", C.c_int), ("op", C.c_int), ("datatype", C.c_int),
+                    ("options", C.c_uint), ("bucket_mapper", C.c_int)]
+    CUDPP_UCHAR, CUDPP_UINT, CUDPP_FLOAT, CUDPP_SORT_RADIX, KEYS_ONLY, PAIRS = 1, 5, 6, 4, 0x20, 0x40
+    vp, sz = C.c_void_p, C.c_size_t
+    L.cudppCreate.argtypes = [C.POINTER(sz)]
+    L.cudppPlan.argtypes = [sz, C.POINTER(sz), Config, sz, sz, sz]
+    L.cudppRadixSort.argtypes = [sz, vp, vp, sz]
+    L.cudppDestroyPlan.argtypes = [sz]
+    L.cudppDestroy.argtypes = [sz]
+    mgr, plan = sz(0), sz(0)
+    assert L.cudppCreate(C.byref(mgr)) == 0
+    assert L.cudppPlan(mgr, C.byref(plan), Config(CUDPP_SORT_RADIX, 0, CUDPP_FLOAT, PAIRS, 0), n, 1, 0) == 2
+    assert L.cudppPlan(mgr, C.byref(plan), Config(CUDPP_SORT_RADIX, 0, CUDPP_UCHAR, PAIRS, 0), n, 1, 0) == 0
+    data = O.cudpp_block(n, "zipf", seed=n % 71)
+    bwt, idx = O.cudpp_oracle_bwt(data)
+    d_keys = _dev(bwt)
+    d_vals = torch.arange(n, dtype=torch.int32, device=DEV)
+    assert L.cudppRadixSort(0, d_keys.data_ptr(), d_vals.data_ptr(), n) == 1           # invalid handle
+    assert L.cudppRadixSort(plan, d_keys.data_ptr(), d_vals.data_ptr(), n + 1) == 2     # larger than the plan
+    assert L.cudppRadixSort(plan, d_keys.data_ptr(), d_vals.data_ptr(), n) == 0
+    torch.cuda.synchronize()
+    order = np.argsort(bwt, kind="stable")
+    assert np.array_equal(d_keys.cpu().numpy(), bwt[order])
+    assert np.array_equal(d_vals.cpu().numpy().view(np.uint32), order.astype(np.uint32))
+    # the walk of test_compress.cpp:346-362 over the sorted values reproduces the input
+    if n <= 1000:
+        vals = d_vals.cpu().numpy()
+        at, out = int(idx), np.zeros(n, np.uint8)
+        for i in range(n):
+            at = int(vals[at])
+            out[i] = bwt[at]
+        assert np.array_equal(out, data)
+    assert L.cudppDestroyPlan(plan) == 0
+    # unsigned int keys, keys only
+    assert L.cudppPlan(mgr, C.byref(plan), Config(CUDPP_SORT_RADIX, 0, CUDPP_UINT, KEYS_ONLY, 0), n, 1, 0) == 0
+    k = np.random.default_rng(n).integers(0, 1 << 32, n, dtype=np.uint32)
+    d_k = _dev(k.view(np.int32))
+    assert L.cudppRadixSort(plan, d_k.data_ptr(), None, n) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_k.cpu().numpy().view(np.uint32), np.sort(k))
+    assert L.cudppDestroyPlan(plan) == 0
+    assert L.cudppDestroy(mgr) == 0
+
+
 # ------------------------------------------------------------------------------------------ decoder (N3)
 def _np_inverse_mtf(r):
     lst = list(range(256))

@@ -144,6 +144,33 @@ def test_planned_encode_is_identical_to_the_two_pass_encode(n, alpha):
     assert np.array_equal(out.cpu().numpy(), data)
 
 
+@pytest.mark.parametrize("n", [1, 131071, 131072, 3 * 131072 + 5, (1 << 23) + 4099])
+def test_planned_encode_equals_oracle_and_reference_encoder(n):
+    """The packer bench.py times, against the checker directly: oracle restatement of
+    llhuffman_encoder.cc:200-238, and the reference encoder itself with its own dictionary."""
+    data = O.zipf_bytes(n, 1.1, seed=n % 983)
+    d = torch.from_numpy(data).to(DEV)
+    _, ph = b200lc.histogram_u8_pieces(d)
+    cases = []
+    hist = np.bincount(data, minlength=256)
+    code, length, _ = b200lc.cuhd_build_table(hist)
+    want, defined = O.cuhd_oracle_encode(data, code, length)
+    cases.append((code, length, want))
+    if O.have_ref("cuhd") and np.unique(data).size > 1:
+        rcode, rlen, _, runits = O.cuhd_ref_encode(data)
+        cases.append((rcode, rlen, runits))
+    for code, length, want in cases:
+        enc = b200lc.cuhd_encode(d, torch.from_numpy(code.view(np.int32)).to(DEV),
+                                 torch.from_numpy(length).to(DEV), piece_hist=ph)
+        bits = int(length[data].astype(np.int64).sum())
+        assert enc.bits == bits and enc.n_units == want.size
+        got = enc.units[: enc.n_units].cpu().numpy().view(np.uint32)
+        assert np.array_equal(got[:-1], want[:-1])
+        used = bits - 32 * (enc.n_units - 1)
+        mask = np.uint32((0xFFFFFFFF << (32 - used)) & 0xFFFFFFFF)
+        assert (got[-1] & mask) == (want[-1] & mask)
+
+
 def test_planned_encode_reports_overflow():
     n = 1 << 20
     data = O.zipf_bytes(n, 1.1, seed=5)

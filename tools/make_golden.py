@@ -7,6 +7,9 @@
   culzss_quant.npz : reference aftercompression_wrapper output for a 64 KiB quant-code buffer
   culzss_text.npz  : same for 64 KiB of the bundled pg1661.txt
   bsc_*.npz        : reference bsc_bwt_encode (divbwt): U, primary index, secondary indexes
+  cuhd_c2_table.npz: the reference's dictionary (llhuffman_encoder.cc:18-198) for the full C2 input,
+                     zipf_bytes(2^30, 1.1, seed 12345): code, length, LUT, histogram, stream units and a
+                     CRC32 per 1 MiB of stream (`python tools/make_golden.py c2`, ~2 min, 6 GiB)
   bzip2_*.npz      : reference generateMTFValues + sendMTFValues on a sorted block: mtfv, mtfFreq,
                      code lengths, selectors, bit string
 """
@@ -27,6 +30,17 @@ def cuhd(name, data):
     _, defined = O.cuhd_oracle_encode(data, code, length)
     np.savez_compressed(os.path.join(OUT, name), data=data, code=code, length=length, lut=lut,
                         units=units, defined_units=np.int64(defined))
+
+
+def cuhd_c2_table():
+    import zlib
+    data = O.zipf_bytes(1 << 30, 1.1, seed=12345)
+    code, length, lut, units = O.cuhd_ref_encode(data)
+    raw = units.view(np.uint8)
+    crcs = np.array([zlib.crc32(raw[i:i + (1 << 20)].tobytes()) for i in range(0, raw.size - 4, 1 << 20)], np.uint32)
+    np.savez_compressed(os.path.join(OUT, "cuhd_c2_table.npz"), code=code, length=length, lut=lut,
+                        hist=np.bincount(data, minlength=256).astype(np.int64), n_units=np.int64(units.size),
+                        unit_crc32_per_mib=crcs)
 
 
 def culzss(name, data):
@@ -94,6 +108,10 @@ def main():
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "c2":
+    cuhd_c2_table()
+    sys.exit(0)
 
 if __name__ == "__main__":
     main()
