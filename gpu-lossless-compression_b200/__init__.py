@@ -76,6 +76,8 @@ def lib():
     L.b200lc_culzss_encode_scratch_bytes.argtypes = [sz, sz]
     L.b200lc_culzss_encode_batch.restype = i32
     L.b200lc_culzss_encode_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, sz, vp]
+    L.b200lc_culzss_encode_fast_batch.restype = i32
+    L.b200lc_culzss_encode_fast_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, sz, i32, vp]
     L.b200lc_culzss_decode_scratch_bytes.restype = sz
     L.b200lc_culzss_decode_scratch_bytes.argtypes = [sz, sz]
     L.b200lc_culzss_decode_batch.restype = i32
@@ -331,10 +333,11 @@ def culzss_out_stride(buf_length):
     return (buf_length + buf_length // 8 + 1024 + 15) // 16 * 16
 
 
-def culzss_encode(data, buf_length=1 << 20, out=None, comp_len=None, scratch=None, stream=None):
+def culzss_encode(data, buf_length=1 << 20, out=None, comp_len=None, scratch=None, stream=None, fast=0):
     """LZSS-encode a cuda uint8 tensor of nbuf * buf_length bytes.  Returns (out, comp_len):
     out[b * stride : b * stride + comp_len[b]] is buffer b incl. trailer; comp_len[b] == 0 means
-    "store raw".  Asynchronous."""
+    "store raw".  Asynchronous.  fast = 1, 2 or 4: the NON-PARITY fast mode
+    (b200lc_culzss_encode_fast_batch, hash-chain depth), same format, different matches."""
     import torch
     assert data.is_cuda and data.dtype == torch.uint8 and data.is_contiguous()
     assert data.numel() % buf_length == 0
@@ -348,9 +351,14 @@ def culzss_encode(data, buf_length=1 << 20, out=None, comp_len=None, scratch=Non
     need = L.b200lc_culzss_encode_scratch_bytes(nbuf, buf_length)
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty(need, dtype=torch.uint8, device=data.device)
-    check(L.b200lc_culzss_encode_batch(data.data_ptr(), nbuf, buf_length, out.data_ptr(), stride,
-                                       comp_len.data_ptr(), scratch.data_ptr(), scratch.numel(),
-                                       _stream_ptr(stream)), "b200lc_culzss_encode_batch")
+    if fast:
+        check(L.b200lc_culzss_encode_fast_batch(data.data_ptr(), nbuf, buf_length, out.data_ptr(), stride,
+                                                comp_len.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                                int(fast), _stream_ptr(stream)), "b200lc_culzss_encode_fast_batch")
+    else:
+        check(L.b200lc_culzss_encode_batch(data.data_ptr(), nbuf, buf_length, out.data_ptr(), stride,
+                                           comp_len.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                           _stream_ptr(stream)), "b200lc_culzss_encode_batch")
     return out, comp_len
 
 

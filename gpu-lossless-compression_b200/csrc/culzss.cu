@@ -17,7 +17,8 @@
 //     aftercompression_wrapper's serial CPU loop and the 2 MiB D2H per MiB of input;
 //   * the decoder runs one packet per LANE (the reference: one packet per single-thread CTA,
 //     gpu_decompress.cu:120-244 with <<<lSize/4096, 1>>>) with the 128-byte window and the
-//     output staging unified in one shared-memory ring per lane and 16-byte global accesses.
+//     output staging unified in one bank-private shared-memory ring per lane, 16-byte global
+//     accesses, and input refills / output flushes at fixed points of the token loop.
 #include "common.cuh"
 #include "../../include/b200lc.h"
 
@@ -44,6 +45,9 @@ struct EncSmem {
             u16 FB[kPacket / 8 + 1];                // output offset of the flag byte of group g
         } b;                                        // packing
         struct {
+            short prev[kPacket + kWindow];          // fast mode: previous position with the same hash
+        } f;
+        struct {
             u16 J[kPacket];                         // first token position selected after pos's 32-block
             u8 E[kPacket / 32];                     // entry offset of the parse into each 32-block
         } s;                                        // selection
@@ -55,6 +59,21 @@ struct EncSmem {
     u32 scan[4];
 };
 
+// four bytes at byte offset `at` of the packet buffer (two aligned words, funnel-shifted)
+__device__ __forceinline__ u32 load4(const u8 *pkt, u32 at)
+{
+    const u32 *w = reinterpret_cast<const u32 *>(pkt + (at & ~3u));
+    return __funnelshift_r(w[0], w[1], 8 * (at & 3));
+}
+
+// DEPTH == 0: the reference's match finder, bit-exact (parity mode).
+// DEPTH  > 0: FAST MODE, NOT bit-exact with the reference encoder: the same token format, window
+//   and packet layout (every stream decodes with the reference's DecodeKernel,
+//   gpu_decompress.cu:164-242), but the match of a position is the longest among the DEPTH most
+//   recent earlier positions whose first three bytes hash alike (shared-memory hash chain), not the
+//   result of the reference's streak scanner over all 127 window positions.  A match never reaches
+//   into its own output (source end <= current position), like the reference's.
+template <int DEPTH>
 __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict__ in, u64 npackets,
                                                             u8 *__restrict__ tmp_out,
                                                             u16 *__restrict__ pkt_size,
@@ -73,16 +92,108 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
             dst[tx] = src[tx];
             dst[tx + 128] = src[tx + 128];
             sm.pkt[tx] = ' ';
-            for (u32 i = tx; i < 256 * kOccStride; i += 128) sm.u.a.occ[i] = 0;
+            if (DEPTH == 0) {
+                for (u32 i = tx; i < 256 * kOccStride; i += 128) sm.u.a.occ[i] = 0;
+            } else {
+                uint4 *const T0 = reinterpret_cast<uint4 *>(smem_raw + ((sizeof(EncSmem) + 15) & ~size_t(15)));
+                for (u32 i = tx; i < (1u << 10); i += 128) T0[i] = make_uint4(0, 0, 0, 0);
+                sm.u.f.prev[tx] = (short)-32768;          // positions -128 .. -1: no predecessor
+                if (tx < 4) reinterpret_cast<u32 *>(sm.pkt + kWindow + kPacket)[tx] = 0;   // defined padding
+            }
         }
         __syncthreads();
+        if (DEPTH > 0) {
+            // Hash table behind EncSmem: per hash of three bytes EIGHT 16-bit slots, one per
+            // (chunk parity, warp): slot [c & 1][w] holds the latest position (+ 129) that warp w
+            // met in a chunk of parity c & 1.  A reader of chunk c sees its own chunk's lower warps
+            // and the whole previous chunk with ONE 16-byte load; anything staler fails the window
+            // test by construction, so the table is never cleared between chunks.
+            uint4 *const T = reinterpret_cast<uint4 *>(smem_raw + ((sizeof(EncSmem) + 15) & ~size_t(15)));
+            u16 *const T16 = reinterpret_cast<u16 *>(T);
+            // the window in front of the packet is 128 spaces: the farthest one can lend the longest
+            // run; position -128 = chunk -1 (parity 1), warp 0
+            if (tx == 0) T16[(((0x202020u * 2654435761u) >> 22) << 3) + 4] = 1;
+            __syncthreads();
+            for (u32 c = 0; c < kChunks; ++c) {
+                const u32 p = c * 128 + tx;
+                const u32 v = sm.pkt[kWindow + p];
+                const bool valid = p + 2 < (u32)kPacket;
+                const u32 h = ((load4(sm.pkt, kWindow + p) & 0xffffffu) * 2654435761u) >> 22;
+                const u32 peers = __match_any_sync(0xffffffffu, valid ? h : (0x80000000u | lane));
+                if (valid && (peers >> lane) == 1u) T16[(h << 3) + ((c & 1) << 2) + warp] = (u16)(p + 129);
+                __syncthreads();     // this chunk's positions are in the table
+                // most recent earlier position with the same hash at distance 3..128 (a closer one
+                // cannot lend three bytes): inside my warp from the peer mask, else from the table
+                int cand = -32768;
+                if (valid) {
+                    const u32 lower = lane >= 3 ? (peers & ((1u << (lane - 2)) - 1u)) : 0u;
+                    if (lower) {
+                        cand = (int)(p - lane) + (31 - __clz(lower));
+                    } else {
+                        const uint4 tv = T[h];
+                        const u32 lo = p + 1, hi = p + 126;          // position + 129 in [p - 128, p - 3]
+                        const u32 lo2 = lo | (lo << 16), hi2 = hi | (hi << 16);
+                        u32 m = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const u32 x = (&tv.x)[k];
+                            m = __vmaxu2(m, x & __vcmpgeu2(x, lo2) & __vcmpleu2(x, hi2));
+                        }
+                        const u32 best = max(m & 0xffffu, m >> 16);
+                        if (best) cand = (int)best - 129;
+                    }
+                }
+                sm.u.f.prev[kWindow + p] = (short)cand;
+                __syncthreads();     // links of this chunk visible
+                u32 best_len = 1;
+                int best_q = 0;
+                if (valid) {
+                    const u32 maxlen = min(127u, (u32)kPacket - p);
+                    const u32 first = load4(sm.pkt, kWindow + p);
+                    int q = cand;
+#pragma unroll 1
+                    for (int d = 0; d < DEPTH;) {
+                        if (q < (int)p - kWindow) break;
+                        const u32 dist = (u32)((int)p - q);
+                        const u32 lim = min(dist, maxlen);
+                        u32 L = 0;
+                        u32 x = load4(sm.pkt, (u32)(kWindow + q)) ^ first;
+                        while (true) {
+                            if (x) { L += (u32)(__ffs(x) - 1) >> 3; break; }
+                            L += 4;
+                            if (L >= lim) break;
+                            x = load4(sm.pkt, (u32)(kWindow + q) + L) ^ load4(sm.pkt, kWindow + p + L);
+                        }
+                        L = min(L, lim);
+                        if (L > best_len) { best_len = L; best_q = q; }
+                        // A match that ends only because it reached its own output (length ==
+                        // distance) means the data repeats with that period: the source twice as far
+                        // back lends twice as much (runs, periodic records).  Does not use up depth.
+                        if (L == dist && L < maxlen && 2 * dist <= (u32)kWindow) {
+                            q = (int)p - (int)(2 * dist);
+                        } else {
+                            q = sm.u.f.prev[kWindow + q];
+                            ++d;
+                        }
+                    }
+                }
+                const bool is_match = best_len > 2;
+                sm.tlen[p] = is_match ? (u8)best_len : (u8)1;
+                sm.toff[p] = is_match ? (u8)((best_q + kWindow) & 255) : (u8)v;
+                const u32 mm = __ballot_sync(0xffffffffu, is_match);
+                if (lane == 0) sm.M[p >> 5] = mm;
+                __syncthreads();     // tokens written
+            }
+        }
         // window slots 128..255 initially hold ' ' (gpu_compress.cu:208), chunk 0 enters slots 0..127
+        if (DEPTH == 0) {
         if (tx < 4) sm.u.a.occ[0x20 * kOccStride + 4 + tx] = 0xffffffffu;
         __syncthreads();
         atomicOr(&sm.u.a.occ[sm.pkt[kWindow + tx] * kOccStride + (tx >> 5)], 1u << (tx & 31));
         __syncthreads();
+        }
 
-        for (u32 c = 0; c < kChunks; ++c) {
+        for (u32 c = 0; DEPTH == 0 && c < kChunks; ++c) {
             const u32 p = c * 128 + tx;
             const u32 v = sm.pkt[kWindow + p];
             // ---- 128-bit occurrence mask over scan index t (t = 0 <-> position p-128)
@@ -468,27 +579,38 @@ __global__ void __launch_bounds__(256) culzss_parse_kernel(const u8 *__restrict_
 }
 
 constexpr int kDecWarps = 4;
-constexpr int kRowStride = 144;    // bytes per lane ring row (128 + pad, 16-byte aligned)
-constexpr int kInChunk = 64;       // bytes of compressed input staged per lane refill
-constexpr int kInStride = 80;
 
+// Per lane: a 128-byte LZSS window and a 128-byte queue of compressed input, both laid out
+// [word][lane] so that lane l only ever touches bank l: whatever offsets the 32 packets of a warp are
+// at, a shared-memory access is ONE wavefront (round 1 kept a contiguous row per lane: 3-4
+// wavefronts per access and 64 % of the shared-memory pipe).
 struct DecSmem {
-    __align__(16) u8 ring[kDecWarps * 32 * kRowStride];
-    __align__(16) u8 inb[kDecWarps * 32 * kInStride];
+    u32 win[kDecWarps][32][32];
+    u32 inq[kDecWarps][32][32];
 };
 
-// One packet per lane.  The lane's 128-byte ring row is both the LZSS window
-// (slot = output position mod 128, gpu_decompress.cu:164-242) and the staging of the output,
-// flushed to global memory 64 bytes at a time.
+// byte offset of ring byte o (0..127) inside a lane's [word][lane] column
+__device__ __forceinline__ u32 ring_at(u32 o) { return ((o & 124u) << 5) | (o & 3u); }
+
+// One packet per lane (gpu_decompress.cu:164-242 semantics: flag bits LSB first, 1 = literal,
+// 0 = (len, off); window slot = output position mod 128, initialised with ' '; a match reads its
+// whole source string before it writes).  Round-2 formulation: everything a lane does at a
+// data-dependent TIME in round 1 (refilling its input, flushing its output: 1.6 and 2.6 active
+// lanes on average) now happens at fixed points of the token loop for all lanes together:
+//   * input: 16-byte chunks travel global -> registers -> queue twice per group of 8 tokens, one
+//     chunk ahead of their use; tokens are cut from a 64-bit register that is topped up a word at
+//     a time;
+//   * output: whatever 32-byte sectors are complete leave at the top of every group;
+//   * a match that does not overlap its own output is copied four bytes per step.
 __global__ void __launch_bounds__(kDecWarps * 32) culzss_decode_kernel(
     const u8 *__restrict__ comp, const u64 *__restrict__ comp_off, u32 nbuf, u32 max_pk,
     u32 buf_length, const u32 *__restrict__ pk_start, const u32 *__restrict__ pk_size,
     const u32 *__restrict__ buf_npk, u8 *__restrict__ out)
 {
     __shared__ DecSmem sm;
-    const u32 tid = threadIdx.x;
-    u8 *row = sm.ring + tid * kRowStride;
-    u8 *inb = sm.inb + tid * kInStride;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u8 *const win = reinterpret_cast<u8 *>(&sm.win[warp][0][lane]);
+    u8 *const inq = reinterpret_cast<u8 *>(&sm.inq[warp][0][lane]);
     const u64 total_slots = (u64)nbuf * max_pk;
     for (u64 slot = (u64)blockIdx.x * blockDim.x + tid; slot < total_slots;
          slot += (u64)gridDim.x * blockDim.x) {
@@ -499,92 +621,125 @@ __global__ void __launch_bounds__(kDecWarps * 32) culzss_decode_kernel(
         const u32 size = pk_size[slot];
         u8 *dst = out + (u64)b * buf_length + (u64)i * kPacket;
 
-        for (int k = 0; k < 128; k += 16)
-            *reinterpret_cast<uint4 *>(row + k) =
-                make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
-        // compressed input is staged 64 bytes at a time through 16-byte aligned vector loads
+#pragma unroll
+        for (int k = 0; k < 32; ++k) *reinterpret_cast<u32 *>(win + 128 * k) = 0x20202020u;
+
+        // ---- input: `base` coordinates = bytes from the 16-byte aligned address in front of the packet
         const u32 mis = (u32)(reinterpret_cast<uintptr_t>(src) & 15);
         const u8 *base = src - mis;
-        const u32 lim = mis + size;          // packet end in `base` coordinates
-        u32 loaded_lo = 0, loaded_hi = 0;    // staged range: base coords [lo, lo+64), packet coords < hi
-        auto get = [&](u32 pos) -> u32 {     // byte `pos` of the packet, pos non-decreasing
-            if (pos >= loaded_hi) {
-                const u32 a = (pos + mis) & ~63u;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (a + 16 * q < lim)
-                        *reinterpret_cast<uint4 *>(inb + 16 * q) =
-                            *reinterpret_cast<const uint4 *>(base + a + 16 * q);
-                loaded_lo = a;
-                loaded_hi = a + kInChunk - mis;
-            }
-            return inb[pos + mis - loaded_lo];
+        const u32 lim = mis + size;          // packet end
+        u32 ld = 0;                          // bytes in the queue so far (multiple of 16)
+        u32 rp = mis & ~3u;                  // next queue word to cut tokens from
+        auto push = [&](const uint4 &v) {    // chunk [ld, ld + 16) into the queue
+            u32 *q = reinterpret_cast<u32 *>(inq + ((ld & 112u) << 5));
+            q[0] = v.x; q[32] = v.y; q[64] = v.z; q[96] = v.w;
+            ld += 16;
         };
+#pragma unroll 1
+        for (int k = 0; k < 6 && ld < lim; ++k) push(__ldg(reinterpret_cast<const uint4 *>(base + ld)));
+        uint4 pf = make_uint4(0, 0, 0, 0);
+        bool pf_valid = ld < lim;
+        if (pf_valid) pf = __ldg(reinterpret_cast<const uint4 *>(base + ld));
+        auto top_up = [&]() {                // the chunk requested last time arrives; request the next
+            if (pf_valid && ld - rp <= 112u) {
+                push(pf);
+                pf_valid = ld < lim;
+                if (pf_valid) pf = __ldg(reinterpret_cast<const uint4 *>(base + ld));
+            }
+        };
+        unsigned long long inreg;            // the next `nb` packet bytes, lowest first
+        u32 nb;
+        {
+            const u32 w0 = *reinterpret_cast<const u32 *>(inq + ((rp & 124u) << 5));
+            inreg = (unsigned long long)(w0 >> (8 * (mis & 3u)));
+            nb = 4 - (mis & 3u);
+            rp += 4;
+        }
+        auto refill = [&]() {                // keeps at least 5 bytes in inreg
+            if (nb <= 4) {
+                const u32 wq = *reinterpret_cast<const u32 *>(inq + ((rp & 124u) << 5));
+                inreg |= (unsigned long long)wq << (8 * nb);
+                nb += 4;
+                rp += 4;
+            }
+        };
+
         u32 fp = 0;            // compressed bytes consumed
         u32 w = 0;             // bytes produced
-        u32 flushed = 0;       // bytes already written to global memory (multiple of 64)
-        // Invariant at every token boundary: w - flushed < 64, so a token of <= 64 bytes never
-        // overwrites ring bytes that are not in global memory yet.
+        u32 flushed = 0;       // bytes already in global memory (multiple of 32)
+        // Invariant: w - flushed <= 128 at all times (a window slot is only overwritten after it
+        // has left), kept by flushing below 64 pending bytes before any copy of <= 64 bytes.
         auto flush_ready = [&]() {
-            while (w - flushed >= 64 && flushed + 64 <= kPacket) {
-                const uint4 *r4 = reinterpret_cast<const uint4 *>(row + (flushed & 127));
+            while (w - flushed >= 32 && flushed + 32 <= (u32)kPacket) {
+                const u32 *r = reinterpret_cast<const u32 *>(win + ((flushed & 96u) << 5));
                 uint4 *g4 = reinterpret_cast<uint4 *>(dst + flushed);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) g4[q] = r4[q];
-                flushed += 64;
+                g4[0] = make_uint4(r[0], r[32], r[64], r[96]);
+                g4[1] = make_uint4(r[128], r[160], r[192], r[224]);
+                flushed += 32;
             }
         };
-        u32 flags = 0, flags_used = 7;
-        while (true) {
-            flags >>= 1;
-            if (++flags_used == 8) {
-                if (fp >= size) break;
-                flags = get(fp++);
-                flags_used = 0;
-            }
-            if (flags & 1) {
-                if (fp >= size) break;
-                const u32 cbyte = get(fp++);
-                if (w < kPacket) row[w & 127] = (u8)cbyte;
-                ++w;
-            } else {
-                if (fp >= size) break;
-                const u32 len = get(fp++);
-                if (fp >= size) break;
-                const u32 off = get(fp++);
-                const u32 a = (w - off) & 127;      // distance from source slot to write slot
-                if ((a == 0 || a >= len) && len <= 64 && w + len <= kPacket) {
-                    // source slots are not overwritten before they are read: forward copy, four
-                    // bytes per step (two aligned ring words funnel-shifted to the source offset;
-                    // a step only overwrites slots whose source bytes earlier steps have consumed)
-                    const u32 *row32 = reinterpret_cast<const u32 *>(row);
-                    for (u32 k = 0; k < len; k += 4) {
-                        const u32 s = (off + k) & 127, i0 = s >> 2;
-                        const u32 x = __funnelshift_r(row32[i0], row32[(i0 + 1) & 31], 8 * (s & 3));
-                        const u32 d = w + k;
-                        row[d & 127] = (u8)x;
-                        if (k + 1 < len) row[(d + 1) & 127] = (u8)(x >> 8);
-                        if (k + 2 < len) row[(d + 2) & 127] = (u8)(x >> 16);
-                        if (k + 3 < len) row[(d + 3) & 127] = (u8)(x >> 24);
+        bool more = true;
+        while (more) {
+            top_up();
+            flush_ready();
+            refill();
+            if (fp >= size) break;
+            u32 flags = (u32)inreg & 0xffu;
+            inreg >>= 8; --nb; ++fp;
+#pragma unroll 1
+            for (int t = 0; t < 8; ++t, flags >>= 1) {
+                if (t == 4) top_up();
+                refill();
+                if (fp >= size) { more = false; break; }
+                const u32 b0 = (u32)inreg & 0xffu, b1 = ((u32)inreg >> 8) & 0xffu;
+                if (flags & 1) {
+                    inreg >>= 8; --nb; ++fp;
+                    if (w < (u32)kPacket) win[ring_at(w & 127u)] = (u8)b0;
+                    ++w;
+                    continue;
+                }
+                if (fp + 1 >= size) { more = false; break; }
+                inreg >>= 16; nb -= 2; fp += 2;
+                const u32 len = b0, off = b1;
+                const u32 a = (w - off) & 127u;      // distance from source slot to write slot
+                if ((a == 0 || a >= len) && w + len <= (u32)kPacket) {
+                    // the source is not overwritten before it is read: forward copy, four bytes per
+                    // step (two ring words funnel-shifted to the source offset), at most 64 bytes
+                    // between two looks at the flush condition
+                    for (u32 done = 0; done < len;) {
+                        const u32 part = min(64u, len - done);
+                        if (w - flushed >= 64) flush_ready();
+                        for (u32 k = 0; k < part; k += 4) {
+                            const u32 s = (off + done + k) & 127u;
+                            const u32 x0 = *reinterpret_cast<const u32 *>(win + ((s & 124u) << 5));
+                            const u32 x1 = *reinterpret_cast<const u32 *>(win + (((s + 4) & 124u) << 5));
+                            const u32 x = __funnelshift_r(x0, x1, 8 * (s & 3u));
+                            const u32 d = w + k;
+                            win[ring_at(d & 127u)] = (u8)x;
+                            if (k + 1 < part) win[ring_at((d + 1) & 127u)] = (u8)(x >> 8);
+                            if (k + 2 < part) win[ring_at((d + 2) & 127u)] = (u8)(x >> 16);
+                            if (k + 3 < part) win[ring_at((d + 3) & 127u)] = (u8)(x >> 24);
+                        }
+                        w += part;
+                        done += part;
                     }
-                    w += len;
                 } else {
                     // general case exactly as the reference (gpu_decompress.cu:220-236):
                     // read the whole string from the old window, then append it
                     u8 tmp[256];
-                    for (u32 k = 0; k < len; ++k) tmp[k] = row[(off + k) & 127];
+                    for (u32 k = 0; k < len; ++k) tmp[k] = win[ring_at((off + k) & 127u)];
                     for (u32 k = 0; k < len; ++k) {
-                        if (w < kPacket) row[w & 127] = tmp[k];
+                        if (w < (u32)kPacket) win[ring_at(w & 127u)] = tmp[k];
                         ++w;
                         flush_ready();
                     }
                 }
             }
-            flush_ready();
         }
         // a well-formed packet ends with w == 4096 and everything flushed; otherwise write the tail
+        flush_ready();
         const u32 wend = min(w, (u32)kPacket);
-        for (u32 k = flushed; k < wend; ++k) dst[k] = row[k & 127];
+        for (u32 k = flushed; k < wend; ++k) dst[k] = win[ring_at(k & 127u)];
     }
 }
 
@@ -614,17 +769,26 @@ extern "C" size_t b200lc_culzss_encode_scratch_bytes(size_t nbuf, size_t buf_len
            ((npk + 255) & ~size_t(255)) + ((npk * 4 + 255) & ~size_t(255)) + 256;
 }
 
-extern "C" int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length,
-                                          uint8_t *d_out, size_t out_stride, uint32_t *d_comp_len,
-                                          void *d_scratch, size_t scratch_bytes, void *stream_)
+static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out, size_t out_stride,
+                        uint32_t *d_comp_len, void *d_scratch, size_t scratch_bytes, int depth, cudaStream_t stream)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
     if (nbuf == 0) return B200LC_OK;
     if (!d_in || !d_out || !d_comp_len || !d_scratch) return B200LC_ERR_ARG;
     if (buf_length == 0 || buf_length % lzss::kPacket || buf_length > (1u << 30)) return B200LC_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_scratch) & 15))
         return B200LC_ERR_ARG;
     if (scratch_bytes < b200lc_culzss_encode_scratch_bytes(nbuf, buf_length)) return B200LC_ERR_SCRATCH;
+    typedef void (*Kern)(const u8 *, u64, u8 *, u16 *, u8 *);
+    static const Kern kerns[4] = {lzss::culzss_encode_kernel<0>, lzss::culzss_encode_kernel<1>,
+                                  lzss::culzss_encode_kernel<2>, lzss::culzss_encode_kernel<4>};
+    int ki;
+    switch (depth) {
+        case 0: ki = 0; break;
+        case 1: ki = 1; break;
+        case 2: ki = 2; break;
+        case 4: ki = 3; break;
+        default: return B200LC_ERR_UNSUPPORTED;
+    }
     const u32 npk_buf = (u32)(buf_length / lzss::kPacket);
     const u64 npk = (u64)nbuf * npk_buf;
     u8 *tmp = reinterpret_cast<u8 *>(d_scratch);
@@ -632,16 +796,16 @@ extern "C" int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size
     u8 *lastg = reinterpret_cast<u8 *>(sizes) + ((npk * 2 + 255) & ~u64(255));
     u32 *pkoff = reinterpret_cast<u32 *>(lastg + ((npk + 255) & ~u64(255)));
 
-    static unsigned attr_done[kMaxDevices] = {0};   // context epoch the attribute was set in
+    // fast mode keeps its hash table (1024 x 16 bytes) behind EncSmem
+    const size_t smem = ((sizeof(lzss::EncSmem) + 15) & ~size_t(15)) + (depth ? (size_t(16) << 10) : 0);
+    static unsigned attr_done[kMaxDevices][4] = {{0}};   // context epoch the attribute was set in
     const int slot = device_slot();
-    if (slot < 0 || attr_done[slot] != context_epoch()) {
-        B200LC_CUDA_TRY(cudaFuncSetAttribute(lzss::culzss_encode_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(lzss::EncSmem)));
-        if (slot >= 0) attr_done[slot] = context_epoch();
+    if (slot < 0 || attr_done[slot][ki] != context_epoch()) {
+        B200LC_CUDA_TRY(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (slot >= 0) attr_done[slot][ki] = context_epoch();
     }
     const u32 grid = (u32)min(npk, (u64)num_sms() * 64);
-    lzss::culzss_encode_kernel<<<grid, 128, sizeof(lzss::EncSmem), stream>>>(d_in, npk, tmp, sizes, lastg);
+    kerns[ki]<<<grid, 128, smem, stream>>>(d_in, npk, tmp, sizes, lastg);
     B200LC_CUDA_TRY(cudaGetLastError());
     lzss::culzss_scan_kernel<<<(u32)nbuf, 256, 0, stream>>>(sizes, lastg, npk_buf, (u32)buf_length,
                                                            d_out, out_stride, pkoff, d_comp_len);
@@ -651,6 +815,23 @@ extern "C" int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size
                                                          d_out, out_stride);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
+}
+
+extern "C" int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length,
+                                          uint8_t *d_out, size_t out_stride, uint32_t *d_comp_len,
+                                          void *d_scratch, size_t scratch_bytes, void *stream_)
+{
+    return encode_batch(d_in, nbuf, buf_length, d_out, out_stride, d_comp_len, d_scratch, scratch_bytes, 0,
+                        (cudaStream_t)stream_);
+}
+
+extern "C" int b200lc_culzss_encode_fast_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length,
+                                               uint8_t *d_out, size_t out_stride, uint32_t *d_comp_len,
+                                               void *d_scratch, size_t scratch_bytes, int depth, void *stream_)
+{
+    if (depth == 0) return B200LC_ERR_ARG;
+    return encode_batch(d_in, nbuf, buf_length, d_out, out_stride, d_comp_len, d_scratch, scratch_bytes, depth,
+                        (cudaStream_t)stream_);
 }
 
 extern "C" size_t b200lc_culzss_decode_scratch_bytes(size_t nbuf, size_t buf_length)

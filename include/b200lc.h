@@ -193,6 +193,16 @@ size_t b200lc_culzss_encode_scratch_bytes(size_t nbuf, size_t buf_length);
 int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out,
                                size_t out_stride, uint32_t *d_comp_len, void *d_scratch,
                                size_t scratch_bytes, void *stream);
+/* FAST MODE -- NOT bit-exact with the reference encoder (every table and test labels it
+ * non-parity).  Same buffer format, token format, window (128) and packets (4096) as
+ * b200lc_culzss_encode_batch, so the output decodes with the reference's DecodeKernel
+ * (gpu_decompress.cu:164-242) and with b200lc_culzss_decode_batch, but the match finder is a
+ * shared-memory hash chain over three-byte prefixes that looks at the `depth` (1, 2 or 4) most
+ * recent candidates instead of the reference's exhaustive streak scanner: ~20-35x the throughput of
+ * parity mode for a 10-25 % larger output.  Same arguments otherwise. */
+int b200lc_culzss_encode_fast_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out,
+                                    size_t out_stride, uint32_t *d_comp_len, void *d_scratch,
+                                    size_t scratch_bytes, int depth, void *stream);
 /* Decode: compressed buffer b occupies d_comp[d_comp_offsets[b] .. d_comp_offsets[b+1]) and is
  * decoded to d_out + b * buf_length (d_out 16-byte aligned).  A buffer whose stored size equals
  * buf_length is raw and copied (decompression.c:90-108, deculzss.c:94-95).  Asynchronous. */

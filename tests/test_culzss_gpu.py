@@ -302,3 +302,94 @@ def test_file_container_ragged_size_round_trips():
     assert blen.value == data.size and np.array_equal(back, data)
     small = np.zeros(1000, np.uint8)
     assert L.b200lc_culzss_compress_container(small, small.size, out, cap, C.byref(olen)) == b200lc.ERR_UNSUPPORTED
+
+
+# ------------------------------------------------------------------------------------------ fast mode
+# NON-PARITY: b200lc_culzss_encode_fast_batch writes the reference's format with other matches.
+# What is pinned: every stream decodes to the input with the oracle's decoder, the product decoder
+# and the reference's own DecodeKernel; tokens obey the format's limits; the size is within a
+# stated factor of the parity encoder's.
+def _fast_encode(data, depth, buf_length=MIB):
+    d = torch.from_numpy(data).to(DEV)
+    out, clen = b200lc.culzss_encode(d, buf_length, fast=depth)
+    torch.cuda.synchronize()
+    stride = b200lc.culzss_out_stride(buf_length)
+    out = out.cpu().numpy()
+    clen = clen.cpu().numpy()
+    return [out[b * stride: b * stride + clen[b]] for b in range(clen.size)], clen
+
+
+def _walk_tokens(comp, n):
+    """Parses one compressed buffer: every match has 3 <= len <= 127 and packets produce exactly
+    4096 bytes.  Returns the number of matches."""
+    npk = n // 4096
+    sizes = [int.from_bytes(comp[comp.size - 6 - 2 * npk + 2 * i: comp.size - 6 - 2 * npk + 2 * i + 2].tobytes(), "big")
+             for i in range(npk)]
+    assert int.from_bytes(comp[-6:-2].tobytes(), "big") == n
+    at, matches = 0, 0
+    for sz in sizes:
+        body = comp[at: at + sz].tolist()
+        at += sz
+        i, produced = 0, 0
+        while i < len(body):
+            flags = body[i]
+            i += 1
+            for bit in range(8):
+                if i >= len(body):
+                    break
+                if flags >> bit & 1:
+                    i += 1
+                    produced += 1
+                else:
+                    ln = body[i]
+                    assert 3 <= ln <= 127
+                    i += 2
+                    produced += ln
+                    matches += 1
+        assert produced == 4096
+    assert at == comp.size - 6 - 2 * npk
+    return matches
+
+
+@pytest.mark.parametrize("depth", [1, 2, 4])
+@pytest.mark.parametrize("name", ["quant32", "quant16", "spaces", "zeros", "text", "mix", "carets", "ramp"])
+def test_fast_mode_streams_decode_everywhere(name, depth):
+    data = _cases()[name]
+    bufs, clen = _fast_encode(data, depth)
+    assert clen[0] > 0
+    comp = bufs[0]
+    dok, back = O.culzss_oracle_decompress(comp, data.size)
+    assert dok and np.array_equal(back, data)
+    assert np.array_equal(_decode_gpu([comp], MIB), data)
+    ok, parity = O.culzss_oracle_compress(data)
+    assert ok and comp.size <= 1.6 * parity.size + 4096, (comp.size, parity.size)
+    if name in ("quant32", "text"):
+        assert _walk_tokens(comp[: comp.size], MIB) > 0
+
+
+def test_fast_mode_incompressible_buffer_is_stored_raw_and_small_buffers():
+    rng = np.random.default_rng(12)
+    parts = [O.quant_codes(1 << 16, seed=5), rng.integers(0, 256, 1 << 16, dtype=np.uint8), np.full(1 << 16, 0x20, np.uint8)]
+    data = np.concatenate(parts)
+    bufs, clen = _fast_encode(data, 2, 1 << 16)
+    assert clen[1] == 0 and clen[0] > 0 and clen[2] > 0
+    comps = [bufs[0], parts[1], bufs[2]]
+    assert np.array_equal(_decode_gpu(comps, 1 << 16), data)
+    with pytest.raises(b200lc.B200LCError):
+        b200lc.culzss_encode(torch.from_numpy(data).to(DEV), 1 << 16, fast=3)      # unsupported depth
+
+
+@pytest.mark.skipif(not O.have_ref("culzss"), reason="oracle/_ref/libref_culzss.so not built")
+@pytest.mark.parametrize("depth", [1, 2, 4])
+def test_fast_mode_streams_decode_with_the_reference_kernel(depth):
+    """The reference's own DecodeKernel (gpu_decompress.cu:164-242, sm_100a build) on fast-mode output."""
+    ref = O.ref_culzss()
+    ref.initGPU()
+    for name in ("quant32", "text", "mix", "spaces"):
+        data = _cases()[name]
+        bufs, _ = _fast_encode(data, depth)
+        work = np.zeros(MIB + MIB // 8 + 1024, np.uint8)
+        work[: bufs[0].size] = bufs[0]
+        dlen = C.c_int(0)
+        assert ref.decompression_kernel_wrapper(work, int(bufs[0].size), C.byref(dlen), 0, 0, 1) == 1
+        assert dlen.value == MIB and np.array_equal(work[:MIB], data), name

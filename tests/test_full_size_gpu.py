@@ -134,12 +134,9 @@ def test_c2_one_gib_reference_input_dictionary_and_stream():
     assert enc.bits == bits and enc.n_units == ref_units.size == (bits + 31) // 32
     want = torch.from_numpy(ref_units.view(np.int32))
     got = enc.units[: enc.n_units].cpu()
-    # every unit but the last: the reference leaves the unused low bits of the final unit
-    # unspecified; compare its defined bits
+    # every unit but the last: the reference loses the codeword that straddles into its final unit
+    # (SURVEY.md R3), so that unit is not comparable
     assert torch.equal(got[:-1], want[:-1])
-    used = bits - 32 * (enc.n_units - 1)
-    mask = np.uint32((0xFFFFFFFF << (32 - used)) & 0xFFFFFFFF)
-    assert (np.uint32(got[-1].item() & 0xFFFFFFFF) & mask) == (ref_units[-1] & mask)
     # two-pass packer too
     enc2 = b200lc.cuhd_encode(d, d_code, d_len)
     assert torch.equal(enc2.units[: enc2.n_units], enc.units[: enc.n_units])
