@@ -703,22 +703,33 @@ __global__ void __launch_bounds__(kDecWarps * 32) culzss_decode_kernel(
                 const u32 len = b0, off = b1;
                 const u32 a = (w - off) & 127u;      // distance from source slot to write slot
                 if ((a == 0 || a >= len) && w + len <= (u32)kPacket) {
-                    // the source is not overwritten before it is read: forward copy, four bytes per
-                    // step (two ring words funnel-shifted to the source offset), at most 64 bytes
-                    // between two looks at the flush condition
+                    // The source is not overwritten before it is read.  The copy runs over the
+                    // DESTINATION words of the window: each is the funnel shift of two source words
+                    // merged into the old word under a byte mask (first and last word of the string
+                    // only) -- one shared-memory store per four bytes instead of four.  At most 64
+                    // bytes between two looks at the flush condition.
                     for (u32 done = 0; done < len;) {
                         const u32 part = min(64u, len - done);
                         if (w - flushed >= 64) flush_ready();
-                        for (u32 k = 0; k < part; k += 4) {
-                            const u32 s = (off + done + k) & 127u;
-                            const u32 x0 = *reinterpret_cast<const u32 *>(win + ((s & 124u) << 5));
-                            const u32 x1 = *reinterpret_cast<const u32 *>(win + (((s + 4) & 124u) << 5));
-                            const u32 x = __funnelshift_r(x0, x1, 8 * (s & 3u));
-                            const u32 d = w + k;
-                            win[ring_at(d & 127u)] = (u8)x;
-                            if (k + 1 < part) win[ring_at((d + 1) & 127u)] = (u8)(x >> 8);
-                            if (k + 2 < part) win[ring_at((d + 2) & 127u)] = (u8)(x >> 16);
-                            if (k + 3 < part) win[ring_at((d + 3) & 127u)] = (u8)(x >> 24);
+                        const u32 d0 = w & 127u, s0 = (off + done) & 127u;
+                        const u32 head = d0 & 3u;                       // bytes of the first word in front of the string
+                        const u32 sh = 8 * ((s0 - d0) & 3u);
+                        u32 sw = (s0 - head) & 124u;                    // source word that holds the byte for dest byte 0
+                        u32 x0 = *reinterpret_cast<const u32 *>(win + (sw << 5));
+                        const u32 nw = (head + part + 3) >> 2;
+                        for (u32 j = 0; j < nw; ++j) {
+                            sw = (sw + 4) & 124u;
+                            const u32 x1 = *reinterpret_cast<const u32 *>(win + (sw << 5));
+                            u32 x = __funnelshift_r(x0, x1, sh);
+                            x0 = x1;
+                            u32 *const dp = reinterpret_cast<u32 *>(win + (((d0 + 4 * j) & 124u) << 5));
+                            const u32 lo = j == 0 ? head : 0u;
+                            const u32 hi = min(4u, head + part - 4 * j);
+                            if (lo != 0 || hi != 4) {
+                                const u32 m = (0xffffffffu << (8 * lo)) & (0xffffffffu >> (8 * (4 - hi)));
+                                x = (*dp & ~m) | (x & m);
+                            }
+                            *dp = x;
                         }
                         w += part;
                         done += part;
@@ -743,7 +754,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) culzss_decode_kernel(
     }
 }
 
-// Raw (stored) buffers: plain copy.
+// Raw (stored) buffers: plain copy, 16 bytes per thread and step when both sides are aligned.
 __global__ void culzss_copy_raw_kernel(const u8 *__restrict__ comp, const u64 *__restrict__ comp_off,
                                        const u32 *__restrict__ buf_npk, u32 buf_length,
                                        u8 *__restrict__ out)
@@ -752,8 +763,15 @@ __global__ void culzss_copy_raw_kernel(const u8 *__restrict__ comp, const u64 *_
     if (buf_npk[b] != 0xffffffffu) return;
     const u8 *s = comp + comp_off[b];
     u8 *d = out + (u64)b * buf_length;
-    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < buf_length; k += gridDim.x * blockDim.x)
-        d[k] = s[k];
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+        uint4 *d4 = reinterpret_cast<uint4 *>(d);
+        for (u32 k = tid; k < (buf_length >> 4); k += nthr) d4[k] = s4[k];
+        for (u32 k = (buf_length & ~15u) + tid; k < buf_length; k += nthr) d[k] = s[k];
+    } else {
+        for (u32 k = tid; k < buf_length; k += nthr) d[k] = s[k];
+    }
 }
 
 }  // namespace lzss

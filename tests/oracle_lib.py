@@ -338,6 +338,17 @@ def ref_cudpp():
     return lib
 
 
+def ref_cudpp_gpu():
+    """The reference's own Huffman kernels for sm_100a (oracle/_ref/libref_cudpp_gpu.so); needs a GPU."""
+    if "ref_cudpp_gpu" in _cache:
+        return _cache["ref_cudpp_gpu"]
+    lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libref_cudpp_gpu.so"))
+    lib.ref_cudpp_huffman_gpu.restype = C.c_int
+    lib.ref_cudpp_huffman_gpu.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _cache["ref_cudpp_gpu"] = lib
+    return lib
+
+
 def cudpp_test_vector(n=1 << 20, seed=95835, lo=1, span=255, sentinel=True):
     """The reference test input: srand(seed); bytes rand() % span + lo; for the compress test
     the last byte is a 0 sentinel (test_compress.cpp:552-556,687-692).  glibc rand()."""

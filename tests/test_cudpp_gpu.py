@@ -212,6 +212,36 @@ def test_cudpp_named_entry_points():
     assert L.cudppDestroy(mgr) == 0
 
 
+@pytest.mark.skipif(not O.have_ref("cudpp_gpu"), reason="oracle/_ref/libref_cudpp_gpu.so not built")
+@pytest.mark.parametrize("kind,seed", [("zipf", 21), ("text", 22), ("markov", 23), ("vector", 95835)])
+def test_reference_huffman_kernels_write_the_same_words(kind, seed):
+    """The reference's own huffman_build_histogram / _build_tree / huffman_kernel_en /
+    huffman_datapack kernels (compress_kernel.cuh:2037-2750, compiled for sm_100a, launched as
+    compress_app.cu:65-125 does) on the MTF bytes of a 1 MiB block: histogram, block offsets, size
+    and every compressed word equal the product's and the oracle's."""
+    data = O.cudpp_test_vector() if kind == "vector" else O.cudpp_block(MIB, kind, seed=seed)
+    bwt, _ = O.cudpp_oracle_bwt(data)
+    mtf = O.cudpp_oracle_mtf(bwt)
+    d_mtf = _dev(mtf)
+    d_hist = torch.zeros(256, dtype=torch.int32, device=DEV)
+    d_off = torch.zeros(256, dtype=torch.int32, device=DEV)
+    d_size = torch.zeros(1, dtype=torch.int32, device=DEV)
+    d_comp = torch.zeros(256 * 1537, dtype=torch.int32, device=DEV)
+    torch.cuda.synchronize()
+    assert O.ref_cudpp_gpu().ref_cudpp_huffman_gpu(d_mtf.data_ptr(), MIB, d_hist.data_ptr(), d_off.data_ptr(),
+                                                   d_size.data_ptr(), d_comp.data_ptr()) == 0
+    rc, whist, woffs, wwords = O.cudpp_oracle_huffman(mtf)
+    assert rc == 0
+    nw = int(d_size.cpu()[0])
+    assert nw == wwords.size
+    assert np.array_equal(d_hist.cpu().numpy().view(np.uint32), whist)
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint32), woffs)
+    assert np.array_equal(d_comp.cpu().numpy()[:nw].view(np.uint32), wwords)
+    res = b200lc.cudpp_compress_batch(_dev(data), 1, MIB)
+    assert int(res.total_words.cpu()[0]) == nw
+    assert torch.equal(res.words[:nw], d_comp[:nw]) and torch.equal(res.offsets.view(-1)[:256], d_off)
+
+
 @pytest.mark.parametrize("n", [1, 1000, MIB, MIB + 5])
 def test_cudpp_radix_sort_is_the_sort_of_the_reference_tests_decoder(n):
     """cudppRadixSort as apps/cudpp_testrig/test_compress.cpp:318-344 calls it: plan
