@@ -483,6 +483,8 @@ def c4_strong(pkg, dev, rank, world, total_blocks):
     lo, hi = shard.plan_blocks(total_blocks, world)[rank]
     torch.cuda.synchronize()
     if world > 1:
+        # the first all_gather of a communicator sets up its channels (10 ms): not part of the step
+        shard.gather_offsets(torch.ones(hi - lo, dtype=torch.int64, device=dev), total_blocks)
         dist.barrier()
     t = _events(2)
     t[0].record()
@@ -701,11 +703,19 @@ def run_ours(args, rank, world, local_rank):
         raise errors[0]
     assert torch.equal(h_outs[0], h_in) and torch.equal(h_outs[1], h_in), "e2e round trip mismatch after the timed region"
     nu = nus[-1]
-    # serial figure (one session, encode then decode) for comparison with round 1
+    # serial figure: one session, encode then decode, step after step (round 1's e2e).  With many
+    # ranks on one host the copies of ONE step per rank already saturate the host's memory path
+    # and four sessions per rank only add contention (N = 8: 58.9 GB/s serial, 37.7 pipelined), so
+    # both are measured and `e2e.value` is the better of the two, named in `e2e.mode`.
+    serial_steps = max(2, e2e_steps // 4)
+    barrier()
     t0 = time.perf_counter()
-    nu1 = s_enc[0].encode(h_in, h_units[0], h_codes[0], h_lens[0], h_luts[0], MAX_LEN)
-    s_enc[0].decode(h_units[0], nu1 + 1, h_luts[0], h_outs[0], MAX_LEN)
-    e2e_serial_s = time.perf_counter() - t0
+    for _ in range(serial_steps):
+        nu1 = s_enc[0].encode(h_in, h_units[0], h_codes[0], h_lens[0], h_luts[0], MAX_LEN)
+        s_enc[0].decode(h_units[0], nu1 + 1, h_luts[0], h_outs[0], MAX_LEN)
+    torch.cuda.synchronize()
+    e2e_serial_s = (time.perf_counter() - t0) / serial_steps
+    assert torch.equal(h_outs[0], h_in), "e2e round trip mismatch (serial)"
     for s_ in s_enc + s_dec:
         s_.close()
     del h_units, h_outs
@@ -765,8 +775,10 @@ def run_ours(args, rank, world, local_rank):
                      "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak, "traffic": traffic,
                      "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes": dec_bytes, "launch_ms": dec_mean},
-        "e2e": {"value": world * n / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+        "e2e": {"value": world * n / min(e2e_s, e2e_serial_s) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "mode": "pipelined" if e2e_s <= e2e_serial_s else "serial",
+                "pipelined_value": world * n / e2e_s / 1e9,
                 "serial_value": world * n / e2e_serial_s / 1e9,
                 "api": "b200lc_cuhd_session_encode + b200lc_cuhd_session_decode, pinned host buffers; two "
                        "encode and two decode sessions, one host thread each, free-running over the steps "

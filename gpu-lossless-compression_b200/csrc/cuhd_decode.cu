@@ -122,6 +122,7 @@ __device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v)
 // array still cost one IADD3 per step.  Hence ONE inlined call site for pass A in the kernel.
 struct Tables {
     const u32 *wtab;     // write pass: <= 3 symbols per entry, window LM bits (write_entry3)
+    smem_addr wtab_s;    //   the same as a 32-bit shared address (walk_write3)
     const u8 *mtab;      // counting: <= 3 codewords per entry, window LM bits
     const u8 *stab;      // counting: 1 codeword per entry, window L bits
     u32 shift, shift_m;  // 32 - L, 32 - LM
@@ -269,7 +270,7 @@ __device__ __forceinline__ u64 segment_pass_a(const Segment &g, const Tables &tb
 // index of the segment's first symbol.
 template <int K>
 __device__ __forceinline__ void segment_pass_b(const Segment &g, const Tables &tb, const u16 *saved,
-                                               u8 *stage, u8 *out, u64 n_out, u64 gstart)
+                                               u8 *stage, smem_addr stage_s, u8 *out, u64 n_out, u64 gstart)
 {
     const u32 lane = threadIdx.x & 31;
     if (g.seg_subs == 0 || gstart >= n_out) return;
@@ -297,7 +298,7 @@ __device__ __forceinline__ void segment_pass_b(const Segment &g, const Tables &t
             const u32 d0 = fill + pre - lo;
             u32 pend = 0;
             if (fast)
-                pend = walk_write3<S>(u, tb.wtab, tb.shift_m, my_start, my_cnt, stage, d0,
+                pend = walk_write3<S>(u, tb.wtab_s, tb.shift_m, my_start, my_cnt, stage_s, d0,
                                       walk_write3_head(stage, d0, fill));
             __syncwarp();
             // bytes that share a word with a neighbour's first word, and the rare lane that
@@ -371,7 +372,12 @@ __global__ void __launch_bounds__(kThreads, 2) cuhd_decode_kernel(const DecodePa
         mtab[i] = (u8)(e >> 24);       // == count_entry(p.lut, i, L, LM, 3)
     }
     Tables tb;
+    const smem_addr smem_base = smem_of(smem_raw);
     tb.wtab = wtab; tb.mtab = mtab; tb.stab = stab;
+    tb.wtab_s = smem_base + (smem_addr)(reinterpret_cast<unsigned char *>(wtab) - smem_raw);
+    // keep the address in a register: the compiler otherwise rebuilds the shared window base
+    // (S2R SR_CgaCtaId, MOV, LEA) in front of every 32-bit unit of the write walk
+    asm volatile("mov.u32 %0, %0;" : "+r"(tb.wtab_s));
     tb.shift = 32 - L; tb.shift_m = 32 - LM;
 
     if (tid == 0) {
@@ -562,7 +568,8 @@ __global__ void __launch_bounds__(kThreads, 2) cuhd_decode_kernel(const DecodePa
             u64 gstart = sm.base;                    // output index of my segment's first symbol
             for (u32 w = 0; w < warp; ++w) gstart += sm.wt[pb3][w];
             const Segment g = make_segment<K>(V, lp, warp);
-            segment_pass_b<K>(g, tb, &sm.saved[pb2][warp][0][0], sm.stage[warp], V.out, V.n_out, gstart);
+            segment_pass_b<K>(g, tb, &sm.saved[pb2][warp][0][0], sm.stage[warp],
+                              smem_base + (smem_addr)(sm.stage[warp] - smem_raw), V.out, V.n_out, gstart);
         }
         have_prev = have_cur;
         ppiece = piece;

@@ -113,8 +113,16 @@ __global__ void __launch_bounds__(kThreads) cuhd_encode_kernel(const EncParams p
     const u32 lane = tid & 31;
 
     if (tid < 256) {
-        sm.tab[tid] = p.code_of_symbol[tid] | ((u32)p.len_of_symbol[tid] << 16);
-        sm.len8[tid] = p.len_of_symbol[tid];
+        // the staging buffer and the two-symbols-per-step pack are sized for codes of <= 13 bits: a
+        // longer entry in a caller-supplied dictionary is reported through the overflow flag and
+        // clamped (the output of such a call is not a valid stream) instead of overrunning
+        u32 len = p.len_of_symbol[tid];
+        if (len > 13) {
+            atomicExch(p.overflow, 1u);
+            len = 13;
+        }
+        sm.tab[tid] = (p.code_of_symbol[tid] & ((1u << len) - 1u)) | (len << 16);
+        sm.len8[tid] = (u8)len;
     }
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);

@@ -353,6 +353,26 @@ B200LC_HD u32 write_entry3(const u16 *lut, u32 i, u32 L, u32 LW)
 
 B200LC_HD u32 rotl32(u32 x, u32 s) { return fsl(x, x, s); }
 
+// Shared-memory accesses of the packed write walk through 32-bit shared addresses on the device:
+// with generic pointers the compiler rebuilt the shared window base (S2R SR_CgaCtaId + LEA) in every
+// unit loop and added base + offset in front of every staging store.
+#if defined(__CUDA_ARCH__)
+typedef u32 smem_addr;
+__device__ __forceinline__ smem_addr smem_of(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 smem_ld32(smem_addr a)
+{
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void smem_st32(smem_addr a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+#else
+typedef uintptr_t smem_addr;
+inline smem_addr smem_of(const void *p) { return reinterpret_cast<uintptr_t>(p); }
+inline u32 smem_ld32(smem_addr a) { return *reinterpret_cast<const u32 *>(a); }
+inline void smem_st32(smem_addr a, u32 v) { *reinterpret_cast<u32 *>(a) = v; }
+#endif
+
 // Phase 1 of the packed write: the `cnt` symbols of the subsequence entered at bit `a` go to
 // stage[d0 .. d0 + cnt) (stage 4-byte aligned).  Stores every word that fills up, INCLUDING the
 // first one whose bytes below d0 are zero -- they belong to the lanes in front, which hold them
@@ -362,13 +382,13 @@ B200LC_HD u32 rotl32(u32 x, u32 s) { return fsl(x, x, s); }
 // will store again (bytes carried over from the previous staging round), else 0.  Returns the
 // pending bytes (word (d0 + cnt) >> 2).
 template <int S>
-B200LC_HD u32 walk_write3(const u32 (&u)[S + 1], const u32 *tab3, u32 shift_w, u32 a, u32 cnt, u8 *stage,
+B200LC_HD u32 walk_write3(const u32 (&u)[S + 1], smem_addr tab, u32 shift_w, u32 a, u32 cnt, smem_addr stage,
                           u32 d0, u32 buf0)
 {
     u32 acc = a, buf = buf0;
     u32 pow = 1u << (8 * (d0 & 3u));
-    const u32 wo0 = d0 & ~3u;
-    u32 wo = wo0;                                      // byte offset of the word being filled
+    const smem_addr wa0 = stage + (d0 & ~3u);
+    smem_addr wa = wa0;                                // address of the word being filled
 #define B200LC_EMIT3(e, syms, r)                                           \
     {                                                                      \
         const unsigned long long prod = (unsigned long long)(syms) * pow;  \
@@ -376,8 +396,8 @@ B200LC_HD u32 walk_write3(const u32 (&u)[S + 1], const u32 *tab3, u32 shift_w, u
         const u32 pow2 = rotl32(pow, (r));                                 \
         buf = lo;                                                          \
         if (pow2 < pow) {                                                  \
-            *reinterpret_cast<u32 *>(stage + wo) = lo;                     \
-            wo += 4;                                                       \
+            smem_st32(wa, lo);                                             \
+            wa += 4;                                                       \
             buf = (u32)(prod >> 32);                                       \
         }                                                                  \
         pow = pow2;                                                        \
@@ -387,7 +407,7 @@ B200LC_HD u32 walk_write3(const u32 (&u)[S + 1], const u32 *tab3, u32 shift_w, u
         const u32 cur = u[j], nxt = u[j + 1];
         while (!(acc & 32u)) {
             const u32 w = fsl(nxt, cur, acc);
-            const u32 e = tab3[w >> shift_w];
+            const u32 e = smem_ld32(tab + 4 * (smem_addr)(w >> shift_w));
             acc += e >> 24;
             B200LC_EMIT3(e, e & 0xffffffu, (e >> 27) & 0x18u)
         }
@@ -398,15 +418,15 @@ B200LC_HD u32 walk_write3(const u32 (&u)[S + 1], const u32 *tab3, u32 shift_w, u
         const u32 lim = shift_w;                       // 32 - LW: every codeword of the window starts inside
         while ((acc & 63u) <= lim) {
             const u32 w = fsl(nxt, cur, acc);
-            const u32 e = tab3[w >> shift_w];
+            const u32 e = smem_ld32(tab + 4 * (smem_addr)(w >> shift_w));
             acc += e >> 24;
             B200LC_EMIT3(e, e & 0xffffffu, (e >> 27) & 0x18u)
         }
         const u32 k = (31u - clz32(pow)) >> 3;
-        u32 rem = cnt - ((wo - wo0) + k - (d0 & 3u));
+        u32 rem = cnt - ((u32)(wa - wa0) + k - (d0 & 3u));
         while ((int)rem > 0 && !(acc & 32u)) {
             const u32 w = fsl(nxt, cur, acc);
-            const u32 e = tab3[w >> shift_w];
+            const u32 e = smem_ld32(tab + 4 * (smem_addr)(w >> shift_w));
             acc += e >> 24;
             u32 n = e >> 30;
             if (n > rem) n = rem;

@@ -452,7 +452,9 @@ __global__ void __launch_bounds__(256) culzss_scan_kernel(const u16 *__restrict_
     __syncthreads();
     const bool took_more = total - last_group_size[(u64)b * npk + npk - 1] > buf_length;
     const u32 clen = total + 2 * npk + 6;
-    if (took_more || clen > out_stride) {
+    // clen == buf_length would be read back as a stored (raw) buffer by every decoder of the
+    // container, the reference's included (culzss.c:241-242, deculzss.c:94-95): store it raw
+    if (took_more || clen > out_stride || clen == buf_length) {
         if (tx == 0) comp_len[b] = 0;   // caller stores the buffer raw (culzss.c:177-183)
         return;
     }

@@ -111,6 +111,26 @@ extern "C" void deleteGPUStreams(void)
     g_init = false;
 }
 
+// B200LC_CULZSS_FAST=1|2|4 makes the reference-named wrappers and the container writer use the
+// NON-PARITY fast encoder mode (same format, other matches); unset = the reference's bytes.
+static int fast_depth()
+{
+    static int d = -1;
+    if (d < 0) {
+        const char *e = getenv("B200LC_CULZSS_FAST");
+        const int v = e ? atoi(e) : 0;
+        d = (v == 1 || v == 2 || v == 4) ? v : 0;
+    }
+    return d;
+}
+static int encode_any(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out, size_t stride,
+                      uint32_t *d_len, void *scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    const int d = fast_depth();
+    return d ? b200lc_culzss_encode_fast_batch(d_in, nbuf, buf_length, d_out, stride, d_len, scratch, scratch_bytes, d, st)
+             : b200lc_culzss_encode_batch(d_in, nbuf, buf_length, d_out, stride, d_len, scratch, scratch_bytes, st);
+}
+
 // bufferout layout handed from compression_kernel_wrapper to aftercompression_wrapper:
 //   [0,4) compressed size incl. trailer, 0 = "compression took more"; [16, 16 + size) the buffer.
 extern "C" int compression_kernel_wrapper(unsigned char *buffer, int buf_length,
@@ -129,7 +149,7 @@ extern "C" int compression_kernel_wrapper(unsigned char *buffer, int buf_length,
     if (!ok(cudaMemcpyAsync(in_d, buffer, (size_t)buf_length, cudaMemcpyHostToDevice, st), "H2D")) return 0;
     // out_d holds 2 * buf_length bytes: more than the worst-case compressed buffer
     const size_t stride = 2 * (size_t)buf_length;
-    if (b200lc_culzss_encode_batch(in_d, 1, (size_t)buf_length, out_d, stride, g_len_d[index],
+    if (encode_any(in_d, 1, (size_t)buf_length, out_d, stride, g_len_d[index],
                                    g_scratch[index], g_scratch_bytes[index], st) != B200LC_OK)
         return 0;
     const size_t max_comp = (size_t)buf_length + 2 * ((size_t)buf_length / 4096) + 6 + 32;
@@ -235,7 +255,7 @@ extern "C" int b200lc_culzss_compress_container(const uint8_t *h_in, size_t n, u
             !ok(cudaMemset(d_in + n, 0, padding), "memset"))
             rc = B200LC_ERR_CUDA;
     }
-    if (rc == B200LC_OK) rc = b200lc_culzss_encode_batch(d_in, nb, kBuf, d_out, stride, d_len, d_scratch, sb, st);
+    if (rc == B200LC_OK) rc = encode_any(d_in, nb, kBuf, d_out, stride, d_len, d_scratch, sb, st);
     if (rc == B200LC_OK && !ok(cudaMemcpy(len.data(), d_len, nb * 4, cudaMemcpyDeviceToHost), "D2H"))
         rc = B200LC_ERR_CUDA;
     if (rc == B200LC_OK) {

@@ -363,7 +363,7 @@ int main(int argc, char **argv)
                     u32 un[S + 1];
                     memcpy(un, &units[(size_t)l * S], sizeof(un));
                     const u32 d0 = fill + pre[l] - lo;
-                    pend[l] = walk_write3<S>(un, tab3.data(), 32 - LW, entry[l], cnt[l], stage.data(), d0,
+                    pend[l] = walk_write3<S>(un, smem_of(tab3.data()), 32 - LW, entry[l], cnt[l], smem_of(stage.data()), d0,
                                              walk_write3_head(stage.data(), d0, fill));
                 }
                 std::shuffle(order, order + nl, rng);
