@@ -306,6 +306,10 @@ def path_culzss(pkg, dev, rank, world, mib, peak, with_cpu):
     out = torch.empty(nbuf * stride, dtype=torch.uint8, device=dev)
     clen = torch.empty(nbuf, dtype=torch.int32, device=dev)
     scratch = torch.empty(L.b200lc_culzss_encode_scratch_bytes(nbuf, buf), dtype=torch.uint8, device=dev)
+    # fast mode (NON-PARITY: the reference's format, not the reference encoder's bytes), hash-chain depth 1
+    fast_ms = _best_ms(lambda: pkg.culzss_encode(data, buf, out, clen, scratch, fast=1), iters=2, warm=1)
+    fcl = clen.cpu().numpy().astype(np.int64)
+    fast_bytes = int(np.where(fcl == 0, buf, fcl).sum())
     enc_ms = _best_ms(lambda: pkg.culzss_encode(data, buf, out, clen, scratch), iters=2, warm=1)
     cl = clen.cpu().numpy().astype(np.int64)
     sizes = np.where(cl == 0, buf, cl)
@@ -352,8 +356,8 @@ def path_culzss(pkg, dev, rank, world, mib, peak, with_cpu):
         e2e_s = min(e2e_s, time.perf_counter() - t0)
     assert blen.value == h_in.size and np.array_equal(h_back, h_in), "CULZSS container round trip mismatch"
 
-    enc_max, dec_max, e2e_max = _reduce_max([enc_ms, dec_ms, e2e_s], dev, world)
-    (csum,) = _reduce_sum([float(cbytes)], dev, world)
+    enc_max, dec_max, e2e_max, fast_max = _reduce_max([enc_ms, dec_ms, e2e_s, fast_ms], dev, world)
+    csum, fsum = _reduce_sum([float(cbytes), float(fast_bytes)], dev, world)
     res = {
         "workload": "CULZSS encode+decode, %d MiB of cuSZ-like int32 quantisation codes per GPU, 1 MiB buffers, "
                     "4 KiB packets, W = 128 (bit-exact parity mode)" % mib,
@@ -366,6 +370,11 @@ def path_culzss(pkg, dev, rank, world, mib, peak, with_cpu):
         "encode_roofline": {"kernel": "culzss_encode_kernel", "bound": "integer issue (parity mode), reported against hbm",
                             "achieved": (n + cbytes) / enc_ms / 1e6, "peak": peak, "unit": "GB/s",
                             "frac": (n + cbytes) / enc_ms / 1e6 / peak},
+        "fast_mode_non_parity": {"encode_gbs": world * n / fast_max / 1e6, "encode_ms": fast_max, "ratio": world * n / fsum,
+                                 "depth": 1, "frac": (n + fast_bytes) / fast_ms / 1e6 / peak,
+                                 "note": "b200lc_culzss_encode_fast_batch: same buffer/token format (decodes with the "
+                                         "reference DecodeKernel), hash-chain match finder, NOT bit-exact with the "
+                                         "reference encoder"},
         "e2e": {"value": world * h_in.size / e2e_max / 1e9, "unit": "GB/s", "sample_mib": e2e_mib,
                 "h2d_bytes_per_step": int(h_in.size + olen.value), "d2h_bytes_per_step": int(h_in.size + olen.value),
                 "api": "b200lc_culzss_compress_container + _decompress_container, host buffers"},
