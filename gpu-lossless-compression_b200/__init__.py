@@ -329,6 +329,9 @@ class CuhdSession:
 
 
 # ------------------------------------------------------------------------------- CULZSS
+CULZSS_FAST_LANE = -1      # include/b200lc.h B200LC_CULZSS_FAST_LANE
+
+
 def culzss_out_stride(buf_length):
     return (buf_length + buf_length // 8 + 1024 + 15) // 16 * 16
 
@@ -337,7 +340,8 @@ def culzss_encode(data, buf_length=1 << 20, out=None, comp_len=None, scratch=Non
     """LZSS-encode a cuda uint8 tensor of nbuf * buf_length bytes.  Returns (out, comp_len):
     out[b * stride : b * stride + comp_len[b]] is buffer b incl. trailer; comp_len[b] == 0 means
     "store raw".  Asynchronous.  fast = 1, 2 or 4: the NON-PARITY fast mode
-    (b200lc_culzss_encode_fast_batch, hash-chain depth), same format, different matches."""
+    (b200lc_culzss_encode_fast_batch, hash-chain depth), same format, different matches;
+    fast = "lane" (CULZSS_FAST_LANE = -1): its packet-per-lane formulation, also NON-PARITY."""
     import torch
     assert data.is_cuda and data.dtype == torch.uint8 and data.is_contiguous()
     assert data.numel() % buf_length == 0
@@ -351,6 +355,8 @@ def culzss_encode(data, buf_length=1 << 20, out=None, comp_len=None, scratch=Non
     need = L.b200lc_culzss_encode_scratch_bytes(nbuf, buf_length)
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty(need, dtype=torch.uint8, device=data.device)
+    if fast == "lane":
+        fast = CULZSS_FAST_LANE
     if fast:
         check(L.b200lc_culzss_encode_fast_batch(data.data_ptr(), nbuf, buf_length, out.data_ptr(), stride,
                                                 comp_len.data_ptr(), scratch.data_ptr(), scratch.numel(),

@@ -20,6 +20,7 @@
 //     output staging unified in one bank-private shared-memory ring per lane, 16-byte global
 //     accesses, and input refills / output flushes at fixed points of the token loop.
 #include "common.cuh"
+#include "culzss_lane.cuh"
 #include "../../include/b200lc.h"
 
 namespace b200lc {
@@ -423,6 +424,66 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
     }
 }
 
+// ====================================================================================== encode, lane mode
+// FAST MODE, second formulation (NON-PARITY, csrc/culzss_lane.cuh): one packet per LANE.  A lane
+// parses its packet greedily through a private 128-entry hash of three-byte prefixes, emits tokens
+// and flag bytes as it goes and streams the result to the packet's slot -- no CTA barrier, no
+// token arrays, no separate selection and packing passes.  All per-lane state sits in
+// shared-memory columns laid out [word][lane] (one wavefront per access whatever the 32 packets
+// of a warp are doing).  Input travels global -> registers (one 16-byte chunk ahead of its use,
+// the line after next prefetched into L2) -> ring; output ring -> 16-byte stores.
+constexpr int kLaneWarps = 4;
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+__global__ void __launch_bounds__(kLaneWarps * 32) culzss_encode_lane_kernel(const u8 *__restrict__ in, u64 npackets,
+                                                                            u8 *__restrict__ tmp_out,
+                                                                            u16 *__restrict__ pkt_size,
+                                                                            u8 *__restrict__ last_group_size)
+{
+    using namespace lzss_lane;
+    extern __shared__ __align__(16) u32 lane_cols[];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 pid = (u64)blockIdx.x * (kLaneWarps * 32) + threadIdx.x;
+    const bool live = pid < npackets;
+    const u64 pk = live ? pid : npackets - 1;         // idle lanes keep valid addresses
+    Lane<32> ln;
+    ln.init(lane_cols + warp * (kColumnWords * 32) + lane, in + pk * kPacket, tmp_out + pk * (u64)kSlotBytes);
+    if (!live) { ln.p = kPacket; ln.hi = kPacket; }
+    uint4 pf = make_uint4(0, 0, 0, 0);
+    if (live) {
+        pf = __ldg(reinterpret_cast<const uint4 *>(ln.src));
+        prefetch_l2(ln.src + 128);
+        prefetch_l2(ln.src + 256);
+    }
+    for (;;) {
+        while (ln.wants_input()) {
+            ln.put_input(pf.x, pf.y, pf.z, pf.w);
+            if (ln.hi < kPacket) pf = __ldg(reinterpret_cast<const uint4 *>(ln.src + ln.hi));
+            if ((ln.hi & 127u) == 0 && ln.hi + 256u < kPacket) prefetch_l2(ln.src + ln.hi + 256u);
+        }
+        const bool more = ln.p < kPacket;
+        if (!__any_sync(0xffffffffu, more)) break;
+        if (more) ln.step();
+        if (ln.has_output()) {
+            uint4 v;
+            uint4 *g = reinterpret_cast<uint4 *>(ln.dst + ln.flushed);
+            ln.take_output(v.x, v.y, v.z, v.w);
+            *g = v;
+        }
+    }
+    if (live) {
+        ln.finish();
+        while (ln.flushed < ln.o) {
+            uint4 v;
+            uint4 *g = reinterpret_cast<uint4 *>(ln.dst + ln.flushed);
+            ln.take_output(v.x, v.y, v.z, v.w);
+            *g = v;
+        }
+        pkt_size[pid] = (u16)ln.o;
+        last_group_size[pid] = (u8)ln.last_group_bytes();
+    }
+}
+
 // Per buffer: packet offsets (exclusive scan of the packet sizes), the trailer
 // (gpu_compress.cu:624-657) and the "compression took more" decision, exactly like aftercomp's
 // `if (j > finish)` test (:494-498): the test runs before every token, so it fires iff the
@@ -803,6 +864,7 @@ static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uin
                                   lzss::culzss_encode_kernel<2>, lzss::culzss_encode_kernel<4>};
     int ki;
     switch (depth) {
+        case B200LC_CULZSS_FAST_LANE: ki = -1; break;
         case 0: ki = 0; break;
         case 1: ki = 1; break;
         case 2: ki = 2; break;
@@ -816,6 +878,21 @@ static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uin
     u8 *lastg = reinterpret_cast<u8 *>(sizes) + ((npk * 2 + 255) & ~u64(255));
     u32 *pkoff = reinterpret_cast<u32 *>(lastg + ((npk + 255) & ~u64(255)));
 
+    if (ki < 0) {
+        // lane mode: one packet per lane, 448 bytes of shared-memory columns per lane
+        const size_t lsmem = (size_t)lzss::kLaneWarps * 32 * lzss_lane::kColumnWords * 4;
+        static unsigned lane_attr_done[kMaxDevices] = {0};
+        const int lslot = device_slot();
+        if (lslot < 0 || lane_attr_done[lslot] != context_epoch()) {
+            B200LC_CUDA_TRY(cudaFuncSetAttribute(lzss::culzss_encode_lane_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+            if (lslot >= 0) lane_attr_done[lslot] = context_epoch();
+        }
+        const u32 per_cta = lzss::kLaneWarps * 32;
+        lzss::culzss_encode_lane_kernel<<<(u32)((npk + per_cta - 1) / per_cta), per_cta, lsmem, stream>>>(
+            d_in, npk, tmp, sizes, lastg);
+        B200LC_CUDA_TRY(cudaGetLastError());
+    } else {
     // fast mode keeps its hash table (1024 x 16 bytes) behind EncSmem
     const size_t smem = ((sizeof(lzss::EncSmem) + 15) & ~size_t(15)) + (depth ? (size_t(16) << 10) : 0);
     static unsigned attr_done[kMaxDevices][4] = {{0}};   // context epoch the attribute was set in
@@ -827,6 +904,7 @@ static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uin
     const u32 grid = (u32)min(npk, (u64)num_sms() * 64);
     kerns[ki]<<<grid, 128, smem, stream>>>(d_in, npk, tmp, sizes, lastg);
     B200LC_CUDA_TRY(cudaGetLastError());
+    }
     lzss::culzss_scan_kernel<<<(u32)nbuf, 256, 0, stream>>>(sizes, lastg, npk_buf, (u32)buf_length,
                                                            d_out, out_stride, pkoff, d_comp_len);
     B200LC_CUDA_TRY(cudaGetLastError());

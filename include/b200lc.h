@@ -199,7 +199,14 @@ int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_leng
  * (gpu_decompress.cu:164-242) and with b200lc_culzss_decode_batch, but the match finder is a
  * shared-memory hash chain over three-byte prefixes that looks at the `depth` (1, 2 or 4) most
  * recent candidates instead of the reference's exhaustive streak scanner: ~20-35x the throughput of
- * parity mode for a 10-25 % larger output.  Same arguments otherwise. */
+ * parity mode for a 10-25 % larger output.  Same arguments otherwise.
+ *
+ * depth = B200LC_CULZSS_FAST_LANE selects the second fast formulation (also NON-PARITY, same
+ * format): one packet per GPU lane, a greedy parse through a lane-private 128-entry hash of
+ * three-byte prefixes with tokens and flag bytes emitted in the same serial walk
+ * (csrc/culzss_lane.cuh).  Matches are at most 108 bytes long.  It needs >= ~10^5 packets in flight
+ * to fill the GPU (one packet per lane), i.e. it is the mode for large batches. */
+#define B200LC_CULZSS_FAST_LANE (-1)
 int b200lc_culzss_encode_fast_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out,
                                     size_t out_stride, uint32_t *d_comp_len, void *d_scratch,
                                     size_t scratch_bytes, int depth, void *stream);

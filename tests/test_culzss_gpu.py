@@ -351,7 +351,7 @@ def _walk_tokens(comp, n):
     return matches
 
 
-@pytest.mark.parametrize("depth", [1, 2, 4])
+@pytest.mark.parametrize("depth", [1, 2, 4, "lane"])
 @pytest.mark.parametrize("name", ["quant32", "quant16", "spaces", "zeros", "text", "mix", "carets", "ramp"])
 def test_fast_mode_streams_decode_everywhere(name, depth):
     data = _cases()[name]
@@ -380,7 +380,7 @@ def test_fast_mode_incompressible_buffer_is_stored_raw_and_small_buffers():
 
 
 @pytest.mark.skipif(not O.have_ref("culzss"), reason="oracle/_ref/libref_culzss.so not built")
-@pytest.mark.parametrize("depth", [1, 2, 4])
+@pytest.mark.parametrize("depth", [1, 2, 4, "lane"])
 def test_fast_mode_streams_decode_with_the_reference_kernel(depth):
     """The reference's own DecodeKernel (gpu_decompress.cu:164-242, sm_100a build) on fast-mode output."""
     ref = O.ref_culzss()
