@@ -432,8 +432,27 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
 // shared-memory columns laid out [word][lane] (one wavefront per access whatever the 32 packets
 // of a warp are doing).  Input travels global -> registers (one 16-byte chunk ahead of its use,
 // the line after next prefetched into L2) -> ring; output ring -> 16-byte stores.
-constexpr int kLaneWarps = 4;
+constexpr int kLaneWarps = 2;      // 12 KiB of columns per warp: nine CTAs = 18 warps per SM
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+struct LaneDevIO {
+    const u8 *src;      // the packet (16-byte aligned)
+    u8 *dst;            // its output slot (16-byte aligned, kSlotBytes)
+    __device__ __forceinline__ bool any(bool b) const { return __any_sync(0xffffffffu, b) != 0; }
+    __device__ __forceinline__ void load(u32 off, lzss_lane::Chunk32 &c) const
+    {
+        const uint4 *g = reinterpret_cast<const uint4 *>(src + off);
+        const uint4 a = __ldg(g), b = __ldg(g + 1);
+        c.w[0] = a.x; c.w[1] = a.y; c.w[2] = a.z; c.w[3] = a.w;
+        c.w[4] = b.x; c.w[5] = b.y; c.w[6] = b.z; c.w[7] = b.w;
+        // the line after next, once per 128-byte line
+        if ((off & 127u) == 0 && off + 256u < lzss_lane::kPacket) prefetch_l2(src + off + 256u);
+    }
+    __device__ __forceinline__ void store(u32 off, const u32 (&x)[4]) const
+    {
+        *reinterpret_cast<uint4 *>(dst + off) = make_uint4(x[0], x[1], x[2], x[3]);
+    }
+};
 
 __global__ void __launch_bounds__(kLaneWarps * 32) culzss_encode_lane_kernel(const u8 *__restrict__ in, u64 npackets,
                                                                             u8 *__restrict__ tmp_out,
@@ -446,41 +465,13 @@ __global__ void __launch_bounds__(kLaneWarps * 32) culzss_encode_lane_kernel(con
     const u64 pid = (u64)blockIdx.x * (kLaneWarps * 32) + threadIdx.x;
     const bool live = pid < npackets;
     const u64 pk = live ? pid : npackets - 1;         // idle lanes keep valid addresses
-    Lane<32> ln;
-    ln.init(lane_cols + warp * (kColumnWords * 32) + lane, in + pk * kPacket, tmp_out + pk * (u64)kSlotBytes);
-    if (!live) { ln.p = kPacket; ln.hi = kPacket; }
-    uint4 pf = make_uint4(0, 0, 0, 0);
+    LaneDevIO io{in + pk * kPacket, tmp_out + pk * (u64)kSlotBytes};
+    if (live) prefetch_l2(io.src + 128);
+    u32 last_group = 0;
+    const u32 size = encode_packet<32>(lane_cols + warp * (kColumnWords * 32) + lane, live, io, last_group);
     if (live) {
-        pf = __ldg(reinterpret_cast<const uint4 *>(ln.src));
-        prefetch_l2(ln.src + 128);
-        prefetch_l2(ln.src + 256);
-    }
-    for (;;) {
-        while (ln.wants_input()) {
-            ln.put_input(pf.x, pf.y, pf.z, pf.w);
-            if (ln.hi < kPacket) pf = __ldg(reinterpret_cast<const uint4 *>(ln.src + ln.hi));
-            if ((ln.hi & 127u) == 0 && ln.hi + 256u < kPacket) prefetch_l2(ln.src + ln.hi + 256u);
-        }
-        const bool more = ln.p < kPacket;
-        if (!__any_sync(0xffffffffu, more)) break;
-        if (more) ln.step();
-        if (ln.has_output()) {
-            uint4 v;
-            uint4 *g = reinterpret_cast<uint4 *>(ln.dst + ln.flushed);
-            ln.take_output(v.x, v.y, v.z, v.w);
-            *g = v;
-        }
-    }
-    if (live) {
-        ln.finish();
-        while (ln.flushed < ln.o) {
-            uint4 v;
-            uint4 *g = reinterpret_cast<uint4 *>(ln.dst + ln.flushed);
-            ln.take_output(v.x, v.y, v.z, v.w);
-            *g = v;
-        }
-        pkt_size[pid] = (u16)ln.o;
-        last_group_size[pid] = (u8)ln.last_group_bytes();
+        pkt_size[pid] = (u16)size;
+        last_group_size[pid] = (u8)last_group;
     }
 }
 

@@ -111,15 +111,18 @@ extern "C" void deleteGPUStreams(void)
     g_init = false;
 }
 
-// B200LC_CULZSS_FAST=1|2|4 makes the reference-named wrappers and the container writer use the
+// B200LC_CULZSS_FAST=1|2|4|lane makes the reference-named wrappers and the container writer use the
 // NON-PARITY fast encoder mode (same format, other matches); unset = the reference's bytes.
 static int fast_depth()
 {
-    static int d = -1;
-    if (d < 0) {
+    static int d = 0;
+    static bool read = false;
+    if (!read) {
         const char *e = getenv("B200LC_CULZSS_FAST");
         const int v = e ? atoi(e) : 0;
         d = (v == 1 || v == 2 || v == 4) ? v : 0;
+        if (e && (!strcmp(e, "lane") || v == B200LC_CULZSS_FAST_LANE)) d = B200LC_CULZSS_FAST_LANE;
+        read = true;
     }
     return d;
 }

@@ -10,9 +10,17 @@
 // Per lane (STRIDE = 32 words on the GPU: word w of a lane's column sits at column[w * 32], so a
 // lane only ever touches its own shared-memory bank; STRIDE = 1 on the host):
 //   ring   256 bytes   input bytes of positions [hi - 256, hi), index = position & 255; holds the
-//                      128-byte window behind p and >= kLaneMaxLen + 3 bytes of lookahead
-//   hash   2^kLaneHashBits bytes   low 8 bits of the latest token start whose three bytes hash here
-//   outq   64 bytes    compressed bytes [flushed, o), index = offset & 63; leaves 16 bytes at a time
+//                      128-byte window behind p and 45..128 bytes of lookahead (32-byte refills);
+//                      a 65th word mirrors word 0 so that an unaligned 4-byte read never wraps
+//   hash   2^kHashBits bytes   low 8 bits of the latest token start whose three bytes hash here
+//   outq   32 bytes    compressed bytes [flushed, o), index = offset & 31; leaves 16 bytes at a time
+//
+// Everything a lane does at a data-dependent TIME is moved to warp-uniform points (encode_packet):
+// every live lane codes exactly one token per step, so the eight tokens of a group, the flag byte
+// and the output flush sit at the same place of the loop for all 32 packets; input is topped up for
+// ALL lanes that have room as soon as ANY lane runs low, and a match is simply cut at the lookahead
+// a lane has (a lane that just coded a long match asks for input at once, so that costs nothing on
+// compressible data).
 //
 // The hash table needs no valid bits and no clearing between packets beyond the initial fill: a
 // candidate is (p - entry) & 255 bytes back, it is used only if that distance is 3..128, and the
@@ -43,11 +51,11 @@ typedef uint32_t u32;
 constexpr u32 kPacket = 4096;
 constexpr u32 kWindow = 128;
 constexpr u32 kRingWords = 64;
-constexpr u32 kHashBits = 7;
+constexpr u32 kHashBits = 6;
 constexpr u32 kHashWords = (1u << kHashBits) / 4;
-constexpr u32 kOutWords = 16;
-constexpr u32 kColumnWords = kRingWords + kHashWords + kOutWords;     // 112 words = 448 bytes per lane
-constexpr u32 kMaxLen = 108;      // ring: 128 behind + (113..128) ahead in 16-byte refills
+constexpr u32 kOutWords = 8;       // a group is <= 17 bytes and everything but < 16 bytes leaves after each group
+constexpr u32 kColumnWords = kRingWords + 1 + kHashWords + kOutWords; // 89 words = 356 bytes per lane
+constexpr u32 kMaxLen = 124;      // <= lookahead - 3 <= 125
 constexpr u32 kSlotBytes = kPacket + kPacket / 8;                     // output slot of a packet
 
 B200LC_LANE_HD u32 fsr(u32 lo, u32 hi, u32 s)
@@ -67,92 +75,102 @@ B200LC_LANE_HD u32 ffs32(u32 x)
     return (u32)__builtin_ffs((int)x);
 #endif
 }
+B200LC_LANE_HD u32 min_u(u32 a, u32 b) { return a < b ? a : b; }
+
+struct Chunk32 { u32 w[8]; };     // 32 bytes of input on their way from global memory to the ring
 
 template <int STRIDE>
 struct Lane {
     u32 *ring, *hash, *outq;    // this lane's columns
-    const u8 *src;              // the packet (16-byte aligned)
-    u8 *dst;                    // the packet's output slot (16-byte aligned, kSlotBytes)
     u32 p;                      // next position to code
-    u32 hi;                     // input loaded so far (multiple of 16)
+    u32 hi;                     // input in the ring so far (multiple of 32)
     u32 o;                      // compressed bytes produced so far
-    u32 flushed;                // compressed bytes stored to dst (multiple of 16)
+    u32 flushed;                // compressed bytes stored to the slot (multiple of 16)
     u32 fpos;                   // offset of the open group's flag byte
-    u32 flags, nt;              // flag bits and tokens of the open group
+    u32 flags;                  // flag bits of the open group
+    u32 need;                   // lookahead below which this lane asks for input
 
     B200LC_LANE_HD u8 *byte_of(u32 *col, u32 i) const
     {
         return reinterpret_cast<u8 *>(col + (i >> 2) * STRIDE) + (i & 3u);
     }
-    // four bytes at ring index i (two aligned words, funnel-shifted)
+    // four bytes at ring index i in 0..255 (two aligned words, funnel-shifted; word 64 mirrors word 0)
     B200LC_LANE_HD u32 ring4(u32 i) const
     {
-        const u32 w = i >> 2;
-        const u32 a = ring[(w & (kRingWords - 1)) * STRIDE];
-        const u32 b = ring[((w + 1) & (kRingWords - 1)) * STRIDE];
-        return fsr(a, b, 8 * (i & 3u));
+        const u32 *w = ring + (i >> 2) * STRIDE;
+        return fsr(w[0], w[STRIDE], 8 * i);
     }
 
-    B200LC_LANE_HD void init(u32 *column, const u8 *src_, u8 *dst_)
+    B200LC_LANE_HD void init(u32 *column, bool live)
     {
         ring = column;
-        hash = column + kRingWords * STRIDE;
+        hash = column + (kRingWords + 1) * STRIDE;
         outq = hash + kHashWords * STRIDE;
-        src = src_;
-        dst = dst_;
         // positions -128 .. -1 are spaces (gpu_compress.cu:208); every hash entry points at -128
         for (u32 w = kRingWords / 2; w < kRingWords; ++w) ring[w * STRIDE] = 0x20202020u;
+        ring[0] = ring[kRingWords * STRIDE] = 0;
         for (u32 w = 0; w < kHashWords; ++w) hash[w * STRIDE] = 0x80808080u;
-        p = 0; hi = 0; o = 1; flushed = 0; fpos = 0; flags = 0; nt = 0;
+        p = hi = live ? 0u : kPacket;
+        o = 0; flushed = 0; fpos = 0; flags = 0; need = 48;
     }
 
-    // input: 16 bytes at a time while the chunk's ring slots hold positions behind the window
-    B200LC_LANE_HD bool wants_input() const { return hi < kPacket && hi <= p + 112u; }
-    B200LC_LANE_HD void put_input(u32 x0, u32 x1, u32 x2, u32 x3)
+    // input: 32 bytes at a time into ring slots that hold positions behind the window
+    B200LC_LANE_HD bool has_room() const { return hi < kPacket && hi <= p + 96u; }
+    B200LC_LANE_HD bool hungry() const { return has_room() && hi - p < need; }
+    B200LC_LANE_HD void put_input(const Chunk32 &c)
     {
         u32 *q = ring + ((hi >> 2) & (kRingWords - 1)) * STRIDE;
-        q[0] = x0; q[STRIDE] = x1; q[2 * STRIDE] = x2; q[3 * STRIDE] = x3;
-        hi += 16;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 8; ++j) q[j * STRIDE] = c.w[j];
+        if ((hi & 255u) == 0) ring[kRingWords * STRIDE] = c.w[0];      // the mirror of word 0
+        hi += 32;
     }
 
-    // output: 16 bytes leave once they lie in front of the open group's flag byte
-    B200LC_LANE_HD bool has_output() const { return fpos - flushed >= 16u; }
-    B200LC_LANE_HD void take_output(u32 &x0, u32 &x1, u32 &x2, u32 &x3)
+    // output: whole 16-byte vectors of [flushed, o)
+    B200LC_LANE_HD void take_output(u32 (&x)[4])
     {
         const u32 *q = outq + ((flushed >> 2) & (kOutWords - 1)) * STRIDE;
-        x0 = q[0]; x1 = q[STRIDE]; x2 = q[2 * STRIDE]; x3 = q[3 * STRIDE];
+        x[0] = q[0]; x[1] = q[STRIDE]; x[2] = q[2 * STRIDE]; x[3] = q[3 * STRIDE];
         flushed += 16;
     }
 
     B200LC_LANE_HD void emit(u32 b) { *byte_of(outq, o & (4 * kOutWords - 1)) = (u8)b; ++o; }
-    B200LC_LANE_HD void close_group()
-    {
-        *byte_of(outq, fpos & (4 * kOutWords - 1)) = (u8)flags;
-        flags = 0; nt = 0;
-    }
+    B200LC_LANE_HD void open_group() { fpos = o; ++o; flags = 0; }
+    B200LC_LANE_HD void close_group() { *byte_of(outq, fpos & (4 * kOutWords - 1)) = (u8)flags; }
 
-    // One token.  Requires p < kPacket and !wants_input().
-    B200LC_LANE_HD void step()
+    // Token number t (0..7) of the open group.  Requires p < kPacket and >= 48 bytes of lookahead
+    // (or all of the packet's input in the ring).
+    B200LC_LANE_HD void step(u32 t)
     {
-        if (nt == 8) {          // open the next group: its flag byte is written when it closes
-            close_group();
-            fpos = o;
-            ++o;
-        }
         const u32 x = ring4(p & 255u);
         const u32 h = ((x & 0xffffffu) * 2654435761u) >> (32 - kHashBits);
         u8 *const he = byte_of(hash, h);
         const u32 dist = (p - (u32)*he) & 255u;
-        const u32 lim = min_u(min_u(dist, kMaxLen), kPacket - p);
+        // bytes [p, p + lim + 3) must be in the ring (beyond the packet's end garbage is compared and
+        // cut off by kPacket - p)
+        const u32 avail = hi < kPacket ? hi - p - 3u : kPacket - p;
+        const u32 lim = min_u(min_u(dist, kMaxLen), avail);
         u32 L = 0;
         if (dist - 3u <= kWindow - 3u && lim >= 3u) {
-            const u32 q = p - dist;
-            u32 d = ring4(q & 255u) ^ x;
+            const u32 q = (p - dist) & 255u;
+            u32 d = ring4(q) ^ x;
             if ((d & 0xffffffu) == 0) {
                 L = 4;
-                while (d == 0 && L < lim) {
-                    d = ring4((q + L) & 255u) ^ ring4((p + L) & 255u);
-                    L += 4;
+                if (d == 0 && L < lim) {
+                    // longer than four bytes: walk both strings a word at a time, one new aligned word
+                    // per side and step (the other half of each unaligned word is the previous one)
+                    u32 ws = (q >> 2) + 1, wp = ((p & 255u) >> 2) + 1;
+                    u32 s1 = ring[(ws & (kRingWords - 1)) * STRIDE], p1 = ring[(wp & (kRingWords - 1)) * STRIDE];
+                    do {
+                        ++ws; ++wp;
+                        const u32 s0 = s1, p0 = p1;
+                        s1 = ring[(ws & (kRingWords - 1)) * STRIDE];
+                        p1 = ring[(wp & (kRingWords - 1)) * STRIDE];
+                        d = fsr(s0, s1, 8 * q) ^ fsr(p0, p1, 8 * p);
+                        L += 4;
+                    } while (d == 0 && L < lim);
                 }
                 if (d) L -= 4u - ((ffs32(d) - 1u) >> 3);
                 L = min_u(L, lim);
@@ -162,22 +180,66 @@ struct Lane {
         const bool is_match = L >= 3u;
         emit(is_match ? L : (x & 0xffu));
         if (is_match) emit((p - dist) & 127u);
-        else flags |= 1u << nt;
+        else flags |= 1u << t;
         // Hash entry := p, except:  a source that runs right up to p (L == dist) means the data
         // repeats with period `dist` -- keeping the entry lets the next token reach twice as far back
         // and copy twice as much;  an entry closer than 3 becomes usable in a moment.
-        const bool keep = is_match ? (L == dist && 2u * dist <= kWindow) : (dist < 3u);
+        const bool keep = is_match ? bool((L == dist) & (2u * dist <= kWindow)) : (dist < 3u);
         if (!keep) *he = (u8)p;
         p += is_match ? L : 1u;
-        ++nt;
+        need = L >= 32u ? 97u : 48u;      // after a long match: top up at once
     }
-
-    // After the last token: close the open group.  Compressed size = o.
-    B200LC_LANE_HD void finish() { close_group(); }
-    B200LC_LANE_HD u32 last_group_bytes() const { return o - fpos; }
-
-    static B200LC_LANE_HD u32 min_u(u32 a, u32 b) { return a < b ? a : b; }
 };
+
+// The packet loop.  IO supplies the three things that differ between a GPU lane and the host:
+//   bool any(bool)                         warp vote (host: identity)
+//   void load(u32 offset, Chunk32 &)       32 input bytes at `offset` of the packet
+//   void store(u32 offset, const u32 (&)[4])   16 output bytes at `offset` of the packet's slot
+// Returns the compressed size; last_group = bytes of the last group incl. its flag byte.
+template <int STRIDE, class IO>
+B200LC_LANE_HD u32 encode_packet(u32 *column, bool live, IO &io, u32 &last_group)
+{
+    Lane<STRIDE> ln;
+    ln.init(column, live);
+    Chunk32 pf;
+    for (int j = 0; j < 8; ++j) pf.w[j] = 0;
+    if (live) io.load(0, pf);
+    for (;;) {
+        const bool open = ln.p < kPacket;
+        if (!io.any(open)) break;
+        if (open) ln.open_group();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (u32 t = 0; t < 8; ++t) {
+            if (io.any(ln.hungry())) {
+                while (ln.has_room()) {
+                    ln.put_input(pf);
+                    if (ln.hi < kPacket) io.load(ln.hi, pf);
+                }
+            }
+            if (ln.p < kPacket) ln.step(t);
+        }
+        if (open) ln.close_group();
+        // a group is at most 17 bytes: two vectors at most
+        for (int k = 0; k < 2; ++k) {
+            if (ln.o - ln.flushed >= 16u) {
+                u32 x[4];
+                const u32 at = ln.flushed;
+                ln.take_output(x);
+                io.store(at, x);
+            }
+        }
+    }
+    if (ln.flushed < ln.o) {      // the tail (< 16 bytes; the rest of the vector is padding in the slot)
+        u32 x[4];
+        const u32 at = ln.flushed;
+        ln.take_output(x);
+        io.store(at, x);
+    }
+    last_group = ln.o - ln.fpos;
+    return ln.o;
+}
 
 }  // namespace lzss_lane
 }  // namespace b200lc

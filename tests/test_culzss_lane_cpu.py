@@ -1,7 +1,7 @@
 """CPU: the lane-serial CULZSS fast-mode encoder (csrc/culzss_lane.cuh, the code a GPU lane runs in
 culzss_encode_lane_kernel) compiled for the host with STRIDE = 1.  NON-PARITY mode: what is pinned
 is the FORMAT -- every packet decodes to its input with the oracle's restatement of the reference
-DecodeKernel (gpu_decompress.cu:164-242) -- plus the format's limits (3 <= length <= 108 <= 127,
+DecodeKernel (gpu_decompress.cu:164-242) -- plus the format's limits (3 <= length <= 124 <= 127,
 packet <= 4608 bytes) and a floor on the compression ratio per data kind."""
 import ctypes as C
 import os
@@ -57,7 +57,7 @@ def _check_tokens(body):
                 i += 1
                 produced += 1
             else:
-                assert 3 <= body[i] <= 108 and body[i + 1] < 128
+                assert 3 <= body[i] <= 124 and body[i + 1] < 128
                 produced += body[i]
                 i += 2
     assert produced == PKT
@@ -70,8 +70,8 @@ CASES = {
     "text": (lambda n: np.frombuffer((b"the quick brown fox jumps over the lazy dog. " * (n // 45 + 1))[:n], np.uint8).copy(), 25.0),
     "random": (lambda n: np.random.default_rng(1).integers(0, 256, n, dtype=np.uint8), 0.88),
     "zeros": (lambda n: np.zeros(n, np.uint8), 35.0),
-    "spaces": (lambda n: np.full(n, 0x20, np.uint8), 45.0),
-    "ramp": (lambda n: (np.arange(n) % 97).astype(np.uint8), 20.0),
+    "spaces": (lambda n: np.full(n, 0x20, np.uint8), 40.0),
+    "ramp": (lambda n: (np.arange(n) % 97).astype(np.uint8), 15.0),
     "period3": (lambda n: (np.arange(n) % 3).astype(np.uint8), 30.0),
     "zipf": (lambda n: O.zipf_bytes(n, 1.1, 12345)[:n].copy(), 0.88),
 }
