@@ -76,6 +76,8 @@ def lib():
     L.b200lc_culzss_encode_scratch_bytes.argtypes = [sz, sz]
     L.b200lc_culzss_encode_batch.restype = i32
     L.b200lc_culzss_encode_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, sz, vp]
+    L.b200lc_culzss_encode_batch_ex.restype = i32
+    L.b200lc_culzss_encode_batch_ex.argtypes = [vp, sz, sz, vp, sz, vp, vp, sz, i32, vp]
     L.b200lc_culzss_encode_fast_batch.restype = i32
     L.b200lc_culzss_encode_fast_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, sz, i32, vp]
     L.b200lc_culzss_decode_scratch_bytes.restype = sz
@@ -336,12 +338,18 @@ def culzss_out_stride(buf_length):
     return (buf_length + buf_length // 8 + 1024 + 15) // 16 * 16
 
 
-def culzss_encode(data, buf_length=1 << 20, out=None, comp_len=None, scratch=None, stream=None, fast=0):
+CULZSS_KERNEL_AUTO, CULZSS_KERNEL_CTA, CULZSS_KERNEL_LANE = 0, 1, 2
+
+
+def culzss_encode(data, buf_length=1 << 20, out=None, comp_len=None, scratch=None, stream=None, fast=0,
+                  kernel=CULZSS_KERNEL_AUTO):
     """LZSS-encode a cuda uint8 tensor of nbuf * buf_length bytes.  Returns (out, comp_len):
     out[b * stride : b * stride + comp_len[b]] is buffer b incl. trailer; comp_len[b] == 0 means
     "store raw".  Asynchronous.  fast = 1, 2 or 4: the NON-PARITY fast mode
     (b200lc_culzss_encode_fast_batch, hash-chain depth), same format, different matches;
-    fast = "lane" (CULZSS_FAST_LANE = -1): its packet-per-lane formulation, also NON-PARITY."""
+    fast = "lane" (CULZSS_FAST_LANE = -1): its packet-per-lane formulation, also NON-PARITY.
+    kernel (parity mode only): CULZSS_KERNEL_CTA / _LANE force one of the two bit-identical kernels
+    (b200lc_culzss_encode_batch_ex)."""
     import torch
     assert data.is_cuda and data.dtype == torch.uint8 and data.is_contiguous()
     assert data.numel() % buf_length == 0
@@ -361,6 +369,10 @@ def culzss_encode(data, buf_length=1 << 20, out=None, comp_len=None, scratch=Non
         check(L.b200lc_culzss_encode_fast_batch(data.data_ptr(), nbuf, buf_length, out.data_ptr(), stride,
                                                 comp_len.data_ptr(), scratch.data_ptr(), scratch.numel(),
                                                 int(fast), _stream_ptr(stream)), "b200lc_culzss_encode_fast_batch")
+    elif kernel != CULZSS_KERNEL_AUTO:
+        check(L.b200lc_culzss_encode_batch_ex(data.data_ptr(), nbuf, buf_length, out.data_ptr(), stride,
+                                              comp_len.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                              int(kernel), _stream_ptr(stream)), "b200lc_culzss_encode_batch_ex")
     else:
         check(L.b200lc_culzss_encode_batch(data.data_ptr(), nbuf, buf_length, out.data_ptr(), stride,
                                            comp_len.data_ptr(), scratch.data_ptr(), scratch.numel(),

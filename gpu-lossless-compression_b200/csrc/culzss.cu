@@ -425,10 +425,14 @@ __global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict
 }
 
 // ====================================================================================== encode, lane mode
-// FAST MODE, second formulation (NON-PARITY, csrc/culzss_lane.cuh): one packet per LANE.  A lane
-// parses its packet greedily through a private 128-entry hash of three-byte prefixes, emits tokens
-// and flag bytes as it goes and streams the result to the packet's slot -- no CTA barrier, no
-// token arrays, no separate selection and packing passes.  All per-lane state sits in
+// One packet per LANE (csrc/culzss_lane.cuh), two match finders:
+//   PARITY = false  FAST MODE (NON-PARITY): greedy parse through a lane-private 64-entry hash of
+//                   three-byte prefixes;
+//   PARITY = true   the reference's streak scanner, bit-exact, evaluated only at the positions the
+//                   greedy selection visits (the reference and culzss_encode_kernel<0> above compute
+//                   a match for all 4096 positions and drop the ones a longer match jumped over).
+// A lane emits tokens and flag bytes as it goes and streams the result to the packet's slot -- no
+// CTA barrier, no token arrays, no separate selection and packing passes.  All per-lane state sits in
 // shared-memory columns laid out [word][lane] (one wavefront per access whatever the 32 packets
 // of a warp are doing).  Input travels global -> registers (one 16-byte chunk ahead of its use,
 // the line after next prefetched into L2) -> ring; output ring -> 16-byte stores.
@@ -448,13 +452,22 @@ struct LaneDevIO {
         // the line after next, once per 128-byte line
         if ((off & 127u) == 0 && off + 256u < lzss_lane::kPacket) prefetch_l2(src + off + 256u);
     }
+    __device__ __forceinline__ u32 bytes4(u32 off) const      // rare: lookahead beyond the ring
+    {
+        u32 v = 0;
+#pragma unroll
+        for (u32 j = 0; j < 4; ++j)
+            if (off + j < lzss_lane::kPacket) v |= (u32)__ldg(src + off + j) << (8 * j);
+        return v;
+    }
     __device__ __forceinline__ void store(u32 off, const u32 (&x)[4]) const
     {
         *reinterpret_cast<uint4 *>(dst + off) = make_uint4(x[0], x[1], x[2], x[3]);
     }
 };
 
-__global__ void __launch_bounds__(kLaneWarps * 32) culzss_encode_lane_kernel(const u8 *__restrict__ in, u64 npackets,
+template <bool PARITY>
+__global__ void __launch_bounds__(kLaneWarps * 32, 11) culzss_encode_lane_kernel(const u8 *__restrict__ in, u64 npackets,
                                                                             u8 *__restrict__ tmp_out,
                                                                             u16 *__restrict__ pkt_size,
                                                                             u8 *__restrict__ last_group_size)
@@ -468,7 +481,8 @@ __global__ void __launch_bounds__(kLaneWarps * 32) culzss_encode_lane_kernel(con
     LaneDevIO io{in + pk * kPacket, tmp_out + pk * (u64)kSlotBytes};
     if (live) prefetch_l2(io.src + 128);
     u32 last_group = 0;
-    const u32 size = encode_packet<32>(lane_cols + warp * (kColumnWords * 32) + lane, live, io, last_group);
+    constexpr u32 kCol = PARITY ? kColumnWordsParity : kColumnWordsFast;
+    const u32 size = encode_packet<32, PARITY>(lane_cols + warp * (kCol * 32) + lane, live, io, last_group);
     if (live) {
         pkt_size[pid] = (u16)size;
         last_group_size[pid] = (u8)last_group;
@@ -841,8 +855,12 @@ extern "C" size_t b200lc_culzss_encode_scratch_bytes(size_t nbuf, size_t buf_len
            ((npk + 255) & ~size_t(255)) + ((npk * 4 + 255) & ~size_t(255)) + 256;
 }
 
+// parity mode switches to the packet-per-lane kernel from this many packets (64 MiB) on
+constexpr size_t kLaneParityMinPackets = 16384;
+
 static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out, size_t out_stride,
-                        uint32_t *d_comp_len, void *d_scratch, size_t scratch_bytes, int depth, cudaStream_t stream)
+                        uint32_t *d_comp_len, void *d_scratch, size_t scratch_bytes, int depth, cudaStream_t stream,
+                        int parity_kernel = B200LC_CULZSS_KERNEL_AUTO)
 {
     if (nbuf == 0) return B200LC_OK;
     if (!d_in || !d_out || !d_comp_len || !d_scratch) return B200LC_ERR_ARG;
@@ -869,19 +887,32 @@ static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uin
     u8 *lastg = reinterpret_cast<u8 *>(sizes) + ((npk * 2 + 255) & ~u64(255));
     u32 *pkoff = reinterpret_cast<u32 *>(lastg + ((npk + 255) & ~u64(255)));
 
-    if (ki < 0) {
-        // lane mode: one packet per lane, 448 bytes of shared-memory columns per lane
-        const size_t lsmem = (size_t)lzss::kLaneWarps * 32 * lzss_lane::kColumnWords * 4;
-        static unsigned lane_attr_done[kMaxDevices] = {0};
+    // Parity mode has two bit-identical kernels: a CTA per packet (any batch size) and a packet per
+    // lane, which needs tens of thousands of packets in flight to fill the GPU.
+    bool lane_kernel = ki < 0;
+    if (ki == 0) {
+        static int mode = -1;      // B200LC_CULZSS_PARITY_LANE = 0 never | 1 always | unset: by batch size
+        if (mode < 0) {
+            const char *e = getenv("B200LC_CULZSS_PARITY_LANE");
+            mode = e ? (atoi(e) ? 1 : 0) : 2;
+        }
+        lane_kernel = mode == 1 || (mode == 2 && npk >= (u64)kLaneParityMinPackets);
+        if (parity_kernel == B200LC_CULZSS_KERNEL_CTA) lane_kernel = false;
+        if (parity_kernel == B200LC_CULZSS_KERNEL_LANE) lane_kernel = true;
+    }
+    if (lane_kernel) {
+        const bool parity = ki == 0;
+        const size_t lsmem = (size_t)lzss::kLaneWarps * 32 * 4 *
+                             (parity ? lzss_lane::kColumnWordsParity : lzss_lane::kColumnWordsFast);
+        auto kern = parity ? lzss::culzss_encode_lane_kernel<true> : lzss::culzss_encode_lane_kernel<false>;
+        static unsigned lane_attr_done[kMaxDevices][2] = {{0}};
         const int lslot = device_slot();
-        if (lslot < 0 || lane_attr_done[lslot] != context_epoch()) {
-            B200LC_CUDA_TRY(cudaFuncSetAttribute(lzss::culzss_encode_lane_kernel,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
-            if (lslot >= 0) lane_attr_done[lslot] = context_epoch();
+        if (lslot < 0 || lane_attr_done[lslot][parity] != context_epoch()) {
+            B200LC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+            if (lslot >= 0) lane_attr_done[lslot][parity] = context_epoch();
         }
         const u32 per_cta = lzss::kLaneWarps * 32;
-        lzss::culzss_encode_lane_kernel<<<(u32)((npk + per_cta - 1) / per_cta), per_cta, lsmem, stream>>>(
-            d_in, npk, tmp, sizes, lastg);
+        kern<<<(u32)((npk + per_cta - 1) / per_cta), per_cta, lsmem, stream>>>(d_in, npk, tmp, sizes, lastg);
         B200LC_CUDA_TRY(cudaGetLastError());
     } else {
     // fast mode keeps its hash table (1024 x 16 bytes) behind EncSmem
@@ -912,6 +943,15 @@ extern "C" int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size
 {
     return encode_batch(d_in, nbuf, buf_length, d_out, out_stride, d_comp_len, d_scratch, scratch_bytes, 0,
                         (cudaStream_t)stream_);
+}
+
+extern "C" int b200lc_culzss_encode_batch_ex(const uint8_t *d_in, size_t nbuf, size_t buf_length,
+                                             uint8_t *d_out, size_t out_stride, uint32_t *d_comp_len,
+                                             void *d_scratch, size_t scratch_bytes, int kernel, void *stream_)
+{
+    if (kernel < B200LC_CULZSS_KERNEL_AUTO || kernel > B200LC_CULZSS_KERNEL_LANE) return B200LC_ERR_ARG;
+    return encode_batch(d_in, nbuf, buf_length, d_out, out_stride, d_comp_len, d_scratch, scratch_bytes, 0,
+                        (cudaStream_t)stream_, kernel);
 }
 
 extern "C" int b200lc_culzss_encode_fast_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length,

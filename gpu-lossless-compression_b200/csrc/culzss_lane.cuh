@@ -1,7 +1,14 @@
-// CULZSS fast mode, second formulation: ONE PACKET PER LANE, greedy hash parse, token emission and
-// flag-byte packing in one serial walk (NON-PARITY: the reference's buffer / token format, window
-// 128, packets of 4096 bytes -- every stream decodes with the reference's DecodeKernel,
-// gpu_decompress.cu:164-242 -- but not the reference encoder's matches).
+// CULZSS encoders with ONE PACKET PER LANE: match finding, greedy token selection, token emission
+// and flag-byte packing in one serial walk over the packet.  Two match finders share the walk:
+//
+//   PARITY = true   bit-exact with the reference: FindMatch's streak scanner (gpu_compress.cu:104-168,
+//                   SURVEY.md appendix A.2 "LCP walk") evaluated ONLY at the positions the greedy
+//                   selection of aftercomp (:500-517) visits -- the reference computes a match for all
+//                   4096 positions of a packet and then throws away those a longer match jumped over;
+//   PARITY = false  FAST MODE, NON-PARITY: the reference's buffer / token format, window 128, packets
+//                   of 4096 bytes -- every stream decodes with the reference's DecodeKernel,
+//                   gpu_decompress.cu:164-242 -- but matches from a lane-private hash of three-byte
+//                   prefixes instead of the reference's exhaustive scanner.
 //
 // The code a lane runs lives in this header, which also compiles for the host, so that the CPU test
 // (tests/c/culzss_lane_host.cc, tests/test_culzss_lane_cpu.py) can run it without a GPU and hand its
@@ -54,7 +61,8 @@ constexpr u32 kRingWords = 64;
 constexpr u32 kHashBits = 6;
 constexpr u32 kHashWords = (1u << kHashBits) / 4;
 constexpr u32 kOutWords = 8;       // a group is <= 17 bytes and everything but < 16 bytes leaves after each group
-constexpr u32 kColumnWords = kRingWords + 1 + kHashWords + kOutWords; // 89 words = 356 bytes per lane
+constexpr u32 kColumnWordsFast = kRingWords + 1 + kHashWords + kOutWords;   // 89 words = 356 bytes per lane
+constexpr u32 kColumnWordsParity = kRingWords + 1 + kOutWords;              // 73 words = 292 bytes per lane
 constexpr u32 kMaxLen = 124;      // <= lookahead - 3 <= 125
 constexpr u32 kSlotBytes = kPacket + kPacket / 8;                     // output slot of a packet
 
@@ -76,10 +84,17 @@ B200LC_LANE_HD u32 ffs32(u32 x)
 #endif
 }
 B200LC_LANE_HD u32 min_u(u32 a, u32 b) { return a < b ? a : b; }
+B200LC_LANE_HD u32 max_u(u32 a, u32 b) { return a > b ? a : b; }
+// 0x80 in every byte of w that equals the corresponding byte of b (exact, no carries between bytes)
+B200LC_LANE_HD u32 eq_bytes(u32 w, u32 b)
+{
+    const u32 x = w ^ b;
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
 
 struct Chunk32 { u32 w[8]; };     // 32 bytes of input on their way from global memory to the ring
 
-template <int STRIDE>
+template <int STRIDE, bool PARITY>
 struct Lane {
     u32 *ring, *hash, *outq;    // this lane's columns
     u32 p;                      // next position to code
@@ -105,18 +120,19 @@ struct Lane {
     {
         ring = column;
         hash = column + (kRingWords + 1) * STRIDE;
-        outq = hash + kHashWords * STRIDE;
+        outq = hash + (PARITY ? 0u : kHashWords) * STRIDE;
         // positions -128 .. -1 are spaces (gpu_compress.cu:208); every hash entry points at -128
         for (u32 w = kRingWords / 2; w < kRingWords; ++w) ring[w * STRIDE] = 0x20202020u;
         ring[0] = ring[kRingWords * STRIDE] = 0;
-        for (u32 w = 0; w < kHashWords; ++w) hash[w * STRIDE] = 0x80808080u;
+        if (!PARITY)
+            for (u32 w = 0; w < kHashWords; ++w) hash[w * STRIDE] = 0x80808080u;
         p = hi = live ? 0u : kPacket;
         o = 0; flushed = 0; fpos = 0; flags = 0; need = 48;
     }
 
     // input: 32 bytes at a time into ring slots that hold positions behind the window
     B200LC_LANE_HD bool has_room() const { return hi < kPacket && hi <= p + 96u; }
-    B200LC_LANE_HD bool hungry() const { return has_room() && hi - p < need; }
+    B200LC_LANE_HD bool hungry() const { return has_room() && hi < p + need; }   // parity mode: p may have passed hi
     B200LC_LANE_HD void put_input(const Chunk32 &c)
     {
         u32 *q = ring + ((hi >> 2) & (kRingWords - 1)) * STRIDE;
@@ -189,17 +205,107 @@ struct Lane {
         p += is_match ? L : 1u;
         need = L >= 32u ? 97u : 48u;      // after a long match: top up at once
     }
+
+    // ------------------------------------------------------------------------------ parity mode
+    // Bytes [p + k, p + k + 4) of the packet: from the ring while they are there, else straight from
+    // global memory (only a streak longer than the ~97..128 bytes of lookahead gets that far).
+    template <class IO>
+    B200LC_LANE_HD u32 look4(u32 k, const IO &io) const
+    {
+        if (hi >= kPacket || p + k + 4u <= hi) return ring4((p + k) & 255u);
+        return io.bytes4(p + k);
+    }
+
+    // Token number t (0..7) of the open group, the reference's match:
+    // scan index q = 0 .. n-1 stands for window position p - 128 + q (ring index (p + 128 + q) & 255);
+    // walk q <- q + LCP(q) + 1 where LCP(q) is the common prefix of the window string at q and the
+    // lookahead, cut so that q + LCP <= n; the first strictly longest wins; n = 127, shrinking with
+    // the position inside the packet's last chunk (maxcheck, gpu_compress.cu:120,149).
+    // Here: u = q + a counts ring bytes from the aligned word that holds q = 0.  Phase 1 (all lanes in
+    // step, 33 independent loads): the bit mask of the window bytes that equal the first lookahead
+    // byte -- only those can start a streak.  Phase 2: the walk over the set bits, skipping
+    // LCP + 1 bytes after each.
+    template <class IO>
+    B200LC_LANE_HD void step_parity(u32 t, const IO &io)
+    {
+        const u32 n = p < kPacket - 128u ? 127u : max_u(1u, kPacket - 1u - p);
+        const u32 x = ring4(p & 255u);
+        const u32 b4 = (x & 0xffu) * 0x01010101u;
+        const u32 i0 = (p + 128u) & 255u;
+        const u32 a = i0 & 3u, wbase = i0 >> 2;
+        const u32 end = n + a;                      // <= 130
+        u32 M[5] = {0u, 0u, 0u, 0u, 0u};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (u32 k = 0; k < 33; ++k) {
+            const u32 W = ring[((wbase + k) & (kRingWords - 1)) * STRIDE];
+            // 0x80 flags of the four bytes -> four adjacent bits
+            const u32 nib = (((eq_bytes(W, b4) >> 7) * 0x00204081u) >> 21) & 0xfu;
+            M[k >> 3] |= nib << (4 * (k & 7));
+        }
+        M[0] &= 0xffffffffu << a;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (u32 w = 0; w < 5; ++w) {               // keep u < end
+            const int top = (int)end - (int)(32 * w);
+            if (top <= 0) M[w] = 0;
+            else if (top < 32) M[w] &= (1u << top) - 1u;
+        }
+        u32 best = 1, best_u = a;
+        u32 next = 0;                               // candidates below `next` were swallowed by a streak
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (u32 w = 0; w < 5; ++w) {
+            u32 m = M[w];
+            if (next > 32 * w) m = next - 32 * w >= 32u ? 0u : m & (0xffffffffu << (next - 32 * w));
+            while (m) {
+                const u32 bit = ffs32(m) - 1u;
+                const u32 u = 32 * w + bit;
+                const u32 cap = end - u;
+                const u32 q = (4 * wbase + u) & 255u;             // ring index of the streak's first byte
+                u32 d = ring4(q) ^ x;
+                u32 L = 4;
+                if (d == 0 && L < cap) {
+                    u32 ws = (q >> 2) + 1;
+                    u32 s1 = ring[(ws & (kRingWords - 1)) * STRIDE];
+                    do {
+                        ++ws;
+                        const u32 s0 = s1;
+                        s1 = ring[(ws & (kRingWords - 1)) * STRIDE];
+                        d = fsr(s0, s1, 8 * q) ^ look4(L, io);
+                        L += 4;
+                    } while (d == 0 && L < cap);
+                }
+                if (d) L -= 4u - ((ffs32(d) - 1u) >> 3);
+                L = min_u(L, cap);
+                if (L > best) { best = L; best_u = u; }
+                next = u + L + 1;
+                m = bit + L + 1 >= 32u ? 0u : m & (0xffffffffu << (bit + L + 1));
+            }
+        }
+        // gpu_compress.cu:251-274: a match of 3 or more becomes {length, ring offset of its source}
+        const bool is_match = best >= 3u;
+        emit(is_match ? best : (x & 0xffu));
+        if (is_match) emit((p + best_u - a) & 255u);
+        else flags |= 1u << t;
+        p += is_match ? best : 1u;
+        need = best >= 32u ? 97u : 48u;
+    }
 };
 
-// The packet loop.  IO supplies the three things that differ between a GPU lane and the host:
+// The packet loop.  IO supplies the things that differ between a GPU lane and the host:
 //   bool any(bool)                         warp vote (host: identity)
 //   void load(u32 offset, Chunk32 &)       32 input bytes at `offset` of the packet
+//   u32 bytes4(u32 offset)                 4 input bytes at any offset (zero beyond the packet)
 //   void store(u32 offset, const u32 (&)[4])   16 output bytes at `offset` of the packet's slot
 // Returns the compressed size; last_group = bytes of the last group incl. its flag byte.
-template <int STRIDE, class IO>
+template <int STRIDE, bool PARITY, class IO>
 B200LC_LANE_HD u32 encode_packet(u32 *column, bool live, IO &io, u32 &last_group)
 {
-    Lane<STRIDE> ln;
+    Lane<STRIDE, PARITY> ln;
     ln.init(column, live);
     Chunk32 pf;
     for (int j = 0; j < 8; ++j) pf.w[j] = 0;
@@ -218,7 +324,10 @@ B200LC_LANE_HD u32 encode_packet(u32 *column, bool live, IO &io, u32 &last_group
                     if (ln.hi < kPacket) io.load(ln.hi, pf);
                 }
             }
-            if (ln.p < kPacket) ln.step(t);
+            if (ln.p < kPacket) {
+                if (PARITY) ln.step_parity(t, io);
+                else ln.step(t);
+            }
         }
         if (open) ln.close_group();
         // a group is at most 17 bytes: two vectors at most

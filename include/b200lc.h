@@ -193,6 +193,20 @@ size_t b200lc_culzss_encode_scratch_bytes(size_t nbuf, size_t buf_length);
 int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out,
                                size_t out_stride, uint32_t *d_comp_len, void *d_scratch,
                                size_t scratch_bytes, void *stream);
+/* The same with the kernel chosen by the caller.  Both kernels write the reference's bytes:
+ * B200LC_CULZSS_KERNEL_CTA   one CTA per packet, a match for every position, selection and packing
+ *                            afterwards (any batch size);
+ * B200LC_CULZSS_KERNEL_LANE  one packet per GPU lane, the reference's match finder evaluated only at
+ *                            the positions the greedy selection visits (csrc/culzss_lane.cuh); 3-4x
+ *                            the throughput once >= ~10^5 packets are in flight;
+ * B200LC_CULZSS_KERNEL_AUTO  what b200lc_culzss_encode_batch does: LANE from 16384 packets (64 MiB)
+ *                            per call on (environment B200LC_CULZSS_PARITY_LANE=0|1 overrides). */
+#define B200LC_CULZSS_KERNEL_AUTO 0
+#define B200LC_CULZSS_KERNEL_CTA 1
+#define B200LC_CULZSS_KERNEL_LANE 2
+int b200lc_culzss_encode_batch_ex(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out,
+                                  size_t out_stride, uint32_t *d_comp_len, void *d_scratch,
+                                  size_t scratch_bytes, int kernel, void *stream);
 /* FAST MODE -- NOT bit-exact with the reference encoder (every table and test labels it
  * non-parity).  Same buffer format, token format, window (128) and packets (4096) as
  * b200lc_culzss_encode_batch, so the output decodes with the reference's DecodeKernel

@@ -32,9 +32,9 @@ def _cases():
     }
 
 
-def _gpu_encode(data, buf_length=MIB):
+def _gpu_encode(data, buf_length=MIB, kernel=0):
     d = torch.from_numpy(data).to(DEV)
-    out, clen = b200lc.culzss_encode(d, buf_length)
+    out, clen = b200lc.culzss_encode(d, buf_length, kernel=kernel)
     torch.cuda.synchronize()
     stride = b200lc.culzss_out_stride(buf_length)
     out = out.cpu().numpy()
@@ -42,11 +42,17 @@ def _gpu_encode(data, buf_length=MIB):
     return [out[b * stride: b * stride + clen[b]] for b in range(clen.size)], clen
 
 
+# both parity kernels (a CTA per packet / a packet per lane, b200lc_culzss_encode_batch_ex) must write
+# the reference's bytes
+KERNELS = [b200lc.CULZSS_KERNEL_CTA, b200lc.CULZSS_KERNEL_LANE]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name", list(_cases().keys()))
-def test_encode_matches_oracle(name):
+def test_encode_matches_oracle(name, kernel):
     data = _cases()[name]
     ok, want = O.culzss_oracle_compress(data)
-    bufs, clen = _gpu_encode(data)
+    bufs, clen = _gpu_encode(data, kernel=kernel)
     if not ok:
         assert clen[0] == 0
         return
@@ -54,14 +60,48 @@ def test_encode_matches_oracle(name):
     assert np.array_equal(bufs[0], want)
 
 
-def test_encode_small_and_multi_buffer():
+def test_encode_kernels_agree_on_a_large_batch_and_auto_picks_the_lane_kernel():
+    """96 MiB (24576 packets: above the AUTO threshold) of mixed data: CTA kernel == lane kernel ==
+    b200lc_culzss_encode_batch byte for byte; three buffers checked against the oracle."""
+    rng = np.random.default_rng(21)
+    nbuf = 96
+    parts = []
+    for b in range(nbuf):
+        kind = b % 4
+        if kind == 0:
+            parts.append(O.quant_codes(MIB, seed=100 + b))
+        elif kind == 1:
+            parts.append(O.quant_codes(MIB, seed=100 + b, dtype=np.uint16))
+        elif kind == 2:
+            parts.append(rng.integers(0, 3, MIB, dtype=np.uint8))
+        else:
+            parts.append(np.frombuffer((b"lorem ipsum dolor sit amet %d " % b) * 40000, np.uint8)[:MIB].copy())
+    data = np.concatenate(parts)
+    d = torch.from_numpy(data).to(DEV)
+    outs = []
+    for kernel in (b200lc.CULZSS_KERNEL_CTA, b200lc.CULZSS_KERNEL_LANE, b200lc.CULZSS_KERNEL_AUTO):
+        out, clen = b200lc.culzss_encode(d, MIB, kernel=kernel)
+        torch.cuda.synchronize()
+        outs.append((out.cpu().numpy(), clen.cpu().numpy()))
+    stride = b200lc.culzss_out_stride(MIB)
+    for out, clen in outs[1:]:
+        assert np.array_equal(clen, outs[0][1])
+        for b in range(nbuf):
+            assert np.array_equal(out[b * stride: b * stride + clen[b]], outs[0][0][b * stride: b * stride + clen[b]]), b
+    for b in (0, 1, 3):
+        ok, want = O.culzss_oracle_compress(parts[b])
+        assert ok and np.array_equal(outs[1][0][b * stride: b * stride + outs[1][1][b]], want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_encode_small_and_multi_buffer(kernel):
     # 64 KiB buffers (16 packets) and a 5-buffer batch with one expanding buffer in the middle
     rng = np.random.default_rng(4)
     parts = [O.quant_codes(1 << 16, seed=s) for s in (1, 2)] + \
             [rng.integers(0, 256, 1 << 16, dtype=np.uint8)] + \
             [np.zeros(1 << 16, np.uint8), O.quant_codes(1 << 16, seed=9, dtype=np.uint16)]
     data = np.concatenate(parts)
-    bufs, clen = _gpu_encode(data, 1 << 16)
+    bufs, clen = _gpu_encode(data, 1 << 16, kernel=kernel)
     for b, part in enumerate(parts):
         ok, want = O.culzss_oracle_compress(part)
         if ok:

@@ -1,8 +1,13 @@
-"""CPU: the lane-serial CULZSS fast-mode encoder (csrc/culzss_lane.cuh, the code a GPU lane runs in
-culzss_encode_lane_kernel) compiled for the host with STRIDE = 1.  NON-PARITY mode: what is pinned
-is the FORMAT -- every packet decodes to its input with the oracle's restatement of the reference
-DecodeKernel (gpu_decompress.cu:164-242) -- plus the format's limits (3 <= length <= 124 <= 127,
-packet <= 4608 bytes) and a floor on the compression ratio per data kind."""
+"""CPU: the lane-serial CULZSS encoders (csrc/culzss_lane.cuh, the code a GPU lane runs in
+culzss_encode_lane_kernel) compiled for the host with STRIDE = 1.
+
+PARITY mode: the packet bytes and sizes equal the oracle's restatement of the reference encoder
+(FindMatch + EncodeKernel + aftercomp, gpu_compress.cu:104-566) bit for bit.
+
+FAST mode (NON-PARITY): what is pinned is the FORMAT -- every packet decodes to its input with the
+oracle's restatement of the reference DecodeKernel (gpu_decompress.cu:164-242) -- plus the format's
+limits (3 <= length <= 124 <= 127, packet <= 4608 bytes) and a floor on the compression ratio per
+data kind."""
 import ctypes as C
 import os
 import subprocess
@@ -27,21 +32,21 @@ def lane(tmp_path_factory):
     lib = C.CDLL(so)
     u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
     u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
-    lib.lane_encode_packets.argtypes = [u8p, C.c_uint, u8p, u16p, u8p]
+    lib.lane_encode_packets.argtypes = [u8p, C.c_uint, u8p, u16p, u8p, C.c_int]
     lib.lane_encode_packets.restype = None
     return lib
 
 
-def _encode(lane, data):
+def _encode(lane, data, parity=0):
     npk = data.size // PKT
     out = np.zeros(npk * SLOT, np.uint8)
     sizes = np.zeros(npk, np.uint16)
     last = np.zeros(npk, np.uint8)
-    lane.lane_encode_packets(data, npk, out, sizes, last)
+    lane.lane_encode_packets(data, npk, out, sizes, last, parity)
     return out, sizes.astype(np.int64), last.astype(np.int64)
 
 
-def _check_tokens(body):
+def _check_tokens(body, max_len=124):
     """walks one packet: match lengths within the limits, 4096 bytes produced; returns the offset of
     the last flag byte"""
     i, produced, last_flag = 0, 0, 0
@@ -57,7 +62,7 @@ def _check_tokens(body):
                 i += 1
                 produced += 1
             else:
-                assert 3 <= body[i] <= 124 and body[i + 1] < 128
+                assert 3 <= body[i] <= max_len
                 produced += body[i]
                 i += 2
     assert produced == PKT
@@ -104,3 +109,65 @@ def test_lane_encoder_packets_are_independent(lane):
     for j in range(2):
         assert sizes_b[j] == sizes[3 + j]
         assert np.array_equal(out_b[j * SLOT: j * SLOT + sizes_b[j]], out[(3 + j) * SLOT: (3 + j) * SLOT + sizes[3 + j]])
+
+
+# ------------------------------------------------------------------------------------- parity mode
+def _select(tokens, n):
+    """aftercomp's greedy walk over the oracle's position-major tokens (gpu_compress.cu:500-562)
+    for data the whole-buffer function refuses ("compression took more"): packet bodies."""
+    bodies = []
+    for k in range(n // PKT):
+        tk = tokens[2 * PKT * k: 2 * PKT * (k + 1)]
+        out, i = bytearray(), 0
+        while i < PKT:
+            flags, group = 0, bytearray()
+            for bit in range(8):
+                if i >= PKT:
+                    break
+                if tk[2 * i] == 1:
+                    flags |= 1 << bit
+                    group.append(tk[2 * i + 1])
+                    i += 1
+                else:
+                    group += bytes([tk[2 * i], tk[2 * i + 1]])
+                    i += int(tk[2 * i])
+            out.append(flags)
+            out += group
+        bodies.append(np.frombuffer(bytes(out), np.uint8))
+    return bodies
+
+
+def _parity_cases():
+    rng = np.random.default_rng(5)
+    n = 64 * PKT
+    text = np.frombuffer((b"the quick brown fox jumps over the lazy dog. " * (n // 45 + 1))[:n], np.uint8).copy()
+    return {
+        "quant32": O.quant_codes(n), "quant16": O.quant_codes(n, dtype=np.uint16), "text": text,
+        "zeros": np.zeros(n, np.uint8), "spaces": np.full(n, 0x20, np.uint8),
+        "carets": np.full(n, ord("^"), np.uint8), "ramp": (np.arange(n) % 97).astype(np.uint8),
+        "period3": (np.arange(n) % 3).astype(np.uint8), "period130": (np.arange(n) % 130).astype(np.uint8),
+        "two": rng.integers(0, 2, n, dtype=np.uint8), "three": rng.integers(0, 3, n, dtype=np.uint8),
+        "zipf": O.zipf_bytes(n, 1.1, 12345)[:n].copy(),
+        "random": rng.integers(0, 256, n, dtype=np.uint8),
+        "mix": np.concatenate([O.quant_codes(n // 4, seed=3), np.zeros(n // 4, np.uint8), text[: n // 4],
+                               rng.integers(0, 4, n // 4, dtype=np.uint8)]),
+        # long runs that end just before / after the packet's last chunk (maxcheck shrinks there)
+        "tail": np.concatenate([np.r_[rng.integers(0, 256, PKT - k, dtype=np.uint8), np.full(k, 7, np.uint8)]
+                                for k in (1, 2, 3, 5, 64, 126, 127, 128, 129, 130, 200, 255, 256, 300, 1000, 4000)]),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_parity_cases()))
+def test_lane_parity_encoder_equals_the_oracle_encoder(lane, name):
+    data = _parity_cases()[name]
+    n = data.size
+    out, sizes, last = _encode(lane, data, parity=1)
+    want = _select(O.culzss_oracle_tokens(data), n)
+    for k in range(n // PKT):
+        got = out[k * SLOT: k * SLOT + sizes[k]]
+        assert sizes[k] == want[k].size and np.array_equal(got, want[k]), (name, k)
+        assert sizes[k] - _check_tokens(got.tolist(), max_len=127) == last[k]
+    ok, whole = O.culzss_oracle_compress(data)
+    if ok:      # and through the oracle's own aftercomp + trailer
+        body = np.concatenate([out[k * SLOT: k * SLOT + sizes[k]] for k in range(n // PKT)])
+        assert np.array_equal(body, whole[: body.size]) and whole.size == body.size + 2 * (n // PKT) + 6

@@ -76,6 +76,7 @@ def bench_culzss(mib, dev, kind="quant32"):
         cbytes = int(np.where(cf == 0, buf_len, cf).sum())
         fast["lane" if depth == "lane" else "depth%d" % depth] = {"encode_ms": ms, "encode_gbs": n / ms / 1e6, "ratio": n / cbytes,
                                    "encode_hbm_frac": (n + cbytes) / ms / 1e6 / PEAK}
+    cta_ms = timeit(lambda: pkg.culzss_encode(data, buf_len, out, clen, scratch, kernel=pkg.CULZSS_KERNEL_CTA), iters=2, warm=1)
     enc_ms = timeit(lambda: pkg.culzss_encode(data, buf_len, out, clen, scratch))
     cl = clen.cpu().numpy().astype(np.int64)
     raw = int((cl == 0).sum())
@@ -97,7 +98,7 @@ def bench_culzss(mib, dev, kind="quant32"):
                       "encode_gbs": n / enc_ms / 1e6, "decode_gbs": n / dec_ms / 1e6,
                       "encode_hbm_frac": (n + C) / enc_ms / 1e6 / PEAK,
                       "decode_hbm_frac": (n + C) / dec_ms / 1e6 / PEAK,
-                      "fast_mode_non_parity": fast}))
+                      "encode_cta_kernel_gbs": n / cta_ms / 1e6, "fast_mode_non_parity": fast}))
 
 
 def cudpp_blocks_gpu(nblocks, n, dev, kind="zipf", seed=95835):

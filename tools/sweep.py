@@ -2,7 +2,9 @@
 """BASELINE.json configs[4]: block-size x entropy sweep, encode + decode GB/s and ratio for the
 three paths on one GPU (device-resident, CUDA events, best of 3).  One JSON line per point.
 
-  python tools/sweep.py [--mib 256] [--paths cuhd,culzss,cudpp] [--md out.md]
+  python tools/sweep.py [--mib 256] [--paths cuhd,cuhd_batch,culzss,culzss_lane,cudpp] [--md out.md]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+      tools/sweep.py ...      # N GPUs: every rank sweeps its own data, rank 0 prints whole-job GB/s
 
 Input: order-0 bytes with Zipf exponent solved for the target entropy H (H = 8: uniform).
 Block size means: CULZSS buffer length (the reference fixes 1 MiB, main.c:62 -- other sizes are
@@ -155,7 +157,12 @@ def point_cuhd_batch(data, block, dev):
     return enc_ms, dec_ms, comp, bool(torch.equal(out, data))
 
 
-def point_culzss(data, block, dev):
+def point_culzss_lane(data, block, dev):
+    """NON-PARITY fast mode (packet-per-lane formulation), same format and decoder."""
+    return point_culzss(data, block, dev, fast="lane")
+
+
+def point_culzss(data, block, dev, fast=0):
     n = data.numel()
     nbuf = n // block
     L = pkg.lib()
@@ -163,7 +170,7 @@ def point_culzss(data, block, dev):
     out = torch.empty(nbuf * stride, dtype=torch.uint8, device=dev)
     clen = torch.empty(nbuf, dtype=torch.int32, device=dev)
     scr = torch.empty(L.b200lc_culzss_encode_scratch_bytes(nbuf, block), dtype=torch.uint8, device=dev)
-    enc_ms = timeit(lambda: pkg.culzss_encode(data, block, out, clen, scr), iters=3, warm=1)
+    enc_ms = timeit(lambda: pkg.culzss_encode(data, block, out, clen, scr, fast=fast), iters=3, warm=1)
     cl = clen.cpu().numpy().astype(np.int64)
     sizes = np.where(cl == 0, block, cl)
     offs = np.zeros(nbuf + 1, np.int64)
@@ -223,29 +230,47 @@ def main():
     ap.add_argument("--entropies", default="1,2,3,4,5,6,7,8")
     ap.add_argument("--md", default=None)
     args = ap.parse_args()
-    dev = torch.device("cuda:0")
+    # under torchrun: every rank sweeps its own data (weak scaling, blocks are independent), the times
+    # are reduced with MAX and the compressed sizes with SUM over NCCL, rank 0 reports the aggregate
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dev = torch.device("cuda:%d" % int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     rows = []
     for path in args.paths.split(","):
-        fn = {"cuhd": point_cuhd, "cuhd_batch": point_cuhd_batch, "culzss": point_culzss, "cudpp": point_cudpp}[path]
+        fn = {"cuhd": point_cuhd, "cuhd_batch": point_cuhd_batch, "culzss": point_culzss,
+              "culzss_lane": point_culzss_lane, "cudpp": point_cudpp}[path]
         total = (args.mib if path != "cudpp" else min(args.mib, 128)) * MIB
         for H in [float(x) for x in args.entropies.split(",")]:
-            data = gen(total, H, dev, seed=1000 + int(H * 10), lo_sym=1 if path == "cudpp" else 0)
+            data = gen(total, H, dev, seed=1000 + int(H * 10) + 7919 * rank, lo_sym=1 if path == "cudpp" else 0)
             for block in [int(x) for x in args.blocks.split(",")]:
-                rec = {"path": path, "H": H, "block": block, "mib": total // MIB}
-                if False:
-                    pass
-                else:
-                    enc_ms, dec_ms, comp, ok = fn(data, block, dev)
-                    rec.update({"encode_gbs": total / enc_ms / 1e6,
-                                "decode_gbs": total / dec_ms / 1e6 if dec_ms else None,
-                                "ratio": total / comp if comp else None, "round_trip": ok,
-                                "encode_hbm_frac": (total + comp) / enc_ms / 1e6 / PEAK if comp else None,
-                                "decode_hbm_frac": (total + comp) / dec_ms / 1e6 / PEAK if comp and dec_ms else None})
+                rec = {"path": path, "H": H, "block": block, "mib": total // MIB, "n_gpus": world}
+                enc_ms, dec_ms, comp, ok = fn(data, block, dev)
+                if world > 1:
+                    t = torch.tensor([enc_ms, dec_ms or 0.0, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    c = torch.tensor([float(comp or 0)], dtype=torch.float64, device=dev)
+                    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+                    enc_ms, dec_ms, ok = float(t[0]), (float(t[1]) or None), float(t[2]) == 0.0
+                    comp = int(c[0]) or None
+                job = total * world        # bytes of the whole job; per-GPU fractions below
+                rec.update({"encode_gbs": job / enc_ms / 1e6,
+                            "decode_gbs": job / dec_ms / 1e6 if dec_ms else None,
+                            "ratio": job / comp if comp else None, "round_trip": ok,
+                            "encode_hbm_frac": (job + comp) / world / enc_ms / 1e6 / PEAK if comp else None,
+                            "decode_hbm_frac": (job + comp) / world / dec_ms / 1e6 / PEAK if comp and dec_ms else None})
                 rows.append(rec)
-                print(json.dumps(rec), flush=True)
+                if rank == 0:
+                    print(json.dumps(rec), flush=True)
             del data
             torch.cuda.empty_cache()
-    if args.md:
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if args.md and rank == 0:
         with open(args.md, "w") as f:
             f.write("| path | H (bits/byte) | block | encode GB/s | decode GB/s | ratio | %HBM enc / dec | round trip |\n")
             f.write("|---|---|---|---|---|---|---|---|\n")
