@@ -367,7 +367,7 @@ def path_culzss(pkg, dev, rank, world, mib, peak, with_cpu):
         "roofline": {"kernel": "culzss_decode_kernel", "bound": "hbm", "achieved": (n + cbytes) / dec_ms / 1e6,
                      "peak": peak, "unit": "GB/s", "frac": (n + cbytes) / dec_ms / 1e6 / peak,
                      "algorithmic_bytes": n + cbytes},
-        "encode_roofline": {"kernel": "culzss_encode_kernel", "bound": "integer issue (parity mode), reported against hbm",
+        "encode_roofline": {"kernel": "culzss_encode_lane_kernel<parity> (packet per lane; batches under 160 MiB: culzss_encode_kernel<0>)", "bound": "integer issue (parity mode), reported against hbm",
                             "achieved": (n + cbytes) / enc_ms / 1e6, "peak": peak, "unit": "GB/s",
                             "frac": (n + cbytes) / enc_ms / 1e6 / peak},
         "fast_mode_non_parity": {"encode_gbs": world * n / fast_max / 1e6, "encode_ms": fast_max, "ratio": world * n / fsum,

@@ -855,8 +855,10 @@ extern "C" size_t b200lc_culzss_encode_scratch_bytes(size_t nbuf, size_t buf_len
            ((npk + 255) & ~size_t(255)) + ((npk * 4 + 255) & ~size_t(255)) + 256;
 }
 
-// parity mode switches to the packet-per-lane kernel from this many packets (64 MiB) on
-constexpr size_t kLaneParityMinPackets = 16384;
+// Parity mode switches to the packet-per-lane kernel from this many packets (160 MiB) on: a lane takes
+// ~10 ms for a packet of quantisation codes whatever the batch size (one wave = 148 SMs x 22 warps x
+// 32 lanes = 104k packets), the CTA kernel 0.24 us per packet -- they meet at ~41k packets.
+constexpr size_t kLaneParityMinPackets = 40960;
 
 static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uint8_t *d_out, size_t out_stride,
                         uint32_t *d_comp_len, void *d_scratch, size_t scratch_bytes, int depth, cudaStream_t stream,

@@ -207,15 +207,6 @@ struct Lane {
     }
 
     // ------------------------------------------------------------------------------ parity mode
-    // Bytes [p + k, p + k + 4) of the packet: from the ring while they are there, else straight from
-    // global memory (only a streak longer than the ~97..128 bytes of lookahead gets that far).
-    template <class IO>
-    B200LC_LANE_HD u32 look4(u32 k, const IO &io) const
-    {
-        if (hi >= kPacket || p + k + 4u <= hi) return ring4((p + k) & 255u);
-        return io.bytes4(p + k);
-    }
-
     // Token number t (0..7) of the open group, the reference's match:
     // scan index q = 0 .. n-1 stands for window position p - 128 + q (ring index (p + 128 + q) & 255);
     // walk q <- q + LCP(q) + 1 where LCP(q) is the common prefix of the window string at q and the
@@ -269,15 +260,26 @@ struct Lane {
                 u32 d = ring4(q) ^ x;
                 u32 L = 4;
                 if (d == 0 && L < cap) {
-                    u32 ws = (q >> 2) + 1;
-                    u32 s1 = ring[(ws & (kRingWords - 1)) * STRIDE];
-                    do {
+                    // Longer than four bytes: a word at a time, one new aligned word per side and step
+                    // while the lookahead is in the ring (capr), from global memory beyond it.
+                    const u32 capr = hi >= kPacket ? cap : min_u(cap, hi - p - 3u);
+                    u32 ws = (q >> 2) + 1, wp = ((p & 255u) >> 2) + 1;
+                    u32 s1 = ring[(ws & (kRingWords - 1)) * STRIDE], p1 = ring[(wp & (kRingWords - 1)) * STRIDE];
+                    while (d == 0 && L < capr) {
+                        ++ws; ++wp;
+                        const u32 s0 = s1, p0 = p1;
+                        s1 = ring[(ws & (kRingWords - 1)) * STRIDE];
+                        p1 = ring[(wp & (kRingWords - 1)) * STRIDE];
+                        d = fsr(s0, s1, 8 * q) ^ fsr(p0, p1, 8 * p);
+                        L += 4;
+                    }
+                    while (d == 0 && L < cap) {
                         ++ws;
                         const u32 s0 = s1;
                         s1 = ring[(ws & (kRingWords - 1)) * STRIDE];
-                        d = fsr(s0, s1, 8 * q) ^ look4(L, io);
+                        d = fsr(s0, s1, 8 * q) ^ io.bytes4(p + L);
                         L += 4;
-                    } while (d == 0 && L < cap);
+                    }
                 }
                 if (d) L -= 4u - ((ffs32(d) - 1u) >> 3);
                 L = min_u(L, cap);

@@ -199,7 +199,7 @@ int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_leng
  * B200LC_CULZSS_KERNEL_LANE  one packet per GPU lane, the reference's match finder evaluated only at
  *                            the positions the greedy selection visits (csrc/culzss_lane.cuh); 3-4x
  *                            the throughput once >= ~10^5 packets are in flight;
- * B200LC_CULZSS_KERNEL_AUTO  what b200lc_culzss_encode_batch does: LANE from 16384 packets (64 MiB)
+ * B200LC_CULZSS_KERNEL_AUTO  what b200lc_culzss_encode_batch does: LANE from 40960 packets (160 MiB)
  *                            per call on (environment B200LC_CULZSS_PARITY_LANE=0|1 overrides). */
 #define B200LC_CULZSS_KERNEL_AUTO 0
 #define B200LC_CULZSS_KERNEL_CTA 1

@@ -61,21 +61,22 @@ def test_encode_matches_oracle(name, kernel):
 
 
 def test_encode_kernels_agree_on_a_large_batch_and_auto_picks_the_lane_kernel():
-    """96 MiB (24576 packets: above the AUTO threshold) of mixed data: CTA kernel == lane kernel ==
-    b200lc_culzss_encode_batch byte for byte; three buffers checked against the oracle."""
+    """168 MiB (43008 packets: above the AUTO threshold of 40960) of mixed data: CTA kernel == lane
+    kernel == b200lc_culzss_encode_batch byte for byte; three buffers checked against the oracle."""
     rng = np.random.default_rng(21)
-    nbuf = 96
-    parts = []
-    for b in range(nbuf):
+    nbuf = 168
+    distinct = []
+    for b in range(12):
         kind = b % 4
         if kind == 0:
-            parts.append(O.quant_codes(MIB, seed=100 + b))
+            distinct.append(O.quant_codes(MIB, seed=100 + b))
         elif kind == 1:
-            parts.append(O.quant_codes(MIB, seed=100 + b, dtype=np.uint16))
+            distinct.append(O.quant_codes(MIB, seed=100 + b, dtype=np.uint16))
         elif kind == 2:
-            parts.append(rng.integers(0, 3, MIB, dtype=np.uint8))
+            distinct.append(rng.integers(0, 3, MIB, dtype=np.uint8))
         else:
-            parts.append(np.frombuffer((b"lorem ipsum dolor sit amet %d " % b) * 40000, np.uint8)[:MIB].copy())
+            distinct.append(np.frombuffer((b"lorem ipsum dolor sit amet %d " % b) * 40000, np.uint8)[:MIB].copy())
+    parts = [distinct[b % 12] for b in range(nbuf)]
     data = np.concatenate(parts)
     d = torch.from_numpy(data).to(DEV)
     outs = []
