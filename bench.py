@@ -333,8 +333,10 @@ def path_culzss(pkg, dev, rank, world, mib, peak, with_cpu):
     cbytes = int(offs[-1])
 
     # e2e: host buffers through the container call (what the reference CLI does around its kernels)
-    e2e_mib = min(mib, 512)
-    h_in = data[: e2e_mib * MIB].cpu().numpy()
+    e2e_mib = min(mib, 1024)
+    h_in_t = torch.empty(e2e_mib * MIB, dtype=torch.uint8).pin_memory()      # pinned host buffers
+    h_in_t.copy_(data[: e2e_mib * MIB])
+    h_in = h_in_t.numpy()
     u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
     L.b200lc_culzss_container_bound.restype = C.c_size_t
     L.b200lc_culzss_container_bound.argtypes = [C.c_size_t]
@@ -342,13 +344,14 @@ def path_culzss(pkg, dev, rank, world, mib, peak, with_cpu):
         f.restype = C.c_int
         f.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.POINTER(C.c_size_t)]
     cap = L.b200lc_culzss_container_bound(h_in.size)
-    h_comp = np.zeros(cap, np.uint8)
-    h_back = np.zeros(h_in.size, np.uint8)
+    h_comp_t = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    h_back_t = torch.zeros(h_in.size, dtype=torch.uint8).pin_memory()
+    h_comp, h_back = h_comp_t.numpy(), h_back_t.numpy()
     olen, blen = C.c_size_t(0), C.c_size_t(0)
     del data, dec, comp
     torch.cuda.empty_cache()
     e2e_s = 1e30
-    for it in range(2):
+    for it in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         pkg.check(L.b200lc_culzss_compress_container(h_in, h_in.size, h_comp, cap, C.byref(olen)), "container")
@@ -378,7 +381,8 @@ def path_culzss(pkg, dev, rank, world, mib, peak, with_cpu):
                                          "encoder"},
         "e2e": {"value": world * h_in.size / e2e_max / 1e9, "unit": "GB/s", "sample_mib": e2e_mib,
                 "h2d_bytes_per_step": int(h_in.size + olen.value), "d2h_bytes_per_step": int(h_in.size + olen.value),
-                "api": "b200lc_culzss_compress_container + _decompress_container, host buffers"},
+                "api": "b200lc_culzss_compress_container + _decompress_container, pinned host buffers, "
+                       "best of 3 calls (the work area is kept between calls)"},
     }
     if with_cpu:
         import oracle_lib as O
@@ -796,6 +800,8 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": 6 * args.steps,   # piece histograms, their reduction, piece bits, plan, pack, decode
         "clocks": clocks,
     }
+    if HOST_PLACEMENT is not None:
+        line["host_placement"] = HOST_PLACEMENT      # rank 0's; every rank pins to its own GPU's node
     if cpu:
         line["cpu_baseline"] = cpu
     if paths:
@@ -803,6 +809,9 @@ def run_ours(args, rank, world, local_rank):
     if strong:
         line["c4_strong"] = strong
     print(json.dumps(line))
+
+
+HOST_PLACEMENT = None
 
 
 def main():
@@ -845,6 +854,11 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", rank=rank, world_size=world,
                                 device_id=torch.device("cuda", local_rank))
+    # host placement: CPUs and memory of the GPU's NUMA node, before any pinned buffer exists
+    global HOST_PLACEMENT
+    if os.environ.get("B200LC_NO_NUMA_PIN", "0") != "1":
+        import importlib
+        HOST_PLACEMENT = importlib.import_module("gpu-lossless-compression_b200.hostpin").pin_to_gpu(local_rank)
     try:
         run_ours(args, rank, world, local_rank)
     finally:

@@ -14,6 +14,7 @@
 using namespace b200lc;
 
 struct b200lc_cuhd_session {
+    int device = 0;          // the device the session was created on; every call runs there
     size_t max_symbols = 0;
     size_t max_units = 0;
     cudaStream_t stream = nullptr;
@@ -28,6 +29,21 @@ struct b200lc_cuhd_session {
     std::vector<cudaEvent_t> events;
 };
 
+// A session may be driven from any host thread (a fresh thread's current device is 0, not the
+// session's): run the call on the session's device and put the caller's device back afterwards.
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceScope(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceScope()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 static const size_t kMaxChunks = 512;
 static const size_t kChunkBytesMin = size_t(8) << 20;
 
@@ -38,6 +54,7 @@ extern "C" int b200lc_cuhd_session_create(size_t max_symbols, b200lc_cuhd_sessio
     if (!out || max_symbols == 0) return B200LC_ERR_ARG;
     b200lc_cuhd_session *s = new (std::nothrow) b200lc_cuhd_session();
     if (!s) return B200LC_ERR_ARG;
+    cudaGetDevice(&s->device);
     s->max_symbols = max_symbols;
     s->max_units = (max_symbols * 13 + 31) / 32 + 2;  // worst case for 13-bit codes + pad unit
     size_t sa = b200lc_cuhd_decode_scratch_bytes(s->max_units);
@@ -64,6 +81,7 @@ extern "C" int b200lc_cuhd_session_create(size_t max_symbols, b200lc_cuhd_sessio
 extern "C" int b200lc_cuhd_session_destroy(b200lc_cuhd_session *s)
 {
     if (!s) return B200LC_OK;
+    DeviceScope on(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_symbols);
     cudaFree(s->d_units);
@@ -93,6 +111,7 @@ extern "C" int b200lc_cuhd_session_encode(b200lc_cuhd_session *s, const uint8_t 
         return B200LC_ERR_ARG;
     if (n == 0 || n > s->max_symbols) return B200LC_ERR_ARG;
     if (max_len < 1 || max_len > 13) return B200LC_ERR_UNSUPPORTED;
+    DeviceScope on(s->device);
     u64 *d_hist = reinterpret_cast<u64 *>(s->d_small);
     u32 *d_code = reinterpret_cast<u32 *>(s->d_small + 2048);
     u8 *d_len = s->d_small + 3072;
@@ -152,6 +171,7 @@ extern "C" int b200lc_cuhd_session_decode(b200lc_cuhd_session *s, const uint32_t
     if (!s || !h_units || !h_lut || !h_out) return B200LC_ERR_ARG;
     if (n_units == 0 || n_units > s->max_units || n_out > s->max_symbols) return B200LC_ERR_ARG;
     if (max_len < 1 || max_len > 13) return B200LC_ERR_UNSUPPORTED;
+    DeviceScope on(s->device);
     u8 *d_lut = s->d_small + 4096;
     B200LC_CUDA_TRY(cudaMemcpyAsync(d_lut, h_lut, size_t(2) << max_len, cudaMemcpyHostToDevice,
                                     s->stream));

@@ -233,6 +233,76 @@ extern "C" size_t b200lc_culzss_container_bound(size_t n)
     return 8 + 4 * nb + nb * (kBuf + 2 * (kBuf / 4096) + 6 + 32);
 }
 
+// ------------------------------------------------------------------------------ file container
+// Work area of the container functions, kept between calls (cudaMalloc / cudaFree of gigabytes per
+// call cost more than the kernels) and guarded by a mutex; it follows the caller's current device.
+namespace {
+struct ContainerArea {
+    int device = -1;
+    unsigned epoch = 0;
+    void *in = nullptr, *out = nullptr, *scratch = nullptr, *compact = nullptr, *small = nullptr;
+    size_t in_b = 0, out_b = 0, scratch_b = 0, compact_b = 0, small_b = 0;
+    void drop()
+    {
+        cudaFree(in); cudaFree(out); cudaFree(scratch); cudaFree(compact); cudaFree(small);
+        in = out = scratch = compact = small = nullptr;
+        in_b = out_b = scratch_b = compact_b = small_b = 0;
+    }
+};
+ContainerArea g_ct;
+std::mutex g_ct_mu;
+
+bool container_area(size_t in_b, size_t out_b, size_t scratch_b, size_t compact_b, size_t small_b)
+{
+    int dev = 0;
+    if (!ok(cudaGetDevice(&dev), "cudaGetDevice")) return false;
+    if (g_ct.epoch != context_epoch()) {        // the context was reset: the old pointers are gone
+        g_ct = ContainerArea();
+        g_ct.epoch = context_epoch();
+    }
+    if (g_ct.device != dev) {
+        if (g_ct.device >= 0) {
+            cudaSetDevice(g_ct.device);
+            g_ct.drop();
+            cudaSetDevice(dev);
+        }
+        g_ct.device = dev;
+    }
+    return grow(&g_ct.in, &g_ct.in_b, in_b) && grow(&g_ct.out, &g_ct.out_b, out_b) &&
+           grow(&g_ct.scratch, &g_ct.scratch_b, scratch_b) && grow(&g_ct.compact, &g_ct.compact_b, compact_b) &&
+           grow(&g_ct.small, &g_ct.small_b, small_b);
+}
+
+// buffer b of the container = its compressed bytes, or the raw input buffer when len[b] == 0
+// ("compression took more", culzss.c:177-183,241-242), at byte offset offs[b] of dst
+__global__ void __launch_bounds__(256) culzss_compact_kernel(const u8 *__restrict__ comp, size_t stride,
+                                                             const u8 *__restrict__ raw, size_t buf,
+                                                             const u32 *__restrict__ len,
+                                                             const u64 *__restrict__ offs, u8 *__restrict__ dst)
+{
+    const size_t b = blockIdx.y;
+    const u32 l = len[b];
+    const size_t sz = l ? l : buf;
+    const u8 *src = l ? comp + b * stride : raw + b * buf;
+    u8 *d = dst + offs[b];
+    // destination words are 4-byte aligned from `head` on; the sources are 16-byte aligned
+    const size_t head = min(sz, (size_t)((4 - (reinterpret_cast<uintptr_t>(d) & 3)) & 3));
+    const size_t words = (sz - head) >> 2;
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, tn = (size_t)gridDim.x * blockDim.x;
+    if (t0 < head) d[t0] = src[t0];
+    const u32 sh = 8 * (u32)(head & 3);
+    const u32 *sw = reinterpret_cast<const u32 *>(src);       // source word i holds bytes 4 i ..
+    u32 *dw = reinterpret_cast<u32 *>(d + head);
+    for (size_t i = t0; i < words; i += tn) {
+        const size_t at = head + 4 * i;                      // source byte offset of this word
+        const u32 lo = sw[at >> 2], hi = sh ? sw[(at >> 2) + 1] : 0u;
+        dw[i] = __funnelshift_r(lo, hi, sh);
+    }
+    const size_t done = head + 4 * words;
+    if (t0 < sz - done) d[done + t0] = src[done + t0];
+}
+}  // namespace
+
 extern "C" int b200lc_culzss_compress_container(const uint8_t *h_in, size_t n, uint8_t *h_out,
                                                 size_t cap, size_t *out_len)
 {
@@ -241,54 +311,45 @@ extern "C" int b200lc_culzss_compress_container(const uint8_t *h_in, size_t n, u
     const size_t nb = (n + kBuf - 1) / kBuf;
     const size_t padding = nb * kBuf - n;
     const size_t stride = (kBuf + kBuf / 8 + 1024 + 15) & ~size_t(15);
-    u8 *d_in = nullptr, *d_out = nullptr;
-    u32 *d_len = nullptr;
-    void *d_scratch = nullptr;
     const size_t sb = b200lc_culzss_encode_scratch_bytes(nb, kBuf);
-    int rc = B200LC_OK;
-    std::vector<u32> len(nb);
-    std::vector<u8> comp;
+    std::lock_guard<std::mutex> lk(g_ct_mu);
+    // small: len[nb] (u32) | offs[nb] (u64)
+    const size_t small_b = ((nb * 4 + 255) & ~size_t(255)) + nb * 8;
+    if (!container_area(nb * kBuf + 16, nb * stride, sb, nb * kBuf + 64, small_b)) return B200LC_ERR_CUDA;
+    u8 *d_in = static_cast<u8 *>(g_ct.in), *d_out = static_cast<u8 *>(g_ct.out);
+    u8 *d_compact = static_cast<u8 *>(g_ct.compact);
+    u32 *d_len = static_cast<u32 *>(g_ct.small);
+    u64 *d_offs = reinterpret_cast<u64 *>(static_cast<u8 *>(g_ct.small) + ((nb * 4 + 255) & ~size_t(255)));
     cudaStream_t st = nullptr;
-    if (cudaMalloc(&d_in, nb * kBuf) != cudaSuccess || cudaMalloc(&d_out, nb * stride) != cudaSuccess ||
-        cudaMalloc(&d_len, nb * 4) != cudaSuccess || cudaMalloc(&d_scratch, sb) != cudaSuccess) {
-        rc = B200LC_ERR_CUDA;
+    if (!ok(cudaMemcpy(d_in, h_in, n, cudaMemcpyHostToDevice), "H2D") ||
+        !ok(cudaMemset(d_in + n, 0, padding + 16), "memset"))
+        return B200LC_ERR_CUDA;
+    int rc = encode_any(d_in, nb, kBuf, d_out, stride, d_len, g_ct.scratch, sb, st);
+    if (rc != B200LC_OK) return rc;
+    std::vector<u32> len(nb);
+    if (!ok(cudaMemcpy(len.data(), d_len, nb * 4, cudaMemcpyDeviceToHost), "D2H")) return B200LC_ERR_CUDA;
+    // header: buffer count, padding, cumulative ends (culzss.c:220,243-264)
+    std::vector<u64> offs(nb);
+    const size_t hdr_bytes = 8 + 4 * nb;
+    if (hdr_bytes > cap) return B200LC_ERR_OVERFLOW;
+    u32 *hdr = reinterpret_cast<u32 *>(h_out);
+    hdr[0] = (u32)nb;
+    hdr[1] = (u32)padding;
+    size_t cum = 0;
+    for (size_t b = 0; b < nb; ++b) {
+        offs[b] = cum;
+        cum += len[b] ? len[b] : kBuf;
+        if (hdr_bytes + cum > cap) return B200LC_ERR_OVERFLOW;
+        hdr[2 + b] = (u32)cum;
     }
-    if (rc == B200LC_OK) {
-        if (!ok(cudaMemcpy(d_in, h_in, n, cudaMemcpyHostToDevice), "H2D") ||
-            !ok(cudaMemset(d_in + n, 0, padding), "memset"))
-            rc = B200LC_ERR_CUDA;
-    }
-    if (rc == B200LC_OK) rc = encode_any(d_in, nb, kBuf, d_out, stride, d_len, d_scratch, sb, st);
-    if (rc == B200LC_OK && !ok(cudaMemcpy(len.data(), d_len, nb * 4, cudaMemcpyDeviceToHost), "D2H"))
-        rc = B200LC_ERR_CUDA;
-    if (rc == B200LC_OK) {
-        size_t total = 8 + 4 * nb;
-        for (size_t b = 0; b < nb; ++b) total += len[b] ? len[b] : kBuf;
-        if (total > cap) rc = B200LC_ERR_OVERFLOW;
-        else {
-            u32 *hdr = reinterpret_cast<u32 *>(h_out);
-            hdr[0] = (u32)nb;
-            hdr[1] = (u32)padding;
-            size_t off = 8 + 4 * nb, cum = 0;
-            for (size_t b = 0; b < nb && rc == B200LC_OK; ++b) {
-                const size_t sz = len[b] ? len[b] : kBuf;
-                if (len[b]) {
-                    if (!ok(cudaMemcpy(h_out + off, d_out + b * stride, sz, cudaMemcpyDeviceToHost), "D2H"))
-                        rc = B200LC_ERR_CUDA;
-                } else {   // "compression took more": the raw buffer (culzss.c:177-183,241-242)
-                    const size_t have = std::min(kBuf, n - b * kBuf);
-                    memcpy(h_out + off, h_in + b * kBuf, have);
-                    memset(h_out + off + have, 0, kBuf - have);
-                }
-                cum += sz;
-                hdr[2 + b] = (u32)cum;
-                off += sz;
-            }
-            *out_len = off;
-        }
-    }
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_len); cudaFree(d_scratch);
-    return rc;
+    // the buffers are gathered on the device and leave with ONE copy
+    if (!ok(cudaMemcpy(d_offs, offs.data(), nb * 8, cudaMemcpyHostToDevice), "H2D")) return B200LC_ERR_CUDA;
+    culzss_compact_kernel<<<dim3(16, (unsigned)nb), 256, 0, st>>>(d_out, stride, d_in, kBuf, d_len, d_offs, d_compact);
+    if (!ok(cudaGetLastError(), "compact") ||
+        !ok(cudaMemcpy(h_out + hdr_bytes, d_compact, cum, cudaMemcpyDeviceToHost), "D2H"))
+        return B200LC_ERR_CUDA;
+    *out_len = hdr_bytes + cum;
+    return B200LC_OK;
 }
 
 extern "C" int b200lc_culzss_decompress_container(const uint8_t *h_in, size_t n, uint8_t *h_out,
@@ -311,22 +372,17 @@ extern "C" int b200lc_culzss_decompress_container(const uint8_t *h_in, size_t n,
         if (offs[b + 1] <= offs[b] || offs[b + 1] - offs[b] > kBuf + 2 * (kBuf / 4096) + 6 + 32)
             return B200LC_ERR_ARG;
     }
-    u8 *d_comp = nullptr, *d_out = nullptr;
-    u64 *d_offs = nullptr;
-    void *d_scratch = nullptr;
     const size_t sb = b200lc_culzss_decode_scratch_bytes(nb, kBuf);
-    int rc = B200LC_OK;
-    if (cudaMalloc(&d_comp, payload + 64) != cudaSuccess || cudaMalloc(&d_out, nb * kBuf) != cudaSuccess ||
-        cudaMalloc(&d_offs, (nb + 1) * 8) != cudaSuccess || cudaMalloc(&d_scratch, sb) != cudaSuccess)
-        rc = B200LC_ERR_CUDA;
-    if (rc == B200LC_OK &&
-        (!ok(cudaMemcpy(d_comp, h_in + 8 + 4 * nb, payload, cudaMemcpyHostToDevice), "H2D") ||
-         !ok(cudaMemcpy(d_offs, offs.data(), (nb + 1) * 8, cudaMemcpyHostToDevice), "H2D")))
-        rc = B200LC_ERR_CUDA;
-    if (rc == B200LC_OK) rc = b200lc_culzss_decode_batch(d_comp, d_offs, nb, kBuf, d_out, d_scratch, sb, nullptr);
-    if (rc == B200LC_OK && !ok(cudaMemcpy(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost), "D2H"))
-        rc = B200LC_ERR_CUDA;
-    if (rc == B200LC_OK) *out_len = out_bytes;
-    cudaFree(d_comp); cudaFree(d_out); cudaFree(d_offs); cudaFree(d_scratch);
-    return rc;
+    std::lock_guard<std::mutex> lk(g_ct_mu);
+    if (!container_area(payload + 64, nb * kBuf, sb, 0, (nb + 1) * 8)) return B200LC_ERR_CUDA;
+    u8 *d_comp = static_cast<u8 *>(g_ct.in), *d_out = static_cast<u8 *>(g_ct.out);
+    u64 *d_offs = static_cast<u64 *>(g_ct.small);
+    if (!ok(cudaMemcpy(d_comp, h_in + 8 + 4 * nb, payload, cudaMemcpyHostToDevice), "H2D") ||
+        !ok(cudaMemcpy(d_offs, offs.data(), (nb + 1) * 8, cudaMemcpyHostToDevice), "H2D"))
+        return B200LC_ERR_CUDA;
+    const int rc = b200lc_culzss_decode_batch(d_comp, d_offs, nb, kBuf, d_out, g_ct.scratch, sb, nullptr);
+    if (rc != B200LC_OK) return rc;
+    if (!ok(cudaMemcpy(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost), "D2H")) return B200LC_ERR_CUDA;
+    *out_len = out_bytes;
+    return B200LC_OK;
 }

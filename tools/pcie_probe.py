@@ -28,6 +28,9 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    placement = None
+    if "--pin" in sys.argv:      # CPUs / memory of the GPU's NUMA node before the pinned buffers exist
+        placement = importlib.import_module("gpu-lossless-compression_b200.hostpin").pin_to_gpu(local)
     n = 1 << 30
     h_a = torch.empty(n, dtype=torch.uint8).pin_memory()
     h_b = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -98,6 +101,7 @@ def main():
 
     res["encode_and_decode_concurrent_ms"] = 1e3 * timed(together)
     assert torch.equal(h_b, h_a)
+    res["host_placement"] = placement
     print(json.dumps(res), flush=True)
     if world > 1:
         import torch.distributed as dist
