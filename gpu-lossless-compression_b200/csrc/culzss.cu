@@ -74,18 +74,22 @@ __device__ __forceinline__ u32 load4(const u8 *pkt, u32 at)
 //   recent earlier positions whose first three bytes hash alike (shared-memory hash chain), not the
 //   result of the reference's streak scanner over all 127 window positions.  A match never reaches
 //   into its own output (source end <= current position), like the reference's.
+// Packets [first, npackets).  sel != nullptr: run only if *sel == want (AUTO mode launches both
+// parity kernels behind a probe; the one the probe did not pick returns at once).
 template <int DEPTH>
-__global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict__ in, u64 npackets,
+__global__ void __launch_bounds__(128) culzss_encode_kernel(const u8 *__restrict__ in, u64 first, u64 npackets,
                                                             u8 *__restrict__ tmp_out,
                                                             u16 *__restrict__ pkt_size,
-                                                            u8 *__restrict__ last_group_size)
+                                                            u8 *__restrict__ last_group_size,
+                                                            const int *__restrict__ sel, int want)
 {
+    if (sel && *sel != want) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
     const u32 tx = threadIdx.x;
     const u32 lane = tx & 31, warp = tx >> 5;
 
-    for (u64 pid = blockIdx.x; pid < npackets; pid += gridDim.x) {
+    for (u64 pid = first + blockIdx.x; pid < npackets; pid += gridDim.x) {
         // ---------------------------------------------------------------- load packet, reset state
         {
             const uint4 *src = reinterpret_cast<const uint4 *>(in + pid * kPacket);
@@ -467,15 +471,18 @@ struct LaneDevIO {
 };
 
 template <bool PARITY>
-__global__ void __launch_bounds__(kLaneWarps * 32, 11) culzss_encode_lane_kernel(const u8 *__restrict__ in, u64 npackets,
+__global__ void __launch_bounds__(kLaneWarps * 32, 11) culzss_encode_lane_kernel(const u8 *__restrict__ in, u64 first,
+                                                                            u64 npackets,
                                                                             u8 *__restrict__ tmp_out,
                                                                             u16 *__restrict__ pkt_size,
-                                                                            u8 *__restrict__ last_group_size)
+                                                                            u8 *__restrict__ last_group_size,
+                                                                            const int *__restrict__ sel, int want)
 {
     using namespace lzss_lane;
+    if (sel && *sel != want) return;
     extern __shared__ __align__(16) u32 lane_cols[];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u64 pid = (u64)blockIdx.x * (kLaneWarps * 32) + threadIdx.x;
+    const u64 pid = first + (u64)blockIdx.x * (kLaneWarps * 32) + threadIdx.x;
     const bool live = pid < npackets;
     const u64 pk = live ? pid : npackets - 1;         // idle lanes keep valid addresses
     LaneDevIO io{in + pk * kPacket, tmp_out + pk * (u64)kSlotBytes};
@@ -486,6 +493,29 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 11) culzss_encode_lane_kernel
     if (live) {
         pkt_size[pid] = (u16)size;
         last_group_size[pid] = (u8)last_group;
+    }
+}
+
+// AUTO mode: the first `count` packets were coded by the CTA kernel (a probe whose output is kept);
+// the packet-per-lane kernel only evaluates the positions the greedy selection visits, so it wins
+// where matches are frequent and loses on nearly incompressible data, where every position is
+// visited and its serial scan costs more than the CTA kernel's bit-parallel one (measured: quant
+// codes 38.9 vs 17.2 GB/s, order-0 bytes of 6 bits/byte 11.3 vs 27.6).  Pick by the probe's ratio.
+constexpr int kSelCta = 1, kSelLane = 2;
+__global__ void __launch_bounds__(256) culzss_select_kernel(const u16 *__restrict__ pkt_size, u32 count,
+                                                            int *__restrict__ sel)
+{
+    __shared__ u32 part[8];
+    u32 sum = 0;
+    for (u32 i = threadIdx.x; i < count; i += 256) sum += pkt_size[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+        for (int i = 0; i < 8; ++i) tot += part[i];
+        *sel = (u64)tot * 2 <= (u64)count * kPacket ? kSelLane : kSelCta;      // ratio >= 2
     }
 }
 
@@ -870,7 +900,7 @@ static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uin
     if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_scratch) & 15))
         return B200LC_ERR_ARG;
     if (scratch_bytes < b200lc_culzss_encode_scratch_bytes(nbuf, buf_length)) return B200LC_ERR_SCRATCH;
-    typedef void (*Kern)(const u8 *, u64, u8 *, u16 *, u8 *);
+    typedef void (*Kern)(const u8 *, u64, u64, u8 *, u16 *, u8 *, const int *, int);
     static const Kern kerns[4] = {lzss::culzss_encode_kernel<0>, lzss::culzss_encode_kernel<1>,
                                   lzss::culzss_encode_kernel<2>, lzss::culzss_encode_kernel<4>};
     int ki;
@@ -888,21 +918,26 @@ static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uin
     u16 *sizes = reinterpret_cast<u16 *>(tmp + npk * lzss::kMaxPacketOut + 16);
     u8 *lastg = reinterpret_cast<u8 *>(sizes) + ((npk * 2 + 255) & ~u64(255));
     u32 *pkoff = reinterpret_cast<u32 *>(lastg + ((npk + 255) & ~u64(255)));
+    int *sel = reinterpret_cast<int *>(reinterpret_cast<u8 *>(pkoff) + ((npk * 4 + 255) & ~u64(255)));   // the 256 spare bytes
 
     // Parity mode has two bit-identical kernels: a CTA per packet (any batch size) and a packet per
-    // lane, which needs tens of thousands of packets in flight to fill the GPU.
-    bool lane_kernel = ki < 0;
+    // lane, which needs tens of thousands of packets in flight to fill the GPU and frequent matches
+    // to pay off.  AUTO: small batches -> CTA kernel; large ones -> the CTA kernel codes a probe of
+    // 512 packets, culzss_select_kernel looks at its ratio and both kernels are launched on the
+    // rest, one of which returns at once (no host round trip: the call stays asynchronous).
+    enum { kCta, kLane, kProbe } plan = ki < 0 ? kLane : kCta;
     if (ki == 0) {
-        static int mode = -1;      // B200LC_CULZSS_PARITY_LANE = 0 never | 1 always | unset: by batch size
+        static int mode = -1;      // B200LC_CULZSS_PARITY_LANE = 0 never | 1 always | unset: probe
         if (mode < 0) {
             const char *e = getenv("B200LC_CULZSS_PARITY_LANE");
             mode = e ? (atoi(e) ? 1 : 0) : 2;
         }
-        lane_kernel = mode == 1 || (mode == 2 && npk >= (u64)kLaneParityMinPackets);
-        if (parity_kernel == B200LC_CULZSS_KERNEL_CTA) lane_kernel = false;
-        if (parity_kernel == B200LC_CULZSS_KERNEL_LANE) lane_kernel = true;
+        if (mode == 1) plan = kLane;
+        if (mode == 2 && npk >= (u64)kLaneParityMinPackets) plan = kProbe;
+        if (parity_kernel == B200LC_CULZSS_KERNEL_CTA) plan = kCta;
+        if (parity_kernel == B200LC_CULZSS_KERNEL_LANE) plan = kLane;
     }
-    if (lane_kernel) {
+    const auto launch_lane = [&](u64 first, const int *sel_p) -> int {
         const bool parity = ki == 0;
         const size_t lsmem = (size_t)lzss::kLaneWarps * 32 * 4 *
                              (parity ? lzss_lane::kColumnWordsParity : lzss_lane::kColumnWordsFast);
@@ -914,21 +949,40 @@ static int encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_length, uin
             if (lslot >= 0) lane_attr_done[lslot][parity] = context_epoch();
         }
         const u32 per_cta = lzss::kLaneWarps * 32;
-        kern<<<(u32)((npk + per_cta - 1) / per_cta), per_cta, lsmem, stream>>>(d_in, npk, tmp, sizes, lastg);
+        kern<<<(u32)((npk - first + per_cta - 1) / per_cta), per_cta, lsmem, stream>>>(d_in, first, npk, tmp, sizes, lastg,
+                                                                                     sel_p, lzss::kSelLane);
         B200LC_CUDA_TRY(cudaGetLastError());
-    } else {
-    // fast mode keeps its hash table (1024 x 16 bytes) behind EncSmem
-    const size_t smem = ((sizeof(lzss::EncSmem) + 15) & ~size_t(15)) + (depth ? (size_t(16) << 10) : 0);
-    static unsigned attr_done[kMaxDevices][4] = {{0}};   // context epoch the attribute was set in
-    const int slot = device_slot();
-    if (slot < 0 || attr_done[slot][ki] != context_epoch()) {
-        B200LC_CUDA_TRY(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (slot >= 0) attr_done[slot][ki] = context_epoch();
+        return B200LC_OK;
+    };
+    const auto launch_cta = [&](u64 first, u64 end, const int *sel_p) -> int {
+        const int k = ki < 0 ? 0 : ki;
+        // fast mode keeps its hash table (1024 x 16 bytes) behind EncSmem
+        const size_t smem = ((sizeof(lzss::EncSmem) + 15) & ~size_t(15)) + (k ? (size_t(16) << 10) : 0);
+        static unsigned attr_done[kMaxDevices][4] = {{0}};   // context epoch the attribute was set in
+        const int slot = device_slot();
+        if (slot < 0 || attr_done[slot][k] != context_epoch()) {
+            B200LC_CUDA_TRY(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (slot >= 0) attr_done[slot][k] = context_epoch();
+        }
+        const u32 grid = (u32)min(end - first, (u64)num_sms() * 64);
+        kerns[k]<<<grid, 128, smem, stream>>>(d_in, first, end, tmp, sizes, lastg, sel_p, lzss::kSelCta);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        return B200LC_OK;
+    };
+    int rc = B200LC_OK;
+    if (plan == kLane) rc = launch_lane(0, nullptr);
+    else if (plan == kCta) rc = launch_cta(0, npk, nullptr);
+    else {
+        const u64 probe = 512;
+        rc = launch_cta(0, probe, nullptr);
+        if (rc == B200LC_OK) {
+            lzss::culzss_select_kernel<<<1, 256, 0, stream>>>(sizes, (u32)probe, sel);
+            B200LC_CUDA_TRY(cudaGetLastError());
+            rc = launch_lane(probe, sel);
+        }
+        if (rc == B200LC_OK) rc = launch_cta(probe, npk, sel);
     }
-    const u32 grid = (u32)min(npk, (u64)num_sms() * 64);
-    kerns[ki]<<<grid, 128, smem, stream>>>(d_in, npk, tmp, sizes, lastg);
-    B200LC_CUDA_TRY(cudaGetLastError());
-    }
+    if (rc != B200LC_OK) return rc;
     lzss::culzss_scan_kernel<<<(u32)nbuf, 256, 0, stream>>>(sizes, lastg, npk_buf, (u32)buf_length,
                                                            d_out, out_stride, pkoff, d_comp_len);
     B200LC_CUDA_TRY(cudaGetLastError());

@@ -199,8 +199,12 @@ int b200lc_culzss_encode_batch(const uint8_t *d_in, size_t nbuf, size_t buf_leng
  * B200LC_CULZSS_KERNEL_LANE  one packet per GPU lane, the reference's match finder evaluated only at
  *                            the positions the greedy selection visits (csrc/culzss_lane.cuh); 3-4x
  *                            the throughput once >= ~10^5 packets are in flight;
- * B200LC_CULZSS_KERNEL_AUTO  what b200lc_culzss_encode_batch does: LANE from 40960 packets (160 MiB)
- *                            per call on (environment B200LC_CULZSS_PARITY_LANE=0|1 overrides). */
+ * B200LC_CULZSS_KERNEL_AUTO  what b200lc_culzss_encode_batch does: CTA below 40960 packets (160 MiB) per
+ *                            call; from there on the CTA kernel codes a probe of 512 packets, a
+ *                            one-CTA kernel looks at the probe's ratio and both kernels are launched
+ *                            on the rest, one of which returns at once -- LANE if the probe shrank
+ *                            to half or less (frequent matches), else CTA.  No host round trip.
+ *                            Environment B200LC_CULZSS_PARITY_LANE=0|1 overrides (never / always). */
 #define B200LC_CULZSS_KERNEL_AUTO 0
 #define B200LC_CULZSS_KERNEL_CTA 1
 #define B200LC_CULZSS_KERNEL_LANE 2
