@@ -83,6 +83,15 @@ B200LC_LANE_HD u32 ffs32(u32 x)
     return (u32)__builtin_ffs((int)x);
 #endif
 }
+// number of low bytes of d that are zero (0..4): d = xor of two little-endian 4-byte strings
+B200LC_LANE_HD u32 same_bytes(u32 d)
+{
+#if defined(__CUDA_ARCH__)
+    return (u32)__clz((int)__brev(d)) >> 3;
+#else
+    return d ? ((u32)__builtin_ctz(d) >> 3) : 4u;
+#endif
+}
 B200LC_LANE_HD u32 min_u(u32 a, u32 b) { return a < b ? a : b; }
 B200LC_LANE_HD u32 max_u(u32 a, u32 b) { return a > b ? a : b; }
 // 0x80 in every byte of w that equals the corresponding byte of b (exact, no carries between bytes)
@@ -171,24 +180,33 @@ struct Lane {
         u32 L = 0;
         if (dist - 3u <= kWindow - 3u && lim >= 3u) {
             const u32 q = (p - dist) & 255u;
-            u32 d = ring4(q) ^ x;
-            if ((d & 0xffffffu) == 0) {
-                L = 4;
-                if (d == 0 && L < lim) {
-                    // longer than four bytes: walk both strings a word at a time, one new aligned word
-                    // per side and step (the other half of each unaligned word is the previous one)
-                    u32 ws = (q >> 2) + 1, wp = ((p & 255u) >> 2) + 1;
-                    u32 s1 = ring[(ws & (kRingWords - 1)) * STRIDE], p1 = ring[(wp & (kRingWords - 1)) * STRIDE];
+            // the first eight bytes of both strings at once (three aligned words per side): most
+            // matches end there and never see the loop
+            const u32 *sw = ring + (q >> 2) * STRIDE;
+            const u32 s0 = sw[0], s1 = sw[STRIDE];
+            const u32 d0 = fsr(s0, s1, 8 * q) ^ x;
+            if ((d0 & 0xffffffu) == 0) {
+                u32 ws = (q >> 2) + 2, wp = ((p & 255u) >> 2) + 1;
+                u32 s2 = ring[(ws & (kRingWords - 1)) * STRIDE];
+                const u32 p1a = ring[(wp & (kRingWords - 1)) * STRIDE];
+                u32 p2 = ring[((wp + 1) & (kRingWords - 1)) * STRIDE];
+                const u32 d1 = fsr(s1, s2, 8 * q) ^ fsr(p1a, p2, 8 * p);
+                const u32 l0 = same_bytes(d0);
+                L = l0 == 4u ? 4u + same_bytes(d1) : l0;
+                if (L == 8u && L < lim) {
+                    // longer: a word at a time, one new aligned word per side and step
+                    u32 d = 0;
+                    ++wp;
                     do {
                         ++ws; ++wp;
-                        const u32 s0 = s1, p0 = p1;
-                        s1 = ring[(ws & (kRingWords - 1)) * STRIDE];
-                        p1 = ring[(wp & (kRingWords - 1)) * STRIDE];
-                        d = fsr(s0, s1, 8 * q) ^ fsr(p0, p1, 8 * p);
+                        const u32 a0 = s2, b0 = p2;
+                        s2 = ring[(ws & (kRingWords - 1)) * STRIDE];
+                        p2 = ring[(wp & (kRingWords - 1)) * STRIDE];
+                        d = fsr(a0, s2, 8 * q) ^ fsr(b0, p2, 8 * p);
                         L += 4;
                     } while (d == 0 && L < lim);
+                    L -= 4u - same_bytes(d);
                 }
-                if (d) L -= 4u - ((ffs32(d) - 1u) >> 3);
                 L = min_u(L, lim);
             }
         }
@@ -220,7 +238,7 @@ struct Lane {
     B200LC_LANE_HD void step_parity(u32 t, const IO &io)
     {
         const u32 n = p < kPacket - 128u ? 127u : max_u(1u, kPacket - 1u - p);
-        const u32 x = ring4(p & 255u);
+        const u32 x = ring4(p & 255u), x2 = ring4((p + 4u) & 255u);     // the first eight lookahead bytes
         const u32 b4 = (x & 0xffu) * 0x01010101u;
         const u32 i0 = (p + 128u) & 255u;
         const u32 a = i0 & 3u, wbase = i0 >> 2;
@@ -257,31 +275,38 @@ struct Lane {
                 const u32 u = 32 * w + bit;
                 const u32 cap = end - u;
                 const u32 q = (4 * wbase + u) & 255u;             // ring index of the streak's first byte
-                u32 d = ring4(q) ^ x;
-                u32 L = 4;
-                if (d == 0 && L < cap) {
-                    // Longer than four bytes: a word at a time, one new aligned word per side and step
-                    // while the lookahead is in the ring (capr), from global memory beyond it.
+                // eight bytes of the window string at once (three aligned words): most streaks end
+                // there and never see the loops
+                const u32 *sw = ring + (q >> 2) * STRIDE;
+                const u32 s0 = sw[0], s1 = sw[STRIDE];
+                u32 ws = (q >> 2) + 2;
+                u32 s2 = ring[(ws & (kRingWords - 1)) * STRIDE];
+                const u32 l0 = same_bytes(fsr(s0, s1, 8 * q) ^ x);
+                u32 L = l0 == 4u ? 4u + same_bytes(fsr(s1, s2, 8 * q) ^ x2) : l0;
+                if (L == 8u && L < cap) {
+                    // Longer: a word at a time, one new aligned word per side and step while the
+                    // lookahead is in the ring (capr), from global memory beyond it.
                     const u32 capr = hi >= kPacket ? cap : min_u(cap, hi - p - 3u);
-                    u32 ws = (q >> 2) + 1, wp = ((p & 255u) >> 2) + 1;
-                    u32 s1 = ring[(ws & (kRingWords - 1)) * STRIDE], p1 = ring[(wp & (kRingWords - 1)) * STRIDE];
+                    u32 wp = ((p & 255u) >> 2) + 2;
+                    u32 p1 = ring[(wp & (kRingWords - 1)) * STRIDE];
+                    u32 d = 0;
                     while (d == 0 && L < capr) {
                         ++ws; ++wp;
-                        const u32 s0 = s1, p0 = p1;
-                        s1 = ring[(ws & (kRingWords - 1)) * STRIDE];
+                        const u32 a0 = s2, b0 = p1;
+                        s2 = ring[(ws & (kRingWords - 1)) * STRIDE];
                         p1 = ring[(wp & (kRingWords - 1)) * STRIDE];
-                        d = fsr(s0, s1, 8 * q) ^ fsr(p0, p1, 8 * p);
+                        d = fsr(a0, s2, 8 * q) ^ fsr(b0, p1, 8 * p);
                         L += 4;
                     }
                     while (d == 0 && L < cap) {
                         ++ws;
-                        const u32 s0 = s1;
-                        s1 = ring[(ws & (kRingWords - 1)) * STRIDE];
-                        d = fsr(s0, s1, 8 * q) ^ io.bytes4(p + L);
+                        const u32 a0 = s2;
+                        s2 = ring[(ws & (kRingWords - 1)) * STRIDE];
+                        d = fsr(a0, s2, 8 * q) ^ io.bytes4(p + L);
                         L += 4;
                     }
+                    if (d) L -= 4u - same_bytes(d);
                 }
-                if (d) L -= 4u - ((ffs32(d) - 1u) >> 3);
                 L = min_u(L, cap);
                 if (L > best) { best = L; best_u = u; }
                 next = u + L + 1;

@@ -13,10 +13,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-fi
     > gpurun_out/r2_ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cuhd_decode_kernel -c 1 -f -o gpurun_out/r2_dec \
     python tools/bench_paths.py cuhd --mib 1024 > gpurun_out/r2_ncu_dec.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mtf_apply_kernel -c 1 -f -o gpurun_out/r2_mtf \
-    python tools/bench_paths.py cudpp --mib 128 > /dev/null 2>&1
+# lane kernels of tools/bench_paths.py culzss: launches 0-3 = fast mode (non-parity), 4.. = parity mode
+ncu --set full --clock-control none --import-source on -k regex:culzss_encode_lane_kernel -c 1 -f -o gpurun_out/r2_lzenc_lane_fast \
+    python tools/bench_paths.py culzss --mib 1024 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:culzss_encode_lane_kernel -s 5 -c 1 -f -o gpurun_out/r2_lzenc_lane_parity \
+    python tools/bench_paths.py culzss --mib 1024 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:culzss_decode_kernel -c 1 -f -o gpurun_out/r2_lzdec \
     python tools/bench_paths.py culzss --mib 1024 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:culzss_encode_kernel -c 1 -f -o gpurun_out/r2_lzenc_fast1 \
-    python tools/bench_paths.py culzss --mib 256 > /dev/null 2>&1
 tail -2 gpurun_out/r2_pytest.log; cat gpurun_out/r2_smoke.log | tail -1; cut -c1-400 gpurun_out/r2_bench.json; tail -3 gpurun_out/r2_bench.err
