@@ -219,7 +219,7 @@ struct Lane {
         // repeats with period `dist` -- keeping the entry lets the next token reach twice as far back
         // and copy twice as much;  an entry closer than 3 becomes usable in a moment.
         const bool keep = is_match ? bool((L == dist) & (2u * dist <= kWindow)) : (dist < 3u);
-        if (!keep) *he = (u8)p;
+        *he = (u8)(keep ? p - dist : p);      // p - dist is the old entry (mod 256): one store, no branch
         p += is_match ? L : 1u;
         need = L >= 32u ? 97u : 48u;      // after a long match: top up at once
     }

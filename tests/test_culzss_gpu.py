@@ -434,3 +434,51 @@ def test_fast_mode_streams_decode_with_the_reference_kernel(depth):
         dlen = C.c_int(0)
         assert ref.decompression_kernel_wrapper(work, int(bufs[0].size), C.byref(dlen), 0, 0, 1) == 1
         assert dlen.value == MIB and np.array_equal(work[:MIB], data), name
+
+
+def test_fast_lane_mode_behind_the_container_by_environment():
+    """B200LC_CULZSS_FAST=lane switches the container writer (and the reference-named wrappers) to
+    the NON-PARITY lane encoder: the file still decodes -- with the product decoder and, per buffer,
+    with the oracle's restatement of the reference decoder -- but is not the parity file.  The
+    switch is read once per process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent("""
+        import ctypes as C, sys, numpy as np
+        sys.path.insert(0, %r)
+        import oracle_lib as O
+        from pkg import b200lc
+        L = b200lc.lib()
+        u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        L.b200lc_culzss_container_bound.restype = C.c_size_t
+        L.b200lc_culzss_container_bound.argtypes = [C.c_size_t]
+        for f in (L.b200lc_culzss_compress_container, L.b200lc_culzss_decompress_container):
+            f.restype = C.c_int
+            f.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.POINTER(C.c_size_t)]
+        MIB = 1 << 20
+        data = np.concatenate([O.quant_codes(2 * MIB, seed=4), np.zeros(MIB, np.uint8)])
+        cap = L.b200lc_culzss_container_bound(data.size)
+        out = np.zeros(cap, np.uint8); olen = C.c_size_t(0)
+        assert L.b200lc_culzss_compress_container(data, data.size, out, cap, C.byref(olen)) == 0
+        back = np.zeros(data.size, np.uint8); blen = C.c_size_t(0)
+        assert L.b200lc_culzss_decompress_container(out[: olen.value].copy(), olen.value, back, back.size, C.byref(blen)) == 0
+        assert blen.value == data.size and np.array_equal(back, data)
+        hdr = out[: 8 + 12].view(np.uint32)
+        ends = hdr[2:5].astype(np.int64)
+        first = out[20: 20 + ends[0]].copy()
+        ok, dec = O.culzss_oracle_decompress(first, MIB)
+        assert ok and np.array_equal(dec, data[:MIB])
+        print("SIZE", olen.value)
+    """ % os.path.dirname(os.path.abspath(__file__)))
+    sizes = {}
+    for mode in ("", "lane"):
+        env = dict(os.environ)
+        env.pop("B200LC_CULZSS_FAST", None)
+        if mode:
+            env["B200LC_CULZSS_FAST"] = mode
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        sizes[mode] = int(r.stdout.split("SIZE")[1])
+    assert sizes["lane"] != sizes[""] and sizes["lane"] < 1.4 * sizes[""]
