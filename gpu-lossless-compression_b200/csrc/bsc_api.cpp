@@ -23,7 +23,7 @@ namespace {
 constexpr int kHeader = 28;               // LIBBSC_HEADER_SIZE
 constexpr int kNoError = 0, kBadParameter = -1, kNotEnoughMemory = -2, kNotSupported = -4,
               kUnexpectedEob = -5, kDataCorrupt = -6;
-constexpr int kSorterBwt = 1, kCoderStatic = 1, kCoderAdaptive = 2;
+constexpr int kSorterBwt = 1, kSorterSt5 = 5, kSorterSt8 = 8, kCoderStatic = 1, kCoderAdaptive = 2;   // libbsc.h:64-73
 
 std::mutex g_mutex;
 b200lc_bsc_stages g_stages = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -83,8 +83,8 @@ bool parse_mode(int mode, Mode &m)
     m.lzp_min = (mode >> 8) & 0xff;
     m.lzp_hash = (mode >> 16) & 0xff;
     int again = 0;
-    if (m.sorter == kSorterBwt) again = kSorterBwt;
-    else if (m.sorter > 0) return false;      // ST3..ST8 blocks: sort transform is not built (libbsc default)
+    if (m.sorter == kSorterBwt || (m.sorter >= kSorterSt5 && m.sorter <= kSorterSt8)) again = m.sorter;
+    else if (m.sorter > 0) return false;      // ST3 / ST4 blocks: CPU-only sort transforms, not built
     if (m.coder == kCoderStatic || m.coder == kCoderAdaptive) again += m.coder << 5;
     else if (m.coder > 0) return false;
     if (m.lzp_min || m.lzp_hash) {
@@ -100,7 +100,7 @@ extern "C" void b200lc_bsc_set_stages(const b200lc_bsc_stages *s)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (s) g_stages = *s;
-    else g_stages = b200lc_bsc_stages{nullptr, nullptr, nullptr, nullptr, nullptr};
+    else g_stages = b200lc_bsc_stages{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 }
 
 extern "C" int bsc_init_full(int features, void *(*malloc_fn)(size_t), void *(*zero_malloc_fn)(size_t),
@@ -137,9 +137,11 @@ extern "C" int bsc_compress(const unsigned char *input, unsigned char *output, i
                             int lzpMinLen, int blockSorter, int coder, int features)
 {
     if (!input || !output) return kBadParameter;
-    if (blockSorter != kSorterBwt) return kBadParameter;       // sort transform not built
+    // BWT, or the sort transforms that have a GPU path in the reference (ST5..ST8, st.cpp:1011-1017);
+    // ST3 / ST4 are CPU-only there and not built here
+    if (blockSorter != kSorterBwt && (blockSorter < kSorterSt5 || blockSorter > kSorterSt8)) return kBadParameter;
     if (coder != kCoderStatic && coder != kCoderAdaptive) return kBadParameter;
-    int mode = kSorterBwt + (coder << 5);
+    int mode = blockSorter + (coder << 5);
     if (lzpMinLen != 0 || lzpHashSize != 0) {
         if (lzpMinLen < 4 || lzpMinLen > 255) return kBadParameter;
         if (lzpHashSize < 10 || lzpHashSize > 28) return kBadParameter;
@@ -171,9 +173,15 @@ extern "C" int bsc_compress(const unsigned char *input, unsigned char *output, i
         memcpy(output, input, (size_t)n);
     }
 
+    if (lz_size <= kHeader) {                                  // libbsc.cpp:290-294
+        blockSorter = kSorterBwt;
+        mode = (mode & ~0x1f) | kSorterBwt;
+    }
     int indexes[256];
     unsigned char num_indexes = 0;
-    const int index = bsc_bwt_encode(output, lz_size, &num_indexes, indexes, features);   // GPU
+    const int index = blockSorter == kSorterBwt
+                          ? bsc_bwt_encode(output, lz_size, &num_indexes, indexes, features)          // GPU
+                          : bsc_st_encode_cuda(output, lz_size, blockSorter, features);               // GPU
     if (n < 64 * 1024) num_indexes = 0;
     if (index < kNoError) return finish(index);
 
@@ -229,9 +237,10 @@ extern "C" int bsc_decompress(const unsigned char *input, int inputSize, unsigne
         return kNoError;
     }
     const b200lc_bsc_stages st = stages();
-    if (!st.coder_decompress || !st.bwt_decode) return kNotSupported;
     Mode m;
     parse_mode(mode, m);
+    if (!st.coder_decompress || !(m.sorter == kSorterBwt ? (void *)st.bwt_decode : (void *)st.st_decode))
+        return kNotSupported;
     if (mode != (mode & 0xff) && !st.lzp_decompress) return kNotSupported;
 
     // the stages read the block while they write the output: an aliased block is copied first
@@ -254,7 +263,8 @@ extern "C" int bsc_decompress(const unsigned char *input, int inputSize, unsigne
     const int lz_size = st.coder_decompress(input + kHeader, output, m.coder, features);
     if (lz_size < kNoError) return finish(lz_size);
     if (lz_size > outputSize) return finish(kDataCorrupt);
-    int result = st.bwt_decode(output, lz_size, index, num_indexes, indexes, features);
+    int result = m.sorter == kSorterBwt ? st.bwt_decode(output, lz_size, index, num_indexes, indexes, features)
+                                        : st.st_decode(output, lz_size, m.sorter, index, features);
     if (result < kNoError) return finish(result);
     int produced = lz_size;
     if (mode != (mode & 0xff)) {

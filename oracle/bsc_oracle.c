@@ -40,3 +40,41 @@ int bsc_oracle_bwt_encode(const uint8_t *T, int n, uint8_t *U, uint8_t *num_inde
     free(sa);
     return pidx + 1;
 }
+
+/* Sort Transform of order k (ST5..ST8), the definition behind libbsc's bsc_st_encode
+ * (cuda-bsc/libbsc/st/st.h:64-72) as its CUDA path computes it (st/st2.cu:113-428): position i's
+ * context is the k bytes T[i .. i+k-1] of the CYCLIC text; positions are sorted by context, equal
+ * contexts keep text order (a stable radix sort of keys laid out in text order, st2.cu:236-250);
+ * the output is the byte IN FRONT of each position in that order (T[i-1] cyclic, the top key byte,
+ * st2.cu:192); the returned index is the sorted rank of position 0 (the first sorted entry equal to
+ * position 0's key, st2.cu:255-262, and position 0 is the first among equal contexts).
+ * Pinned against the reference's CPU bsc_st_encode (k = 5, 6) and bsc_st_decode (k = 5..8) from
+ * oracle/_ref/libref_bsc.so in tests/test_oracle_bsc.py. */
+static const uint8_t *st_text;
+static int st_n, st_k;
+static int st_cmp(const void *a, const void *b)
+{
+    const int i = *(const int *)a, j = *(const int *)b;
+    for (int d = 0; d < st_k; ++d) {
+        const uint8_t x = st_text[(i + d) % st_n], y = st_text[(j + d) % st_n];
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return i < j ? -1 : (i > j ? 1 : 0);
+}
+int bsc_oracle_st_encode(const uint8_t *T, int n, int k, uint8_t *out)
+{
+    if (!T || !out || n < 0 || k < 3 || k > 8) return -1;
+    if (n <= 1) { if (n == 1) out[0] = T[0]; return 0; }
+    int *order = (int *)malloc((size_t)n * sizeof(int));
+    if (!order) return -2;
+    for (int i = 0; i < n; ++i) order[i] = i;
+    st_text = T; st_n = n; st_k = k;
+    qsort(order, (size_t)n, sizeof(int), st_cmp);
+    int index = -1;
+    for (int j = 0; j < n; ++j) {
+        out[j] = T[(order[j] + n - 1) % n];
+        if (order[j] == 0) index = j;
+    }
+    free(order);
+    return index;
+}

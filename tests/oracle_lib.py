@@ -572,9 +572,40 @@ def ref_bsc():
     lib.bsc_bwt_decode.argtypes = [_u8p, C.c_int, C.c_int, C.c_ubyte, _i32p, C.c_int]
     lib.bsc_init.restype = C.c_int
     lib.bsc_init.argtypes = [C.c_int]
+    lib.bsc_st_encode.restype = C.c_int
+    lib.bsc_st_encode.argtypes = [_u8p, C.c_int, C.c_int, C.c_int]
+    lib.bsc_st_decode.restype = C.c_int
+    lib.bsc_st_decode.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bsc_init(0)
     _cache["ref_bsc"] = lib
     return lib
+
+
+def bsc_ref_st_encode(data, k):
+    """Reference CPU bsc_st_encode (k = 3..6; 7 and 8 exist on its GPU path only) -> (bytes, index)."""
+    n = int(np.asarray(data).size)
+    t = np.zeros(n + 4096, np.uint8)          # the reference reads / writes a few bytes past n
+    t[:n] = data
+    idx = ref_bsc().bsc_st_encode(t, n, k, 0)
+    return t[:n].copy(), idx
+
+
+def bsc_ref_st_decode(data, k, index):
+    n = int(np.asarray(data).size)
+    t = np.zeros(n + 4096, np.uint8)
+    t[:n] = data
+    rc = ref_bsc().bsc_st_decode(t, n, k, index, 0)
+    return rc, t[:n].copy()
+
+
+def bsc_oracle_st_encode(data, k):
+    lib = oracle()
+    lib.bsc_oracle_st_encode.restype = C.c_int
+    lib.bsc_oracle_st_encode.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
+    t = np.ascontiguousarray(data)
+    out = np.zeros(max(t.size, 1), np.uint8)
+    idx = lib.bsc_oracle_st_encode(t, t.size, k, out)
+    return out[: t.size].copy(), idx
 
 
 def bsc_ref_bwt_encode(data):

@@ -20,7 +20,7 @@ u8p = C.POINTER(C.c_ubyte)
 
 class Stages(C.Structure):
     _fields_ = [("coder_compress", C.c_void_p), ("coder_decompress", C.c_void_p), ("lzp_compress", C.c_void_p),
-                ("lzp_decompress", C.c_void_p), ("bwt_decode", C.c_void_p)]
+                ("lzp_decompress", C.c_void_p), ("bwt_decode", C.c_void_p), ("st_decode", C.c_void_p)]
 
 
 def _protos(lib):
@@ -49,7 +49,7 @@ def ref_stages():
     r = O.ref_bsc()
     addr = lambda name: C.cast(getattr(r, name), C.c_void_p).value
     return Stages(addr("bsc_coder_compress"), addr("bsc_coder_decompress"), addr("bsc_lzp_compress"),
-                  addr("bsc_lzp_decompress"), addr("bsc_bwt_decode"))
+                  addr("bsc_lzp_decompress"), addr("bsc_bwt_decode"), addr("bsc_st_decode"))
 
 
 def _store(lib, data):
@@ -149,7 +149,8 @@ def test_compress_argument_errors_before_any_cuda_call():
     lib = ours()
     d = np.zeros(100, np.uint8)
     o = np.zeros(200, np.uint8)
-    assert lib.bsc_compress(d.ctypes.data, o.ctypes.data, 100, 0, 0, 5, 1, 0) == BAD_PARAMETER     # ST5 not built
+    assert lib.bsc_compress(d.ctypes.data, o.ctypes.data, 100, 0, 0, 3, 1, 0) == BAD_PARAMETER     # ST3 / ST4: CPU-only, not built
+    assert lib.bsc_compress(d.ctypes.data, o.ctypes.data, 100, 0, 0, 9, 1, 0) == BAD_PARAMETER
     assert lib.bsc_compress(d.ctypes.data, o.ctypes.data, 100, 0, 0, 1, 3, 0) == BAD_PARAMETER     # unknown coder
     assert lib.bsc_compress(d.ctypes.data, o.ctypes.data, 100, 16, 3, 1, 1, 0) == BAD_PARAMETER    # lzpMinLen < 4
     assert lib.bsc_compress(d.ctypes.data, o.ctypes.data, 100, 9, 128, 1, 1, 0) == BAD_PARAMETER   # lzpHashSize < 10
@@ -185,6 +186,39 @@ def test_bsc_compress_on_gpu_bwt_equals_reference_block(n, lzp_hash, lzp_min, co
         assert rc == 0 and np.array_equal(out, data)
         rc, out = _decompress(ref(), got[:gn].copy(), n)
         assert rc == 0 and np.array_equal(out, data)
+    finally:
+        lib.b200lc_bsc_set_stages(None)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not O.have_ref("bsc"), reason="oracle/_ref/libref_bsc.so not built")
+@pytest.mark.parametrize("n,lzp_hash,lzp_min,coder,sorter", [(3569598, 16, 128, 1, 5), (1 << 20, 0, 0, 2, 6),
+                                                             (70000, 15, 32, 1, 7), (1 << 20, 16, 128, 1, 8),
+                                                             (40, 0, 0, 1, 6)])
+def test_bsc_compress_with_sort_transform_blocks(n, lzp_hash, lzp_min, coder, sorter):
+    """blockSorter = LIBBSC_BLOCKSORTER_ST5..ST8 (libbsc.h:70-73): ST on the GPU (bsc_st_encode_cuda).
+    ST5 / ST6 blocks equal the reference library's (its CPU transform); ST7 / ST8 have no CPU encoder
+    in the reference (st.cpp:1026) -- the reference library decompresses them back to the input."""
+    data = np.frombuffer(synthetic_largefile(n, seed=n % 83 + sorter), np.uint8)
+    lib = ours()
+    st = ref_stages()
+    lib.b200lc_bsc_set_stages(C.byref(st))
+    try:
+        got = np.zeros(n + HEADER, np.uint8)
+        gn = lib.bsc_compress(data.ctypes.data, got.ctypes.data, n, lzp_hash, lzp_min, sorter, coder, 0)
+        assert gn > 0
+        if sorter <= 6:
+            want = np.zeros(n + HEADER, np.uint8)
+            wn = ref().bsc_compress(data.ctypes.data, want.ctypes.data, n, lzp_hash, lzp_min, sorter, coder, 0)
+            assert gn == wn and np.array_equal(got[:gn], want[:wn])
+        if n > 64:
+            assert got[8] & 0x1f == sorter                      # mode word: the block sorter
+        rc, out = _decompress(lib, got[:gn].copy(), n)
+        assert rc == 0 and np.array_equal(out, data)
+        rc, out = _decompress(ref(), got[:gn].copy(), n)
+        assert rc == 0 and np.array_equal(out, data)
+        assert lib.bsc_compress(data.ctypes.data, got.ctypes.data, n, lzp_hash, lzp_min, 3, coder, 0) == BAD_PARAMETER
+        assert lib.bsc_compress(data.ctypes.data, got.ctypes.data, n, lzp_hash, lzp_min, 4, coder, 0) == BAD_PARAMETER
     finally:
         lib.b200lc_bsc_set_stages(None)
 

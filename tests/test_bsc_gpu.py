@@ -3,6 +3,7 @@ libb200lc.so against the oracle restatement (oracle/bsc_oracle.c), the reference
 (oracle/_ref/libref_bsc.so) and, end to end, the reference's bsc program linked against the GPU
 implementation (oracle/_ref/bsc_b200) against the all-CPU reference program (oracle/_ref/bsc).
 Bar: bit-exact arrays, byte-identical .bsc files."""
+import ctypes as C
 import os
 import subprocess
 
@@ -76,3 +77,98 @@ def test_reference_bsc_program_on_gpu_bwt_is_byte_identical(tmp_path, n, args, e
     r = subprocess.run([os.path.join(REF_DIR, "bsc"), "d", str(tmp_path / "bsc_b200.bsc"), str(back)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and back.read_bytes() == data
+
+
+# ------------------------------------------------------------------------------ Sort Transform ST5-8
+def _st_gpu(data, k):
+    lib = b200lc.lib()
+    lib.bsc_st_encode_cuda.restype = C.c_int
+    lib.bsc_st_encode_cuda.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    t = np.ascontiguousarray(data).copy()
+    idx = lib.bsc_st_encode_cuda(t.ctypes.data if t.size else None, t.size, k, 0)
+    return t, idx
+
+
+def _st_cases():
+    rng = np.random.default_rng(3)
+    return {
+        "text": np.frombuffer((b"the quick brown fox jumps over the lazy dog. " * 3000)[:100000], np.uint8).copy(),
+        "rand4": rng.integers(0, 4, 50000, dtype=np.uint8),
+        "rand": rng.integers(0, 256, 70001, dtype=np.uint8),
+        "zeros": np.zeros(4097, np.uint8),
+        "quant": O.quant_codes(1 << 18),
+        "tiny2": np.array([5, 5], np.uint8),
+        "tiny3": np.array([3, 1, 2], np.uint8),
+        "tiny9": rng.integers(0, 3, 9, dtype=np.uint8),
+        "period7": (np.arange(7000) % 7).astype(np.uint8),
+    }
+
+
+@pytest.mark.parametrize("k", [5, 6, 7, 8])
+@pytest.mark.parametrize("name", list(_st_cases().keys()))
+def test_st_encode_matches_oracle_and_reference(name, k):
+    """bsc_st_encode_cuda (st.cuh:64-72) == the oracle's restatement of the transform; k = 5, 6 also ==
+    the reference's CPU bsc_st_encode; every k inverted by the reference's CPU bsc_st_decode."""
+    data = _st_cases()[name]
+    got, gi = _st_gpu(data, k)
+    want, wi = O.bsc_oracle_st_encode(data, k)
+    assert gi == wi and np.array_equal(got, want)
+    if O.have_ref("bsc"):
+        if k <= 6:
+            ref, ri = O.bsc_ref_st_encode(data, k)
+            assert gi == ri and np.array_equal(got, ref)
+        rc, back = O.bsc_ref_st_decode(got, k, gi)
+        assert rc == 0 and np.array_equal(back, data)
+
+
+def test_st_encode_arguments_and_default_block():
+    lib = b200lc.lib()
+    lib.bsc_st_encode_cuda.restype = C.c_int
+    lib.bsc_st_encode_cuda.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    one = np.array([7], np.uint8)
+    assert lib.bsc_st_encode_cuda(None, 5, 5, 0) == -1                  # LIBBSC_BAD_PARAMETER
+    assert lib.bsc_st_encode_cuda(one.ctypes.data, 1, 4, 0) == -1       # k outside 5..8 (st2.cu:372)
+    assert lib.bsc_st_encode_cuda(one.ctypes.data, 1, 9, 0) == -1
+    assert lib.bsc_st_encode_cuda(one.ctypes.data, 1, 5, 0) == 0 and one[0] == 7
+    assert lib.bsc_st_cuda_init(0) == 0
+    if not O.have_ref("bsc"):
+        return
+    # bsc's default block size, 25 MiB: ST6 against the reference CPU encoder, ST8 through its decoder
+    n = 25 << 20
+    data = np.frombuffer(synthetic_largefile(n, seed=5), np.uint8)
+    got, gi = _st_gpu(data, 6)
+    ref, ri = O.bsc_ref_st_encode(data, 6)
+    assert gi == ri and np.array_equal(got, ref)
+    got8, gi8 = _st_gpu(data, 8)
+    rc, back = O.bsc_ref_st_decode(got8, 8, gi8)
+    assert rc == 0 and np.array_equal(back, data)
+    lib.b200lc_bsc_st_release()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_DIR, "bsc_b200")), reason="oracle/_ref/bsc_b200 not built")
+@pytest.mark.parametrize("k", [5, 6, 7, 8])
+def test_reference_bsc_program_with_sort_transform_on_the_gpu(tmp_path, k):
+    """The reference's bsc program built with its own LIBBSC_CUDA_SUPPORT flag and linked against
+    libb200lc.so instead of st2.cu + b40c: `bsc e -m<k> -G` runs ST-k through bsc_st_encode_cuda.
+    ST5 / ST6: the file equals the all-CPU reference program's (same transform on its CPU path);
+    ST7 / ST8 exist on the GPU only (st.cpp:1016,1026: the CPU program refuses them) -- the all-CPU
+    reference program decodes the file back to the input."""
+    n = 6 << 20
+    data = synthetic_largefile(n, seed=k)
+    src = tmp_path / "in"
+    src.write_bytes(data)
+    gpu = tmp_path / "gpu.bsc"
+    r = subprocess.run([os.path.join(REF_DIR, "bsc_b200"), "e", str(src), str(gpu), "-m%d" % k, "-G", "-t", "-b2"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and gpu.exists(), r.stdout + r.stderr
+    assert "error" not in (r.stdout + r.stderr).lower(), r.stdout + r.stderr
+    if k <= 6:
+        cpu = tmp_path / "cpu.bsc"
+        r = subprocess.run([os.path.join(REF_DIR, "bsc"), "e", str(src), str(cpu), "-m%d" % k, "-t", "-b2"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert cpu.read_bytes() == gpu.read_bytes()
+    back = tmp_path / "back"
+    r = subprocess.run([os.path.join(REF_DIR, "bsc"), "d", str(gpu), str(back)], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and back.read_bytes() == data, r.stdout + r.stderr

@@ -50,3 +50,35 @@ def test_oracle_equals_reference_divbwt(name):
     idx[: oi.size] = oi
     assert O.ref_bsc().bsc_bwt_decode(back, back.size, op, oi.size, idx, 0) == 0
     assert np.array_equal(back, data)
+
+
+# ------------------------------------------------------------------------------ Sort Transform ST5-8
+def _st_cases():
+    rng = np.random.default_rng(3)
+    return {
+        "text": np.frombuffer((b"the quick brown fox jumps over the lazy dog. " * 3000)[:100000], np.uint8).copy(),
+        "rand4": rng.integers(0, 4, 50000, dtype=np.uint8),
+        "rand": rng.integers(0, 256, 70001, dtype=np.uint8),
+        "zeros": np.zeros(4097, np.uint8),
+        "quant": O.quant_codes(1 << 16),
+        "tiny2": np.array([5, 5], np.uint8),
+        "tiny3": np.array([3, 1, 2], np.uint8),
+        "tiny9": rng.integers(0, 3, 9, dtype=np.uint8),
+        "period7": (np.arange(7000) % 7).astype(np.uint8),
+    }
+
+
+@pytest.mark.skipif(not O.have_ref("bsc"), reason="oracle/_ref/libref_bsc.so not built")
+@pytest.mark.parametrize("name", list(_st_cases().keys()))
+def test_st_oracle_is_pinned_to_the_reference(name):
+    """oracle/bsc_oracle.c::bsc_oracle_st_encode == the reference's CPU bsc_st_encode for k = 5, 6
+    (st/st.cpp:1005-1027; k = 7, 8 exist on the reference's GPU path only) and is inverted by the
+    reference's CPU bsc_st_decode for k = 5..8."""
+    data = _st_cases()[name]
+    for k in (5, 6, 7, 8):
+        out, idx = O.bsc_oracle_st_encode(data, k)
+        if k <= 6:
+            ref, ri = O.bsc_ref_st_encode(data, k)
+            assert ri == idx and np.array_equal(ref, out), k
+        rc, back = O.bsc_ref_st_decode(out, k, idx)
+        assert rc == 0 and np.array_equal(back, data), k

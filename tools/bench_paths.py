@@ -387,6 +387,29 @@ def bench_bsc(mib):
                 rec["identical"] = bool(rp == gp and np.array_equal(t, gu))
             rec["host_cores"] = os.cpu_count()
         print(json.dumps(rec))
+    # Sort Transform ST5..ST8 (bsc_st_encode_cuda, row N4), HOST buffers; the reference's CPU path
+    # covers k = 5, 6 only (st.cpp:1021-1026)
+    import ctypes as C
+    L = pkg.lib()
+    L.bsc_st_encode_cuda.restype = C.c_int
+    L.bsc_st_encode_cuda.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    data = np.frombuffer(synthetic_largefile(n, seed=11), np.uint8)
+    for k in (5, 6, 7, 8):
+        t = data.copy()
+        L.bsc_st_encode_cuda(t.ctypes.data, n, k, 0)          # warm-up: work area
+        t = data.copy()
+        t0 = time.perf_counter()
+        gi = L.bsc_st_encode_cuda(t.ctypes.data, n, k, 0)
+        gpu_s = time.perf_counter() - t0
+        rec = {"path": "bsc_st_encode", "k": k, "data": "text", "mib": mib, "gpu_ms": gpu_s * 1e3,
+               "gpu_gbs_host_buffers": n / gpu_s / 1e9, "index": int(gi)}
+        if O.have_ref("bsc") and k <= 6:
+            t0 = time.perf_counter()
+            ref, ri = O.bsc_ref_st_encode(data, k)
+            s_ = time.perf_counter() - t0
+            rec.update({"cpu_1thread_ms": s_ * 1e3, "cpu_1thread_gbs": n / s_ / 1e9,
+                        "identical": bool(ri == gi and np.array_equal(ref, t))})
+        print(json.dumps(rec))
 
 
 def main():
