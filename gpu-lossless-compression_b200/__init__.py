@@ -127,6 +127,8 @@ def lib():
     L.b200lc_bzip2_send_mtf_values.argtypes = [vp, i32, vp, vp, i32, vp, sz, C.POINTER(C.c_ulonglong), vp, vp]
     L.bsc_bwt_encode.restype = i32
     L.bsc_bwt_encode.argtypes = [vp, i32, vp, vp, i32]
+    L.bsc_bwt_decode.restype = i32
+    L.bsc_bwt_decode.argtypes = [vp, i32, i32, C.c_ubyte, vp, i32]
     L.b200lc_bsc_release.restype = None
     _lib = L
     return L
@@ -556,6 +558,16 @@ def bsc_bwt_encode(data):
     if p < 0:
         raise B200LCError("bsc_bwt_encode failed with LIBBSC code %d" % p)
     return t, p, idx[: int(num[0])].copy()
+
+
+def bsc_bwt_decode(u, index):
+    """libbsc's bsc_bwt_decode on the GPU: (U, primary index) as bsc_bwt_encode returns them -> block."""
+    import numpy as np
+    t = np.ascontiguousarray(u, dtype=np.uint8).copy()
+    rc = lib().bsc_bwt_decode(t.ctypes.data, t.size, int(index), 0, None, 0)
+    if rc < 0:
+        raise B200LCError("bsc_bwt_decode failed with LIBBSC code %d" % rc)
+    return t
 
 
 # ------------------------------------------------------------------------------- bzip2 MTF + RLE stage

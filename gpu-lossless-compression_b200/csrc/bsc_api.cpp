@@ -239,8 +239,9 @@ extern "C" int bsc_decompress(const unsigned char *input, int inputSize, unsigne
     const b200lc_bsc_stages st = stages();
     Mode m;
     parse_mode(mode, m);
-    if (!st.coder_decompress || !(m.sorter == kSorterBwt ? (void *)st.bwt_decode : (void *)st.st_decode))
-        return kNotSupported;
+    // the inverse BWT runs on the GPU unless the host program registered its own; the inverse sort
+    // transform exists on the CPU only (st.cpp:1506-1548)
+    if (!st.coder_decompress || (m.sorter != kSorterBwt && !st.st_decode)) return kNotSupported;
     if (mode != (mode & 0xff) && !st.lzp_decompress) return kNotSupported;
 
     // the stages read the block while they write the output: an aliased block is copied first
@@ -263,8 +264,9 @@ extern "C" int bsc_decompress(const unsigned char *input, int inputSize, unsigne
     const int lz_size = st.coder_decompress(input + kHeader, output, m.coder, features);
     if (lz_size < kNoError) return finish(lz_size);
     if (lz_size > outputSize) return finish(kDataCorrupt);
-    int result = m.sorter == kSorterBwt ? st.bwt_decode(output, lz_size, index, num_indexes, indexes, features)
-                                        : st.st_decode(output, lz_size, m.sorter, index, features);
+    int result = m.sorter != kSorterBwt ? st.st_decode(output, lz_size, m.sorter, index, features)
+                 : st.bwt_decode    ? st.bwt_decode(output, lz_size, index, num_indexes, indexes, features)
+                                    : bsc_bwt_decode(output, lz_size, index, num_indexes, indexes, features);
     if (result < kNoError) return finish(result);
     int produced = lz_size;
     if (mode != (mode & 0xff)) {

@@ -6,6 +6,7 @@
 // suffix sorter of bwt.cu as one segment; the output contract (U[0] = T[n-1], the row of suffix 0
 // dropped, primary index = that row + 1, secondary indexes = rows of the suffixes at multiples of
 // the step) is produced by two small kernels from the suffix array.
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -66,9 +67,9 @@ static int ensure(size_t n)
 {
     if (g_work.cap >= n) return 0;
     g_work.release();
-    g_work.scratch_bytes = b200lc_bwt_scratch_bytes(1, n) + 256;
+    g_work.scratch_bytes = std::max(b200lc_bwt_scratch_bytes(1, n), b200lc_inverse_bwt_primary_scratch_bytes(n)) + 256;
     if (cudaMalloc(&g_work.d_in, n) != cudaSuccess || cudaMalloc(&g_work.d_last, n) != cudaSuccess ||
-        cudaMalloc(&g_work.d_out, n) != cudaSuccess || cudaMalloc(&g_work.d_sa, n * 4) != cudaSuccess ||
+        cudaMalloc(&g_work.d_out, n + 16) != cudaSuccess || cudaMalloc(&g_work.d_sa, n * 4) != cudaSuccess ||
         cudaMalloc(&g_work.d_small, 257 * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&g_work.d_scratch, g_work.scratch_bytes) != cudaSuccess) {
         cudaGetLastError();
@@ -112,8 +113,41 @@ static int encode(unsigned char *T, int n, unsigned char *num_indexes, int *inde
     return small[0] + 1;
 }
 
+// bsc_bwt_decode (bwt.cpp:359-397): the reference rebuilds the text with a serial (or, with the
+// secondary indexes, 8-way parallel) LF walk on the CPU.  Here the block goes through the inverse
+// BWT of the cudppCompress decoder (csrc/cudpp_decode.cu: one 8-bit sort pass = the LF mapping,
+// then the walk cut at <= 4096 splitter rows that are walked in parallel, ranked, and walked again
+// writing output) with a VIRTUAL end marker -- libbsc's alphabet has none, and without one equal
+// bytes do not come in the same order in the first and the last column; blocks of 2^24 rows and
+// more use 64-bit row entries.  The secondary indexes are not needed.
+static int decode(unsigned char *T, int n, int index)
+{
+    if (T == nullptr || n < 0 || index <= 0 || index > n) return kBadParameter;     // bwt.cpp:361-364
+    if (n <= 1) return 0;
+    if ((u64)n > prims::kSortMaxElems) return kGpuNotSupported;
+    std::lock_guard<std::mutex> guard(g_lock);
+    int rc = ensure((size_t)n);
+    if (rc) return rc;
+    Work &w = g_work;
+    u32 *d_error = reinterpret_cast<u32 *>(w.d_small + 1);
+    if (cudaMemcpy(w.d_in, T, (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) return kGpuError;
+    // d_out holds n + 1 bytes: the walk also emits the virtual end marker
+    rc = b200lc_inverse_bwt_primary(w.d_in, (size_t)n, index, w.d_out, d_error, w.d_scratch, w.scratch_bytes, nullptr);
+    if (rc) return rc == B200LC_ERR_UNSUPPORTED ? kGpuNotSupported : kGpuError;
+    u32 h_error = 0;
+    if (cudaMemcpy(T, w.d_out, (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&h_error, d_error, sizeof(u32), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return kGpuError;
+    return h_error ? kGpuError : 0;
+}
+
 }  // namespace bsc
 }  // namespace b200lc
+
+extern "C" int bsc_bwt_decode(unsigned char *T, int n, int index, unsigned char, int *, int)
+{
+    return b200lc::bsc::decode(T, n, index);
+}
 
 extern "C" int bsc_bwt_encode(unsigned char *T, int n, unsigned char *num_indexes, int *indexes, int)
 {

@@ -244,12 +244,49 @@ __global__ void __launch_bounds__(256) ibwt_keys_kernel(const u8 *__restrict__ b
     vals[i] = (u32)(i - (u64)blk * n);
 }
 
+// One entry per row of the sorted first column: the row the walk goes to next and the row's first
+// byte.  u32 entries (24-bit row + byte) serve the batches of small blocks; one block of more than
+// 2^24 rows (libbsc: 25 MiB by default) uses u64 entries (32-bit row, byte above it).
+__device__ __forceinline__ u32 entry_next(u32 e) { return e & 0xffffffu; }
+__device__ __forceinline__ u32 entry_byte(u32 e) { return e >> 24; }
+__device__ __forceinline__ u32 entry_next(u64 e) { return (u32)e; }
+__device__ __forceinline__ u32 entry_byte(u64 e) { return (u32)(e >> 32); }
+__device__ __forceinline__ void entry_make(u32 &e, u32 row, u32 key) { e = row | (key << 24); }
+__device__ __forceinline__ void entry_make(u64 &e, u32 row, u32 key) { e = (u64)row | ((u64)(key & 0xffu) << 32); }
+
+template <typename E>
 __global__ void __launch_bounds__(256) ibwt_pack_kernel(const u32 *__restrict__ keys, const u32 *__restrict__ vals,
-                                                        u64 N, u32 *__restrict__ packed)
+                                                        u64 N, E *__restrict__ packed)
 {
     const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
-    packed[i] = vals[i] | (keys[i] << 24);
+    entry_make(packed[i], vals[i], keys[i]);
+}
+
+// ---- one block WITHOUT an end marker in its alphabet (libbsc, bsc_bwt_decode): the order of equal
+// bytes in the first and in the last column only agrees when the text ends with a unique smallest
+// symbol.  The cudppCompress blocks carry one (their final 0 byte); for libbsc's blocks the marker
+// '$' is virtual: row 0 of an (n + 1)-row problem.  `u` = what bsc_bwt_encode wrote (U[0] = T[n-1],
+// then the last column without the row of suffix 0), `primary` = its return value = the row of
+// suffix 0 among the n + 1 rows, where the last column holds '$'.
+__global__ void __launch_bounds__(256) ibwt_sentinel_keys_kernel(const u8 *__restrict__ u, u32 n, u32 primary,
+                                                                 u32 *__restrict__ keys, u32 *__restrict__ vals)
+{
+    const u32 j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    keys[j] = u[j];
+    vals[j] = j < primary ? j : j + 1;        // row of u[j] in the (n + 1)-row last column
+}
+
+// entries of rows 1..n from the sorted bytes; row 0 = '$', whose last-column copy sits in row `primary`
+template <typename E>
+__global__ void __launch_bounds__(256) ibwt_sentinel_pack_kernel(const u32 *__restrict__ keys,
+                                                                 const u32 *__restrict__ vals, u32 n, u32 primary,
+                                                                 E *__restrict__ packed)
+{
+    const u32 i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) entry_make(packed[i + 1], vals[i], keys[i]);
+    if (i == 0) entry_make(packed[0], primary, 0u);
 }
 
 struct Splitters {
@@ -259,7 +296,8 @@ struct Splitters {
 
 __device__ __forceinline__ bool is_splitter(u32 j, u32 start, u32 gap_mask) { return (j & gap_mask) == 0 || j == start; }
 
-__global__ void __launch_bounds__(128) ibwt_walk1_kernel(const u32 *__restrict__ packed, u32 n, Splitters sp,
+template <typename E>
+__global__ void __launch_bounds__(128) ibwt_walk1_kernel(const E *__restrict__ packed, u32 n, Splitters sp,
                                                          const int *__restrict__ bwt_index, u32 nblocks,
                                                          u32 *__restrict__ succ, u32 *__restrict__ plen,
                                                          u32 *__restrict__ error)
@@ -271,26 +309,29 @@ __global__ void __launch_bounds__(128) ibwt_walk1_kernel(const u32 *__restrict__
     u32 start = (u32)bwt_index[blk];
     if (start >= n) { if (k == 0) atomicExch(error, 6u); start = 0; }
     const u32 gap_mask = (1u << sp.gap_log2) - 1;
-    const u32 *T = packed + (u64)blk * n;
+    const E *T = packed + (u64)blk * n;
     u32 j = k < sp.ns ? k << sp.gap_log2 : start;
     u32 steps = 0;
     do {
-        j = T[j] & 0xffffffu;
+        j = entry_next(T[j]);
         ++steps;
     } while (!is_splitter(j, start, gap_mask) && steps < n);
     succ[gid] = j == start ? sp.ns : j >> sp.gap_log2;
     plen[gid] = steps;
 }
 
-constexpr u32 kMaxSplitters = 4096;
+constexpr u32 kMaxSplitters = 4096;          // per block of a batch
+constexpr u32 kMaxSplittersOne = 24576;      // one long block (libbsc): more walkers, 192 KiB of shared memory
 
 // CTA per block: positions of the splitters along the walk that starts at the start row.
+// Dynamic shared memory: 2 x (ns + 1) words.
 __global__ void __launch_bounds__(256) ibwt_rank_kernel(const u32 *__restrict__ succ, const u32 *__restrict__ plen,
                                                         u32 n, Splitters sp, u32 *__restrict__ task_pos,
                                                         u32 *__restrict__ period)
 {
-    __shared__ u32 s_succ[kMaxSplitters + 1], s_len[kMaxSplitters + 1];
+    extern __shared__ u32 s_rank[];
     const u32 per = sp.ns + 1;
+    u32 *s_succ = s_rank, *s_len = s_rank + per;
     const u64 base = (u64)blockIdx.x * per;
     for (u32 i = threadIdx.x; i < per; i += 256) {
         s_succ[i] = succ[base + i];
@@ -309,7 +350,8 @@ __global__ void __launch_bounds__(256) ibwt_rank_kernel(const u32 *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(128) ibwt_walk2_kernel(const u32 *__restrict__ packed, u32 n, Splitters sp,
+template <typename E>
+__global__ void __launch_bounds__(128) ibwt_walk2_kernel(const E *__restrict__ packed, u32 n, Splitters sp,
                                                          const int *__restrict__ bwt_index, u32 nblocks,
                                                          const u32 *__restrict__ task_pos,
                                                          const u32 *__restrict__ plen, u8 *__restrict__ out)
@@ -322,14 +364,14 @@ __global__ void __launch_bounds__(128) ibwt_walk2_kernel(const u32 *__restrict__
     if (pos == 0xffffffffu) return;
     u32 start = (u32)bwt_index[blk];
     if (start >= n) start = 0;
-    const u32 *T = packed + (u64)blk * n;
+    const E *T = packed + (u64)blk * n;
     u8 *dst = out + (u64)blk * n;
     u32 j = k < sp.ns ? k << sp.gap_log2 : start;
     const u32 cnt = min(plen[gid], n - pos);
     for (u32 t = 0; t < cnt; ++t) {
-        const u32 e = T[j];
-        dst[pos + t] = (u8)(e >> 24);
-        j = e & 0xffffffu;
+        const E e = T[j];
+        dst[pos + t] = (u8)entry_byte(e);
+        j = entry_next(e);
     }
 }
 
@@ -345,18 +387,21 @@ __global__ void __launch_bounds__(256) ibwt_extend_kernel(u8 *__restrict__ out, 
     if (local >= m) out[i] = out[(u64)blk * n + local % m];
 }
 
-static Splitters splitters_for(u32 n)
+static Splitters splitters_for(u32 n, u32 max_splitters = kMaxSplitters)
 {
     Splitters sp;
     sp.gap_log2 = 8;
-    while (((u64)n + (1ull << sp.gap_log2) - 1) >> sp.gap_log2 > kMaxSplitters) ++sp.gap_log2;
+    while (((u64)n + (1ull << sp.gap_log2) - 1) >> sp.gap_log2 > max_splitters) ++sp.gap_log2;
     sp.ns = (u32)(((u64)n + (1ull << sp.gap_log2) - 1) >> sp.gap_log2);
     return sp;
 }
 
 struct IbwtLayout {
-    size_t keys_a, keys_b, vals_a, vals_b, succ, plen, task, period, sort_temp, sort_bytes, total;
+    size_t keys_a, keys_b, vals_a, vals_b, succ, plen, task, period, sort_temp, sort_bytes, packed64, total;
 };
+
+// rows fit the 24-bit field of a u32 entry
+static bool narrow_rows(u32 n) { return n < (1u << 24); }
 
 static IbwtLayout ibwt_layout(u64 nblocks, u32 n)
 {
@@ -364,7 +409,8 @@ static IbwtLayout ibwt_layout(u64 nblocks, u32 n)
     const u64 N = nblocks * n;
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     L.sort_bytes = prims::sort_scratch_bytes(N, n);
-    const Splitters sp = splitters_for(n);
+    // a single block may be walked with the larger splitter budget (inverse_bwt_sentinel)
+    const Splitters sp = splitters_for(n, nblocks == 1 ? kMaxSplittersOne : kMaxSplitters);
     const size_t per = (size_t)nblocks * (sp.ns + 1) * 4;
     size_t o = 0;
     L.keys_a = o; o += up(N * 4);
@@ -376,6 +422,8 @@ static IbwtLayout ibwt_layout(u64 nblocks, u32 n)
     L.task = o; o += up(per);
     L.period = o; o += up(nblocks * 4);
     L.sort_temp = o; o += up(L.sort_bytes);
+    L.packed64 = o;
+    if (!narrow_rows(n)) o += up(N * 8);
     L.total = o;
     return L;
 }
@@ -401,26 +449,80 @@ static int inverse_bwt(const u8 *d_bwt, const int *d_index, u64 nblocks, u32 n, 
     const int rc = prims::sort_pairs<u32>(keys_a, keys_b, vals_a, vals_b, N, n, 0, 8, scratch + L.sort_temp,
                                           L.sort_bytes, stream, &in_b);
     if (rc) return rc;
-    u32 *packed = in_b ? keys_a : keys_b;
-    ibwt_pack_kernel<<<grid_n, 256, 0, stream>>>(in_b ? keys_b : keys_a, in_b ? vals_b : vals_a, N, packed);
-    B200LC_CUDA_TRY(cudaGetLastError());
     const Splitters sp = splitters_for(n);
     const u64 tasks = nblocks * (sp.ns + 1);
     const u32 grid_t = (u32)((tasks + 127) / 128);
-    ibwt_walk1_kernel<<<grid_t, 128, 0, stream>>>(packed, n, sp, d_index, (u32)nblocks, succ, plen, d_error);
-    B200LC_CUDA_TRY(cudaGetLastError());
-    ibwt_rank_kernel<<<(u32)nblocks, 256, 0, stream>>>(succ, plen, n, sp, task, period);
-    B200LC_CUDA_TRY(cudaGetLastError());
-    ibwt_walk2_kernel<<<grid_t, 128, 0, stream>>>(packed, n, sp, d_index, (u32)nblocks, task, plen, d_out);
-    B200LC_CUDA_TRY(cudaGetLastError());
+    const u32 *skeys = in_b ? keys_b : keys_a, *svals = in_b ? vals_b : vals_a;
+    const auto walks = [&](auto *packed) -> int {
+        ibwt_pack_kernel<<<grid_n, 256, 0, stream>>>(skeys, svals, N, packed);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        ibwt_walk1_kernel<<<grid_t, 128, 0, stream>>>(packed, n, sp, d_index, (u32)nblocks, succ, plen, d_error);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        ibwt_rank_kernel<<<(u32)nblocks, 256, 2 * (sp.ns + 1) * sizeof(u32), stream>>>(succ, plen, n, sp, task, period);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        ibwt_walk2_kernel<<<grid_t, 128, 0, stream>>>(packed, n, sp, d_index, (u32)nblocks, task, plen, d_out);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        return B200LC_OK;
+    };
+    // u32 entries are written over the key buffer the sort left free; u64 entries have their own
+    const int wrc = narrow_rows(n) ? walks(in_b ? keys_a : keys_b)
+                                   : walks(reinterpret_cast<u64 *>(scratch + L.packed64));
+    if (wrc) return wrc;
     ibwt_extend_kernel<<<grid_n, 256, 0, stream>>>(d_out, N, n, period);
     B200LC_CUDA_TRY(cudaGetLastError());
     return B200LC_OK;
 }
 
+// u[0..n) + primary (device int at d_primary, host copy `primary`) -> n text bytes at d_out, which
+// needs n + 1 bytes (the walk also emits the virtual end marker).  L = ibwt_layout(1, n + 1).
+static int inverse_bwt_sentinel(const u8 *d_u, u32 n, u32 primary, const int *d_primary, u8 *d_out, u32 *d_error,
+                                char *scratch, const IbwtLayout &L, cudaStream_t stream)
+{
+    u32 *keys_a = reinterpret_cast<u32 *>(scratch + L.keys_a), *keys_b = reinterpret_cast<u32 *>(scratch + L.keys_b);
+    u32 *vals_a = reinterpret_cast<u32 *>(scratch + L.vals_a), *vals_b = reinterpret_cast<u32 *>(scratch + L.vals_b);
+    u32 *succ = reinterpret_cast<u32 *>(scratch + L.succ), *plen = reinterpret_cast<u32 *>(scratch + L.plen);
+    u32 *task = reinterpret_cast<u32 *>(scratch + L.task), *period = reinterpret_cast<u32 *>(scratch + L.period);
+    const u32 rows = n + 1;
+    const u32 grid_n = (n + 255) / 256;
+    ibwt_sentinel_keys_kernel<<<grid_n, 256, 0, stream>>>(d_u, n, primary, keys_a, vals_a);
+    B200LC_CUDA_TRY(cudaGetLastError());
+    int in_b = 0;
+    const int rc = prims::sort_pairs<u32>(keys_a, keys_b, vals_a, vals_b, n, n, 0, 8, scratch + L.sort_temp,
+                                          L.sort_bytes, stream, &in_b);
+    if (rc) return rc;
+    const Splitters sp = splitters_for(rows, kMaxSplittersOne);
+    const u32 grid_t = (sp.ns + 1 + 127) / 128;
+    const size_t rank_smem = 2 * (size_t)(sp.ns + 1) * sizeof(u32);
+    if (rank_smem > 48 * 1024) {
+        static unsigned attr_done[kMaxDevices] = {0};
+        const int slot = device_slot();
+        if (slot < 0 || attr_done[slot] != context_epoch()) {
+            B200LC_CUDA_TRY(cudaFuncSetAttribute(ibwt_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(2 * (kMaxSplittersOne + 1) * sizeof(u32))));
+            if (slot >= 0) attr_done[slot] = context_epoch();
+        }
+    }
+    const u32 *skeys = in_b ? keys_b : keys_a, *svals = in_b ? vals_b : vals_a;
+    const auto walks = [&](auto *packed) -> int {
+        ibwt_sentinel_pack_kernel<<<grid_n, 256, 0, stream>>>(skeys, svals, n, primary, packed);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        ibwt_walk1_kernel<<<grid_t, 128, 0, stream>>>(packed, rows, sp, d_primary, 1u, succ, plen, d_error);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        ibwt_rank_kernel<<<1, 256, rank_smem, stream>>>(succ, plen, rows, sp, task, period);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        ibwt_walk2_kernel<<<grid_t, 128, 0, stream>>>(packed, rows, sp, d_primary, 1u, task, plen, d_out);
+        B200LC_CUDA_TRY(cudaGetLastError());
+        return B200LC_OK;
+    };
+    // the u32 entries need rows * 4 bytes: the free key buffer was sized for n + 1 elements
+    return narrow_rows(rows) ? walks(in_b ? keys_a : keys_b) : walks(reinterpret_cast<u64 *>(scratch + L.packed64));
+}
+
+// blocks of up to 2^24 - 1 rows in any number; longer blocks (u64 entries) one at a time
 static bool shape_ok(size_t nblocks, size_t n)
 {
-    return n < (1ull << 24) && nblocks <= (1ull << 23) && (u64)nblocks * n <= prims::kSortMaxElems;
+    if ((u64)nblocks * n > prims::kSortMaxElems || nblocks > (1ull << 23)) return false;
+    return n < (1ull << 24) || nblocks == 1;
 }
 
 }  // namespace cdec
@@ -480,6 +582,35 @@ extern "C" int b200lc_inverse_bwt_batch(const uint8_t *d_bwt, const int *d_bwt_i
     B200LC_CUDA_TRY(cudaMemsetAsync(d_error, 0, sizeof(u32), stream));
     return cdec::inverse_bwt(d_bwt, d_bwt_index, nblocks, (u32)n, d_out, d_error,
                              reinterpret_cast<char *>(d_scratch), L, false, stream);
+}
+
+// One block in libbsc's convention (no end marker in the alphabet): d_u = what bsc_bwt_encode wrote,
+// primary = its return value (1..n).  d_out needs n + 1 bytes; the first n are the block.
+extern "C" size_t b200lc_inverse_bwt_primary_scratch_bytes(size_t n)
+{
+    if (n == 0 || n + 1 > prims::kSortMaxElems) return 256;
+    return cdec::ibwt_layout(1, (u32)n + 1).total + 256;
+}
+
+extern "C" int b200lc_inverse_bwt_primary(const uint8_t *d_u, size_t n, int primary, uint8_t *d_out,
+                                          uint32_t *d_error, void *d_scratch, size_t scratch_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return B200LC_OK;
+    if (!d_u || !d_out || !d_error || !d_scratch) return B200LC_ERR_ARG;
+    if (primary <= 0 || (size_t)primary > n) return B200LC_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_scratch) & 255) return B200LC_ERR_ARG;
+    if (n + 1 > prims::kSortMaxElems) return B200LC_ERR_UNSUPPORTED;
+    const cdec::IbwtLayout L = cdec::ibwt_layout(1, (u32)n + 1);
+    if (scratch_bytes < L.total + 256) return B200LC_ERR_SCRATCH;
+    int *d_primary = reinterpret_cast<int *>(reinterpret_cast<char *>(d_scratch) + L.total);
+    B200LC_CUDA_TRY(cudaMemsetAsync(d_error, 0, sizeof(u32), stream));
+    B200LC_CUDA_TRY(cudaMemcpyAsync(d_primary, &primary, sizeof(int), cudaMemcpyHostToDevice, stream));
+    const int rc = cdec::inverse_bwt_sentinel(d_u, (u32)n, (u32)primary, d_primary, d_out, d_error,
+                                              reinterpret_cast<char *>(d_scratch), L, stream);
+    // `primary` is a stack variable: the copy above must have happened before we return
+    B200LC_CUDA_TRY(cudaStreamSynchronize(stream));
+    return rc;
 }
 
 extern "C" size_t b200lc_cudpp_decompress_scratch_bytes(size_t nblocks, size_t n)

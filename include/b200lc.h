@@ -302,6 +302,15 @@ size_t b200lc_inverse_bwt_scratch_bytes(size_t nblocks, size_t n);
 int b200lc_inverse_bwt_batch(const uint8_t *d_bwt, const int *d_bwt_index, size_t nblocks, size_t n,
                              uint8_t *d_out, uint32_t *d_error, void *d_scratch,
                              size_t scratch_bytes, void *stream);
+/* The same for ONE block whose alphabet has no end marker (libbsc's bsc_bwt_encode output, bwt.h:38-61):
+ * d_u[0] = T[n-1] followed by the last column without the row of suffix 0, primary = that row + 1
+ * (1..n).  The end marker is virtual (row 0 of an (n + 1)-row problem).  d_out needs n + 1 bytes,
+ * the first n are the block.  Blocks of 2^24 rows and more use 64-bit row entries.  Synchronous
+ * at its end (it copies `primary` to the device). */
+size_t b200lc_inverse_bwt_primary_scratch_bytes(size_t n);
+int b200lc_inverse_bwt_primary(const uint8_t *d_u, size_t n, int primary, uint8_t *d_out, uint32_t *d_error,
+                               void *d_scratch, size_t scratch_bytes, void *stream);
+
 size_t b200lc_cudpp_decompress_scratch_bytes(size_t nblocks, size_t n);
 int b200lc_cudpp_decompress_batch(const int *d_bwt_index, const uint32_t *d_hist,
                                   const uint32_t *d_offsets, const uint32_t *d_comp,

@@ -31,6 +31,16 @@ extern "C" {
 int bsc_bwt_encode(unsigned char *T, int n, unsigned char *num_indexes, int *indexes, int features);
 
 /*
+ * The inverse, with the reference's name and contract (bwt.h:50-61, bwt.cpp:359-397): T holds what
+ * bsc_bwt_encode wrote, `index` its return value; on return T is the original block.  The secondary
+ * indexes (the reference's 8-way CPU parallelism) are accepted and not needed: the walk is cut at
+ * up to 4096 splitter rows on the GPU.  Returns LIBBSC_NO_ERROR (0), LIBBSC_BAD_PARAMETER (-1: index
+ * outside 1..n), LIBBSC_GPU_ERROR (-7), LIBBSC_GPU_NOT_SUPPORTED (-8), LIBBSC_GPU_NOT_ENOUGH_MEMORY (-9).
+ * HOST pointer, synchronous, serialised on the same work area as bsc_bwt_encode.
+ */
+int bsc_bwt_decode(unsigned char *T, int n, int index, unsigned char num_indexes, int *indexes, int features);
+
+/*
  * libbsc's Sort Transform of order k = 5..8 on the GPU under the reference's names
  * (cuda-bsc/libbsc/st/st.cuh:56-72; st/st2.cu:367-428): what bsc_st_encode calls when libbsc is built
  * with LIBBSC_SORT_TRANSFORM_SUPPORT and LIBBSC_CUDA_SUPPORT (st/st.cpp:1011-1017), so such a build

@@ -186,6 +186,12 @@ def test_bsc_compress_on_gpu_bwt_equals_reference_block(n, lzp_hash, lzp_min, co
         assert rc == 0 and np.array_equal(out, data)
         rc, out = _decompress(ref(), got[:gn].copy(), n)
         assert rc == 0 and np.array_equal(out, data)
+        # without a registered bwt_decode the inverse BWT runs on the GPU (bsc_bwt_decode of the library)
+        st2 = ref_stages()
+        st2.bwt_decode = None
+        lib.b200lc_bsc_set_stages(C.byref(st2))
+        rc, out = _decompress(lib, got[:gn].copy(), n)
+        assert rc == 0 and np.array_equal(out, data)
     finally:
         lib.b200lc_bsc_set_stages(None)
 

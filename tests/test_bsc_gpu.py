@@ -77,6 +77,12 @@ def test_reference_bsc_program_on_gpu_bwt_is_byte_identical(tmp_path, n, args, e
     r = subprocess.run([os.path.join(REF_DIR, "bsc"), "d", str(tmp_path / "bsc_b200.bsc"), str(back)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and back.read_bytes() == data
+    # and the other way round: the program on the library (bsc_bwt_decode on the GPU) decodes the
+    # all-CPU program's file
+    back2 = tmp_path / "back2"
+    r = subprocess.run([os.path.join(REF_DIR, "bsc_b200"), "d", str(tmp_path / "bsc.bsc"), str(back2)] +
+                       [a for a in args if a == "-t"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and back2.read_bytes() == data, r.stdout + r.stderr
 
 
 # ------------------------------------------------------------------------------ Sort Transform ST5-8
@@ -172,3 +178,36 @@ def test_reference_bsc_program_with_sort_transform_on_the_gpu(tmp_path, k):
     r = subprocess.run([os.path.join(REF_DIR, "bsc"), "d", str(gpu), str(back)], capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0 and back.read_bytes() == data, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------------------ inverse BWT
+@pytest.mark.parametrize("name", list(_cases().keys()))
+def test_bwt_decode_inverts_encode_and_matches_reference(name):
+    """bsc_bwt_decode (bwt.h:61) on the GPU: inverts the GPU encoder's and the reference encoder's
+    output, and equals the reference's CPU bsc_bwt_decode."""
+    data = _cases()[name]
+    gu, gp, _ = b200lc.bsc_bwt_encode(data)
+    assert np.array_equal(b200lc.bsc_bwt_decode(gu, gp), data)
+    if O.have_ref("bsc"):
+        ru, rp, ri = O.bsc_ref_bwt_encode(data)
+        assert np.array_equal(b200lc.bsc_bwt_decode(ru, rp), data)
+        t = ru.copy()
+        idx = np.zeros(256, np.int32)
+        assert O.ref_bsc().bsc_bwt_decode(t, t.size, rp, 0, idx, 0) == 0 and np.array_equal(t, data)
+
+
+def test_bwt_decode_arguments_and_blocks_beyond_24_bit_rows():
+    lib = b200lc.lib()
+    one = np.array([9, 8, 7], np.uint8)
+    assert lib.bsc_bwt_decode(None, 3, 1, 0, None, 0) == -1            # LIBBSC_BAD_PARAMETER (bwt.cpp:361)
+    assert lib.bsc_bwt_decode(one.ctypes.data, 3, 0, 0, None, 0) == -1
+    assert lib.bsc_bwt_decode(one.ctypes.data, 3, 4, 0, None, 0) == -1
+    assert lib.bsc_bwt_decode(one.ctypes.data, 1, 1, 0, None, 0) == 0 and one[0] == 9
+    # bsc's default block (25 MiB) and one just past 2^24 rows: the 64-bit row entries
+    for n, seed in ((25 << 20, 11), ((1 << 24) + 12345, 12)):
+        data = np.frombuffer(synthetic_largefile(n, seed=seed), np.uint8)
+        gu, gp, _ = b200lc.bsc_bwt_encode(data)
+        assert np.array_equal(b200lc.bsc_bwt_decode(gu, gp), data)
+    periodic = np.tile(np.frombuffer(b"abracadabra-", np.uint8), (1 << 21) // 12 + 1)[: 1 << 21]
+    gu, gp, _ = b200lc.bsc_bwt_encode(periodic)
+    assert np.array_equal(b200lc.bsc_bwt_decode(gu, gp), periodic)

@@ -386,6 +386,23 @@ def bench_bsc(mib):
                 rec[label + "_gbs"] = n / s_ / 1e9
                 rec["identical"] = bool(rp == gp and np.array_equal(t, gu))
             rec["host_cores"] = os.cpu_count()
+        # the inverse: GPU bsc_bwt_decode next to the reference's CPU one (serial; its parallel mode
+        # needs the secondary indexes)
+        pkg.bsc_bwt_decode(gu, gp)
+        t0 = time.perf_counter()
+        back = pkg.bsc_bwt_decode(gu, gp)
+        dec_s = time.perf_counter() - t0
+        rec["decode_gpu_ms"] = dec_s * 1e3
+        rec["decode_gpu_gbs_host_buffers"] = n / dec_s / 1e9
+        rec["decode_ok"] = bool(np.array_equal(back, data))
+        if O.have_ref("bsc"):
+            t = gu.copy()
+            idx = np.zeros(256, np.int32)
+            t0 = time.perf_counter()
+            O.ref_bsc().bsc_bwt_decode(t, n, gp, 0, idx, 0)
+            s_ = time.perf_counter() - t0
+            rec["decode_cpu_1thread_ms"] = s_ * 1e3
+            rec["decode_cpu_1thread_gbs"] = n / s_ / 1e9
         print(json.dumps(rec))
     # Sort Transform ST5..ST8 (bsc_st_encode_cuda, row N4), HOST buffers; the reference's CPU path
     # covers k = 5, 6 only (st.cpp:1021-1026)
