@@ -5,6 +5,9 @@
 //
 // Host pointers handed to these functions should be pinned (cudaHostAlloc / cudaHostRegister);
 // pageable memory works but copies are then staged by the driver.
+#include <stdlib.h>
+
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -45,7 +48,26 @@ struct DeviceScope {
 };
 
 static const size_t kMaxChunks = 512;
-static const size_t kChunkBytesMin = size_t(8) << 20;
+// Chunks of the pipelined copies: a sixteenth of the transfer, between 8 and 32 MiB of stream for
+// the decoder and between 16 and 64 MiB of symbols for the encoder.  Measured on C2 with two encode
+// and two decode sessions in flight (bench.py e2e): 4 / 16 MiB chunks 23.2 GB/s, 8 / 32 MiB 24.9,
+// 16 / 32 MiB 26.2, 32 / 64 MiB 26.9, 64 / 128 MiB 27.2, 128 / 128 MiB 27.0 -- many small copies
+// from four streams leave gaps on the two copy engines.  B200LC_CUHD_CHUNK_MB /
+// B200LC_CUHD_ENC_CHUNK_MB fix the sizes (tuning).
+static size_t env_mb(const char *name)
+{
+    const char *e = getenv(name);
+    const long v = e ? atol(e) : 0;
+    return v >= 1 && v <= 1024 ? (size_t)v << 20 : 0;
+}
+static size_t chunk_bytes(size_t total, size_t lo, size_t hi, bool encoder)
+{
+    static const size_t fixed_dec = env_mb("B200LC_CUHD_CHUNK_MB"), fixed_enc = env_mb("B200LC_CUHD_ENC_CHUNK_MB");
+    const size_t fixed = encoder ? fixed_enc : fixed_dec;
+    if (fixed) return fixed;
+    const size_t c = (total / 16 + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    return c < lo ? lo : (c > hi ? hi : c);
+}
 
 static const size_t kSmallBytes = 4096 + (size_t(2) << 13) + 64;
 
@@ -118,7 +140,8 @@ extern "C" int b200lc_cuhd_session_encode(b200lc_cuhd_session *s, const uint8_t 
     u64 *d_bits = reinterpret_cast<u64 *>(s->d_small + 4096 + (size_t(2) << 13));
 
     const size_t ps = b200lc_cuhd_piece_symbols();
-    size_t chunk = (kChunkBytesMin * 4 / ps) * ps;           // 32 MiB, a whole number of pieces
+    size_t chunk = std::max<size_t>(1, chunk_bytes(n, size_t(16) << 20, size_t(64) << 20, true) / ps) *
+                   ps;                                         // a whole number of pieces
     while ((n + chunk - 1) / chunk > kMaxChunks) chunk *= 2;
     const size_t nchunks = (n + chunk - 1) / chunk;
     while (s->events.size() < 2 * nchunks) {
@@ -177,7 +200,7 @@ extern "C" int b200lc_cuhd_session_decode(b200lc_cuhd_session *s, const uint32_t
                                     s->stream));
     const size_t pu = b200lc_cuhd_decode_piece_units();
     const size_t pieces = (n_units + pu - 1) / pu;
-    size_t chunk_units = kChunkBytesMin / 4;
+    size_t chunk_units = chunk_bytes(n_units * 4, size_t(8) << 20, size_t(32) << 20, false) / 4;
     while ((n_units + chunk_units - 1) / chunk_units > kMaxChunks) chunk_units *= 2;
     const size_t nchunks = (n_units + chunk_units - 1) / chunk_units;
     while (s->events.size() < 2 * nchunks) {
