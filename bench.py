@@ -404,6 +404,12 @@ def path_culzss(pkg, dev, rank, world, mib, peak, with_cpu):
     return res
 
 
+# Blocks per cudppCompress call.  The kernels are batched over blocks: 64 / 128 / 256 / 512 blocks per
+# call give 7.3 / 8.2 / 8.6 / 8.9 GB/s encode and 7.1 / 10.4 / 12.9 / 15.1 GB/s decode on Zipf(1.3)
+# (tools/bench_paths.py) -- the inverse-BWT walks are latency-bound and want walkers.
+CUDPP_BATCH = 512
+
+
 def _cudpp_run(pkg, dev, first_block, nblocks, batch, iters, seed0=95835, check=True):
     """Compress blocks [first_block, first_block + nblocks) of the C4 input (block b is generated
     from seed0 + b // batch ... on the GPU) in batches; returns (encode_ms, decode_ms, sizes
@@ -445,11 +451,11 @@ def _cudpp_run(pkg, dev, first_block, nblocks, batch, iters, seed0=95835, check=
 
 def path_cudpp(pkg, dev, rank, world, blocks, peak, with_cpu):
     """C4, one GPU's share: `blocks` independent 1 MiB blocks through BWT + MTF + Huffman
-    (b200lc_cudpp_compress_batch) and back (b200lc_cudpp_decompress_batch), 128 blocks per call."""
+    (b200lc_cudpp_compress_batch) and back (b200lc_cudpp_decompress_batch), CUDPP_BATCH blocks per call."""
     import numpy as np
     import torch
     n = MIB
-    enc_ms, dec_ms, sizes = _cudpp_run(pkg, dev, rank * blocks, blocks, 128, iters=1)
+    enc_ms, dec_ms, sizes = _cudpp_run(pkg, dev, rank * blocks, blocks, CUDPP_BATCH, iters=1)
     words = int(sizes.sum().item())
     enc_max, dec_max = _reduce_max([enc_ms, dec_ms], dev, world)
     (wsum,) = _reduce_sum([float(words)], dev, world)
@@ -457,7 +463,7 @@ def path_cudpp(pkg, dev, rank, world, blocks, peak, with_cpu):
     alg = N + 4 * words + blocks * 4 * (256 + 256 + 2)
     res = {
         "workload": "cudppCompress (BWT + MTF + Huffman) and its inverse, %d blocks of 1 MiB per GPU "
-                    "(Zipf(1.3) / Markov bytes in 1..255, last byte 0), 128 blocks per call" % blocks,
+                    "(Zipf(1.3) / Markov bytes in 1..255, last byte 0), %d blocks per call" % (blocks, CUDPP_BATCH),
         "encode_gbs": world * N / enc_max / 1e6, "decode_gbs": world * N / dec_max / 1e6,
         "value": world * N / (enc_max + dec_max) / 1e6, "unit": "GB/s",
         "encode_ms": enc_max, "decode_ms": dec_max, "ratio": world * N / (4.0 * wsum),
@@ -502,7 +508,7 @@ def c4_strong(pkg, dev, rank, world, total_blocks):
         dist.barrier()
     t = _events(2)
     t[0].record()
-    enc_ms, dec_ms, sizes = _cudpp_run(pkg, dev, lo, hi - lo, 128, iters=1, check=False)
+    enc_ms, dec_ms, sizes = _cudpp_run(pkg, dev, lo, hi - lo, CUDPP_BATCH, iters=1, check=False)
     g = _events(2)
     g[0].record()
     if world > 1:
