@@ -301,8 +301,45 @@ __global__ void __launch_bounds__(256) culzss_compact_kernel(const u8 *__restric
     const size_t done = head + 4 * words;
     if (t0 < sz - done) d[done + t0] = src[done + t0];
 }
+
+// Three streams per call: copies up, kernels, copies down.  Created once per device context.
+struct ContainerStreams {
+    cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+    std::vector<cudaEvent_t> ev;
+    unsigned epoch = 0;
+    int device = -1;
+};
+ContainerStreams g_cs;
+
+bool container_streams(size_t events)
+{
+    int dev = 0;
+    if (!ok(cudaGetDevice(&dev), "cudaGetDevice")) return false;
+    if (g_cs.epoch != context_epoch() || g_cs.device != dev) {      // new context / device: start over
+        g_cs = ContainerStreams();
+        g_cs.epoch = context_epoch();
+        g_cs.device = dev;
+    }
+    if (!g_cs.up && (!ok(cudaStreamCreateWithFlags(&g_cs.up, cudaStreamNonBlocking), "stream") ||
+                     !ok(cudaStreamCreateWithFlags(&g_cs.run, cudaStreamNonBlocking), "stream") ||
+                     !ok(cudaStreamCreateWithFlags(&g_cs.down, cudaStreamNonBlocking), "stream")))
+        return false;
+    while (g_cs.ev.size() < events) {
+        cudaEvent_t e;
+        if (!ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return false;
+        g_cs.ev.push_back(e);
+    }
+    return true;
+}
+
+// buffers per pipeline chunk: large enough for the packet-per-lane encoder (>= 160 MiB per call)
+constexpr size_t kChunkBufs = 256;
 }  // namespace
 
+// Pipelined over chunks of 256 buffers: while chunk c is being coded, chunk c + 1 travels up and the
+// gathered image of chunk c - 1 travels down (pinned host buffers overlap fully; pageable ones are
+// staged by the driver).  The header needs the sizes of all buffers, the payload of a chunk only
+// those of the chunks before it.
 extern "C" int b200lc_culzss_compress_container(const uint8_t *h_in, size_t n, uint8_t *h_out,
                                                 size_t cap, size_t *out_len)
 {
@@ -311,43 +348,65 @@ extern "C" int b200lc_culzss_compress_container(const uint8_t *h_in, size_t n, u
     const size_t nb = (n + kBuf - 1) / kBuf;
     const size_t padding = nb * kBuf - n;
     const size_t stride = (kBuf + kBuf / 8 + 1024 + 15) & ~size_t(15);
-    const size_t sb = b200lc_culzss_encode_scratch_bytes(nb, kBuf);
+    const size_t cb = std::min(nb, kChunkBufs);                      // buffers per chunk
+    const size_t nchunks = (nb + cb - 1) / cb;
+    const size_t sb = b200lc_culzss_encode_scratch_bytes(cb, kBuf);
     std::lock_guard<std::mutex> lk(g_ct_mu);
     // small: len[nb] (u32) | offs[nb] (u64)
     const size_t small_b = ((nb * 4 + 255) & ~size_t(255)) + nb * 8;
-    if (!container_area(nb * kBuf + 16, nb * stride, sb, nb * kBuf + 64, small_b)) return B200LC_ERR_CUDA;
+    if (!container_area(nb * kBuf + 16, cb * stride, sb, nb * kBuf + 64, small_b)) return B200LC_ERR_CUDA;
+    if (!container_streams(2 * nchunks)) return B200LC_ERR_CUDA;
     u8 *d_in = static_cast<u8 *>(g_ct.in), *d_out = static_cast<u8 *>(g_ct.out);
     u8 *d_compact = static_cast<u8 *>(g_ct.compact);
     u32 *d_len = static_cast<u32 *>(g_ct.small);
     u64 *d_offs = reinterpret_cast<u64 *>(static_cast<u8 *>(g_ct.small) + ((nb * 4 + 255) & ~size_t(255)));
-    cudaStream_t st = nullptr;
-    if (!ok(cudaMemcpy(d_in, h_in, n, cudaMemcpyHostToDevice), "H2D") ||
-        !ok(cudaMemset(d_in + n, 0, padding + 16), "memset"))
-        return B200LC_ERR_CUDA;
-    int rc = encode_any(d_in, nb, kBuf, d_out, stride, d_len, g_ct.scratch, sb, st);
-    if (rc != B200LC_OK) return rc;
-    std::vector<u32> len(nb);
-    if (!ok(cudaMemcpy(len.data(), d_len, nb * 4, cudaMemcpyDeviceToHost), "D2H")) return B200LC_ERR_CUDA;
-    // header: buffer count, padding, cumulative ends (culzss.c:220,243-264)
-    std::vector<u64> offs(nb);
     const size_t hdr_bytes = 8 + 4 * nb;
     if (hdr_bytes > cap) return B200LC_ERR_OVERFLOW;
     u32 *hdr = reinterpret_cast<u32 *>(h_out);
     hdr[0] = (u32)nb;
     hdr[1] = (u32)padding;
-    size_t cum = 0;
-    for (size_t b = 0; b < nb; ++b) {
-        offs[b] = cum;
-        cum += len[b] ? len[b] : kBuf;
-        if (hdr_bytes + cum > cap) return B200LC_ERR_OVERFLOW;
-        hdr[2 + b] = (u32)cum;
+
+    // everything up, chunk by chunk (the copy engine works through them while the kernels start)
+    for (size_t c = 0; c < nchunks; ++c) {
+        const size_t lo = c * cb * kBuf, hi = std::min(n, (c + 1) * cb * kBuf);
+        if (!ok(cudaMemcpyAsync(d_in + lo, h_in + lo, hi - lo, cudaMemcpyHostToDevice, g_cs.up), "H2D")) return B200LC_ERR_CUDA;
+        if (c + 1 == nchunks && !ok(cudaMemsetAsync(d_in + n, 0, padding + 16, g_cs.up), "memset")) return B200LC_ERR_CUDA;
+        if (!ok(cudaEventRecord(g_cs.ev[2 * c], g_cs.up), "event")) return B200LC_ERR_CUDA;
     }
-    // the buffers are gathered on the device and leave with ONE copy
-    if (!ok(cudaMemcpy(d_offs, offs.data(), nb * 8, cudaMemcpyHostToDevice), "H2D")) return B200LC_ERR_CUDA;
-    culzss_compact_kernel<<<dim3(16, (unsigned)nb), 256, 0, st>>>(d_out, stride, d_in, kBuf, d_len, d_offs, d_compact);
-    if (!ok(cudaGetLastError(), "compact") ||
-        !ok(cudaMemcpy(h_out + hdr_bytes, d_compact, cum, cudaMemcpyDeviceToHost), "D2H"))
-        return B200LC_ERR_CUDA;
+    std::vector<u32> len(nb);
+    std::vector<u64> offs(nb);
+    size_t cum = 0;
+    int rc = B200LC_OK;
+    for (size_t c = 0; c < nchunks && rc == B200LC_OK; ++c) {
+        const size_t b0 = c * cb, nbc = std::min(cb, nb - b0);
+        if (!ok(cudaStreamWaitEvent(g_cs.run, g_cs.ev[2 * c], 0), "wait")) { rc = B200LC_ERR_CUDA; break; }
+        // the gather of the chunk before must have read d_out before this chunk's encoder rewrites it:
+        // both run on g_cs.run, in order
+        rc = encode_any(d_in + b0 * kBuf, nbc, kBuf, d_out, stride, d_len + b0, g_ct.scratch, sb, g_cs.run);
+        if (rc != B200LC_OK) break;
+        if (!ok(cudaMemcpyAsync(len.data() + b0, d_len + b0, nbc * 4, cudaMemcpyDeviceToHost, g_cs.run), "D2H") ||
+            !ok(cudaStreamSynchronize(g_cs.run), "sync")) { rc = B200LC_ERR_CUDA; break; }
+        const size_t chunk_base = cum;
+        for (size_t b = b0; b < b0 + nbc; ++b) {
+            offs[b] = cum;
+            cum += len[b] ? len[b] : kBuf;
+            hdr[2 + b] = (u32)cum;                       // cumulative ends (culzss.c:220,243-264)
+        }
+        if (hdr_bytes + cum > cap) { rc = B200LC_ERR_OVERFLOW; break; }
+        if (!ok(cudaMemcpyAsync(d_offs + b0, offs.data() + b0, nbc * 8, cudaMemcpyHostToDevice, g_cs.run), "H2D")) { rc = B200LC_ERR_CUDA; break; }
+        culzss_compact_kernel<<<dim3(16, (unsigned)nbc), 256, 0, g_cs.run>>>(d_out, stride, d_in + b0 * kBuf, kBuf, d_len + b0,
+                                                                            d_offs + b0, d_compact);
+        if (!ok(cudaGetLastError(), "compact") || !ok(cudaEventRecord(g_cs.ev[2 * c + 1], g_cs.run), "event") ||
+            !ok(cudaStreamWaitEvent(g_cs.down, g_cs.ev[2 * c + 1], 0), "wait") ||
+            !ok(cudaMemcpyAsync(h_out + hdr_bytes + chunk_base, d_compact + chunk_base, cum - chunk_base,
+                                cudaMemcpyDeviceToHost, g_cs.down), "D2H"))
+            rc = B200LC_ERR_CUDA;
+    }
+    // nothing may still be in flight when the buffers go back to the caller (or to the next call)
+    const bool drained = ok(cudaStreamSynchronize(g_cs.up), "sync") & ok(cudaStreamSynchronize(g_cs.run), "sync") &
+                         ok(cudaStreamSynchronize(g_cs.down), "sync");
+    if (rc != B200LC_OK) return rc;
+    if (!drained) return B200LC_ERR_CUDA;
     *out_len = hdr_bytes + cum;
     return B200LC_OK;
 }
@@ -372,17 +431,46 @@ extern "C" int b200lc_culzss_decompress_container(const uint8_t *h_in, size_t n,
         if (offs[b + 1] <= offs[b] || offs[b + 1] - offs[b] > kBuf + 2 * (kBuf / 4096) + 6 + 32)
             return B200LC_ERR_ARG;
     }
-    const size_t sb = b200lc_culzss_decode_scratch_bytes(nb, kBuf);
+    // pipelined like the compressor: chunk c + 1 travels up while chunk c is decoded and chunk c - 1
+    // travels down
+    const size_t cb = std::min(nb, kChunkBufs);
+    const size_t nchunks = (nb + cb - 1) / cb;
+    const size_t sb = b200lc_culzss_decode_scratch_bytes(cb, kBuf);
     std::lock_guard<std::mutex> lk(g_ct_mu);
-    if (!container_area(payload + 64, nb * kBuf, sb, 0, (nb + 1) * 8)) return B200LC_ERR_CUDA;
+    if (!container_area(payload + 64, nb * kBuf, sb, 0, (nb + nchunks) * 8)) return B200LC_ERR_CUDA;
+    if (!container_streams(2 * nchunks)) return B200LC_ERR_CUDA;
     u8 *d_comp = static_cast<u8 *>(g_ct.in), *d_out = static_cast<u8 *>(g_ct.out);
     u64 *d_offs = static_cast<u64 *>(g_ct.small);
-    if (!ok(cudaMemcpy(d_comp, h_in + 8 + 4 * nb, payload, cudaMemcpyHostToDevice), "H2D") ||
-        !ok(cudaMemcpy(d_offs, offs.data(), (nb + 1) * 8, cudaMemcpyHostToDevice), "H2D"))
-        return B200LC_ERR_CUDA;
-    const int rc = b200lc_culzss_decode_batch(d_comp, d_offs, nb, kBuf, d_out, g_ct.scratch, sb, nullptr);
+    // per chunk its own offset table (nbc + 1 entries, absolute offsets into d_comp)
+    std::vector<u64> table(nb + nchunks);
+    for (size_t c = 0, t = 0; c < nchunks; ++c) {
+        const size_t b0 = c * cb, nbc = std::min(cb, nb - b0);
+        for (size_t k = 0; k <= nbc; ++k) table[t++] = offs[b0 + k];
+    }
+    int rc = B200LC_OK;
+    if (!ok(cudaMemcpyAsync(d_offs, table.data(), table.size() * 8, cudaMemcpyHostToDevice, g_cs.up), "H2D")) rc = B200LC_ERR_CUDA;
+    for (size_t c = 0; c < nchunks && rc == B200LC_OK; ++c) {
+        const size_t b0 = c * cb, nbc = std::min(cb, nb - b0);
+        const size_t lo = offs[b0], hi = offs[b0 + nbc];
+        if (!ok(cudaMemcpyAsync(d_comp + lo, h_in + 8 + 4 * nb + lo, hi - lo, cudaMemcpyHostToDevice, g_cs.up), "H2D") ||
+            !ok(cudaEventRecord(g_cs.ev[2 * c], g_cs.up), "event"))
+            rc = B200LC_ERR_CUDA;
+    }
+    for (size_t c = 0; c < nchunks && rc == B200LC_OK; ++c) {
+        const size_t b0 = c * cb, nbc = std::min(cb, nb - b0);
+        if (!ok(cudaStreamWaitEvent(g_cs.run, g_cs.ev[2 * c], 0), "wait")) { rc = B200LC_ERR_CUDA; break; }
+        rc = b200lc_culzss_decode_batch(d_comp, d_offs + b0 + c, nbc, kBuf, d_out + b0 * kBuf, g_ct.scratch, sb, g_cs.run);
+        if (rc != B200LC_OK) break;
+        const size_t out_lo = b0 * kBuf, out_hi = std::min(out_bytes, (b0 + nbc) * kBuf);
+        if (!ok(cudaEventRecord(g_cs.ev[2 * c + 1], g_cs.run), "event") ||
+            !ok(cudaStreamWaitEvent(g_cs.down, g_cs.ev[2 * c + 1], 0), "wait") ||
+            !ok(cudaMemcpyAsync(h_out + out_lo, d_out + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, g_cs.down), "D2H"))
+            rc = B200LC_ERR_CUDA;
+    }
+    const bool drained = ok(cudaStreamSynchronize(g_cs.up), "sync") & ok(cudaStreamSynchronize(g_cs.run), "sync") &
+                         ok(cudaStreamSynchronize(g_cs.down), "sync");
     if (rc != B200LC_OK) return rc;
-    if (!ok(cudaMemcpy(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost), "D2H")) return B200LC_ERR_CUDA;
+    if (!drained) return B200LC_ERR_CUDA;
     *out_len = out_bytes;
     return B200LC_OK;
 }
