@@ -532,14 +532,21 @@ def c4_strong(pkg, dev, rank, world, total_blocks):
         want = np.zeros(total_blocks + 1, np.int64)
         want[1:] = np.cumsum(h)
         ok = bool(np.array_equal(offsets.cpu().numpy(), want)) and bool((h > 0).all())
-    enc_max, dec_max, wall_max, gather_max = _reduce_max([enc_ms, dec_ms, wall_ms, gather_ms], dev, world)
+    # A rank that finishes early WAITS in the all_gather for the slowest one, so its gather_ms holds the
+    # imbalance that enc_max + dec_max already contain: the step is the max over ranks of each rank's
+    # own encode + decode + gather, and the collective itself is what the LAST rank to arrive sees
+    # (the minimum over ranks).
+    step_ms = enc_ms + dec_ms + gather_ms
+    enc_max, dec_max, wall_max, gather_max, step_max, neg_gather_min = _reduce_max(
+        [enc_ms, dec_ms, wall_ms, gather_ms, step_ms, -gather_ms], dev, world)
     N = total_blocks * MIB
     return {"workload": "cudppCompress encode+decode, %d x 1 MiB blocks sharded over %d GPU(s), contiguous "
                         "block ranges, one all_gather of %d block sizes" % (total_blocks, world, total_blocks),
             "blocks": total_blocks, "blocks_per_rank": hi - lo, "scaling": "strong",
-            "value": N / (enc_max + dec_max + gather_max) / 1e6, "unit": "GB/s",
+            "value": N / step_max / 1e6, "unit": "GB/s",
             "encode_gbs": N / enc_max / 1e6, "decode_gbs": N / dec_max / 1e6,
-            "encode_ms": enc_max, "decode_ms": dec_max, "gather_ms": gather_max,
+            "step_ms": step_max, "encode_ms": enc_max, "decode_ms": dec_max,
+            "gather_ms": -neg_gather_min, "gather_ms_incl_wait_for_slowest_rank": gather_max,
             "wall_ms_with_input_generation": wall_max,
             "compressed_bytes": int(offsets[-1].item()), "offsets_ok": ok,
             "collective": "all_gather(int64[%d]) over %s" % (-(-total_blocks // world), "nccl" if world > 1 else "none (1 rank)")}
