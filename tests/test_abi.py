@@ -78,6 +78,36 @@ def test_new_entry_points_reject_bad_arguments_before_touching_cuda():
     assert lib.b200lc_cuhd_encode_blocks_scratch_bytes(1 << 20, 1 << 16) >= 256 + 16 * 16
 
 
+def test_round2_entry_points_reject_bad_arguments_before_touching_cuda():
+    """The entry points added in round 2 (include/b200lc.h, include/libbsc_gpu.h): argument errors
+    and trivial sizes come back before any CUDA call, so this runs without a GPU."""
+    lib = b200lc.lib()
+    E = b200lc
+    vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.b200lc_culzss_encode_batch_ex.argtypes = [vp, sz, sz, vp, sz, vp, vp, sz, i32, vp]
+    assert lib.b200lc_culzss_encode_batch_ex(None, 1, 4096, None, 0, None, None, 0, 3, None) == E.ERR_ARG    # unknown kernel
+    assert lib.b200lc_culzss_encode_batch_ex(None, 1, 4096, None, 0, None, None, 0, E.CULZSS_KERNEL_LANE, None) == E.ERR_ARG
+    assert lib.b200lc_culzss_encode_batch_ex(None, 0, 4096, None, 0, None, None, 0, E.CULZSS_KERNEL_LANE, None) == E.OK
+    assert lib.b200lc_culzss_encode_fast_batch(None, 1, 4096, None, 0, None, None, 0, 0, None) == E.ERR_ARG   # depth 0
+    lib.b200lc_inverse_bwt_primary.restype = i32
+    lib.b200lc_inverse_bwt_primary.argtypes = [vp, sz, i32, vp, vp, vp, sz, vp]
+    lib.b200lc_inverse_bwt_primary_scratch_bytes.restype = sz
+    lib.b200lc_inverse_bwt_primary_scratch_bytes.argtypes = [sz]
+    assert lib.b200lc_inverse_bwt_primary(None, 0, 1, None, None, None, 0, None) == E.OK
+    assert lib.b200lc_inverse_bwt_primary(None, 10, 1, None, None, None, 0, None) == E.ERR_ARG
+    assert lib.b200lc_inverse_bwt_primary_scratch_bytes(1 << 20) > (1 << 20) * 16
+    assert lib.b200lc_inverse_bwt_primary_scratch_bytes(0) == 256
+    one = (ctypes.c_ubyte * 4)(9, 8, 7, 6)
+    lib.bsc_st_encode_cuda.restype = i32
+    lib.bsc_st_encode_cuda.argtypes = [vp, i32, i32, i32]
+    assert lib.bsc_st_encode_cuda(None, 5, 5, 0) == -1                    # LIBBSC_BAD_PARAMETER (st2.cu:371)
+    assert lib.bsc_st_encode_cuda(one, 4, 4, 0) == -1 and lib.bsc_st_encode_cuda(one, 4, 9, 0) == -1
+    assert lib.bsc_st_encode_cuda(one, 1, 5, 0) == 0 and lib.bsc_st_cuda_init(0) == 0
+    assert lib.bsc_bwt_decode(None, 4, 1, 0, None, 0) == -1               # bwt.cpp:361-364
+    assert lib.bsc_bwt_decode(one, 4, 0, 0, None, 0) == -1 and lib.bsc_bwt_decode(one, 4, 5, 0, None, 0) == -1
+    assert lib.bsc_bwt_decode(one, 1, 1, 0, None, 0) == 0 and one[0] == 9
+
+
 def test_culzss_container_header_is_validated_before_touching_cuda():
     """u32 nblocks, u32 padding, u32 cumulative_end[nblocks] (cuda-lzss-cluster/culzss.c:220,243-264):
     non-increasing ends, a buffer larger than the worst case, a truncated payload and an output
